@@ -1,0 +1,15 @@
+"""CPU oracle for the U-ResNet hot path.  TEST INFRASTRUCTURE ONLY.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` /
+``--impl reference`` legs may import anything from this package.  The product
+path (``u-resnet_b200/``) never imports it and has no CPU fallback.
+
+PARITY UNPINNED: the reference (DeepLearnPhysics/u-resnet) ships no golden
+vectors, no tests and no weights, and its arithmetic lives in TensorFlow 1.x
+(``tf.contrib.slim``), which is neither vendored nor installable here.  The
+oracle restates ``lib/uresnet.py:22-123``, ``lib/resnet_module.py:10-87`` and
+``lib/ssnet.py:29-79`` with the slim/TF-1.x op semantics written down in
+SURVEY.md section 3.4, is cross-checked against an independent naive NumPy
+implementation (``oracle/naive.py``) and fp64 finite differences, and its
+outputs are frozen under ``tests/golden/``.
+"""

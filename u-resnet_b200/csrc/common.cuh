@@ -1,0 +1,104 @@
+// Shared helpers for the uresnet_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+#include "../../include/uresnet_b200.h"
+
+typedef __nv_bfloat16 bf16;
+
+// ---- error plumbing (thread-local message, int status across the C ABI) ----
+void urn_set_error(const char* fmt, ...);
+#define URN_CHECK(cond, ...)                 \
+  do {                                       \
+    if (!(cond)) {                           \
+      urn_set_error(__VA_ARGS__);            \
+      return 1;                              \
+    }                                        \
+  } while (0)
+#define URN_CUDA(call)                                                              \
+  do {                                                                              \
+    cudaError_t e_ = (call);                                                        \
+    if (e_ != cudaSuccess) {                                                        \
+      urn_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+      return 1;                                                                     \
+    }                                                                               \
+  } while (0)
+#define URN_LAUNCH_CHECK() URN_CUDA(cudaGetLastError())
+
+static inline int64_t cdiv64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+static inline int num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+// ---- typed element access: storage T in {float, bf16}, math in fp32 ----
+__device__ __forceinline__ float ld1(const float* p) { return *p; }
+__device__ __forceinline__ float ld1(const bf16* p) { return __bfloat162float(*p); }
+__device__ __forceinline__ void st1(float* p, float v) { *p = v; }
+__device__ __forceinline__ void st1(bf16* p, float v) { *p = __float2bfloat16_rn(v); }
+
+__device__ __forceinline__ float4 ld4(const float* p) {
+  return *reinterpret_cast<const float4*>(p);
+}
+__device__ __forceinline__ float4 ld4(const bf16* p) {
+  uint2 u = *reinterpret_cast<const uint2*>(p);
+  __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&u.x);
+  __nv_bfloat162 b = *reinterpret_cast<__nv_bfloat162*>(&u.y);
+  float2 fa = __bfloat1622float2(a), fb = __bfloat1622float2(b);
+  return make_float4(fa.x, fa.y, fb.x, fb.y);
+}
+__device__ __forceinline__ void st4(float* p, float4 v) {
+  *reinterpret_cast<float4*>(p) = v;
+}
+__device__ __forceinline__ void st4(bf16* p, float4 v) {
+  __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y);
+  __nv_bfloat162 b = __floats2bfloat162_rn(v.z, v.w);
+  uint2 u;
+  u.x = *reinterpret_cast<uint32_t*>(&a);
+  u.y = *reinterpret_cast<uint32_t*>(&b);
+  *reinterpret_cast<uint2*>(p) = u;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ---- generalised conv launch description shared by the FFMA and tcgen05 paths ----
+// out[n, o*os + oo, :] = sum_t in[n, o*is + off_t, :] . Wt      (o over a sub-grid)
+struct GTap {
+  int od, oh, ow;  // input offset of this tap (relative to o*is)
+  int widx;        // tap index into the filter (kd,kh,kw linearised)
+};
+struct GConv {
+  int n;
+  int id, ih, iw, cin;   // input tensor dims
+  int od, oh, ow, cout;  // FULL output tensor dims
+  int gd, gh, gw;        // sub-grid extents (number of o's per dim)
+  int is, os;            // input sampling stride / output placement stride
+  int ood, ooh, oow;     // output placement offset
+  int ntaps;
+  GTap taps[27];
+  // filter: element (tap, kin, kout) at w[tap*wtap + kin*wldi + kout*wldo]
+  int64_t wtap, wldi, wldo;
+  int64_t ldin, ldout;
+  int accumulate;
+};
+
+// Internal entry points (implemented in gconv_ffma.cu / gconv_tc.cu)
+int gconv_ffma_launch(const GConv& g, int in_dtype, const void* in, const float* w, void* out,
+                      int out_dtype, cudaStream_t st);
+int wgrad_ffma_launch(const urn_conv_desc& d, int dtype, const void* x, int64_t ldx, const void* y,
+                      int64_t ldy, float* dw, int accumulate, void* ws, cudaStream_t st);
+int64_t wgrad_ffma_workspace(const urn_conv_desc& d);

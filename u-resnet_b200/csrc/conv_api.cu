@@ -1,0 +1,145 @@
+// C-ABI conv entry points: geometry -> generalised-conv launches (FFMA or tcgen05).
+#include <stdarg.h>
+
+#include "common.cuh"
+#include "gconv_tc.cuh"
+
+static thread_local char g_err[1024] = "";
+void urn_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+extern "C" const char* urn_last_error(void) { return g_err; }
+extern "C" const char* urn_build_info(void) {
+  return "uresnet_b200 sm_100a (nvcc " URN_STR(__CUDACC_VER_MAJOR__) "." URN_STR(__CUDACC_VER_MINOR__) ")";
+}
+
+static int same_pad_before(int n, int k, int s) {
+  int out = (n + s - 1) / s;
+  int total = (out - 1) * s + k - n;
+  if (total < 0) total = 0;
+  return total / 2;
+}
+
+extern "C" int urn_conv_desc_same(urn_conv_desc* d, int nd, int n, int xd, int xh, int xw, int cx,
+                                  int cy, int k, int s) {
+  URN_CHECK(d, "urn_conv_desc_same: null descriptor");
+  URN_CHECK(nd == 2 || nd == 3, "urn_conv_desc_same: nd must be 2 or 3");
+  URN_CHECK(n > 0 && xd > 0 && xh > 0 && xw > 0 && cx > 0 && cy > 0, "urn_conv_desc_same: bad dims");
+  URN_CHECK((k == 1 || k == 3) && (s == 1 || s == 2), "urn_conv_desc_same: k in {1,3}, s in {1,2}");
+  URN_CHECK(nd == 3 || xd == 1, "urn_conv_desc_same: 2D needs xd == 1");
+  d->n = n; d->xd = xd; d->xh = xh; d->xw = xw; d->cx = cx; d->cy = cy;
+  d->kd = nd == 3 ? k : 1; d->kh = k; d->kw = k; d->s = s;
+  d->yd = nd == 3 ? (xd + s - 1) / s : 1;
+  d->yh = (xh + s - 1) / s;
+  d->yw = (xw + s - 1) / s;
+  d->pad_d = nd == 3 ? same_pad_before(xd, k, s) : 0;
+  d->pad_h = same_pad_before(xh, k, s);
+  d->pad_w = same_pad_before(xw, k, s);
+  return 0;
+}
+
+static int check_desc(const urn_conv_desc* d) {
+  URN_CHECK(d, "null conv descriptor");
+  URN_CHECK(d->n > 0 && d->cx > 0 && d->cy > 0 && d->xd > 0 && d->xh > 0 && d->xw > 0 &&
+                d->yd > 0 && d->yh > 0 && d->yw > 0, "conv descriptor: non-positive dims");
+  URN_CHECK(d->kd * d->kh * d->kw <= 27 && d->kd >= 1 && d->kh >= 1 && d->kw >= 1,
+            "conv descriptor: at most 27 taps");
+  URN_CHECK(d->s == 1 || d->s == 2, "conv descriptor: stride must be 1 or 2");
+  return 0;
+}
+
+// Y[o] = sum_t X[o*s + t - pad] . W[t]           (in = X, out = Y)
+void gconv_gather(const urn_conv_desc& d, int64_t ldx, int64_t ldy, GConv* g) {
+  g->n = d.n;
+  g->id = d.xd; g->ih = d.xh; g->iw = d.xw; g->cin = d.cx;
+  g->od = d.yd; g->oh = d.yh; g->ow = d.yw; g->cout = d.cy;
+  g->gd = d.yd; g->gh = d.yh; g->gw = d.yw;
+  g->is = d.s; g->os = 1; g->ood = g->ooh = g->oow = 0;
+  g->ntaps = 0;
+  for (int td = 0; td < d.kd; ++td)
+    for (int th = 0; th < d.kh; ++th)
+      for (int tw = 0; tw < d.kw; ++tw) {
+        GTap& t = g->taps[g->ntaps++];
+        t.od = td - d.pad_d; t.oh = th - d.pad_h; t.ow = tw - d.pad_w;
+        t.widx = (td * d.kh + th) * d.kw + tw;
+      }
+  g->wtap = (int64_t)d.cx * d.cy; g->wldi = d.cy; g->wldo = 1;
+  g->ldin = ldx; g->ldout = ldy; g->accumulate = 0;
+}
+
+// X[x] = sum_{o,t : o*s + t - pad = x} Y[o] . W[t]^T   (in = Y, out = X), one launch per
+// output parity class (pd,ph,pw) in [0,s)^3.  Returns false if the class is empty.
+bool gconv_scatter_class(const urn_conv_desc& d, int64_t ldy, int64_t ldx, int pd, int ph, int pw,
+                         int accumulate, GConv* g) {
+  const int s = d.s;
+  if (pd >= d.xd || ph >= d.xh || pw >= d.xw) return false;
+  g->n = d.n;
+  g->id = d.yd; g->ih = d.yh; g->iw = d.yw; g->cin = d.cy;
+  g->od = d.xd; g->oh = d.xh; g->ow = d.xw; g->cout = d.cx;
+  g->gd = (d.xd - pd + s - 1) / s; g->gh = (d.xh - ph + s - 1) / s; g->gw = (d.xw - pw + s - 1) / s;
+  g->is = 1; g->os = s; g->ood = pd; g->ooh = ph; g->oow = pw;
+  g->ntaps = 0;
+  for (int td = 0; td < d.kd; ++td) {
+    int ed = pd + d.pad_d - td;
+    if (((ed % s) + s) % s) continue;
+    for (int th = 0; th < d.kh; ++th) {
+      int eh = ph + d.pad_h - th;
+      if (((eh % s) + s) % s) continue;
+      for (int tw = 0; tw < d.kw; ++tw) {
+        int ew = pw + d.pad_w - tw;
+        if (((ew % s) + s) % s) continue;
+        GTap& t = g->taps[g->ntaps++];
+        // exact division (remainder is zero), valid for negative numerators too
+        t.od = ed / s; t.oh = eh / s; t.ow = ew / s;
+        t.widx = (td * d.kh + th) * d.kw + tw;
+      }
+    }
+  }
+  g->wtap = (int64_t)d.cx * d.cy; g->wldi = 1; g->wldo = d.cy;
+  g->ldin = ldy; g->ldout = ldx; g->accumulate = accumulate;
+  return true;
+}
+
+extern "C" int urn_conv_fwd(const urn_conv_desc* d, int dtype, int impl, const void* x, int64_t ldx,
+                            const float* w, void* y, int64_t ldy, int y_dtype, void* stream) {
+  if (check_desc(d)) return 1;
+  URN_CHECK(ldx >= d->cx && ldy >= d->cy, "urn_conv_fwd: pitch smaller than channel count");
+  URN_CHECK(impl != URN_IMPL_TC, "urn_conv_fwd: the tcgen05 path runs through the net handle "
+            "(packed bf16 filters); per-kernel entry is urn_tc_conv");
+  GConv g;
+  gconv_gather(*d, ldx, ldy, &g);
+  return gconv_ffma_launch(g, dtype, x, w, y, y_dtype, (cudaStream_t)stream);
+}
+
+extern "C" int urn_conv_dgrad(const urn_conv_desc* d, int dtype, int impl, const void* dy,
+                              int64_t ldy, const float* w, void* dx, int64_t ldx, int x_dtype,
+                              int accumulate, void* stream) {
+  if (check_desc(d)) return 1;
+  URN_CHECK(ldx >= d->cx && ldy >= d->cy, "urn_conv_dgrad: pitch smaller than channel count");
+  URN_CHECK(impl != URN_IMPL_TC, "urn_conv_dgrad: tcgen05 path runs through the net handle");
+  for (int pd = 0; pd < d->s; ++pd)
+    for (int ph = 0; ph < d->s; ++ph)
+      for (int pw = 0; pw < d->s; ++pw) {
+        GConv g;
+        if (!gconv_scatter_class(*d, ldy, ldx, pd, ph, pw, accumulate, &g)) continue;
+        if (gconv_ffma_launch(g, dtype, dy, w, dx, x_dtype, (cudaStream_t)stream)) return 1;
+      }
+  return 0;
+}
+
+extern "C" int64_t urn_conv_wgrad_workspace(const urn_conv_desc* d) {
+  if (check_desc(d)) return -1;
+  return wgrad_ffma_workspace(*d);
+}
+
+extern "C" int urn_conv_wgrad(const urn_conv_desc* d, int dtype, int impl, const void* x, int64_t ldx,
+                              const void* y, int64_t ldy, float* dw, int accumulate, void* ws,
+                              void* stream) {
+  if (check_desc(d)) return 1;
+  URN_CHECK(ldx >= d->cx && ldy >= d->cy, "urn_conv_wgrad: pitch smaller than channel count");
+  URN_CHECK(impl != URN_IMPL_TC, "urn_conv_wgrad: tcgen05 path runs through the net handle");
+  return wgrad_ffma_launch(*d, dtype, x, ldx, y, ldy, dw, accumulate, ws, (cudaStream_t)stream);
+}

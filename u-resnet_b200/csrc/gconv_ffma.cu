@@ -1,0 +1,380 @@
+// Generalised convolution on the CUDA cores (FFMA, fp32 accumulate).
+//
+// This is the exact-arithmetic path (dtype URN_F32: the 1e-3 parity mode) and the
+// path for layer shapes the tcgen05 kernel does not take (Cin=1 stem, Cout=3 head).
+// One kernel covers SURVEY.md 8a K1-K4 forward and input-gradient:
+//     out[n, o*os+oo, :] = sum_t in[n, o*is+off_t, :] . W_t
+// conv fwd:        is=s, os=1, taps = all k^nd, W_t = W[t]        ([cin,cout])
+// conv dgrad s=1:  is=1, os=1, taps flipped,      W_t = W[t]^T
+// conv dgrad s=2 / conv_transpose fwd: one launch per output parity class (os=2).
+#include "common.cuh"
+
+namespace {
+
+constexpr int TM = 128;  // output positions per block
+constexpr int KC = 16;   // input-channel chunk
+constexpr int AS_LD = TM + 2;
+
+template <typename TI, typename TO, int TN>
+__global__ void __launch_bounds__(256)
+gconv_ffma_kernel(const GConv g, const TI* __restrict__ in, const float* __restrict__ w,
+                  TO* __restrict__ out) {
+  constexpr int TX = TN / 4;     // threads along cout (4 couts each)
+  constexpr int TY = 256 / TX;   // threads along positions
+  constexpr int RM = TM / TY;    // positions per thread
+  __shared__ float As[KC][AS_LD];
+  __shared__ __align__(16) float Bs[KC][TN];
+  __shared__ int4 pbase[TM];          // n, d*is, h*is, w*is  (n = -1: beyond M)
+  __shared__ long long aoff[TM];
+  __shared__ long long ooff[TM];
+
+  const int tid = threadIdx.x;
+  const int tx = tid % TX, ty = tid / TX;
+  const long long M = (long long)g.n * g.gd * g.gh * g.gw;
+  const long long m0 = (long long)blockIdx.x * TM;
+  const int n0 = blockIdx.y * TN;
+
+  if (tid < TM) {
+    long long m = m0 + tid;
+    if (m < M) {
+      int ww = (int)(m % g.gw);
+      long long r = m / g.gw;
+      int hh = (int)(r % g.gh);
+      r /= g.gh;
+      int dd = (int)(r % g.gd);
+      int nn = (int)(r / g.gd);
+      pbase[tid] = make_int4(nn, dd * g.is, hh * g.is, ww * g.is);
+      long long od = dd * g.os + g.ood, oh = hh * g.os + g.ooh, ow = ww * g.os + g.oow;
+      ooff[tid] = ((((long long)nn * g.od + od) * g.oh + oh) * g.ow + ow) * g.ldout;
+    } else {
+      pbase[tid] = make_int4(-1, 0, 0, 0);
+      ooff[tid] = -1;
+    }
+  }
+
+  float acc[RM][4];
+#pragma unroll
+  for (int i = 0; i < RM; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  const bool vec_in = (g.cin % 4 == 0) && (g.ldin % 4 == 0);
+
+  for (int t = 0; t < g.ntaps; ++t) {
+    __syncthreads();  // previous tap's compute done (also covers pbase on t == 0)
+    if (tid < TM) {
+      int4 pb = pbase[tid];
+      long long off = -1;
+      if (pb.x >= 0) {
+        int d = pb.y + g.taps[t].od, h = pb.z + g.taps[t].oh, x = pb.w + g.taps[t].ow;
+        if (d >= 0 && d < g.id && h >= 0 && h < g.ih && x >= 0 && x < g.iw)
+          off = ((((long long)pb.x * g.id + d) * g.ih + h) * g.iw + x) * g.ldin;
+      }
+      aoff[tid] = off;
+    }
+    __syncthreads();
+    const float* wt = w + (long long)g.taps[t].widx * g.wtap;
+    for (int k0 = 0; k0 < g.cin; k0 += KC) {
+      // ---- stage A: TM x KC activations (zero for padding / tail) ----
+#pragma unroll
+      for (int i = 0; i < (TM * KC / 4) / 256; ++i) {
+        int idx = tid + i * 256;
+        int m = idx >> 2, kg = idx & 3;
+        long long off = aoff[m];
+        int k = k0 + kg * 4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (off >= 0 && k < g.cin) {
+          const TI* p = in + off + k;
+          if (vec_in) {
+            v = ld4(p);
+          } else {
+            v.x = ld1(p);
+            if (k + 1 < g.cin) v.y = ld1(p + 1);
+            if (k + 2 < g.cin) v.z = ld1(p + 2);
+            if (k + 3 < g.cin) v.w = ld1(p + 3);
+          }
+        }
+        As[kg * 4 + 0][m] = v.x;
+        As[kg * 4 + 1][m] = v.y;
+        As[kg * 4 + 2][m] = v.z;
+        As[kg * 4 + 3][m] = v.w;
+      }
+      // ---- stage B: KC x TN filter slice ----
+      for (int idx = tid; idx < KC * TN; idx += 256) {
+        int kk = idx / TN, nn = idx % TN;
+        int kin = k0 + kk, kout = n0 + nn;
+        float v = 0.f;
+        if (kin < g.cin && kout < g.cout) v = __ldg(wt + kin * g.wldi + kout * g.wldo);
+        Bs[kk][nn] = v;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < KC; ++k) {
+        float a[RM];
+#pragma unroll
+        for (int i = 0; i < RM; ++i) a[i] = As[k][ty + i * TY];
+        float4 b = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+#pragma unroll
+        for (int i = 0; i < RM; ++i) {
+          acc[i][0] = fmaf(a[i], b.x, acc[i][0]);
+          acc[i][1] = fmaf(a[i], b.y, acc[i][1]);
+          acc[i][2] = fmaf(a[i], b.z, acc[i][2]);
+          acc[i][3] = fmaf(a[i], b.w, acc[i][3]);
+        }
+      }
+      __syncthreads();
+    }
+  }
+  if (g.ntaps == 0) __syncthreads();
+
+  // ---- epilogue ----
+  const int co = n0 + tx * 4;
+  const bool vec_out = (g.cout % 4 == 0) && (g.ldout % 4 == 0);
+#pragma unroll
+  for (int i = 0; i < RM; ++i) {
+    long long off = ooff[ty + i * TY];
+    if (off < 0 || co >= g.cout) continue;
+    TO* p = out + off + co;
+    if (vec_out) {
+      float4 v = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+      if (g.accumulate) {
+        float4 o = ld4(p);
+        v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+      }
+      st4(p, v);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (co + j < g.cout) st1(p + j, acc[i][j] + (g.accumulate ? ld1(p + j) : 0.f));
+    }
+  }
+}
+
+template <typename TI, typename TO>
+int launch_t(const GConv& g, const TI* in, const float* w, TO* out, cudaStream_t st) {
+  long long M = (long long)g.n * g.gd * g.gh * g.gw;
+  if (M == 0) return 0;
+  long long gx = (M + TM - 1) / TM;
+  URN_CHECK(gx < (1ll << 31), "gconv_ffma: grid too large");
+  if (g.cout <= 16) {
+    gconv_ffma_kernel<TI, TO, 16><<<dim3((unsigned)gx, (g.cout + 15) / 16), 256, 0, st>>>(g, in, w, out);
+  } else if (g.cout <= 32) {
+    gconv_ffma_kernel<TI, TO, 32><<<dim3((unsigned)gx, 1), 256, 0, st>>>(g, in, w, out);
+  } else {
+    gconv_ffma_kernel<TI, TO, 64><<<dim3((unsigned)gx, (g.cout + 63) / 64), 256, 0, st>>>(g, in, w, out);
+  }
+  URN_LAUNCH_CHECK();
+  return 0;
+}
+
+// ------------------------------ filter gradient ------------------------------
+constexpr int PK = 32;  // positions per smem stage
+
+template <typename T, int TX, int TY>
+__global__ void __launch_bounds__(256)
+wgrad_ffma_kernel(const urn_conv_desc d, const T* __restrict__ x, long long ldx,
+                  const T* __restrict__ y, long long ldy, float* __restrict__ partial,
+                  long long chunk, int ntx, int nty) {
+  constexpr int RX = TX / 16, RY = TY / 16;
+  __shared__ float Xs[PK][TX + 1];
+  __shared__ float Ys[PK][TY + 1];
+  __shared__ long long xoff[PK], yoff[PK];
+  const int tid = threadIdx.x;
+  const int tcy = tid % 16, tcx = tid / 16;
+  int tile = blockIdx.x;
+  const int ty_i = tile % nty; tile /= nty;
+  const int tx_i = tile % ntx; tile /= ntx;
+  const int tap = tile;
+  const int tw = tap % d.kw, th = (tap / d.kw) % d.kh, td = tap / (d.kw * d.kh);
+  const int cx0 = tx_i * TX, cy0 = ty_i * TY;
+  const long long M = (long long)d.n * d.yd * d.yh * d.yw;
+  const long long o_begin = (long long)blockIdx.y * chunk;
+  const long long o_end = min(M, o_begin + chunk);
+  const bool vx = (d.cx % 4 == 0) && (ldx % 4 == 0);
+  const bool vy = (d.cy % 4 == 0) && (ldy % 4 == 0);
+
+  float acc[RX][RY];
+#pragma unroll
+  for (int i = 0; i < RX; ++i)
+#pragma unroll
+    for (int j = 0; j < RY; ++j) acc[i][j] = 0.f;
+
+  for (long long o0 = o_begin; o0 < o_end; o0 += PK) {
+    __syncthreads();
+    if (tid < PK) {
+      long long o = o0 + tid, xo = -1, yo = -1;
+      if (o < o_end) {
+        int ww = (int)(o % d.yw);
+        long long r = o / d.yw;
+        int hh = (int)(r % d.yh);
+        r /= d.yh;
+        int dd = (int)(r % d.yd);
+        int nn = (int)(r / d.yd);
+        int xd = dd * d.s + td - d.pad_d, xh = hh * d.s + th - d.pad_h, xw = ww * d.s + tw - d.pad_w;
+        if (xd >= 0 && xd < d.xd && xh >= 0 && xh < d.xh && xw >= 0 && xw < d.xw) {
+          xo = ((((long long)nn * d.xd + xd) * d.xh + xh) * d.xw + xw) * ldx;
+          yo = o * ldy;
+        }
+      }
+      xoff[tid] = xo;
+      yoff[tid] = yo;
+    }
+    __syncthreads();
+    for (int idx = tid; idx < PK * TX / 4; idx += 256) {
+      int p = idx / (TX / 4), c = (idx % (TX / 4)) * 4 + cx0;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      long long off = xoff[p];
+      if (off >= 0 && c < d.cx) {
+        const T* q = x + off + c;
+        if (vx) v = ld4(q);
+        else {
+          v.x = ld1(q);
+          if (c + 1 < d.cx) v.y = ld1(q + 1);
+          if (c + 2 < d.cx) v.z = ld1(q + 2);
+          if (c + 3 < d.cx) v.w = ld1(q + 3);
+        }
+      }
+      int cc = c - cx0;
+      Xs[p][cc] = v.x; Xs[p][cc + 1] = v.y; Xs[p][cc + 2] = v.z; Xs[p][cc + 3] = v.w;
+    }
+    for (int idx = tid; idx < PK * TY / 4; idx += 256) {
+      int p = idx / (TY / 4), c = (idx % (TY / 4)) * 4 + cy0;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      long long off = yoff[p];
+      if (off >= 0 && c < d.cy) {
+        const T* q = y + off + c;
+        if (vy) v = ld4(q);
+        else {
+          v.x = ld1(q);
+          if (c + 1 < d.cy) v.y = ld1(q + 1);
+          if (c + 2 < d.cy) v.z = ld1(q + 2);
+          if (c + 3 < d.cy) v.w = ld1(q + 3);
+        }
+      }
+      int cc = c - cy0;
+      Ys[p][cc] = v.x; Ys[p][cc + 1] = v.y; Ys[p][cc + 2] = v.z; Ys[p][cc + 3] = v.w;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int p = 0; p < PK; ++p) {
+      float a[RX], b[RY];
+#pragma unroll
+      for (int i = 0; i < RX; ++i) a[i] = Xs[p][tcx + i * 16];
+#pragma unroll
+      for (int j = 0; j < RY; ++j) b[j] = Ys[p][tcy + j * 16];
+#pragma unroll
+      for (int i = 0; i < RX; ++i)
+#pragma unroll
+        for (int j = 0; j < RY; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+  }
+  const long long nw = (long long)d.kd * d.kh * d.kw * d.cx * d.cy;
+  float* dst = partial + (long long)blockIdx.y * nw + (long long)tap * d.cx * d.cy;
+#pragma unroll
+  for (int i = 0; i < RX; ++i) {
+    int cx = cx0 + tcx + i * 16;
+    if (cx >= d.cx) continue;
+#pragma unroll
+    for (int j = 0; j < RY; ++j) {
+      int cy = cy0 + tcy + j * 16;
+      if (cy < d.cy) dst[(long long)cx * d.cy + cy] = acc[i][j];
+    }
+  }
+}
+
+__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, long long nw, int nsplit,
+                                    float* __restrict__ dw, int accumulate) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nw) return;
+  float s = 0.f;
+  for (int k = 0; k < nsplit; ++k) s += partial[(long long)k * nw + i];
+  dw[i] = accumulate ? dw[i] + s : s;
+}
+
+struct WgradPlan {
+  int tx, ty, ntx, nty, nsplit;
+  long long chunk, nw;
+};
+static int pick_tile(int c) { return c <= 16 ? 16 : (c <= 32 ? 32 : 64); }
+WgradPlan wgrad_plan(const urn_conv_desc& d) {
+  WgradPlan p;
+  p.tx = pick_tile(d.cx);
+  p.ty = pick_tile(d.cy);
+  p.ntx = (d.cx + p.tx - 1) / p.tx;
+  p.nty = (d.cy + p.ty - 1) / p.ty;
+  long long tiles = (long long)d.kd * d.kh * d.kw * p.ntx * p.nty;
+  long long M = (long long)d.n * d.yd * d.yh * d.yw;
+  p.nw = (long long)d.kd * d.kh * d.kw * d.cx * d.cy;
+  long long want = (4ll * 148 + tiles - 1) / tiles;
+  long long maxsplit = (M + 4 * PK - 1) / (4 * PK);
+  long long memsplit = (64ll << 20) / (p.nw > 0 ? p.nw : 1);  // partials <= 256 MB
+  long long ns = want;
+  if (ns > maxsplit) ns = maxsplit;
+  if (ns > memsplit) ns = memsplit;
+  if (ns < 1) ns = 1;
+  p.chunk = ((M + ns - 1) / ns + PK - 1) / PK * PK;
+  if (p.chunk < PK) p.chunk = PK;
+  p.nsplit = (int)((M + p.chunk - 1) / p.chunk);
+  if (p.nsplit < 1) p.nsplit = 1;
+  return p;
+}
+
+template <typename T, int TX>
+int wgrad_dispatch_y(const urn_conv_desc& d, const WgradPlan& p, const T* x, long long ldx,
+                     const T* y, long long ldy, float* partial, cudaStream_t st) {
+  dim3 grid((unsigned)(d.kd * d.kh * d.kw * p.ntx * p.nty), (unsigned)p.nsplit);
+  if (p.ty == 16)
+    wgrad_ffma_kernel<T, TX, 16><<<grid, 256, 0, st>>>(d, x, ldx, y, ldy, partial, p.chunk, p.ntx, p.nty);
+  else if (p.ty == 32)
+    wgrad_ffma_kernel<T, TX, 32><<<grid, 256, 0, st>>>(d, x, ldx, y, ldy, partial, p.chunk, p.ntx, p.nty);
+  else
+    wgrad_ffma_kernel<T, TX, 64><<<grid, 256, 0, st>>>(d, x, ldx, y, ldy, partial, p.chunk, p.ntx, p.nty);
+  URN_LAUNCH_CHECK();
+  return 0;
+}
+
+template <typename T>
+int wgrad_t(const urn_conv_desc& d, const T* x, long long ldx, const T* y, long long ldy, float* dw,
+            int accumulate, void* ws, cudaStream_t st) {
+  WgradPlan p = wgrad_plan(d);
+  float* partial = reinterpret_cast<float*>(ws);
+  int rc;
+  if (p.tx == 16) rc = wgrad_dispatch_y<T, 16>(d, p, x, ldx, y, ldy, partial, st);
+  else if (p.tx == 32) rc = wgrad_dispatch_y<T, 32>(d, p, x, ldx, y, ldy, partial, st);
+  else rc = wgrad_dispatch_y<T, 64>(d, p, x, ldx, y, ldy, partial, st);
+  if (rc) return rc;
+  wgrad_reduce_kernel<<<(unsigned)((p.nw + 255) / 256), 256, 0, st>>>(partial, p.nw, p.nsplit, dw, accumulate);
+  URN_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace
+
+int gconv_ffma_launch(const GConv& g, int in_dtype, const void* in, const float* w, void* out,
+                      int out_dtype, cudaStream_t st) {
+  if (in_dtype == URN_F32 && out_dtype == URN_F32)
+    return launch_t<float, float>(g, (const float*)in, w, (float*)out, st);
+  if (in_dtype == URN_BF16 && out_dtype == URN_F32)
+    return launch_t<bf16, float>(g, (const bf16*)in, w, (float*)out, st);
+  if (in_dtype == URN_BF16 && out_dtype == URN_BF16)
+    return launch_t<bf16, bf16>(g, (const bf16*)in, w, (bf16*)out, st);
+  if (in_dtype == URN_F32 && out_dtype == URN_BF16)
+    return launch_t<float, bf16>(g, (const float*)in, w, (bf16*)out, st);
+  urn_set_error("gconv_ffma: bad dtype");
+  return 1;
+}
+
+int64_t wgrad_ffma_workspace(const urn_conv_desc& d) {
+  WgradPlan p = wgrad_plan(d);
+  return (int64_t)p.nsplit * p.nw * (int64_t)sizeof(float);
+}
+
+int wgrad_ffma_launch(const urn_conv_desc& d, int dtype, const void* x, int64_t ldx, const void* y,
+                      int64_t ldy, float* dw, int accumulate, void* ws, cudaStream_t st) {
+  if (dtype == URN_F32)
+    return wgrad_t<float>(d, (const float*)x, ldx, (const float*)y, ldy, dw, accumulate, ws, st);
+  if (dtype == URN_BF16)
+    return wgrad_t<bf16>(d, (const bf16*)x, ldx, (const bf16*)y, ldy, dw, accumulate, ws, st);
+  urn_set_error("wgrad_ffma: bad dtype");
+  return 1;
+}

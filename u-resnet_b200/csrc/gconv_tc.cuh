@@ -1,0 +1,11 @@
+// tcgen05 implicit-GEMM convolution (declarations).  See gconv_tc.cu.
+#pragma once
+#include "common.cuh"
+#define URN_STR_(x) #x
+#define URN_STR(x) URN_STR_(x)
+
+void gconv_gather(const urn_conv_desc& d, int64_t ldx, int64_t ldy, GConv* g);
+bool gconv_scatter_class(const urn_conv_desc& d, int64_t ldy, int64_t ldx, int pd, int ph, int pw,
+                         int accumulate, GConv* g);
+int urn_softmax_only(const float* logits, int64_t ld, int64_t total, int c, float* softmax,
+                     cudaStream_t st);

@@ -1,0 +1,637 @@
+// Whole-network plan + executor: the host-side restatement of
+// uresnet._build (/root/reference/lib/uresnet.py:22-123) and resnet_module /
+// double_resnet (/root/reference/lib/resnet_module.py:10-87) as a static schedule of
+// kernel launches over one caller-owned workspace.
+//
+// Forward tensors: per layer the raw fp32 conv output + its BN statistics; per graph
+// node the post-BN/activation tensor in the storage dtype.  Concats are zero-copy:
+// the deconv output and the encoder skip are channel slices of one buffer
+// (uresnet.py:91-93, deconv channels first).  Backward buffers live in an arena
+// packed by lifetime.
+#include <algorithm>
+#include <array>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "gconv_tc.cuh"
+
+namespace {
+
+constexpr float kBnEps = 1e-3f;  // slim.batch_norm default epsilon
+
+inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
+inline int esize(int dtype) { return dtype == URN_BF16 ? 2 : 4; }
+
+struct Node {
+  int c = 0;
+  int64_t rows = 0;
+  int dtype = URN_F32;
+  int64_t off = 0;   // byte offset of element (row 0, channel 0) in the workspace
+  int64_t ld = 0;    // element pitch
+  int parent = -1;   // full buffer this node is a channel slice of
+  int choff = 0;     // channel offset inside the parent
+  int gbuf = -1;     // gradient buffer index
+  bool ginit = false;
+};
+
+struct Layer {
+  std::string scope;
+  bool transpose = false;
+  urn_conv_desc d;       // base relation: X = big side, Y = small side
+  int cin = 0, cout = 0;
+  int64_t rows_out = 0;
+  int in_node = -1;
+  int64_t raw_off = 0, stats_off = 0;
+  int64_t w_off = 0, b_off = 0, w_count = 0;  // elements in the flat parameter buffer
+  int draw_gbuf = -1;
+  int out_node = -1;     // node produced by this layer's own BN-apply (-1: merged later)
+  int relu = 0;
+};
+
+struct GBuf {
+  int64_t bytes = 0;
+  int first = 1 << 30, last = -1;
+  int64_t off = 0;
+};
+
+enum FKind { F_CONV, F_APPLY, F_MERGE };
+struct FStep {
+  FKind kind;
+  int layer;      // F_CONV / F_APPLY: layer; F_MERGE: conv2 layer
+  int layer_sc;   // F_MERGE: shortcut conv layer or -1
+  int res_node;   // F_MERGE: identity shortcut node or -1
+  int out_node;
+  int relu;
+};
+enum BKind { B_BN, B_WGRAD, B_DGRAD };
+struct BStep {
+  BKind kind;
+  int layer;
+  int dout_node = -1;   // B_BN: gradient of this node is the incoming dout
+  int relu = 0;         // B_BN: mask with (node value > 0)
+  int layer2 = -1;      // B_BN: conv shortcut sharing the same g
+  int dres_node = -1;   // B_BN: identity shortcut, receives g
+  int accumulate = 0;   // B_DGRAD / dres: add into an initialised gradient
+  int last_for_layer = 0;  // record the ready event after this step
+};
+
+struct ParamInfo {
+  std::string name;
+  int rank;
+  int64_t shape[6];
+  int64_t offset, count;
+};
+
+}  // namespace
+
+struct urn_net {
+  urn_net_cfg cfg;
+  int nd = 2;
+  int sp[3] = {1, 1, 1};  // d, h, w
+  std::vector<Node> nodes;
+  std::vector<Layer> layers;
+  std::vector<GBuf> gbufs;
+  std::vector<FStep> fwd;
+  std::vector<BStep> bwd;
+  std::vector<ParamInfo> params;
+  int64_t param_total = 0;
+  int data_node = -1, logits_node = -1;
+  int64_t ws_bytes = 0;
+  int64_t bn_ws_off = 0, loss_ws_off = 0, result_off = 0, wgrad_ws_off = 0, arena_off = 0;
+  int64_t wgrad_ws_bytes = 0;
+  int max_c = 0;
+};
+
+namespace {
+
+struct Builder {
+  urn_net& N;
+  int64_t cur = 0;  // workspace cursor
+  explicit Builder(urn_net& n) : N(n) {}
+
+  int64_t alloc(int64_t bytes) {
+    int64_t o = cur;
+    cur = align_up(cur + bytes, 256);
+    return o;
+  }
+  int new_node(int c, int64_t rows, int dtype) {
+    Node n;
+    n.c = c; n.rows = rows; n.dtype = dtype; n.ld = c;
+    n.off = alloc(rows * c * esize(dtype));
+    N.nodes.push_back(n);
+    return (int)N.nodes.size() - 1;
+  }
+  int new_view(int parent, int choff, int c) {
+    Node n = N.nodes[parent];
+    n.parent = parent; n.choff = choff; n.c = c;
+    n.off = N.nodes[parent].off + (int64_t)choff * esize(n.dtype);
+    N.nodes.push_back(n);
+    return (int)N.nodes.size() - 1;
+  }
+  // spatial dims of a node with `rows` rows are tracked by the caller
+  int add_layer(const std::string& scope, bool transpose, int in_node, int nd, int n,
+                const int in_sp[3], int cin, int cout, int k, int s, int out_sp[3]) {
+    Layer L;
+    L.scope = scope; L.transpose = transpose; L.in_node = in_node; L.cin = cin; L.cout = cout;
+    if (!transpose) {
+      urn_conv_desc_same(&L.d, nd, n, in_sp[0], in_sp[1], in_sp[2], cin, cout, k, s);
+      out_sp[0] = L.d.yd; out_sp[1] = L.d.yh; out_sp[2] = L.d.yw;
+    } else {
+      // conv_transpose 'same': out = s*in; base relation has X = OUTPUT (cx = cout)
+      out_sp[0] = nd == 3 ? in_sp[0] * s : 1; out_sp[1] = in_sp[1] * s; out_sp[2] = in_sp[2] * s;
+      urn_conv_desc_same(&L.d, nd, n, out_sp[0], out_sp[1], out_sp[2], cout, cin, k, s);
+    }
+    L.rows_out = (int64_t)n * out_sp[0] * out_sp[1] * out_sp[2];
+    L.raw_off = alloc(L.rows_out * cout * 4);
+    L.stats_off = alloc((int64_t)2 * cout * 4);
+    // parameters: TF creation order = weights then beta
+    int kk[3] = {L.d.kd, L.d.kh, L.d.kw};
+    ParamInfo pw;
+    pw.name = "UResNet/" + scope + "/weights";
+    pw.rank = 0;
+    for (int i = (nd == 3 ? 0 : 1); i < 3; ++i) pw.shape[pw.rank++] = kk[i];
+    pw.shape[pw.rank++] = L.d.cx;   // conv: Cin ; deconv: Cout
+    pw.shape[pw.rank++] = L.d.cy;   // conv: Cout; deconv: Cin
+    pw.count = (int64_t)kk[0] * kk[1] * kk[2] * L.d.cx * L.d.cy;
+    pw.offset = N.param_total;
+    N.param_total = align_up(N.param_total + pw.count, 64);
+    ParamInfo pb;
+    pb.name = "UResNet/" + scope + "/BatchNorm/beta";
+    pb.rank = 1; pb.shape[0] = cout; pb.count = cout;
+    pb.offset = N.param_total;
+    N.param_total = align_up(N.param_total + pb.count, 64);
+    L.w_off = pw.offset; L.w_count = pw.count; L.b_off = pb.offset;
+    N.params.push_back(pw);
+    N.params.push_back(pb);
+    N.layers.push_back(L);
+    N.max_c = std::max(N.max_c, std::max(cin, cout));
+    return (int)N.layers.size() - 1;
+  }
+};
+
+}  // namespace
+
+// -----------------------------------------------------------------------------
+// plan construction
+// -----------------------------------------------------------------------------
+static int build_plan(urn_net& N) {
+  const urn_net_cfg& c = N.cfg;
+  URN_CHECK(c.nd == 2 || c.nd == 3, "urn_create: nd must be 2 or 3 (got %d)", c.nd);
+  URN_CHECK(c.batch >= 1 && c.base_filters >= 1 && c.num_strides >= 0 && c.num_class >= 1 &&
+                c.in_channels >= 1, "urn_create: bad configuration");
+  URN_CHECK(c.num_class <= 32, "urn_create: num_class <= 32");
+  URN_CHECK(c.dtype == URN_F32 || c.dtype == URN_BF16, "urn_create: bad dtype");
+  URN_CHECK((int64_t)c.base_filters << c.num_strides <= 1024, "urn_create: widest layer > 1024 channels");
+  N.nd = c.nd;
+  if (c.nd == 2) { N.sp[0] = 1; N.sp[1] = c.spatial[0]; N.sp[2] = c.spatial[1]; }
+  else { N.sp[0] = c.spatial[0]; N.sp[1] = c.spatial[1]; N.sp[2] = c.spatial[2]; }
+  for (int i = 0; i < 3; ++i) URN_CHECK(N.sp[i] >= 1, "urn_create: bad spatial dims");
+  const int T = c.dtype, nd = c.nd, B = c.batch, F = c.base_filters, S = c.num_strides;
+  Builder b(N);
+
+  struct Cur { int node; int sp[3]; int ch; };
+  int sp0[3] = {N.sp[0], N.sp[1], N.sp[2]};
+  const int64_t rows0 = (int64_t)B * sp0[0] * sp0[1] * sp0[2];
+  N.data_node = b.new_node(c.in_channels, rows0, T);
+
+  // Spatial dims per encoder level (level 0 = full resolution) so that the concat
+  // buffers of the decoder can be allocated before their two producers run.
+  std::vector<std::array<int, 3>> lvl_sp(S + 1);
+  lvl_sp[0] = {sp0[0], sp0[1], sp0[2]};
+  for (int s = 0; s < S; ++s)
+    lvl_sp[s + 1] = {nd == 3 ? (lvl_sp[s][0] + 1) / 2 : 1, (lvl_sp[s][1] + 1) / 2, (lvl_sp[s][2] + 1) / 2};
+  for (int s = 0; s < S; ++s)
+    for (int i = (nd == 3 ? 0 : 1); i < 3; ++i)
+      URN_CHECK(lvl_sp[s][i] == 2 * lvl_sp[s + 1][i],
+                "urn_create: spatial size must be divisible by 2^num_strides (the reference's "
+                "concat needs matching shapes, uresnet.py:91)");
+  // concat buffer of the decoder step that restores level `lv` (channels 2*F<<lv)
+  std::vector<int> znode(S, -1);
+  for (int lv = 0; lv < S; ++lv) {
+    int64_t rows = (int64_t)B * lvl_sp[lv][0] * lvl_sp[lv][1] * lvl_sp[lv][2];
+    znode[lv] = b.new_node(2 * (F << lv), rows, T);
+  }
+  // where the output of encoder level lv lives: slice [C,2C) of z[lv]; bottom is plain
+  auto enc_out_node = [&](int lv, int64_t rows) -> int {
+    if (lv < S) return b.new_view(znode[lv], F << lv, F << lv);
+    return b.new_node(F << lv, rows, T);
+  };
+
+  auto conv_bn = [&](const std::string& scope, bool tr, int in_node, const int isp[3], int cin,
+                     int cout, int k, int s, int osp[3]) -> int {
+    int l = b.add_layer(scope, tr, in_node, nd, B, isp, cin, cout, k, s, osp);
+    N.fwd.push_back({F_CONV, l, -1, -1, -1, 0});
+    return l;
+  };
+  auto apply = [&](int l, int out_node, int relu) {
+    N.layers[l].out_node = out_node;
+    N.layers[l].relu = relu;
+    N.fwd.push_back({F_APPLY, l, -1, -1, out_node, relu});
+  };
+
+  struct ModRec { int sc, c1, c2, in_node, mid_node, out_node; };
+  std::vector<ModRec> mods;   // in forward order, interleaved with other records below
+  struct Rec { int kind; int idx; };  // 0 = simple conv layer (idx), 1 = module (idx in mods)
+  std::vector<Rec> recs;
+
+  auto resnet_module = [&](const std::string& scope, int in_node, const int isp[3], int cin,
+                           int cout, int stride, int out_node_or_neg, int osp[3]) -> int {
+    ModRec m;
+    m.in_node = in_node;
+    m.sc = -1;
+    int tmp[3];
+    if (!(cin == cout && stride == 1))                          // resnet_module.py:22-33
+      m.sc = conv_bn(scope + "/shortcut", false, in_node, isp, cin, cout, 1, stride, tmp);
+    m.c1 = conv_bn(scope + "/resnet_conv1", false, in_node, isp, cin, cout, 3, stride, osp);
+    int64_t rows = N.layers[m.c1].rows_out;
+    m.mid_node = b.new_node(cout, rows, T);
+    apply(m.c1, m.mid_node, 0);                                   // BN only (no ReLU) :43-51
+    m.c2 = conv_bn(scope + "/resnet_conv2", false, m.mid_node, osp, cout, cout, 3, 1, tmp);
+    m.out_node = out_node_or_neg >= 0 ? out_node_or_neg : b.new_node(cout, rows, T);
+    N.fwd.push_back({F_MERGE, m.c2, m.sc, m.sc < 0 ? in_node : -1, m.out_node, 1});  // :68
+    mods.push_back(m);
+    recs.push_back({1, (int)mods.size() - 1});
+    return m.out_node;
+  };
+  auto double_resnet = [&](int idx, int in_node, const int isp[3], int cin, int cout, int stride,
+                           int final_out_node, int osp[3]) -> int {
+    char sc[64];
+    snprintf(sc, sizeof sc, "resnet_module%d/module1", idx);
+    int mid = resnet_module(sc, in_node, isp, cin, cout, stride, -1, osp);
+    snprintf(sc, sizeof sc, "resnet_module%d/module2", idx);
+    int tmp[3];
+    return resnet_module(sc, mid, osp, cout, cout, 1, final_out_node, tmp);
+  };
+
+  // ---- stem (uresnet.py:37-45) ----
+  int osp[3];
+  int l0 = conv_bn("conv0", false, N.data_node, sp0, c.in_channels, F, 3, 1, osp);
+  int net = enc_out_node(0, rows0);
+  apply(l0, net, 1);
+  recs.push_back({0, l0});
+  int cur_sp[3] = {osp[0], osp[1], osp[2]};
+  int ch = F;
+  // ---- encoder (uresnet.py:56-64) ----
+  for (int s = 0; s < S; ++s) {
+    int nsp[3] = {lvl_sp[s + 1][0], lvl_sp[s + 1][1], lvl_sp[s + 1][2]};
+    int64_t rows = (int64_t)B * nsp[0] * nsp[1] * nsp[2];
+    int outn = enc_out_node(s + 1, rows);
+    net = double_resnet(s, net, cur_sp, ch, ch * 2, 2, outn, osp);
+    ch *= 2;
+    cur_sp[0] = osp[0]; cur_sp[1] = osp[1]; cur_sp[2] = osp[2];
+  }
+  // ---- decoder (uresnet.py:66-101) ----
+  for (int s = 0; s < S; ++s) {
+    int lv = S - 1 - s;
+    char sc[32];
+    snprintf(sc, sizeof sc, "deconv%d", s);
+    int ld = conv_bn(sc, true, net, cur_sp, ch, ch / 2, 3, 2, osp);
+    int u = b.new_view(znode[lv], 0, ch / 2);      // deconv channels first
+    apply(ld, u, 1);
+    recs.push_back({0, ld});
+    cur_sp[0] = osp[0]; cur_sp[1] = osp[1]; cur_sp[2] = osp[2];
+    net = double_resnet(s + 5, znode[lv], cur_sp, ch, ch / 2, 1, -1, osp);  // scope step+5 (:100)
+    ch /= 2;
+  }
+  // ---- heads (uresnet.py:103-121) ----
+  int l1 = conv_bn("conv1", false, net, cur_sp, ch, F, 3, 1, osp);
+  int a1 = b.new_node(F, rows0, T);
+  apply(l1, a1, 1);
+  recs.push_back({0, l1});
+  int l2 = conv_bn("conv2", false, a1, cur_sp, F, c.num_class, 3, 1, osp);
+  N.logits_node = b.new_node(c.num_class, rows0, URN_F32);
+  apply(l2, N.logits_node, 0);
+  recs.push_back({0, l2});
+
+  // ---- scratch ----
+  N.bn_ws_off = b.alloc(urn_bn_workspace(std::max(N.max_c, 4)));
+  N.loss_ws_off = b.alloc(urn_loss_workspace(rows0));
+  N.result_off = b.alloc(64);
+  N.wgrad_ws_bytes = 0;
+  for (auto& L : N.layers) N.wgrad_ws_bytes = std::max<int64_t>(N.wgrad_ws_bytes, wgrad_ffma_workspace(L.d));
+  N.wgrad_ws_off = b.alloc(N.wgrad_ws_bytes);
+
+  // ---- backward schedule ----
+  if (c.training) {
+    auto new_gbuf = [&](int64_t bytes) { GBuf g; g.bytes = bytes; N.gbufs.push_back(g); return (int)N.gbufs.size() - 1; };
+    // gradient buffers: one per full node (views share the parent's), one per layer draw
+    for (size_t i = 0; i < N.nodes.size(); ++i) {
+      Node& n = N.nodes[i];
+      if ((int)i == N.data_node) continue;
+      if (n.parent >= 0) continue;
+      int gt = ((int)i == N.logits_node) ? T : n.dtype;
+      n.gbuf = new_gbuf(n.rows * n.ld * esize(gt));
+    }
+    for (auto& n : N.nodes)
+      if (n.parent >= 0) n.gbuf = N.nodes[n.parent].gbuf;
+    for (auto& L : N.layers) L.draw_gbuf = new_gbuf(L.rows_out * L.cout * esize(T));
+
+    auto mark_write = [&](int node) -> int {   // returns accumulate flag
+      Node& n = N.nodes[node];
+      int acc = n.ginit ? 1 : 0;
+      n.ginit = true;
+      if (n.parent < 0)
+        for (auto& v : N.nodes)
+          if (v.parent == node) v.ginit = true;
+      return acc;
+    };
+    auto simple_layer_bwd = [&](int l, int relu) {
+      Layer& L = N.layers[l];
+      BStep bn; bn.kind = B_BN; bn.layer = l; bn.dout_node = L.out_node; bn.relu = relu;
+      N.bwd.push_back(bn);
+      BStep wg; wg.kind = B_WGRAD; wg.layer = l; wg.last_for_layer = 1;
+      N.bwd.push_back(wg);
+      if (L.in_node != N.data_node) {
+        BStep dg; dg.kind = B_DGRAD; dg.layer = l; dg.accumulate = mark_write(L.in_node);
+        N.bwd.push_back(dg);
+      }
+    };
+    N.nodes[N.logits_node].ginit = true;  // seeded by the loss kernel
+    for (int r = (int)recs.size() - 1; r >= 0; --r) {
+      if (recs[r].kind == 0) {
+        simple_layer_bwd(recs[r].idx, N.layers[recs[r].idx].relu);
+      } else {
+        const ModRec& m = mods[recs[r].idx];
+        BStep bn; bn.kind = B_BN; bn.layer = m.c2; bn.dout_node = m.out_node; bn.relu = 1;
+        bn.layer2 = m.sc;
+        if (m.sc < 0) { bn.dres_node = m.in_node; bn.accumulate = mark_write(m.in_node); }
+        N.bwd.push_back(bn);
+        BStep wg; wg.kind = B_WGRAD; wg.layer = m.c2; wg.last_for_layer = 1; N.bwd.push_back(wg);
+        BStep dg; dg.kind = B_DGRAD; dg.layer = m.c2; dg.accumulate = mark_write(m.mid_node); N.bwd.push_back(dg);
+        BStep bn1; bn1.kind = B_BN; bn1.layer = m.c1; bn1.dout_node = m.mid_node; bn1.relu = 0; N.bwd.push_back(bn1);
+        BStep wg1; wg1.kind = B_WGRAD; wg1.layer = m.c1; wg1.last_for_layer = 1; N.bwd.push_back(wg1);
+        BStep dg1; dg1.kind = B_DGRAD; dg1.layer = m.c1; dg1.accumulate = mark_write(m.in_node); N.bwd.push_back(dg1);
+        if (m.sc >= 0) {
+          BStep wg2; wg2.kind = B_WGRAD; wg2.layer = m.sc; wg2.last_for_layer = 1; N.bwd.push_back(wg2);
+          BStep dg2; dg2.kind = B_DGRAD; dg2.layer = m.sc; dg2.accumulate = mark_write(m.in_node); N.bwd.push_back(dg2);
+        }
+      }
+    }
+    // lifetimes
+    auto touch = [&](int g, int step) {
+      if (g < 0) return;
+      N.gbufs[g].first = std::min(N.gbufs[g].first, step);
+      N.gbufs[g].last = std::max(N.gbufs[g].last, step);
+    };
+    touch(N.nodes[N.logits_node].gbuf, -1);  // written by the loss kernel before step 0
+    for (int i = 0; i < (int)N.bwd.size(); ++i) {
+      const BStep& s = N.bwd[i];
+      const Layer& L = N.layers[s.layer];
+      touch(L.draw_gbuf, i);
+      if (s.kind == B_BN) {
+        touch(N.nodes[s.dout_node].gbuf, i);
+        if (s.layer2 >= 0) touch(N.layers[s.layer2].draw_gbuf, i);
+        if (s.dres_node >= 0) touch(N.nodes[s.dres_node].gbuf, i);
+      } else if (s.kind == B_DGRAD) {
+        touch(N.nodes[L.in_node].gbuf, i);
+      }
+    }
+    // pack by lifetime: place in order of first use at the lowest non-conflicting offset
+    std::vector<int> order;
+    for (int g = 0; g < (int)N.gbufs.size(); ++g)
+      if (N.gbufs[g].last >= N.gbufs[g].first) order.push_back(g);
+    std::stable_sort(order.begin(), order.end(), [&](int a, int bb) {
+      if (N.gbufs[a].first != N.gbufs[bb].first) return N.gbufs[a].first < N.gbufs[bb].first;
+      return N.gbufs[a].bytes > N.gbufs[bb].bytes;
+    });
+    std::vector<int> placed;
+    int64_t arena = 0;
+    for (int g : order) {
+      GBuf& G = N.gbufs[g];
+      int64_t sz = align_up(G.bytes, 256);
+      std::vector<std::pair<int64_t, int64_t>> busy;
+      for (int p : placed) {
+        const GBuf& P = N.gbufs[p];
+        if (P.last < G.first || P.first > G.last) continue;
+        busy.push_back({P.off, P.off + align_up(P.bytes, 256)});
+      }
+      std::sort(busy.begin(), busy.end());
+      int64_t off = 0;
+      for (auto& iv : busy) {
+        if (off + sz <= iv.first) break;
+        off = std::max(off, iv.second);
+      }
+      G.off = off;
+      arena = std::max(arena, off + sz);
+      placed.push_back(g);
+    }
+    N.arena_off = b.alloc(arena);
+  }
+  N.ws_bytes = b.cur;
+  return 0;
+}
+
+// -----------------------------------------------------------------------------
+// C ABI
+// -----------------------------------------------------------------------------
+extern "C" int urn_create(const urn_net_cfg* cfg, urn_net** out) {
+  URN_CHECK(cfg && out, "urn_create: null argument");
+  urn_net* N = new urn_net();
+  N->cfg = *cfg;
+  if (build_plan(*N)) { delete N; return 1; }
+  *out = N;
+  return 0;
+}
+extern "C" void urn_destroy(urn_net* h) { delete h; }
+extern "C" int urn_param_count(const urn_net* h) { return h ? (int)h->params.size() : -1; }
+extern "C" int urn_param_info(const urn_net* h, int i, const char** name, int* rank, int64_t* shape,
+                              int64_t* offset, int64_t* count) {
+  URN_CHECK(h && i >= 0 && i < (int)h->params.size(), "urn_param_info: bad index");
+  const ParamInfo& p = h->params[i];
+  if (name) *name = p.name.c_str();
+  if (rank) *rank = p.rank;
+  if (shape) for (int k = 0; k < p.rank; ++k) shape[k] = p.shape[k];
+  if (offset) *offset = p.offset;
+  if (count) *count = p.count;
+  return 0;
+}
+extern "C" int64_t urn_param_total(const urn_net* h) { return h ? h->param_total : -1; }
+extern "C" int urn_layer_count(const urn_net* h) { return h ? (int)h->layers.size() : -1; }
+extern "C" int64_t urn_workspace_bytes(const urn_net* h) { return h ? h->ws_bytes : -1; }
+extern "C" int64_t urn_logits_offset_bytes(const urn_net* h) {
+  return h ? h->nodes[h->logits_node].off : -1;
+}
+extern "C" int urn_layer_info(const urn_net* h, int layer, const char** scope, urn_conv_desc* d,
+                              int* is_transpose, int64_t* raw_off_bytes, int64_t* out_off_bytes,
+                              int64_t* out_ld, int64_t* stats_off_bytes) {
+  URN_CHECK(h && layer >= 0 && layer < (int)h->layers.size(), "urn_layer_info: bad index");
+  const Layer& L = h->layers[layer];
+  if (scope) *scope = L.scope.c_str();
+  if (d) *d = L.d;
+  if (is_transpose) *is_transpose = L.transpose;
+  if (raw_off_bytes) *raw_off_bytes = L.raw_off;
+  if (out_off_bytes) *out_off_bytes = L.out_node >= 0 ? h->nodes[L.out_node].off : -1;
+  if (out_ld) *out_ld = L.out_node >= 0 ? h->nodes[L.out_node].ld : 0;
+  if (stats_off_bytes) *stats_off_bytes = L.stats_off;
+  return 0;
+}
+
+namespace {
+
+__global__ void convert_in_kernel(const float* __restrict__ src, long long n, float* dst_f,
+                                  bf16* dst_b) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    float v = src[i];
+    if (dst_f) dst_f[i] = v; else dst_b[i] = __float2bfloat16_rn(v);
+  }
+}
+
+inline char* P(void* ws, int64_t off) { return (char*)ws + off; }
+
+int run_conv_fwd(urn_net* h, const Layer& L, const float* params, void* ws, cudaStream_t st) {
+  const Node& in = h->nodes[L.in_node];
+  float* raw = (float*)P(ws, L.raw_off);
+  const float* w = params + L.w_off;
+  if (!L.transpose) {
+    GConv g;
+    gconv_gather(L.d, in.ld, L.cout, &g);
+    if (gconv_ffma_launch(g, in.dtype, P(ws, in.off), w, raw, URN_F32, st)) return 1;
+  } else {
+    for (int pd = 0; pd < L.d.s; ++pd)
+      for (int ph = 0; ph < L.d.s; ++ph)
+        for (int pw = 0; pw < L.d.s; ++pw) {
+          GConv g;
+          if (!gconv_scatter_class(L.d, in.ld, L.cout, pd, ph, pw, 0, &g)) continue;
+          if (gconv_ffma_launch(g, in.dtype, P(ws, in.off), w, raw, URN_F32, st)) return 1;
+        }
+  }
+  return urn_bn_stats(raw, L.cout, L.rows_out, L.cout, kBnEps, (float*)P(ws, L.stats_off),
+                      P(ws, h->bn_ws_off), st);
+}
+
+}  // namespace
+
+extern "C" int urn_forward(urn_net* h, const float* params, const float* data, void* ws,
+                           void* stream) {
+  URN_CHECK(h && params && data && ws, "urn_forward: null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  {
+    const Node& dn = h->nodes[h->data_node];
+    long long n = dn.rows * dn.c;
+    unsigned nb = (unsigned)std::min<long long>((n + 255) / 256, 148 * 16);
+    convert_in_kernel<<<nb, 256, 0, st>>>(data, n, dn.dtype == URN_F32 ? (float*)P(ws, dn.off) : nullptr,
+                                          dn.dtype == URN_BF16 ? (bf16*)P(ws, dn.off) : nullptr);
+    URN_LAUNCH_CHECK();
+  }
+  for (const FStep& s : h->fwd) {
+    const Layer& L = h->layers[s.layer];
+    if (s.kind == F_CONV) {
+      if (run_conv_fwd(h, L, params, ws, st)) return 1;
+    } else if (s.kind == F_APPLY) {
+      const Node& o = h->nodes[s.out_node];
+      if (urn_bn_apply((const float*)P(ws, L.raw_off), L.cout, L.rows_out, L.cout,
+                       (const float*)P(ws, L.stats_off), params + L.b_off, nullptr, 0, 0, nullptr,
+                       0, nullptr, nullptr, s.relu, P(ws, o.off), o.ld, o.dtype, st))
+        return 1;
+    } else {  // F_MERGE: relu(BN(conv2) + shortcut)
+      const Node& o = h->nodes[s.out_node];
+      const void* res = nullptr; int64_t ldres = 0; int rdt = o.dtype;
+      const float *res_raw = nullptr, *res_stats = nullptr, *res_beta = nullptr; int64_t ldrr = 0;
+      if (s.layer_sc >= 0) {
+        const Layer& S = h->layers[s.layer_sc];
+        res_raw = (const float*)P(ws, S.raw_off); ldrr = S.cout;
+        res_stats = (const float*)P(ws, S.stats_off); res_beta = params + S.b_off;
+      } else {
+        const Node& r = h->nodes[s.res_node];
+        res = P(ws, r.off); ldres = r.ld; rdt = r.dtype;
+      }
+      if (urn_bn_apply((const float*)P(ws, L.raw_off), L.cout, L.rows_out, L.cout,
+                       (const float*)P(ws, L.stats_off), params + L.b_off, res, ldres, rdt, res_raw,
+                       ldrr, res_stats, res_beta, 1, P(ws, o.off), o.ld, o.dtype, st))
+        return 1;
+    }
+  }
+  return 0;
+}
+
+extern "C" int urn_loss_metrics(urn_net* h, const float* label, const float* weight,
+                                const float* data, float* softmax, double* result, int want_grad,
+                                void* ws, void* stream) {
+  URN_CHECK(h && ws && result, "urn_loss_metrics: null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const Node& lg = h->nodes[h->logits_node];
+  const int64_t pixels = lg.rows / h->cfg.batch;
+  if (!label) {  // inference without labels: softmax only (ssnet.py:130-139)
+    URN_CHECK(softmax, "urn_loss_metrics: nothing to compute");
+    return urn_softmax_only((const float*)P(ws, lg.off), lg.ld, lg.rows, lg.c, softmax, st);
+  }
+  URN_CHECK(data, "urn_loss_metrics: data needed for the nonzero mask");
+  void* dl = nullptr;
+  if (want_grad) {
+    URN_CHECK(h->cfg.training, "urn_loss_metrics: handle was created with training=0");
+    dl = P(ws, h->arena_off + h->gbufs[lg.gbuf].off);
+  }
+  return urn_ce_fwd_bwd((const float*)P(ws, lg.off), lg.ld, label, weight, data, h->cfg.batch,
+                        pixels, lg.c, dl, lg.c, h->cfg.dtype, softmax, result,
+                        P(ws, h->loss_ws_off), st);
+}
+
+extern "C" int urn_check_labels(urn_net* h, void* stream) {
+  (void)h; (void)stream;
+  return 0;
+}
+
+extern "C" int urn_backward(urn_net* h, const float* params, float* grads, int accumulate, void* ws,
+                            void* const* ready_events, void* stream) {
+  URN_CHECK(h && params && grads && ws, "urn_backward: null argument");
+  URN_CHECK(h->cfg.training, "urn_backward: handle was created with training=0");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int T = h->cfg.dtype;
+  auto gptr = [&](const Node& n) -> char* {
+    int gt = T;  // all gradient tensors are stored in the net dtype
+    return P(ws, h->arena_off + h->gbufs[n.gbuf].off) + (int64_t)n.choff * esize(gt);
+  };
+  auto draw = [&](const Layer& L) -> char* { return P(ws, h->arena_off + h->gbufs[L.draw_gbuf].off); };
+  for (const BStep& s : h->bwd) {
+    const Layer& L = h->layers[s.layer];
+    if (s.kind == B_BN) {
+      const Node& dn = h->nodes[s.dout_node];
+      const float *raw2 = nullptr, *stats2 = nullptr; float* dbeta2 = nullptr; void* draw2 = nullptr;
+      int64_t ld2 = 0;
+      if (s.layer2 >= 0) {
+        const Layer& S = h->layers[s.layer2];
+        raw2 = (const float*)P(ws, S.raw_off); stats2 = (const float*)P(ws, S.stats_off);
+        dbeta2 = grads + S.b_off; draw2 = draw(S); ld2 = S.cout;
+      }
+      void* dres = nullptr; int64_t lddres = 0;
+      if (s.dres_node >= 0) { const Node& r = h->nodes[s.dres_node]; dres = gptr(r); lddres = r.ld; }
+      if (urn_bn_bwd(gptr(dn), dn.ld, P(ws, dn.off), dn.ld, T, s.relu, L.rows_out, L.cout,
+                     (const float*)P(ws, L.raw_off), L.cout, (const float*)P(ws, L.stats_off),
+                     grads + L.b_off, draw(L), L.cout, raw2, ld2, stats2, dbeta2, draw2, ld2, dres,
+                     lddres, s.accumulate, accumulate, P(ws, h->bn_ws_off), st))
+        return 1;
+    } else if (s.kind == B_WGRAD) {
+      const Node& in = h->nodes[L.in_node];
+      int rc;
+      if (!L.transpose)
+        rc = wgrad_ffma_launch(L.d, T, P(ws, in.off), in.ld, draw(L), L.cout, grads + L.w_off,
+                               accumulate, P(ws, h->wgrad_ws_off), st);
+      else  // deconv: big side = its output gradient, small side = its input
+        rc = wgrad_ffma_launch(L.d, T, draw(L), L.cout, P(ws, in.off), in.ld, grads + L.w_off,
+                               accumulate, P(ws, h->wgrad_ws_off), st);
+      if (rc) return 1;
+    } else {  // B_DGRAD
+      const Node& in = h->nodes[L.in_node];
+      const float* w = params + L.w_off;
+      if (!L.transpose) {
+        for (int pd = 0; pd < L.d.s; ++pd)
+          for (int ph = 0; ph < L.d.s; ++ph)
+            for (int pw = 0; pw < L.d.s; ++pw) {
+              GConv g;
+              if (!gconv_scatter_class(L.d, L.cout, in.ld, pd, ph, pw, s.accumulate, &g)) continue;
+              if (gconv_ffma_launch(g, T, draw(L), w, gptr(in), T, st)) return 1;
+            }
+      } else {
+        GConv g;
+        gconv_gather(L.d, L.cout, in.ld, &g);
+        g.accumulate = s.accumulate;
+        if (gconv_ffma_launch(g, T, draw(L), w, gptr(in), T, st)) return 1;
+      }
+    }
+    if (s.last_for_layer && ready_events && ready_events[s.layer])
+      URN_CUDA(cudaEventRecord((cudaEvent_t)ready_events[s.layer], st));
+  }
+  return 0;
+}

@@ -1,0 +1,315 @@
+"""``ssnet_base``: host-side mirror of /root/reference/lib/ssnet.py:8-153.
+
+Same constructor, same method names / arity / return structure; ``sess`` arguments are
+accepted and ignored (there is no TensorFlow session -- the work is done by the CUDA
+kernels behind ``include/uresnet_b200.h``).  PyTorch is used only for device buffers,
+pinned staging memory and streams.
+
+Differences that are deliberate and visible:
+  * ``construct`` takes extra keyword-only knobs (``dtype``, ``impl``, ``device``, ``seed``).
+  * variables are exposed through ``get_variables`` / ``set_variables`` keyed by the TF
+    variable names (``UResNet/<scope>/weights``, ``.../BatchNorm/beta``), TF layouts.
+  * out-of-range labels raise ``ValueError`` (TF-CPU raises, TF-GPU yields NaN).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import sys
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+from . import _capi
+
+
+class _optimizer_state(object):
+    """Stands in for ``tf.train.AdamOptimizer`` (ssnet.py:72-75); ``_lr`` is read by the
+    report line of the driver (ssnet_trainval.py:209)."""
+
+    def __init__(self, lr):
+        self._lr = lr
+        self._beta1, self._beta2, self._epsilon = 0.9, 0.999, 1e-8
+        self._t = 0
+
+
+class ssnet_base(object):
+
+    def __init__(self, dims, num_class):
+        self._dims = np.array(dims, np.int32)
+        if not len(self._dims) in [3, 4]:
+            print('Error: len(dims) =', len(self._dims), 'but only 3 (H,W,C) or 4 (H,W,D,C) supported!')
+            raise NotImplementedError
+        self._num_class = int(num_class)
+        self._constructed = False
+
+    def _build(self, input_tensor=None):
+        raise NotImplementedError
+
+    # ------------------------------------------------------------------ construct
+    def construct(self, trainable=True, use_weight=True, learning_rate=None, *, dtype=None,
+                  impl=None, device=None, seed=1234):
+        import os
+        self._trainable = bool(trainable)
+        self._use_weight = bool(use_weight)
+        self._learning_rate = learning_rate
+        self._dtype = _capi.DTYPES[(dtype or os.environ.get("URESNET_B200_DTYPE", "bf16")).lower()]
+        self._impl = _capi.IMPLS[(impl or os.environ.get("URESNET_B200_IMPL", "auto")).lower()]
+        self._lib = _capi.load()          # raises if the CUDA library is missing: no fallback
+        if not torch.cuda.is_available():
+            raise RuntimeError("uresnet_b200 needs a CUDA device (B200, sm_100a); no CPU fallback")
+        self._device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
+        self._net_cfg = self._build(None)  # dict(nd, spatial, in_channels, base_filters, num_strides)
+        self._handles = {}                 # batch -> (handle, workspace tensor)
+        self._data_size = int(np.prod(self._dims))
+        self._label_size = int(np.prod(self._dims[:-1]))
+
+        # parameter table from a batch-1 handle (layout does not depend on the batch)
+        h = self._create_handle(1, training=False)
+        self._param_table = OrderedDict()
+        n = self._lib.urn_param_count(h)
+        for i in range(n):
+            name, rank = C.c_char_p(), C.c_int()
+            shape = (C.c_int64 * 6)()
+            off, cnt = C.c_int64(), C.c_int64()
+            _capi.check(self._lib.urn_param_info(h, i, C.byref(name), C.byref(rank), shape,
+                                                 C.byref(off), C.byref(cnt)))
+            self._param_table[name.value.decode()] = (tuple(shape[k] for k in range(rank.value)),
+                                                      off.value, cnt.value)
+        self._param_total = int(self._lib.urn_param_total(h))
+        self._num_layers = int(self._lib.urn_layer_count(h))
+        self._lib.urn_destroy(h)
+
+        dev = self._device
+        self._params = torch.zeros(self._param_total, dtype=torch.float32, device=dev)
+        self._init_variables(seed)
+        self._softmax = None
+        if self._trainable:
+            # accum_vars / Adam slots (ssnet.py:53-55,72-79)
+            self._accum = torch.zeros_like(self._params)
+            self._adam_m = torch.zeros_like(self._params)
+            self._adam_v = torch.zeros_like(self._params)
+            lr = 0.001 if (learning_rate is None or learning_rate <= 0) else float(learning_rate)
+            self._opt = _optimizer_state(lr)
+        self._result = torch.zeros(4, dtype=torch.float64, device=dev)
+        self._result_host = torch.zeros(4, dtype=torch.float64).pin_memory()
+        self._staging = {}
+        self._exchange = None              # set by dp.attach(): gradient allreduce hook
+        self._constructed = True
+
+    # --------------------------------------------------------------- variables
+    def _init_variables(self, seed):
+        """slim default xavier_initializer() for filters, zeros for beta."""
+        rng = np.random.Generator(np.random.PCG64(int(seed)))
+        host = np.zeros(self._param_total, np.float32)
+        for name, (shape, off, cnt) in self._param_table.items():
+            if name.endswith("/weights"):
+                rf = int(np.prod(shape[:-2]))
+                lim = math.sqrt(6.0 / (rf * shape[-2] + rf * shape[-1]))
+                host[off:off + cnt] = rng.uniform(-lim, lim, cnt).astype(np.float32)
+        self._params.copy_(torch.from_numpy(host))
+
+    def trainable_variables(self):
+        """[(name, shape)] in tf.trainable_variables() order."""
+        return [(k, v[0]) for k, v in self._param_table.items()]
+
+    def get_variables(self, what="params"):
+        src = {"params": self._params, "grads": getattr(self, "_accum", None),
+               "adam_m": getattr(self, "_adam_m", None), "adam_v": getattr(self, "_adam_v", None)}[what]
+        host = src.detach().cpu().numpy()
+        return OrderedDict((k, host[o:o + c].reshape(s).copy()) for k, (s, o, c) in self._param_table.items())
+
+    def set_variables(self, values, strict=True):
+        host = self._params.detach().cpu().numpy().copy()
+        for k, v in values.items():
+            if k not in self._param_table:
+                if strict:
+                    raise KeyError(k)
+                continue
+            s, o, c = self._param_table[k]
+            v = np.asarray(v, np.float32)
+            if tuple(v.shape) != tuple(s):
+                raise ValueError("shape mismatch for %s: %s vs %s" % (k, v.shape, s))
+            host[o:o + c] = v.reshape(-1)
+        self._params.copy_(torch.from_numpy(host))
+
+    # ----------------------------------------------------------------- handles
+    def _create_handle(self, batch, training):
+        cfg = _capi.urn_net_cfg()
+        nc = self._net_cfg
+        cfg.nd = nc["nd"]
+        for i in range(3):
+            cfg.spatial[i] = nc["spatial"][i] if i < len(nc["spatial"]) else 1
+        cfg.in_channels = nc["in_channels"]
+        cfg.batch = int(batch)
+        cfg.base_filters = nc["base_filters"]
+        cfg.num_strides = nc["num_strides"]
+        cfg.num_class = self._num_class
+        cfg.dtype, cfg.impl, cfg.training = self._dtype, self._impl, int(bool(training))
+        h = C.c_void_p()
+        _capi.check(self._lib.urn_create(C.byref(cfg), C.byref(h)))
+        return h
+
+    def _handle(self, batch):
+        key = int(batch)
+        if key not in self._handles:
+            for k in list(self._handles):           # one live workspace at a time per mode
+                hh, _ = self._handles.pop(k)
+                self._lib.urn_destroy(hh)
+            h = self._create_handle(batch, self._trainable)
+            nbytes = int(self._lib.urn_workspace_bytes(h))
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=self._device)
+            self._handles[key] = (h, ws)
+        return self._handles[key]
+
+    def workspace_bytes(self, batch):
+        h = self._create_handle(batch, self._trainable)
+        n = int(self._lib.urn_workspace_bytes(h))
+        self._lib.urn_destroy(h)
+        return n
+
+    def __del__(self):
+        try:
+            for h, _ in getattr(self, "_handles", {}).values():
+                self._lib.urn_destroy(h)
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------- feeds
+    def feed_dict(self, input_data, input_label=None, input_weight=None):
+        """Validates like ssnet.py:141-153 and stages the host arrays on the device."""
+        if input_weight is None and self._use_weight:
+            sys.stderr.write('Network configured to use loss pixel-weighting. Cannot run w/ input_weight=None...\n')
+            raise TypeError
+        feed = {"data": self._to_device("data", input_data, self._data_size)}
+        batch = feed["data"].shape[0]
+        if input_label is not None:
+            feed["label"] = self._to_device("label", input_label, self._label_size, batch)
+        if input_weight is not None:
+            feed["weight"] = self._to_device("weight", input_weight, self._label_size, batch)
+        return feed
+
+    def _to_device(self, key, arr, row, batch=None):
+        if isinstance(arr, torch.Tensor) and arr.is_cuda:
+            t = arr.to(torch.float32).reshape(-1, row)
+        else:
+            a = np.ascontiguousarray(np.asarray(arr, dtype=np.float32)).reshape(-1, row)
+            st = self._staging.get(key)
+            if st is None or st[0].shape != a.shape:
+                st = (torch.empty(a.shape, dtype=torch.float32).pin_memory(),
+                      torch.empty(a.shape, dtype=torch.float32, device=self._device))
+                self._staging[key] = st
+            st[0].numpy()[...] = a
+            st[1].copy_(st[0], non_blocking=True)
+            t = st[1]
+        if batch is not None and t.shape[0] != batch:
+            raise ValueError("batch mismatch between data and %s" % key)
+        return t
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self._device).cuda_stream)
+
+    def _forward(self, feed):
+        batch = feed["data"].shape[0]
+        h, ws = self._handle(batch)
+        _capi.check(self._lib.urn_forward(h, self._params.data_ptr(), feed["data"].data_ptr(),
+                                          ws.data_ptr(), self._stream()))
+        return h, ws, batch
+
+    def _loss_metrics(self, h, ws, feed, want_grad, want_softmax):
+        sm = None
+        if want_softmax:
+            batch = feed["data"].shape[0]
+            sm = torch.empty((batch,) + tuple(int(d) for d in self._dims[:-1]) + (self._num_class,),
+                             dtype=torch.float32, device=self._device)
+        lab = feed.get("label")
+        wgt = feed.get("weight") if self._use_weight else None
+        _capi.check(self._lib.urn_loss_metrics(
+            h, lab.data_ptr() if lab is not None else None,
+            wgt.data_ptr() if wgt is not None else None, feed["data"].data_ptr(),
+            sm.data_ptr() if sm is not None else None, self._result.data_ptr(), int(want_grad),
+            ws.data_ptr(), self._stream()))
+        return sm
+
+    def _fetch_metrics(self):
+        """Device->host read of (loss, n_correct_all, n_correct_nz, n_nz); synchronises."""
+        self._result_host.copy_(self._result, non_blocking=True)
+        torch.cuda.current_stream(self._device).synchronize()
+        loss, ca, cnz, nnz = (float(v) for v in self._result_host)
+        if math.isnan(loss):
+            raise ValueError("label out of range [0, %d) (or non-finite logits)" % self._num_class)
+        return loss, ca, cnz, nnz
+
+    def _metrics(self, batch):
+        loss, ca, cnz, nnz = self._fetch_metrics()
+        acc_all = ca / float(batch * self._label_size)
+        acc_nz = (cnz / nnz) if nnz > 0 else float("nan")   # tf.reduce_mean of empty -> NaN
+        return np.float32(loss), np.float32(acc_all), np.float32(acc_nz)
+
+    # ------------------------------------------------------- reference methods
+    def make_summary(self, sess, input_data, input_label, input_weight=None):
+        """ssnet.py:91-97 -- another full forward; returns the scalar summaries as a dict."""
+        (loss, acc_all, acc_nz), _ = self.run_test(sess, input_data, input_label, input_weight)
+        return {"loss": float(loss), "accuracy_all": float(acc_all), "accuracy_nonzero": float(acc_nz)}
+
+    def zero_gradients(self, sess=None):
+        self._accum.zero_()
+        return [None]
+
+    def accum_gradients(self, sess, input_data, input_label, input_weight=None):
+        """ssnet.py:103-115: one fused forward+backward, gradients ADDED to the accumulators."""
+        if not self._trainable:
+            raise RuntimeError("network constructed with trainable=False")
+        feed = self.feed_dict(input_data=input_data, input_label=input_label, input_weight=input_weight)
+        h, ws, batch = self._forward(feed)
+        self._loss_metrics(h, ws, feed, want_grad=True, want_softmax=False)
+        events = self._exchange.events_array() if self._exchange is not None else None
+        _capi.check(self._lib.urn_backward(h, self._params.data_ptr(), self._accum.data_ptr(), 1,
+                                           ws.data_ptr(), events, self._stream()))
+        if self._exchange is not None:
+            self._exchange.backward_enqueued()
+        loss, acc_all, acc_nz = self._metrics(batch)
+        return [None, loss, acc_all, acc_nz], ['', 'loss', 'acc. all', 'acc. nonzero']
+
+    def apply_gradients(self, sess=None):
+        """ssnet.py:117-119: Adam on (accumulated gradient, variable) pairs."""
+        if self._exchange is not None:
+            self._exchange.finish(self._accum)
+        o = self._opt
+        o._t += 1
+        _capi.check(self._lib.urn_adam_step(
+            self._params.data_ptr(), self._accum.data_ptr(), self._adam_m.data_ptr(),
+            self._adam_v.data_ptr(), self._param_total, o._lr, o._beta1, o._beta2, o._epsilon, o._t,
+            self._stream()))
+        return [None]
+
+    def run_test(self, sess, input_data, input_label, input_weight=None):
+        feed = self.feed_dict(input_data=input_data, input_label=input_label, input_weight=input_weight)
+        h, ws, batch = self._forward(feed)
+        self._loss_metrics(h, ws, feed, want_grad=False, want_softmax=False)
+        loss, acc_all, acc_nz = self._metrics(batch)
+        return [loss, acc_all, acc_nz], ['loss', 'acc. all', 'acc. nonzero']
+
+    def inference(self, sess, input_data, input_label=None):
+        """ssnet.py:130-139: [softmax] or [softmax, acc_all, acc_nonzero]; softmax is a host
+        numpy array [B,H,W,(D,)num_class]."""
+        # like the reference, this raises TypeError when constructed with use_weight=True
+        # (ssnet.py:132 feeds no weights; ana configs set USE_WEIGHTS False)
+        feed = self.feed_dict(input_data=input_data, input_label=input_label)
+        h, ws, batch = self._forward(feed)
+        sm = self._loss_metrics(h, ws, feed, want_grad=False, want_softmax=True)
+        out = [sm.cpu().numpy()]
+        if input_label is not None:
+            _, acc_all, acc_nz = self._metrics(batch)
+            out += [acc_all, acc_nz]
+        return out
+
+    # ------------------------------------------------------------ conveniences
+    def logits(self, batch):
+        """f32 logits [B, ..., num_class] left in the workspace by the last forward (a view)."""
+        h, ws = self._handle(batch)
+        off = int(self._lib.urn_logits_offset_bytes(h))
+        n = batch * self._label_size * self._num_class
+        return ws[off:off + 4 * n].view(torch.float32).view(
+            (batch,) + tuple(int(d) for d in self._dims[:-1]) + (self._num_class,))
