@@ -15,8 +15,10 @@
  *  - activations are channel-last (NHWC / NDHWC); 2D is handled as 3D with depth 1.
  *    A tensor argument is (pointer, ld) where ld = element pitch between consecutive
  *    pixels (>= channels) so that channel slices of a concat buffer are first class.
- *  - dtype: URN_F32 = float storage + FFMA math; URN_BF16 = bf16 storage, fp32
- *    accumulation (tcgen05 tensor cores where the layer shape allows).
+ *  - storage dtypes: URN_F32 (float), URN_BF16, URN_F16; math is always fp32-accumulate.
+ *    Network modes (urn_net_cfg.dtype): URN_F32 = everything float on the CUDA cores (the
+ *    1e-3 parity mode); URN_F16 = "mix16": activations / filters fp16, gradients bf16
+ *    (tcgen05 tensor cores where the layer shape allows); URN_BF16 = all-bf16 storage.
  */
 #ifndef URESNET_B200_H
 #define URESNET_B200_H
@@ -27,7 +29,7 @@
 extern "C" {
 #endif
 
-enum { URN_F32 = 0, URN_BF16 = 1 };
+enum { URN_F32 = 0, URN_BF16 = 1, URN_F16 = 2 };
 enum { URN_IMPL_AUTO = 0, URN_IMPL_FFMA = 1, URN_IMPL_TC = 2 };
 
 /* Geometry of one conv-type layer, stated as the relation between a "big side"
@@ -78,7 +80,7 @@ int urn_conv_dgrad(const urn_conv_desc* d, int dtype, int impl, const void* dy, 
  * ws must hold urn_conv_wgrad_workspace(d) bytes. */
 int64_t urn_conv_wgrad_workspace(const urn_conv_desc* d);
 int urn_conv_wgrad(const urn_conv_desc* d, int dtype, int impl, const void* x, int64_t ldx,
-                   const void* y, int64_t ldy, float* dw, int accumulate, void* ws,
+                   const void* y, int64_t ldy, int y_dtype, float* dw, int accumulate, void* ws,
                    void* stream);
 
 /* K5  slim.batch_norm forward statistics (normalizer_fn of every conv call site):
@@ -103,9 +105,10 @@ int urn_bn_apply(const float* raw, int64_t ld, int64_t rows, int c, const float*
  * g = dout * (relu ? out>0 : 1);  dbeta = sum g;  draw = rstd*(g - mean(g) - xhat*mean(g*xhat)).
  * If raw2 != NULL the same g also flows through a second BN (conv shortcut) giving
  * dbeta2/draw2.  If dres != NULL, g itself is written (or accumulated) there
- * (identity shortcut).  dbeta(2) are accumulated (+=) when acc_beta != 0. */
+ * (identity shortcut).  dbeta(2) are accumulated (+=) when acc_beta != 0.
+ * dtype = storage of dout/draw/draw2/dres; out_dtype = storage of the forward output. */
 int urn_bn_bwd(const void* dout, int64_t lddout, const void* out, int64_t ldo, int dtype,
-               int relu, int64_t rows, int c,
+               int out_dtype, int relu, int64_t rows, int c,
                const float* raw, int64_t ldraw, const float* stats, float* dbeta, void* draw,
                int64_t lddraw,
                const float* raw2, int64_t ldraw2, const float* stats2, float* dbeta2,
@@ -141,7 +144,7 @@ typedef struct urn_net_cfg {
   int32_t base_filters;    /* BASE_NUM_FILTERS   lib/config.py:9       */
   int32_t num_strides;     /* uresnet(num_strides=5) lib/uresnet.py:15 */
   int32_t num_class;       /* NUM_CLASS          lib/config.py:8       */
-  int32_t dtype;           /* URN_F32 | URN_BF16                       */
+  int32_t dtype;           /* URN_F32 | URN_F16 (mix16) | URN_BF16     */
   int32_t impl;            /* URN_IMPL_*                               */
   int32_t training;        /* keep activations for urn_backward        */
 } urn_net_cfg;

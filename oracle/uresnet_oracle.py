@@ -144,6 +144,76 @@ def batch_norm(x, beta):
 
 
 # --------------------------------------------------------------------------
+# optional bf16 storage model (mirrors WHERE the CUDA bf16 mode rounds, so that
+# the two follow the same trajectory; the arithmetic in between stays fp64)
+# --------------------------------------------------------------------------
+def _bf16(x):
+    return x.to(torch.float32).to(torch.bfloat16).to(x.dtype)
+
+
+def _f16(x):
+    return x.to(torch.float32).to(torch.float16).to(x.dtype)
+
+
+class _RoundValueAndGrad(torch.autograd.Function):
+    """A stored activation: value rounded to bf16; its gradient tensor is bf16 too."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return _bf16(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return _bf16(g)
+
+
+class _RoundValueF16AndGrad(torch.autograd.Function):
+    """mix16: activation stored in fp16, its gradient tensor in bf16."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return _f16(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return _bf16(g)
+
+
+class _RoundValueF16STE(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        return _f16(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g
+
+
+class _RoundGrad(torch.autograd.Function):
+    """fp32 value (raw conv output / logits) whose gradient is stored in bf16."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return _bf16(g)
+
+
+class _RoundValueSTE(torch.autograd.Function):
+    """bf16 operand copy of an fp32 master weight; the gradient goes to the master."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return _bf16(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g
+
+
+# --------------------------------------------------------------------------
 # the graph                                          uresnet.py:22-123
 # --------------------------------------------------------------------------
 def _t(P, name, dtype):
@@ -153,24 +223,42 @@ def _t(P, name, dtype):
     return v.to(dtype) if v.dtype != dtype else v
 
 
-def forward(P, data_nhwc, base=16, num_strides=5, keep=None):
+def forward(P, data_nhwc, base=16, num_strides=5, keep=None, quant=None):
     """data_nhwc: torch tensor [B,H,W,(D,)C].  Returns logits, channel-last.
 
     P values may be numpy arrays or torch tensors (leaf tensors with
     requires_grad for autograd).  ``keep``: optional dict that receives every
     layer's post-BN/activation output (channel-last), keyed by TF scope.
+    ``quant='bf16'`` / ``'mix16'`` insert rounding at the storage points of the CUDA 16-bit
+    modes (input, conv weights, stored activations: bf16 resp. fp16; their gradients, d(raw)
+    and d(logits): bf16).
     """
     nd = data_nhwc.dim() - 2
     dt = data_nhwc.dtype
     x = data_nhwc.permute(0, nd + 1, *range(1, nd + 1))  # -> channel first
+    q = quant in ("bf16", "mix16")
+    if quant == "bf16":
+        x = _bf16(x)
+        store, wround = _RoundValueAndGrad.apply, _RoundValueSTE.apply
+    elif quant == "mix16":
+        x = _f16(x)
+        store, wround = _RoundValueF16AndGrad.apply, _RoundValueF16STE.apply
+    else:
+        store = (lambda t: t)
 
-    def layer(scope, x, stride, relu, transpose=False):
+    def layer(scope, x, stride, relu, transpose=False, node=True):
         w = _t(P, "UResNet/%s/weights" % scope, dt)
         b = _t(P, "UResNet/%s/BatchNorm/beta" % scope, dt)
+        if q:
+            w = wround(w)
         y = conv_transpose_same(x, w, stride) if transpose else conv_same(x, w, stride)
+        if q:
+            y = _RoundGrad.apply(y)                        # d(raw) is a bf16 tensor
         y = batch_norm(y, b)                               # conv -> BN -> act
         if relu:
             y = F.relu(y)
+        if node:
+            y = store(y)
         if keep is not None:
             keep[scope] = y.permute(0, *range(2, nd + 2), 1)
         return y
@@ -179,10 +267,10 @@ def forward(P, data_nhwc, base=16, num_strides=5, keep=None):
         if x.shape[1] == cout and stride == 1:
             sc = x
         else:
-            sc = layer(scope + "/shortcut", x, stride, False)
+            sc = layer(scope + "/shortcut", x, stride, False, node=False)
         r = layer(scope + "/resnet_conv1", x, stride, False)   # no ReLU between
-        r = layer(scope + "/resnet_conv2", r, 1, False)
-        return F.relu(sc + r)
+        r = layer(scope + "/resnet_conv2", r, 1, False, node=False)
+        return store(F.relu(sc + r))
 
     def double_resnet(idx, x, cout, stride):             # resnet_module.py:70-87
         x = resnet_module("resnet_module%d/module1" % idx, x, cout, stride)
@@ -199,7 +287,9 @@ def forward(P, data_nhwc, base=16, num_strides=5, keep=None):
         net = torch.cat([net, fmap[cout]], dim=1)        # deconv channels first
         net = double_resnet(step + 5, net, cout, 1)
     net = layer("conv1", net, 1, True)
-    net = layer("conv2", net, 1, False)
+    net = layer("conv2", net, 1, False, node=False)     # logits stay fp32 ...
+    if q:
+        net = _RoundGrad.apply(net)                      # ... their gradient is bf16
     return net.permute(0, *range(2, nd + 2), 1).contiguous()
 
 
@@ -235,7 +325,7 @@ def loss_and_metrics(logits, data, label, weight=None):
 
 
 def run(P_np, data, label, weight=None, base=16, num_strides=5, dtype=torch.float64,
-        want_grads=True, keep=None):
+        want_grads=True, keep=None, quant=None):
     """Full forward(+backward).  numpy in / numpy out.
 
     data [B,...,Cin], label/weight [B,...].  Returns dict with logits, loss,
@@ -247,7 +337,7 @@ def run(P_np, data, label, weight=None, base=16, num_strides=5, dtype=torch.floa
     lab = torch.tensor(label, dtype=dtype)
     w = None if weight is None else torch.tensor(weight, dtype=dtype)
     with torch.set_grad_enabled(want_grads):
-        logits = forward(P, d, base=base, num_strides=num_strides, keep=keep)
+        logits = forward(P, d, base=base, num_strides=num_strides, keep=keep, quant=quant)
         res = loss_and_metrics(logits, d, lab, w)
     out = dict(logits=logits.detach().numpy(), loss=float(res["loss"].detach()),
                acc_all=res["acc_all"], acc_nonzero=res["acc_nonzero"],
@@ -269,10 +359,15 @@ def run(P_np, data, label, weight=None, base=16, num_strides=5, dtype=torch.floa
 # TF AdamOptimizer                                   ssnet.py:72-79, SURVEY 3.4
 # --------------------------------------------------------------------------
 def adam_tf(var, grad, m, v, t, lr=1e-3, b1=0.9, b2=0.999, eps=1e-8):
-    """One TF-1.x Adam apply (epsilon OUTSIDE the bias correction). fp32 in place
-    semantics mirrored with numpy float32; t is the 1-based step count."""
-    lr_t = np.float32(lr * math.sqrt(1.0 - b2 ** t) / (1.0 - b1 ** t))
-    m[...] = np.float32(b1) * m + np.float32(1 - b1) * grad
-    v[...] = np.float32(b2) * v + np.float32(1 - b2) * grad * grad
-    var[...] = var - lr_t * m / (np.sqrt(v) + np.float32(eps))
+    """One TF-1.x ``ApplyAdam`` step in float32, in place; t is the 1-based step count.
+
+    TF's kernel form (epsilon OUTSIDE the bias correction):
+      alpha = lr*sqrt(1-b2^t)/(1-b1^t);  m += (g-m)*(1-b1);  v += (g*g-v)*(1-b2);
+      var -= m*alpha/(sqrt(v)+eps)     with (1-b) evaluated in float32 like TF does."""
+    f = np.float32
+    alpha = f(lr * math.sqrt(1.0 - b2 ** t) / (1.0 - b1 ** t))
+    omb1, omb2 = f(1) - f(b1), f(1) - f(b2)
+    m[...] = m + (grad - m) * omb1
+    v[...] = v + (grad * grad - v) * omb2
+    var[...] = var - (m * alpha) / (np.sqrt(v) + f(eps))
     return var, m, v

@@ -1,0 +1,279 @@
+"""Per-kernel parity (GPU): every K-row of SURVEY.md 8a through the C ABI vs the CPU oracle."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import uresnet_oracle as O
+from uresnet_b200 import _capi
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+F32, BF16, F16 = _capi.URN_F32, _capi.URN_BF16, _capi.URN_F16
+TOL = {F32: 2e-5, BF16: 1.5e-2, F16: 1.5e-2}   # F16 = mix16: fp16 activations, bf16 gradients
+TORCH_DT = {F32: torch.float32, BF16: torch.bfloat16, F16: torch.float16}     # max|a-b| / max|b| per tensor
+
+
+def relerr(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-30)
+
+
+def dev(x, dt=F32):
+    t = torch.as_tensor(np.ascontiguousarray(x), dtype=torch.float32).to(DEV)
+    return t.to(TORCH_DT[dt])
+
+
+def gdt(dt):
+    """gradient storage dtype of a network mode (mix16 keeps gradients in bf16)"""
+    return BF16 if dt == F16 else dt
+
+
+def host(t):
+    return t.float().cpu().numpy()
+
+
+def st():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def cf(x):
+    nd = x.ndim - 2
+    return torch.tensor(x, dtype=torch.float64).permute(0, nd + 1, *range(1, nd + 1))
+
+
+def cl(y):
+    nd = y.dim() - 2
+    return y.permute(0, *range(2, nd + 2), 1).contiguous().numpy()
+
+
+CONV_CASES = [
+    # nd, n, spatial, cin, cout, k, s
+    (2, 2, (12, 20), 16, 16, 3, 1),
+    (2, 1, (16, 16), 1, 16, 3, 1),       # stem (Cin = 1)
+    (2, 2, (9, 14), 16, 3, 3, 1),        # head (Cout = 3), odd size
+    (2, 2, (16, 24), 16, 32, 3, 2),      # stride-2, asymmetric SAME pad
+    (2, 1, (15, 17), 8, 12, 3, 2),       # odd sizes: pad_before changes
+    (2, 2, (16, 16), 32, 64, 1, 2),      # 1x1 shortcut s2
+    (2, 2, (8, 8), 64, 32, 1, 1),        # 1x1 shortcut s1
+    (2, 1, (8, 8), 128, 80, 3, 1),       # two cout tiles, ragged
+    (3, 2, (6, 8, 10), 16, 16, 3, 1),
+    (3, 1, (8, 8, 8), 16, 32, 3, 2),
+    (3, 1, (8, 6, 4), 32, 64, 1, 2),
+    (3, 1, (4, 4, 4), 1, 16, 3, 1),
+]
+
+
+@pytest.mark.parametrize("dt", [F32, BF16, F16])
+@pytest.mark.parametrize("nd,n,sp,cin,cout,k,s", CONV_CASES)
+def test_conv_fwd_dgrad_wgrad(lib, dt, nd, n, sp, cin, cout, k, s):
+    rng = np.random.default_rng(hash((nd, n, sp, cin, cout, k, s)) % 2**32)
+    x = rng.standard_normal((n,) + sp + (cin,)).astype(np.float32)
+    w = (rng.standard_normal((k,) * nd + (cin, cout)) / np.sqrt(k**nd * cin)).astype(np.float32)
+    if dt != F32:   # feed the oracle the same rounded activations
+        x = host(dev(x, dt))
+    d = _capi.conv_desc_same(nd, n, sp, cin, cout, k, s)
+    osp = (d.yd, d.yh, d.yw)[3 - nd:]
+    xt = torch.tensor(x, dtype=torch.float64, requires_grad=True)
+    wt = torch.tensor(w, dtype=torch.float64, requires_grad=True)
+    yo = O.conv_same(xt.permute(0, nd + 1, *range(1, nd + 1)), wt, s)
+    g = rng.standard_normal(tuple(yo.shape)).astype(np.float32)          # channel first
+    g_cl = np.ascontiguousarray(np.moveaxis(g, 1, -1))
+    if dt != F32:
+        g_cl = host(dev(g_cl, gdt(dt)))
+    dxo, dwo = torch.autograd.grad(yo, [xt, wt], torch.tensor(np.moveaxis(g_cl, -1, 1), dtype=torch.float64))
+    # forward
+    xd, wd = dev(x, dt), dev(w)
+    y = torch.empty((n,) + osp + (cout,), dtype=torch.float32, device=DEV)
+    _capi.check(lib.urn_conv_fwd(C.byref(d), dt, 1, xd.data_ptr(), cin, wd.data_ptr(), y.data_ptr(), cout, F32, st()))
+    assert relerr(host(y), cl(yo.detach())) < 2e-5
+    # dgrad (write, then accumulate)
+    gd = dev(g_cl, gdt(dt))
+    dx = torch.full((n,) + sp + (cin,), 7.0, dtype=TORCH_DT[gdt(dt)], device=DEV)
+    _capi.check(lib.urn_conv_dgrad(C.byref(d), gdt(dt), 1, gd.data_ptr(), cout, wd.data_ptr(), dx.data_ptr(), cin, gdt(dt), 0, st()))
+    assert relerr(host(dx), dxo.numpy()) < TOL[dt]
+    _capi.check(lib.urn_conv_dgrad(C.byref(d), gdt(dt), 1, gd.data_ptr(), cout, wd.data_ptr(), dx.data_ptr(), cin, gdt(dt), 1, st()))
+    assert relerr(host(dx), 2 * dxo.numpy()) < 2 * TOL[dt]
+    # wgrad
+    wsb = lib.urn_conv_wgrad_workspace(C.byref(d))
+    ws = torch.empty(max(int(wsb), 16), dtype=torch.uint8, device=DEV)
+    dw = torch.full(w.shape, 3.0, dtype=torch.float32, device=DEV)
+    _capi.check(lib.urn_conv_wgrad(C.byref(d), dt, 1, xd.data_ptr(), cin, gd.data_ptr(), cout, gdt(dt), dw.data_ptr(), 0, ws.data_ptr(), st()))
+    assert relerr(host(dw), dwo.numpy()) < 2e-5
+    _capi.check(lib.urn_conv_wgrad(C.byref(d), dt, 1, xd.data_ptr(), cin, gd.data_ptr(), cout, gdt(dt), dw.data_ptr(), 1, ws.data_ptr(), st()))
+    assert relerr(host(dw), 2 * dwo.numpy()) < 4e-5
+
+
+@pytest.mark.parametrize("nd,n,sp,cin,cout", [(2, 2, (8, 12), 32, 16), (3, 1, (4, 6, 4), 32, 16), (2, 1, (5, 7), 8, 4)])
+def test_conv_transpose_forward(lib, nd, n, sp, cin, cout):
+    """slim.conv*_transpose forward == urn_conv_dgrad on the deconv's base relation."""
+    rng = np.random.default_rng(11)
+    x = rng.standard_normal((n,) + sp + (cin,)).astype(np.float32)
+    w = rng.standard_normal((3,) * nd + (cout, cin)).astype(np.float32) / 10
+    yo = cl(O.conv_transpose_same(cf(x), torch.tensor(w, dtype=torch.float64), 2))
+    osp = tuple(2 * v for v in sp)
+    d = _capi.conv_desc_same(nd, n, osp, cout, cin, 3, 2)
+    y = torch.empty((n,) + osp + (cout,), dtype=torch.float32, device=DEV)
+    xd, wd = dev(x), dev(w)          # keep the device tensors alive across the call
+    _capi.check(lib.urn_conv_dgrad(C.byref(d), F32, 1, xd.data_ptr(), cin, wd.data_ptr(), y.data_ptr(), cout, F32, 0, st()))
+    assert relerr(host(y), yo) < 2e-5
+
+
+def test_conv_pitched_views(lib):
+    """Channel slices of a concat buffer as conv input (ldx > cin) and dgrad output."""
+    rng = np.random.default_rng(12)
+    n, sp, cin, cout = 2, (8, 8), 16, 16
+    z = rng.standard_normal((n,) + sp + (2 * cin,)).astype(np.float32)
+    w = rng.standard_normal((3, 3, cin, cout)).astype(np.float32) / 12
+    d = _capi.conv_desc_same(2, n, sp, cin, cout, 3, 1)
+    zd, wd = dev(z), dev(w)
+    y = torch.empty((n,) + sp + (cout,), dtype=torch.float32, device=DEV)
+    _capi.check(lib.urn_conv_fwd(C.byref(d), F32, 1, zd.data_ptr() + 4 * cin, 2 * cin, wd.data_ptr(), y.data_ptr(), cout, F32, st()))
+    yo = cl(O.conv_same(cf(z[..., cin:]), torch.tensor(w, dtype=torch.float64), 1))
+    assert relerr(host(y), yo) < 2e-5
+
+
+@pytest.mark.parametrize("c,rows", [(16, 5000), (3, 777), (512, 64), (32, 1)])
+def test_bn_stats_apply(lib, c, rows):
+    rng = np.random.default_rng(c)
+    x = (rng.standard_normal((rows, c)) * rng.random(c) * 3 + rng.standard_normal(c)).astype(np.float32)
+    beta = rng.standard_normal(c).astype(np.float32)
+    xd, bd = dev(x), dev(beta)
+    stats = torch.empty(2 * c, dtype=torch.float32, device=DEV)
+    ws = torch.empty(int(lib.urn_bn_workspace(c)), dtype=torch.uint8, device=DEV)
+    _capi.check(lib.urn_bn_stats(xd.data_ptr(), c, rows, c, 1e-3, stats.data_ptr(), ws.data_ptr(), st()))
+    mu, var = x.astype(np.float64).mean(0), x.astype(np.float64).var(0)
+    np.testing.assert_allclose(host(stats)[:c], mu, atol=1e-5)
+    np.testing.assert_allclose(host(stats)[c:], 1 / np.sqrt(var + 1e-3), rtol=2e-5)
+    ref = (x - mu) / np.sqrt(var + 1e-3) + beta
+    for relu in (0, 1):
+        out = torch.empty((rows, c), dtype=torch.float32, device=DEV)
+        _capi.check(lib.urn_bn_apply(xd.data_ptr(), c, rows, c, stats.data_ptr(), bd.data_ptr(), None, 0, 0, None, 0,
+                                     None, None, relu, out.data_ptr(), c, F32, st()))
+        assert relerr(host(out), np.maximum(ref, 0) if relu else ref) < 2e-5
+    # residual forms: identity tensor, and a second BN (conv shortcut)
+    r = rng.standard_normal((rows, c)).astype(np.float32)
+    out = torch.empty((rows, c), dtype=torch.float32, device=DEV)
+    rd = dev(r)
+    _capi.check(lib.urn_bn_apply(xd.data_ptr(), c, rows, c, stats.data_ptr(), bd.data_ptr(), rd.data_ptr(), c, F32,
+                                 None, 0, None, None, 1, out.data_ptr(), c, F32, st()))
+    assert relerr(host(out), np.maximum(ref + r, 0)) < 2e-5
+    _capi.check(lib.urn_bn_apply(xd.data_ptr(), c, rows, c, stats.data_ptr(), bd.data_ptr(), None, 0, 0,
+                                 xd.data_ptr(), c, stats.data_ptr(), bd.data_ptr(), 1, out.data_ptr(), c, F32, st()))
+    assert relerr(host(out), np.maximum(2 * ref, 0)) < 2e-5
+
+
+@pytest.mark.parametrize("dt", [F32, BF16, F16])
+@pytest.mark.parametrize("c,rows,relu,mode", [(16, 3000, 1, "conv_sc"), (16, 3000, 1, "identity"), (3, 500, 0, "plain"),
+                                              (64, 129, 1, "plain"), (256, 40, 0, "plain")])
+def test_bn_backward(lib, dt, c, rows, relu, mode):
+    rng = np.random.default_rng(rows + c)
+    x = rng.standard_normal((rows, c)).astype(np.float32) * 2 + 0.5
+    x2 = rng.standard_normal((rows, c)).astype(np.float32)
+    res = rng.standard_normal((rows, c)).astype(np.float32)
+    beta = rng.standard_normal(c).astype(np.float32) * 0.3
+    dout = rng.standard_normal((rows, c)).astype(np.float32)
+    if dt != F32:
+        dout, res = host(dev(dout, gdt(dt))), host(dev(res, dt))
+    xt, x2t, rt = (torch.tensor(v, dtype=torch.float64, requires_grad=True) for v in (x, x2, res))
+    bt = torch.tensor(beta, dtype=torch.float64, requires_grad=True)
+
+    def bn(v, b):
+        mu = v.mean(0)
+        var = ((v - mu) ** 2).mean(0)
+        return (v - mu) * torch.rsqrt(var + 1e-3) + b
+    y = bn(xt, bt)
+    if mode == "conv_sc":
+        y = y + bn(x2t, bt * 0)
+    elif mode == "identity":
+        y = y + rt
+    out = torch.relu(y) if relu else y
+    ins = [xt, bt] + ([x2t] if mode == "conv_sc" else []) + ([rt] if mode == "identity" else [])
+    grads = torch.autograd.grad(out, ins, torch.tensor(dout, dtype=torch.float64))
+    # device side
+    def stats_of(v):
+        vd = dev(v)
+        s = torch.empty(2 * c, dtype=torch.float32, device=DEV)
+        _capi.check(lib.urn_bn_stats(vd.data_ptr(), c, rows, c, 1e-3, s.data_ptr(), ws.data_ptr(), st()))
+        return vd, s
+    ws = torch.empty(int(lib.urn_bn_workspace(c)), dtype=torch.uint8, device=DEV)
+    xd, s1 = stats_of(x)
+    x2d, s2 = stats_of(x2)
+    outd = dev(out.detach().numpy(), dt)
+    doutd = dev(dout, gdt(dt))
+    tdt = TORCH_DT[gdt(dt)]
+    draw = torch.empty((rows, c), dtype=tdt, device=DEV)
+    draw2 = torch.empty((rows, c), dtype=tdt, device=DEV)
+    dres = torch.ones((rows, c), dtype=tdt, device=DEV)
+    dbeta = torch.zeros(c, dtype=torch.float32, device=DEV)
+    dbeta2 = torch.zeros(c, dtype=torch.float32, device=DEV)
+    _capi.check(lib.urn_bn_bwd(
+        doutd.data_ptr(), c, outd.data_ptr(), c, gdt(dt), dt, relu, rows, c, xd.data_ptr(), c, s1.data_ptr(), dbeta.data_ptr(),
+        draw.data_ptr(), c,
+        x2d.data_ptr() if mode == "conv_sc" else None, c, s2.data_ptr() if mode == "conv_sc" else None,
+        dbeta2.data_ptr() if mode == "conv_sc" else None, draw2.data_ptr() if mode == "conv_sc" else None, c,
+        dres.data_ptr() if mode == "identity" else None, c, 1, 0, ws.data_ptr(), st()))
+    tol = TOL[dt]
+    assert relerr(host(draw), grads[0].numpy()) < tol
+    assert relerr(host(dbeta), grads[1].numpy()) < 1e-4
+    if mode == "conv_sc":
+        assert relerr(host(draw2), grads[2].numpy()) < tol
+        assert relerr(host(dbeta2), grads[1].numpy()) < 1e-4
+    if mode == "identity":
+        assert relerr(host(dres), 1 + grads[2].numpy()) < tol   # accumulated onto the ones
+
+
+@pytest.mark.parametrize("B,P,c,use_w", [(2, 1000, 3, True), (3, 257, 3, False), (1, 64, 5, True)])
+def test_ce_metrics(lib, B, P, c, use_w):
+    rng = np.random.default_rng(P)
+    logits = (rng.standard_normal((B, P, c)) * 3).astype(np.float32)
+    logits[0, :5] = 1.25                                       # exact ties -> first index wins
+    label = rng.integers(0, c, (B, P)).astype(np.float32)
+    weight = rng.random((B, P)).astype(np.float32)
+    data = (rng.random((B, P)) > 0.7).astype(np.float32) * 3
+    r = O.loss_and_metrics(torch.tensor(logits, dtype=torch.float64).requires_grad_(True), torch.tensor(data)[..., None],
+                           torch.tensor(label), torch.tensor(weight) if use_w else None)
+    lt = torch.tensor(logits, dtype=torch.float64, requires_grad=True)
+    r2 = O.loss_and_metrics(lt, torch.tensor(data)[..., None], torch.tensor(label), torch.tensor(weight) if use_w else None)
+    (dl_ref,) = torch.autograd.grad(r2["loss"], lt)
+    ws = torch.zeros(int(lib.urn_loss_workspace(B * P)), dtype=torch.uint8, device=DEV)
+    res = torch.zeros(4, dtype=torch.float64, device=DEV)
+    dl = torch.empty((B, P, c), dtype=torch.float32, device=DEV)
+    sm = torch.empty((B, P, c), dtype=torch.float32, device=DEV)
+    lgd, labd, wgd, dad = dev(logits), dev(label), dev(weight), dev(data)
+    _capi.check(lib.urn_ce_fwd_bwd(lgd.data_ptr(), c, labd.data_ptr(), wgd.data_ptr() if use_w else None,
+                                   dad.data_ptr(), B, P, c, dl.data_ptr(), c, F32, sm.data_ptr(), res.data_ptr(),
+                                   ws.data_ptr(), st()))
+    out = res.cpu().numpy()
+    assert abs(out[0] - float(r["loss"])) <= 2e-6 * abs(float(r["loss"]))
+    assert (int(out[1]), int(out[2]), int(out[3])) == (r["n_correct_all"], r["n_correct_nz"], r["n_nz"])
+    assert relerr(host(dl), dl_ref.numpy()) < 1e-5
+    assert relerr(host(sm), r["softmax"].detach().numpy()) < 1e-5
+    # out-of-range label -> NaN loss
+    label[0, 0] = c
+    labd = dev(label)
+    _capi.check(lib.urn_ce_fwd_bwd(lgd.data_ptr(), c, labd.data_ptr(), None, dad.data_ptr(), B, P, c,
+                                   None, c, F32, None, res.data_ptr(), ws.data_ptr(), st()))
+    assert np.isnan(res.cpu().numpy()[0])
+
+
+def test_adam_matches_tf_formula(lib):
+    rng = np.random.default_rng(0)
+    n = 1003
+    p, g = rng.standard_normal(n).astype(np.float32), rng.standard_normal(n).astype(np.float32)
+    m, v = np.zeros(n, np.float32), np.zeros(n, np.float32)
+    pd, gd, md, vd = dev(p), dev(g), dev(m), dev(v)
+    for t in (1, 2, 3):
+        O.adam_tf(p, g, m, v, t, lr=1e-3)
+        _capi.check(lib.urn_adam_step(pd.data_ptr(), gd.data_ptr(), md.data_ptr(), vd.data_ptr(), n, 1e-3, 0.9, 0.999, 1e-8, t, st()))
+    np.testing.assert_allclose(host(pd), p, rtol=0, atol=1e-6)
+    np.testing.assert_allclose(host(vd), v, rtol=1e-5, atol=1e-12)
+
+
+def test_error_paths(lib):
+    d = _capi.urn_conv_desc()
+    assert lib.urn_conv_desc_same(C.byref(d), 4, 1, 1, 8, 8, 1, 1, 3, 1) != 0
+    assert b"nd" in lib.urn_last_error()
+    d = _capi.conv_desc_same(2, 1, (8, 8), 4, 4, 3, 1)
+    assert lib.urn_conv_fwd(C.byref(d), F32, 1, None, 2, None, None, 4, F32, None) != 0   # pitch < channels

@@ -11,9 +11,12 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "liburesnet_b200.so")
 
-URN_F32, URN_BF16 = 0, 1
+URN_F32, URN_BF16, URN_F16 = 0, 1, 2
 URN_IMPL_AUTO, URN_IMPL_FFMA, URN_IMPL_TC = 0, 1, 2
-DTYPES = {"f32": URN_F32, "fp32": URN_F32, "float32": URN_F32, "bf16": URN_BF16, "bfloat16": URN_BF16}
+# network modes: f32 = exact CUDA-core path; mix16 = fp16 activations/filters + bf16 gradients
+# (tensor cores); bf16 = all-bf16 storage
+DTYPES = {"f32": URN_F32, "fp32": URN_F32, "float32": URN_F32, "bf16": URN_BF16, "bfloat16": URN_BF16,
+          "mix16": URN_F16, "f16": URN_F16, "fp16": URN_F16}
 IMPLS = {"auto": URN_IMPL_AUTO, "ffma": URN_IMPL_FFMA, "tc": URN_IMPL_TC}
 
 
@@ -41,12 +44,12 @@ SIGNATURES = {
     "urn_conv_fwd": (_i, [_descp, _i, _i, _vp, _i64, _vp, _vp, _i64, _i, _vp]),
     "urn_conv_dgrad": (_i, [_descp, _i, _i, _vp, _i64, _vp, _vp, _i64, _i, _i, _vp]),
     "urn_conv_wgrad_workspace": (_i64, [_descp]),
-    "urn_conv_wgrad": (_i, [_descp, _i, _i, _vp, _i64, _vp, _i64, _vp, _i, _vp, _vp]),
+    "urn_conv_wgrad": (_i, [_descp, _i, _i, _vp, _i64, _vp, _i64, _i, _vp, _i, _vp, _vp]),
     "urn_bn_workspace": (_i64, [_i]),
     "urn_bn_stats": (_i, [_vp, _i64, _i64, _i, _f, _vp, _vp, _vp]),
     "urn_bn_apply": (_i, [_vp, _i64, _i64, _i, _vp, _vp, _vp, _i64, _i, _vp, _i64, _vp, _vp, _i,
                           _vp, _i64, _i, _vp]),
-    "urn_bn_bwd": (_i, [_vp, _i64, _vp, _i64, _i, _i, _i64, _i, _vp, _i64, _vp, _vp, _vp, _i64,
+    "urn_bn_bwd": (_i, [_vp, _i64, _vp, _i64, _i, _i, _i, _i64, _i, _vp, _i64, _vp, _vp, _vp, _i64,
                         _vp, _i64, _vp, _vp, _vp, _i64, _vp, _i64, _i, _i, _vp, _vp]),
     "urn_loss_workspace": (_i64, [_i64]),
     "urn_ce_fwd_bwd": (_i, [_vp, _i64, _vp, _vp, _vp, _i64, _i64, _i, _vp, _i64, _i, _vp, _vp, _vp,

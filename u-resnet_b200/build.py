@@ -30,6 +30,9 @@ def build_library(verbose=False, force=False):
     srcs = sorted(f for f in os.listdir(CSRC) if f.endswith(".cu"))
     hdrs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     hdrs.append(os.path.join(os.path.dirname(HERE), "include", "uresnet_b200.h"))
+    all_src = [os.path.join(CSRC, s) for s in srcs] + hdrs
+    if not force and os.path.exists(LIB) and not _stale(LIB, all_src):
+        return LIB                      # up to date (e.g. the prebuilt .so on the GPU box)
     jobs = []
     for s in srcs:
         src = os.path.join(CSRC, s)

@@ -53,16 +53,22 @@ bn_stats_kernel(const float* __restrict__ raw, long long ld, long long rows, int
   const int lane = tid / m.cg, g = tid % m.cg;
   float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
   if (lane < m.lanes) {
+    // Shifted sums: accumulate (x-K), (x-K)^2 with K = the channel's value in row 0
+    // (a background pixel for LArTPC images) so that var = E[(x-K)^2] - E[x-K]^2 does not
+    // cancel catastrophically on nearly-constant channels.
+    float K[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int v = 0; v < m.vec; ++v) K[v] = raw[g * m.vec + v];
     for (long long r = (long long)blockIdx.x * m.lanes + lane; r < rows;
          r += (long long)gridDim.x * m.lanes) {
       const float* p = raw + r * ld + g * m.vec;
       if (m.vec == 4) {
         float4 v = ld4(p);
+        v.x -= K[0]; v.y -= K[1]; v.z -= K[2]; v.w -= K[3];
         acc[0][0] += v.x; acc[0][1] += v.y; acc[0][2] += v.z; acc[0][3] += v.w;
         acc[1][0] = fmaf(v.x, v.x, acc[1][0]); acc[1][1] = fmaf(v.y, v.y, acc[1][1]);
         acc[1][2] = fmaf(v.z, v.z, acc[1][2]); acc[1][3] = fmaf(v.w, v.w, acc[1][3]);
       } else {
-        float v = *p;
+        float v = *p - K[0];
         acc[0][0] += v;
         acc[1][0] = fmaf(v, v, acc[1][0]);
       }
@@ -72,7 +78,8 @@ bn_stats_kernel(const float* __restrict__ raw, long long ld, long long rows, int
 }
 
 __global__ void bn_stats_finalize_kernel(const double* __restrict__ partial, int nblocks, int c,
-                                         long long rows, float eps, float* __restrict__ stats) {
+                                         long long rows, float eps, const float* __restrict__ raw,
+                                         float* __restrict__ stats) {
   int ch = blockIdx.x * blockDim.x + threadIdx.x;
   if (ch >= c) return;
   double s = 0.0, q = 0.0;
@@ -80,10 +87,10 @@ __global__ void bn_stats_finalize_kernel(const double* __restrict__ partial, int
     s += partial[((long long)b * 2 + 0) * c + ch];
     q += partial[((long long)b * 2 + 1) * c + ch];
   }
-  double mean = s / (double)rows;
-  double var = q / (double)rows - mean * mean;
+  double dm = s / (double)rows;                 // mean of (x - K)
+  double var = q / (double)rows - dm * dm;
   if (var < 0.0) var = 0.0;
-  stats[ch] = (float)mean;
+  stats[ch] = (float)((double)raw[ch] + dm);
   stats[c + ch] = (float)(1.0 / sqrt(var + (double)eps));
 }
 
@@ -130,9 +137,9 @@ bn_apply_kernel(const float* __restrict__ raw, long long ld, long long rows, int
 }
 
 // ---- backward: pass 1, per-channel sums of g, g*xhat (and g*xhat2) ----
-template <typename T>
+template <typename T, typename TA>
 __global__ void __launch_bounds__(BN_THREADS)
-bn_bwd_reduce_kernel(const T* __restrict__ dout, long long lddout, const T* __restrict__ outp,
+bn_bwd_reduce_kernel(const T* __restrict__ dout, long long lddout, const TA* __restrict__ outp,
                      long long ldo, int relu, long long rows, int c, bool aligned,
                      const float* __restrict__ raw, long long ldraw, const float* __restrict__ stats,
                      const float* __restrict__ raw2, long long ldraw2,
@@ -204,9 +211,9 @@ __global__ void bn_bwd_finalize_kernel(const double* __restrict__ partial, int n
 }
 
 // ---- backward: pass 2, elementwise ----
-template <typename T>
+template <typename T, typename TA>
 __global__ void __launch_bounds__(256)
-bn_bwd_apply_kernel(const T* __restrict__ dout, long long lddout, const T* __restrict__ outp,
+bn_bwd_apply_kernel(const T* __restrict__ dout, long long lddout, const TA* __restrict__ outp,
                     long long ldo, int relu, long long rows, int c, int vec,
                     const float* __restrict__ raw, long long ldraw, const float* __restrict__ stats,
                     T* __restrict__ draw, long long lddraw, const float* __restrict__ raw2,
@@ -319,7 +326,7 @@ extern "C" int urn_bn_stats(const float* raw, int64_t ld, int64_t rows, int c, f
   double* partial = (double*)ws;
   bn_stats_kernel<<<nb, BN_THREADS, 0, st>>>(raw, ld, rows, c, al, partial);
   URN_LAUNCH_CHECK();
-  bn_stats_finalize_kernel<<<(c + 127) / 128, 128, 0, st>>>(partial, nb, c, rows, eps, stats);
+  bn_stats_finalize_kernel<<<(c + 127) / 128, 128, 0, st>>>(partial, nb, c, rows, eps, raw, stats);
   URN_LAUNCH_CHECK();
   return 0;
 }
@@ -347,23 +354,17 @@ extern "C" int urn_bn_apply(const float* raw, int64_t ld, int64_t rows, int c, c
   cudaStream_t st = (cudaStream_t)stream;
   URN_CHECK(rows > 0 && c >= 1, "urn_bn_apply: empty input");
   if (!res) res_dtype = out_dtype;
-  if (res_dtype == URN_F32 && out_dtype == URN_F32)
-    return bn_apply_t<float, float>(raw, ld, rows, c, stats, beta, res, ldres, res_raw, ldres_raw,
-                                    res_stats, res_beta, relu, out, ldout, st);
-  if (res_dtype == URN_BF16 && out_dtype == URN_BF16)
-    return bn_apply_t<bf16, bf16>(raw, ld, rows, c, stats, beta, res, ldres, res_raw, ldres_raw,
-                                  res_stats, res_beta, relu, out, ldout, st);
-  if (res_dtype == URN_BF16 && out_dtype == URN_F32)
-    return bn_apply_t<bf16, float>(raw, ld, rows, c, stats, beta, res, ldres, res_raw, ldres_raw,
-                                   res_stats, res_beta, relu, out, ldout, st);
-  if (res_dtype == URN_F32 && out_dtype == URN_BF16)
-    return bn_apply_t<float, bf16>(raw, ld, rows, c, stats, beta, res, ldres, res_raw, ldres_raw,
-                                   res_stats, res_beta, relu, out, ldout, st);
-  urn_set_error("urn_bn_apply: bad dtype");
-  return 1;
+  return dispatch_dtype(res_dtype, [&](auto pr) {
+    using TR = URN_T(pr);
+    return dispatch_dtype(out_dtype, [&](auto po) {
+      using TO = URN_T(po);
+      return bn_apply_t<TR, TO>(raw, ld, rows, c, stats, beta, res, ldres, res_raw, ldres_raw,
+                                res_stats, res_beta, relu, out, ldout, st);
+    });
+  });
 }
 
-template <typename T>
+template <typename T, typename TA>
 static int bn_bwd_t(const void* dout, int64_t lddout, const void* out, int64_t ldo, int relu,
                     int64_t rows, int c, const float* raw, int64_t ldraw, const float* stats,
                     float* dbeta, void* draw, int64_t lddraw, const float* raw2, int64_t ldraw2,
@@ -377,7 +378,7 @@ static int bn_bwd_t(const void* dout, int64_t lddout, const void* out, int64_t l
   double* partial = (double*)ws;
   int64_t pb = ((int64_t)BN_MAX_BLOCKS * 3 * c * 8 + 255) / 256 * 256;
   float* sums = (float*)((char*)ws + pb);
-  bn_bwd_reduce_kernel<T><<<nb, BN_THREADS, 0, st>>>((const T*)dout, lddout, (const T*)out, ldo,
+  bn_bwd_reduce_kernel<T, TA><<<nb, BN_THREADS, 0, st>>>((const T*)dout, lddout, (const TA*)out, ldo,
                                                      relu, rows, c, al, raw, ldraw, stats, raw2,
                                                      ldraw2, stats2, partial);
   URN_LAUNCH_CHECK();
@@ -386,30 +387,32 @@ static int bn_bwd_t(const void* dout, int64_t lddout, const void* out, int64_t l
   URN_LAUNCH_CHECK();
   int vec = al ? 4 : 1;
   long long total = rows * (c / vec);
-  bn_bwd_apply_kernel<T><<<ew_blocks(total), 256, 0, st>>>(
-      (const T*)dout, lddout, (const T*)out, ldo, relu, rows, c, vec, raw, ldraw, stats, (T*)draw,
+  bn_bwd_apply_kernel<T, TA><<<ew_blocks(total), 256, 0, st>>>(
+      (const T*)dout, lddout, (const TA*)out, ldo, relu, rows, c, vec, raw, ldraw, stats, (T*)draw,
       lddraw, raw2, ldraw2, stats2, (T*)draw2, lddraw2, (T*)dres, lddres, dres_acc, sums);
   URN_LAUNCH_CHECK();
   return 0;
 }
 
 extern "C" int urn_bn_bwd(const void* dout, int64_t lddout, const void* out, int64_t ldo, int dtype,
-                          int relu, int64_t rows, int c, const float* raw, int64_t ldraw,
-                          const float* stats, float* dbeta, void* draw, int64_t lddraw,
-                          const float* raw2, int64_t ldraw2, const float* stats2, float* dbeta2,
-                          void* draw2, int64_t lddraw2, void* dres, int64_t lddres,
+                          int out_dtype, int relu, int64_t rows, int c, const float* raw,
+                          int64_t ldraw, const float* stats, float* dbeta, void* draw,
+                          int64_t lddraw, const float* raw2, int64_t ldraw2, const float* stats2,
+                          float* dbeta2, void* draw2, int64_t lddraw2, void* dres, int64_t lddres,
                           int dres_accumulate, int acc_beta, void* ws, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   URN_CHECK(rows > 0 && c >= 1 && c <= 1024, "urn_bn_bwd: bad shape");
   URN_CHECK(!relu || out, "urn_bn_bwd: relu needs the forward output");
-  if (dtype == URN_F32)
-    return bn_bwd_t<float>(dout, lddout, out, ldo, relu, rows, c, raw, ldraw, stats, dbeta, draw,
-                           lddraw, raw2, ldraw2, stats2, dbeta2, draw2, lddraw2, dres, lddres,
-                           dres_accumulate, acc_beta, ws, st);
-  if (dtype == URN_BF16)
-    return bn_bwd_t<bf16>(dout, lddout, out, ldo, relu, rows, c, raw, ldraw, stats, dbeta, draw,
-                          lddraw, raw2, ldraw2, stats2, dbeta2, draw2, lddraw2, dres, lddres,
-                          dres_accumulate, acc_beta, ws, st);
-  urn_set_error("urn_bn_bwd: bad dtype");
+#define URN_BB(GD, AD, TG, TAA)                                                                   \
+  if (dtype == GD && out_dtype == AD)                                                             \
+    return bn_bwd_t<TG, TAA>(dout, lddout, out, ldo, relu, rows, c, raw, ldraw, stats, dbeta, draw, \
+                             lddraw, raw2, ldraw2, stats2, dbeta2, draw2, lddraw2, dres, lddres,  \
+                             dres_accumulate, acc_beta, ws, st);
+  URN_BB(URN_F32, URN_F32, float, float)
+  URN_BB(URN_BF16, URN_BF16, bf16, bf16)
+  URN_BB(URN_BF16, URN_F16, bf16, f16)
+  URN_BB(URN_BF16, URN_F32, bf16, float)
+#undef URN_BB
+  urn_set_error("urn_bn_bwd: unsupported dtype pair (grad %d, act %d)", dtype, out_dtype);
   return 1;
 }

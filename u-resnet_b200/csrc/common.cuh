@@ -2,13 +2,16 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <string>
+#include <type_traits>
 
 #include "../../include/uresnet_b200.h"
 
 typedef __nv_bfloat16 bf16;
+typedef __half f16;
 
 // ---- error plumbing (thread-local message, int status across the C ABI) ----
 void urn_set_error(const char* fmt, ...);
@@ -46,6 +49,8 @@ __device__ __forceinline__ float ld1(const float* p) { return *p; }
 __device__ __forceinline__ float ld1(const bf16* p) { return __bfloat162float(*p); }
 __device__ __forceinline__ void st1(float* p, float v) { *p = v; }
 __device__ __forceinline__ void st1(bf16* p, float v) { *p = __float2bfloat16_rn(v); }
+__device__ __forceinline__ float ld1(const f16* p) { return __half2float(*p); }
+__device__ __forceinline__ void st1(f16* p, float v) { *p = __float2half_rn(v); }
 
 __device__ __forceinline__ float4 ld4(const float* p) {
   return *reinterpret_cast<const float4*>(p);
@@ -56,6 +61,20 @@ __device__ __forceinline__ float4 ld4(const bf16* p) {
   __nv_bfloat162 b = *reinterpret_cast<__nv_bfloat162*>(&u.y);
   float2 fa = __bfloat1622float2(a), fb = __bfloat1622float2(b);
   return make_float4(fa.x, fa.y, fb.x, fb.y);
+}
+__device__ __forceinline__ float4 ld4(const f16* p) {
+  uint2 u = *reinterpret_cast<const uint2*>(p);
+  float2 fa = __half22float2(*reinterpret_cast<__half2*>(&u.x));
+  float2 fb = __half22float2(*reinterpret_cast<__half2*>(&u.y));
+  return make_float4(fa.x, fa.y, fb.x, fb.y);
+}
+__device__ __forceinline__ void st4(f16* p, float4 v) {
+  __half2 a = __floats2half2_rn(v.x, v.y);
+  __half2 b = __floats2half2_rn(v.z, v.w);
+  uint2 u;
+  u.x = *reinterpret_cast<uint32_t*>(&a);
+  u.y = *reinterpret_cast<uint32_t*>(&b);
+  *reinterpret_cast<uint2*>(p) = u;
 }
 __device__ __forceinline__ void st4(float* p, float4 v) {
   *reinterpret_cast<float4*>(p) = v;
@@ -74,6 +93,20 @@ __device__ __forceinline__ float warp_sum(float v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
+
+// ---- storage dtype dispatch: f(T*) is called with a null pointer of the storage type ----
+template <typename F>
+static inline int dispatch_dtype(int dt, F&& f) {
+  switch (dt) {
+    case URN_F32: return f((float*)nullptr);
+    case URN_BF16: return f((bf16*)nullptr);
+    case URN_F16: return f((f16*)nullptr);
+  }
+  urn_set_error("bad dtype %d", dt);
+  return 1;
+}
+#define URN_T(p) typename std::remove_pointer<decltype(p)>::type
+static inline int dtype_size(int dt) { return dt == URN_F32 ? 4 : 2; }
 
 // ---- generalised conv launch description shared by the FFMA and tcgen05 paths ----
 // out[n, o*os + oo, :] = sum_t in[n, o*is + off_t, :] . Wt      (o over a sub-grid)
@@ -99,6 +132,6 @@ struct GConv {
 // Internal entry points (implemented in gconv_ffma.cu / gconv_tc.cu)
 int gconv_ffma_launch(const GConv& g, int in_dtype, const void* in, const float* w, void* out,
                       int out_dtype, cudaStream_t st);
-int wgrad_ffma_launch(const urn_conv_desc& d, int dtype, const void* x, int64_t ldx, const void* y,
-                      int64_t ldy, float* dw, int accumulate, void* ws, cudaStream_t st);
+int wgrad_ffma_launch(const urn_conv_desc& d, int x_dtype, const void* x, int64_t ldx, int y_dtype,
+                      const void* y, int64_t ldy, float* dw, int accumulate, void* ws, cudaStream_t st);
 int64_t wgrad_ffma_workspace(const urn_conv_desc& d);

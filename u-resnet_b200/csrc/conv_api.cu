@@ -136,10 +136,10 @@ extern "C" int64_t urn_conv_wgrad_workspace(const urn_conv_desc* d) {
 }
 
 extern "C" int urn_conv_wgrad(const urn_conv_desc* d, int dtype, int impl, const void* x, int64_t ldx,
-                              const void* y, int64_t ldy, float* dw, int accumulate, void* ws,
-                              void* stream) {
+                              const void* y, int64_t ldy, int y_dtype, float* dw, int accumulate,
+                              void* ws, void* stream) {
   if (check_desc(d)) return 1;
   URN_CHECK(ldx >= d->cx && ldy >= d->cy, "urn_conv_wgrad: pitch smaller than channel count");
   URN_CHECK(impl != URN_IMPL_TC, "urn_conv_wgrad: tcgen05 path runs through the net handle");
-  return wgrad_ffma_launch(*d, dtype, x, ldx, y, ldy, dw, accumulate, ws, (cudaStream_t)stream);
+  return wgrad_ffma_launch(*d, dtype, x, ldx, y_dtype, y, ldy, dw, accumulate, ws, (cudaStream_t)stream);
 }

@@ -170,10 +170,10 @@ int launch_t(const GConv& g, const TI* in, const float* w, TO* out, cudaStream_t
 // ------------------------------ filter gradient ------------------------------
 constexpr int PK = 32;  // positions per smem stage
 
-template <typename T, int TX, int TY>
+template <typename T, typename T2, int TX, int TY>
 __global__ void __launch_bounds__(256)
 wgrad_ffma_kernel(const urn_conv_desc d, const T* __restrict__ x, long long ldx,
-                  const T* __restrict__ y, long long ldy, float* __restrict__ partial,
+                  const T2* __restrict__ y, long long ldy, float* __restrict__ partial,
                   long long chunk, int ntx, int nty) {
   constexpr int RX = TX / 16, RY = TY / 16;
   __shared__ float Xs[PK][TX + 1];
@@ -242,7 +242,7 @@ wgrad_ffma_kernel(const urn_conv_desc d, const T* __restrict__ x, long long ldx,
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       long long off = yoff[p];
       if (off >= 0 && c < d.cy) {
-        const T* q = y + off + c;
+        const T2* q = y + off + c;
         if (vy) v = ld4(q);
         else {
           v.x = ld1(q);
@@ -319,29 +319,29 @@ WgradPlan wgrad_plan(const urn_conv_desc& d) {
   return p;
 }
 
-template <typename T, int TX>
+template <typename T, typename T2, int TX>
 int wgrad_dispatch_y(const urn_conv_desc& d, const WgradPlan& p, const T* x, long long ldx,
-                     const T* y, long long ldy, float* partial, cudaStream_t st) {
+                     const T2* y, long long ldy, float* partial, cudaStream_t st) {
   dim3 grid((unsigned)(d.kd * d.kh * d.kw * p.ntx * p.nty), (unsigned)p.nsplit);
   if (p.ty == 16)
-    wgrad_ffma_kernel<T, TX, 16><<<grid, 256, 0, st>>>(d, x, ldx, y, ldy, partial, p.chunk, p.ntx, p.nty);
+    wgrad_ffma_kernel<T, T2, TX, 16><<<grid, 256, 0, st>>>(d, x, ldx, y, ldy, partial, p.chunk, p.ntx, p.nty);
   else if (p.ty == 32)
-    wgrad_ffma_kernel<T, TX, 32><<<grid, 256, 0, st>>>(d, x, ldx, y, ldy, partial, p.chunk, p.ntx, p.nty);
+    wgrad_ffma_kernel<T, T2, TX, 32><<<grid, 256, 0, st>>>(d, x, ldx, y, ldy, partial, p.chunk, p.ntx, p.nty);
   else
-    wgrad_ffma_kernel<T, TX, 64><<<grid, 256, 0, st>>>(d, x, ldx, y, ldy, partial, p.chunk, p.ntx, p.nty);
+    wgrad_ffma_kernel<T, T2, TX, 64><<<grid, 256, 0, st>>>(d, x, ldx, y, ldy, partial, p.chunk, p.ntx, p.nty);
   URN_LAUNCH_CHECK();
   return 0;
 }
 
-template <typename T>
-int wgrad_t(const urn_conv_desc& d, const T* x, long long ldx, const T* y, long long ldy, float* dw,
+template <typename T, typename T2>
+int wgrad_t(const urn_conv_desc& d, const T* x, long long ldx, const T2* y, long long ldy, float* dw,
             int accumulate, void* ws, cudaStream_t st) {
   WgradPlan p = wgrad_plan(d);
   float* partial = reinterpret_cast<float*>(ws);
   int rc;
-  if (p.tx == 16) rc = wgrad_dispatch_y<T, 16>(d, p, x, ldx, y, ldy, partial, st);
-  else if (p.tx == 32) rc = wgrad_dispatch_y<T, 32>(d, p, x, ldx, y, ldy, partial, st);
-  else rc = wgrad_dispatch_y<T, 64>(d, p, x, ldx, y, ldy, partial, st);
+  if (p.tx == 16) rc = wgrad_dispatch_y<T, T2, 16>(d, p, x, ldx, y, ldy, partial, st);
+  else if (p.tx == 32) rc = wgrad_dispatch_y<T, T2, 32>(d, p, x, ldx, y, ldy, partial, st);
+  else rc = wgrad_dispatch_y<T, T2, 64>(d, p, x, ldx, y, ldy, partial, st);
   if (rc) return rc;
   wgrad_reduce_kernel<<<(unsigned)((p.nw + 255) / 256), 256, 0, st>>>(partial, p.nw, p.nsplit, dw, accumulate);
   URN_LAUNCH_CHECK();
@@ -352,16 +352,13 @@ int wgrad_t(const urn_conv_desc& d, const T* x, long long ldx, const T* y, long 
 
 int gconv_ffma_launch(const GConv& g, int in_dtype, const void* in, const float* w, void* out,
                       int out_dtype, cudaStream_t st) {
-  if (in_dtype == URN_F32 && out_dtype == URN_F32)
-    return launch_t<float, float>(g, (const float*)in, w, (float*)out, st);
-  if (in_dtype == URN_BF16 && out_dtype == URN_F32)
-    return launch_t<bf16, float>(g, (const bf16*)in, w, (float*)out, st);
-  if (in_dtype == URN_BF16 && out_dtype == URN_BF16)
-    return launch_t<bf16, bf16>(g, (const bf16*)in, w, (bf16*)out, st);
-  if (in_dtype == URN_F32 && out_dtype == URN_BF16)
-    return launch_t<float, bf16>(g, (const float*)in, w, (bf16*)out, st);
-  urn_set_error("gconv_ffma: bad dtype");
-  return 1;
+  return dispatch_dtype(in_dtype, [&](auto pi) {
+    using TI = URN_T(pi);
+    return dispatch_dtype(out_dtype, [&](auto po) {
+      using TO = URN_T(po);
+      return launch_t<TI, TO>(g, (const TI*)in, w, (TO*)out, st);
+    });
+  });
 }
 
 int64_t wgrad_ffma_workspace(const urn_conv_desc& d) {
@@ -369,12 +366,17 @@ int64_t wgrad_ffma_workspace(const urn_conv_desc& d) {
   return (int64_t)p.nsplit * p.nw * (int64_t)sizeof(float);
 }
 
-int wgrad_ffma_launch(const urn_conv_desc& d, int dtype, const void* x, int64_t ldx, const void* y,
-                      int64_t ldy, float* dw, int accumulate, void* ws, cudaStream_t st) {
-  if (dtype == URN_F32)
-    return wgrad_t<float>(d, (const float*)x, ldx, (const float*)y, ldy, dw, accumulate, ws, st);
-  if (dtype == URN_BF16)
-    return wgrad_t<bf16>(d, (const bf16*)x, ldx, (const bf16*)y, ldy, dw, accumulate, ws, st);
-  urn_set_error("wgrad_ffma: bad dtype");
+int wgrad_ffma_launch(const urn_conv_desc& d, int x_dtype, const void* x, int64_t ldx, int y_dtype,
+                      const void* y, int64_t ldy, float* dw, int accumulate, void* ws, cudaStream_t st) {
+#define URN_WG(XD, YD, TXT, TYT) \
+  if (x_dtype == XD && y_dtype == YD) \
+    return wgrad_t<TXT, TYT>(d, (const TXT*)x, ldx, (const TYT*)y, ldy, dw, accumulate, ws, st);
+  URN_WG(URN_F32, URN_F32, float, float)
+  URN_WG(URN_BF16, URN_BF16, bf16, bf16)
+  URN_WG(URN_F16, URN_BF16, f16, bf16)     // conv: activations x gradients
+  URN_WG(URN_BF16, URN_F16, bf16, f16)     // deconv: big side is the gradient
+  URN_WG(URN_F16, URN_F16, f16, f16)
+#undef URN_WG
+  urn_set_error("wgrad_ffma: unsupported dtype pair (%d,%d)", x_dtype, y_dtype);
   return 1;
 }

@@ -100,23 +100,25 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
                             float* __restrict__ v, long long n, float lr_t, float b1, float b2,
                             float eps) {
   const long long n4 = n / 4;
+  const float omb1 = 1.f - b1, omb2 = 1.f - b2;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
        i += (long long)gridDim.x * blockDim.x) {
     float4 pp = ld4(p + i * 4), gg = ld4(g + i * 4), mm = ld4(m + i * 4), vv = ld4(v + i * 4);
+    // TF ApplyAdam form: m += (g-m)*(1-b1); v += (g*g-v)*(1-b2); var -= m*alpha/(sqrt(v)+eps)
 #define URN_ADAM1(c)                                   \
-    mm.c = b1 * mm.c + (1.f - b1) * gg.c;               \
-    vv.c = b2 * vv.c + (1.f - b2) * gg.c * gg.c;        \
-    pp.c = pp.c - lr_t * mm.c / (sqrtf(vv.c) + eps);
+    mm.c += (gg.c - mm.c) * omb1;                       \
+    vv.c += (gg.c * gg.c - vv.c) * omb2;                \
+    pp.c -= (mm.c * lr_t) / (sqrtf(vv.c) + eps);
     URN_ADAM1(x) URN_ADAM1(y) URN_ADAM1(z) URN_ADAM1(w)
 #undef URN_ADAM1
     st4(p + i * 4, pp); st4(m + i * 4, mm); st4(v + i * 4, vv);
   }
   if (blockIdx.x == 0)
     for (long long i = n4 * 4 + threadIdx.x; i < n; i += blockDim.x) {
-      float mm = b1 * m[i] + (1.f - b1) * g[i];
-      float vv = b2 * v[i] + (1.f - b2) * g[i] * g[i];
+      float mm = m[i] + (g[i] - m[i]) * omb1;
+      float vv = v[i] + (g[i] * g[i] - v[i]) * omb2;
       m[i] = mm; v[i] = vv;
-      p[i] = p[i] - lr_t * mm / (sqrtf(vv) + eps);
+      p[i] -= (mm * lr_t) / (sqrtf(vv) + eps);
     }
 }
 
@@ -139,12 +141,13 @@ extern "C" int urn_ce_fwd_bwd(const float* logits, int64_t ld, const float* labe
   double* partial = (double*)((char*)ws + 256);
   const float invb = 1.0f / (float)batch;
   URN_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), st));
-  if (dl_dtype == URN_BF16)
-    ce_kernel<bf16><<<nb, CE_THREADS, 0, st>>>(logits, ld, label, weight, data, total, c, invb,
-                                               (bf16*)dlogits, lddl, softmax, flag, partial);
-  else
-    ce_kernel<float><<<nb, CE_THREADS, 0, st>>>(logits, ld, label, weight, data, total, c, invb,
-                                                (float*)dlogits, lddl, softmax, flag, partial);
+  if (dispatch_dtype(dl_dtype, [&](auto pd) {
+        using TD = URN_T(pd);
+        ce_kernel<TD><<<nb, CE_THREADS, 0, st>>>(logits, ld, label, weight, data, total, c, invb,
+                                                 (TD*)dlogits, lddl, softmax, flag, partial);
+        return 0;
+      }))
+    return 1;
   URN_LAUNCH_CHECK();
   ce_finalize_kernel<<<1, 32, 0, st>>>(partial, nb, 1.0 / (double)batch, result);
   URN_LAUNCH_CHECK();

@@ -21,7 +21,7 @@ namespace {
 constexpr float kBnEps = 1e-3f;  // slim.batch_norm default epsilon
 
 inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
-inline int esize(int dtype) { return dtype == URN_BF16 ? 2 : 4; }
+inline int esize(int dtype) { return dtype == URN_F32 ? 4 : 2; }
 
 struct Node {
   int c = 0;
@@ -100,6 +100,10 @@ struct urn_net {
   int64_t ws_bytes = 0;
   int64_t bn_ws_off = 0, loss_ws_off = 0, result_off = 0, wgrad_ws_off = 0, arena_off = 0;
   int64_t wgrad_ws_bytes = 0;
+  // 16-bit modes: fp32 copies of the parameters rounded to the activation-side operand type
+  // (forward / wgrad) and to the gradient-side operand type (dgrad)
+  int64_t wq_off = -1, wqg_off = -1;
+  int TA = URN_F32, TG = URN_F32;   // activation / gradient storage dtypes
   int max_c = 0;
 };
 
@@ -181,13 +185,15 @@ static int build_plan(urn_net& N) {
   URN_CHECK(c.batch >= 1 && c.base_filters >= 1 && c.num_strides >= 0 && c.num_class >= 1 &&
                 c.in_channels >= 1, "urn_create: bad configuration");
   URN_CHECK(c.num_class <= 32, "urn_create: num_class <= 32");
-  URN_CHECK(c.dtype == URN_F32 || c.dtype == URN_BF16, "urn_create: bad dtype");
+  URN_CHECK(c.dtype == URN_F32 || c.dtype == URN_BF16 || c.dtype == URN_F16, "urn_create: bad dtype");
+  N.TA = c.dtype;                                   // activations (and filter operands)
+  N.TG = c.dtype == URN_F16 ? URN_BF16 : c.dtype;   // gradients keep the fp32 exponent range
   URN_CHECK((int64_t)c.base_filters << c.num_strides <= 1024, "urn_create: widest layer > 1024 channels");
   N.nd = c.nd;
   if (c.nd == 2) { N.sp[0] = 1; N.sp[1] = c.spatial[0]; N.sp[2] = c.spatial[1]; }
   else { N.sp[0] = c.spatial[0]; N.sp[1] = c.spatial[1]; N.sp[2] = c.spatial[2]; }
   for (int i = 0; i < 3; ++i) URN_CHECK(N.sp[i] >= 1, "urn_create: bad spatial dims");
-  const int T = c.dtype, nd = c.nd, B = c.batch, F = c.base_filters, S = c.num_strides;
+  const int T = N.TA, TG = N.TG, nd = c.nd, B = c.batch, F = c.base_filters, S = c.num_strides;
   Builder b(N);
 
   struct Cur { int node; int sp[3]; int ch; };
@@ -311,6 +317,10 @@ static int build_plan(urn_net& N) {
   N.wgrad_ws_bytes = 0;
   for (auto& L : N.layers) N.wgrad_ws_bytes = std::max<int64_t>(N.wgrad_ws_bytes, wgrad_ffma_workspace(L.d));
   N.wgrad_ws_off = b.alloc(N.wgrad_ws_bytes);
+  if (T != URN_F32) {
+    N.wq_off = b.alloc(N.param_total * 4);
+    N.wqg_off = TG == T ? N.wq_off : b.alloc(N.param_total * 4);
+  }
 
   // ---- backward schedule ----
   if (c.training) {
@@ -320,12 +330,11 @@ static int build_plan(urn_net& N) {
       Node& n = N.nodes[i];
       if ((int)i == N.data_node) continue;
       if (n.parent >= 0) continue;
-      int gt = ((int)i == N.logits_node) ? T : n.dtype;
-      n.gbuf = new_gbuf(n.rows * n.ld * esize(gt));
+      n.gbuf = new_gbuf(n.rows * n.ld * esize(TG));
     }
     for (auto& n : N.nodes)
       if (n.parent >= 0) n.gbuf = N.nodes[n.parent].gbuf;
-    for (auto& L : N.layers) L.draw_gbuf = new_gbuf(L.rows_out * L.cout * esize(T));
+    for (auto& L : N.layers) L.draw_gbuf = new_gbuf(L.rows_out * L.cout * esize(TG));
 
     auto mark_write = [&](int node) -> int {   // returns accumulate flag
       Node& n = N.nodes[node];
@@ -469,21 +478,40 @@ extern "C" int urn_layer_info(const urn_net* h, int layer, const char** scope, u
 
 namespace {
 
-__global__ void convert_in_kernel(const float* __restrict__ src, long long n, float* dst_f,
-                                  bf16* dst_b) {
+template <typename TT>
+__global__ void convert_in_kernel(const float* __restrict__ src, long long n, TT* __restrict__ dst) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
-       i += (long long)gridDim.x * blockDim.x) {
-    float v = src[i];
-    if (dst_f) dst_f[i] = v; else dst_b[i] = __float2bfloat16_rn(v);
-  }
+       i += (long long)gridDim.x * blockDim.x)
+    st1(dst + i, src[i]);
 }
 
 inline char* P(void* ws, int64_t off) { return (char*)ws + off; }
 
+// bf16 mode: every conv filter is used as a bf16 operand (fp32 master weights stay in the
+// caller's buffer); the FFMA kernels read this rounded fp32 copy so that both conv
+// implementations compute with identical operand values.
+__global__ void round_params_kernel(const float* __restrict__ src, long long n, int dt_a,
+                                    float* __restrict__ dst_a, int dt_g, float* __restrict__ dst_g) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const float v = src[i];
+    const float vb = __bfloat162float(__float2bfloat16_rn(v));
+    const float vh = __half2float(__float2half_rn(v));
+    dst_a[i] = dt_a == URN_F16 ? vh : vb;
+    if (dst_g != dst_a) dst_g[i] = dt_g == URN_F16 ? vh : vb;
+  }
+}
+// grad_side: the operand multiplies a gradient tensor (dgrad) rather than an activation
+inline const float* conv_weights(const urn_net* h, const Layer& L, const float* params, void* ws,
+                                 bool grad_side = false) {
+  if (h->wq_off < 0) return params + L.w_off;
+  return (const float*)P(ws, grad_side ? h->wqg_off : h->wq_off) + L.w_off;
+}
+
 int run_conv_fwd(urn_net* h, const Layer& L, const float* params, void* ws, cudaStream_t st) {
   const Node& in = h->nodes[L.in_node];
   float* raw = (float*)P(ws, L.raw_off);
-  const float* w = params + L.w_off;
+  const float* w = conv_weights(h, L, params, ws);
   if (!L.transpose) {
     GConv g;
     gconv_gather(L.d, in.ld, L.cout, &g);
@@ -511,9 +539,19 @@ extern "C" int urn_forward(urn_net* h, const float* params, const float* data, v
     const Node& dn = h->nodes[h->data_node];
     long long n = dn.rows * dn.c;
     unsigned nb = (unsigned)std::min<long long>((n + 255) / 256, 148 * 16);
-    convert_in_kernel<<<nb, 256, 0, st>>>(data, n, dn.dtype == URN_F32 ? (float*)P(ws, dn.off) : nullptr,
-                                          dn.dtype == URN_BF16 ? (bf16*)P(ws, dn.off) : nullptr);
+    if (dispatch_dtype(dn.dtype, [&](auto pt) {
+          using TT = URN_T(pt);
+          convert_in_kernel<TT><<<nb, 256, 0, st>>>(data, n, (TT*)P(ws, dn.off));
+          return 0;
+        }))
+      return 1;
     URN_LAUNCH_CHECK();
+    if (h->wq_off >= 0) {
+      unsigned nb2 = (unsigned)std::min<long long>((h->param_total + 255) / 256, 148 * 16);
+      round_params_kernel<<<nb2, 256, 0, st>>>(params, h->param_total, h->TA, (float*)P(ws, h->wq_off),
+                                               h->TG, (float*)P(ws, h->wqg_off));
+      URN_LAUNCH_CHECK();
+    }
   }
   for (const FStep& s : h->fwd) {
     const Layer& L = h->layers[s.layer];
@@ -564,7 +602,7 @@ extern "C" int urn_loss_metrics(urn_net* h, const float* label, const float* wei
     dl = P(ws, h->arena_off + h->gbufs[lg.gbuf].off);
   }
   return urn_ce_fwd_bwd((const float*)P(ws, lg.off), lg.ld, label, weight, data, h->cfg.batch,
-                        pixels, lg.c, dl, lg.c, h->cfg.dtype, softmax, result,
+                        pixels, lg.c, dl, lg.c, h->TG, softmax, result,
                         P(ws, h->loss_ws_off), st);
 }
 
@@ -578,10 +616,9 @@ extern "C" int urn_backward(urn_net* h, const float* params, float* grads, int a
   URN_CHECK(h && params && grads && ws, "urn_backward: null argument");
   URN_CHECK(h->cfg.training, "urn_backward: handle was created with training=0");
   cudaStream_t st = (cudaStream_t)stream;
-  const int T = h->cfg.dtype;
+  const int T = h->TG;   // all gradient tensors (node gradients, d(raw)) use the gradient dtype
   auto gptr = [&](const Node& n) -> char* {
-    int gt = T;  // all gradient tensors are stored in the net dtype
-    return P(ws, h->arena_off + h->gbufs[n.gbuf].off) + (int64_t)n.choff * esize(gt);
+    return P(ws, h->arena_off + h->gbufs[n.gbuf].off) + (int64_t)n.choff * esize(T);
   };
   auto draw = [&](const Layer& L) -> char* { return P(ws, h->arena_off + h->gbufs[L.draw_gbuf].off); };
   for (const BStep& s : h->bwd) {
@@ -597,7 +634,7 @@ extern "C" int urn_backward(urn_net* h, const float* params, float* grads, int a
       }
       void* dres = nullptr; int64_t lddres = 0;
       if (s.dres_node >= 0) { const Node& r = h->nodes[s.dres_node]; dres = gptr(r); lddres = r.ld; }
-      if (urn_bn_bwd(gptr(dn), dn.ld, P(ws, dn.off), dn.ld, T, s.relu, L.rows_out, L.cout,
+      if (urn_bn_bwd(gptr(dn), dn.ld, P(ws, dn.off), dn.ld, T, dn.dtype, s.relu, L.rows_out, L.cout,
                      (const float*)P(ws, L.raw_off), L.cout, (const float*)P(ws, L.stats_off),
                      grads + L.b_off, draw(L), L.cout, raw2, ld2, stats2, dbeta2, draw2, ld2, dres,
                      lddres, s.accumulate, accumulate, P(ws, h->bn_ws_off), st))
@@ -606,15 +643,15 @@ extern "C" int urn_backward(urn_net* h, const float* params, float* grads, int a
       const Node& in = h->nodes[L.in_node];
       int rc;
       if (!L.transpose)
-        rc = wgrad_ffma_launch(L.d, T, P(ws, in.off), in.ld, draw(L), L.cout, grads + L.w_off,
-                               accumulate, P(ws, h->wgrad_ws_off), st);
+        rc = wgrad_ffma_launch(L.d, in.dtype, P(ws, in.off), in.ld, T, draw(L), L.cout,
+                               grads + L.w_off, accumulate, P(ws, h->wgrad_ws_off), st);
       else  // deconv: big side = its output gradient, small side = its input
-        rc = wgrad_ffma_launch(L.d, T, draw(L), L.cout, P(ws, in.off), in.ld, grads + L.w_off,
-                               accumulate, P(ws, h->wgrad_ws_off), st);
+        rc = wgrad_ffma_launch(L.d, T, draw(L), L.cout, in.dtype, P(ws, in.off), in.ld,
+                               grads + L.w_off, accumulate, P(ws, h->wgrad_ws_off), st);
       if (rc) return 1;
     } else {  // B_DGRAD
       const Node& in = h->nodes[L.in_node];
-      const float* w = params + L.w_off;
+      const float* w = conv_weights(h, L, params, ws, true);   // rounded copy left by urn_forward
       if (!L.transpose) {
         for (int pd = 0; pd < L.d.s; ++pd)
           for (int ph = 0; ph < L.d.s; ++ph)

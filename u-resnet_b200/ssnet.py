@@ -54,7 +54,7 @@ class ssnet_base(object):
         self._trainable = bool(trainable)
         self._use_weight = bool(use_weight)
         self._learning_rate = learning_rate
-        self._dtype = _capi.DTYPES[(dtype or os.environ.get("URESNET_B200_DTYPE", "bf16")).lower()]
+        self._dtype = _capi.DTYPES[(dtype or os.environ.get("URESNET_B200_DTYPE", "mix16")).lower()]
         self._impl = _capi.IMPLS[(impl or os.environ.get("URESNET_B200_IMPL", "auto")).lower()]
         self._lib = _capi.load()          # raises if the CUDA library is missing: no fallback
         if not torch.cuda.is_available():
