@@ -190,6 +190,19 @@ int urn_layer_info(const urn_net* h, int layer, const char** scope, urn_conv_des
                    int* is_transpose, int64_t* raw_off_bytes, int64_t* out_off_bytes,
                    int64_t* out_ld, int64_t* stats_off_bytes);
 
+/* ---------------- measurement hooks ---------------- */
+/* Number of kernels this library has launched in this process (host-side counter). */
+int64_t urn_launch_count(void);
+
+/* Per-layer, per-phase device timing with CUDA events recorded on the launching stream.
+ * Phases: 0 conv forward, 1 BN statistics, 2 BN apply(+ReLU/+residual), 3 BN backward,
+ * 4 filter gradient, 5 input gradient, 6 loss/metrics + input staging, 7 unused.
+ * urn_profile_collect synchronises, ADDS the elapsed milliseconds and launch-group counts
+ * into ms[layer*8+phase] / counts[layer*8+phase] (arrays of urn_layer_count()*8) and
+ * clears the recorded events. */
+int urn_profile_enable(urn_net* h, int on);
+int urn_profile_collect(urn_net* h, double* ms, int64_t* counts);
+
 #ifdef __cplusplus
 }
 #endif

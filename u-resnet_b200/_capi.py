@@ -68,6 +68,9 @@ SIGNATURES = {
     "urn_loss_metrics": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp]),
     "urn_backward": (_i, [_vp, _vp, _vp, _i, _vp, C.POINTER(_vp), _vp]),
     "urn_check_labels": (_i, [_vp, _vp]),
+    "urn_launch_count": (_i64, []),
+    "urn_profile_enable": (_i, [_vp, _i]),
+    "urn_profile_collect": (_i, [_vp, C.POINTER(C.c_double), C.POINTER(_i64)]),
     "urn_layer_info": (_i, [_vp, _i, C.POINTER(C.c_char_p), _descp, C.POINTER(_i), C.POINTER(_i64),
                             C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64)]),
 }

@@ -30,7 +30,12 @@ void urn_set_error(const char* fmt, ...);
       return 1;                                                                     \
     }                                                                               \
   } while (0)
-#define URN_LAUNCH_CHECK() URN_CUDA(cudaGetLastError())
+extern long long g_urn_launches;   // kernels launched by this library (host-side count)
+#define URN_LAUNCH_CHECK()          \
+  do {                              \
+    ++g_urn_launches;               \
+    URN_CUDA(cudaGetLastError());   \
+  } while (0)
 
 static inline int64_t cdiv64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 static inline int num_sms() {

@@ -5,6 +5,8 @@
 #include "gconv_tc.cuh"
 
 static thread_local char g_err[1024] = "";
+long long g_urn_launches = 0;
+extern "C" int64_t urn_launch_count(void) { return g_urn_launches; }
 void urn_set_error(const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);

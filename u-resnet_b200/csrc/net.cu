@@ -105,7 +105,33 @@ struct urn_net {
   int64_t wq_off = -1, wqg_off = -1;
   int TA = URN_F32, TG = URN_F32;   // activation / gradient storage dtypes
   int max_c = 0;
+  // profiling (urn_profile_*): event pairs recorded around each (layer, phase) launch group
+  bool prof_on = false;
+  std::vector<cudaEvent_t> prof_pool;
+  size_t prof_used = 0;
+  struct ProfRec { int tag; cudaEvent_t a, b; };
+  std::vector<ProfRec> prof_recs;
+  ~urn_net() { for (auto e : prof_pool) cudaEventDestroy(e); }
 };
+
+namespace {
+enum { PH_CONV = 0, PH_STATS = 1, PH_APPLY = 2, PH_BNBWD = 3, PH_WGRAD = 4, PH_DGRAD = 5, PH_MISC = 6 };
+struct ProfScope {
+  urn_net* h; cudaStream_t st; cudaEvent_t b = nullptr;
+  ProfScope(urn_net* h_, int layer, int phase, cudaStream_t st_) : h(h_), st(st_) {
+    if (!h->prof_on) return;
+    auto get = [&]() {
+      if (h->prof_used == h->prof_pool.size()) { cudaEvent_t e; cudaEventCreate(&e); h->prof_pool.push_back(e); }
+      return h->prof_pool[h->prof_used++];
+    };
+    cudaEvent_t a = get(); b = get();
+    cudaEventRecord(a, st);
+    h->prof_recs.push_back({layer * 8 + phase, a, b});
+  }
+  void end() { if (b) { cudaEventRecord(b, st); b = nullptr; } }
+  ~ProfScope() { end(); }
+};
+}  // namespace
 
 namespace {
 
@@ -508,10 +534,13 @@ inline const float* conv_weights(const urn_net* h, const Layer& L, const float* 
   return (const float*)P(ws, grad_side ? h->wqg_off : h->wq_off) + L.w_off;
 }
 
-int run_conv_fwd(urn_net* h, const Layer& L, const float* params, void* ws, cudaStream_t st) {
+int run_conv_fwd(urn_net* h, int li, const float* params, void* ws, cudaStream_t st) {
+  const Layer& L = h->layers[li];
   const Node& in = h->nodes[L.in_node];
   float* raw = (float*)P(ws, L.raw_off);
   const float* w = conv_weights(h, L, params, ws);
+  {
+  ProfScope ps(h, li, PH_CONV, st);
   if (!L.transpose) {
     GConv g;
     gconv_gather(L.d, in.ld, L.cout, &g);
@@ -525,6 +554,8 @@ int run_conv_fwd(urn_net* h, const Layer& L, const float* params, void* ws, cuda
           if (gconv_ffma_launch(g, in.dtype, P(ws, in.off), w, raw, URN_F32, st)) return 1;
         }
   }
+  }
+  ProfScope ps(h, li, PH_STATS, st);
   return urn_bn_stats(raw, L.cout, L.rows_out, L.cout, kBnEps, (float*)P(ws, L.stats_off),
                       P(ws, h->bn_ws_off), st);
 }
@@ -536,6 +567,7 @@ extern "C" int urn_forward(urn_net* h, const float* params, const float* data, v
   URN_CHECK(h && params && data && ws, "urn_forward: null argument");
   cudaStream_t st = (cudaStream_t)stream;
   {
+    ProfScope ps(h, 0, PH_MISC, st);
     const Node& dn = h->nodes[h->data_node];
     long long n = dn.rows * dn.c;
     unsigned nb = (unsigned)std::min<long long>((n + 255) / 256, 148 * 16);
@@ -556,14 +588,16 @@ extern "C" int urn_forward(urn_net* h, const float* params, const float* data, v
   for (const FStep& s : h->fwd) {
     const Layer& L = h->layers[s.layer];
     if (s.kind == F_CONV) {
-      if (run_conv_fwd(h, L, params, ws, st)) return 1;
+      if (run_conv_fwd(h, s.layer, params, ws, st)) return 1;
     } else if (s.kind == F_APPLY) {
+      ProfScope ps(h, s.layer, PH_APPLY, st);
       const Node& o = h->nodes[s.out_node];
       if (urn_bn_apply((const float*)P(ws, L.raw_off), L.cout, L.rows_out, L.cout,
                        (const float*)P(ws, L.stats_off), params + L.b_off, nullptr, 0, 0, nullptr,
                        0, nullptr, nullptr, s.relu, P(ws, o.off), o.ld, o.dtype, st))
         return 1;
     } else {  // F_MERGE: relu(BN(conv2) + shortcut)
+      ProfScope ps(h, s.layer, PH_APPLY, st);
       const Node& o = h->nodes[s.out_node];
       const void* res = nullptr; int64_t ldres = 0; int rdt = o.dtype;
       const float *res_raw = nullptr, *res_stats = nullptr, *res_beta = nullptr; int64_t ldrr = 0;
@@ -591,6 +625,7 @@ extern "C" int urn_loss_metrics(urn_net* h, const float* label, const float* wei
   cudaStream_t st = (cudaStream_t)stream;
   const Node& lg = h->nodes[h->logits_node];
   const int64_t pixels = lg.rows / h->cfg.batch;
+  ProfScope ps(h, (int)h->layers.size() - 1, PH_MISC, st);
   if (!label) {  // inference without labels: softmax only (ssnet.py:130-139)
     URN_CHECK(softmax, "urn_loss_metrics: nothing to compute");
     return urn_softmax_only((const float*)P(ws, lg.off), lg.ld, lg.rows, lg.c, softmax, st);
@@ -623,6 +658,7 @@ extern "C" int urn_backward(urn_net* h, const float* params, float* grads, int a
   auto draw = [&](const Layer& L) -> char* { return P(ws, h->arena_off + h->gbufs[L.draw_gbuf].off); };
   for (const BStep& s : h->bwd) {
     const Layer& L = h->layers[s.layer];
+    ProfScope ps(h, s.layer, s.kind == B_BN ? PH_BNBWD : (s.kind == B_WGRAD ? PH_WGRAD : PH_DGRAD), st);
     if (s.kind == B_BN) {
       const Node& dn = h->nodes[s.dout_node];
       const float *raw2 = nullptr, *stats2 = nullptr; float* dbeta2 = nullptr; void* draw2 = nullptr;
@@ -667,8 +703,29 @@ extern "C" int urn_backward(urn_net* h, const float* params, float* grads, int a
         if (gconv_ffma_launch(g, T, draw(L), w, gptr(in), T, st)) return 1;
       }
     }
-    if (s.last_for_layer && ready_events && ready_events[s.layer])
+    if (s.last_for_layer && ready_events && ready_events[s.layer]) {
+      ps.end();
       URN_CUDA(cudaEventRecord((cudaEvent_t)ready_events[s.layer], st));
+    }
   }
+  return 0;
+}
+
+extern "C" int urn_profile_enable(urn_net* h, int on) {
+  URN_CHECK(h, "urn_profile_enable: null handle");
+  h->prof_on = on != 0;
+  return 0;
+}
+extern "C" int urn_profile_collect(urn_net* h, double* ms, int64_t* counts) {
+  URN_CHECK(h && ms && counts, "urn_profile_collect: null argument");
+  URN_CUDA(cudaDeviceSynchronize());
+  for (auto& r : h->prof_recs) {
+    float t = 0.f;
+    URN_CUDA(cudaEventElapsedTime(&t, r.a, r.b));
+    ms[r.tag] += (double)t;
+    counts[r.tag] += 1;
+  }
+  h->prof_recs.clear();
+  h->prof_used = 0;
   return 0;
 }

@@ -1,0 +1,137 @@
+"""Data-parallel gradient exchange: bucketed all-reduce overlapped with backward.
+
+The reference has no multi-GPU path; its only batch-scaling mechanism is
+``NUM_MINIBATCHES`` gradient accumulation -- a SUM of per-minibatch gradients, each
+minibatch normalised with its own batch-norm statistics, followed by one Adam apply
+(/root/reference/lib/ssnet.py:76-79, lib/ssnet_trainval.py:164-191).  R-rank data
+parallelism with an all-reduce SUM of the accumulators and per-replica batch-norm
+statistics is exactly ``MINIBATCH_SIZE=B/R, NUM_MINIBATCHES=R`` of the reference
+(SURVEY.md 8e); ``average=True`` divides by R instead.
+
+One process per GPU (``torch.distributed``, NCCL over NVLink/NVSwitch).  The flat
+gradient buffer is cut into contiguous buckets of whole layers in the order backward
+finishes them (last layer first).  ``urn_backward`` records one CUDA event per layer when
+that layer's filter+beta gradients are final; the communication stream waits on the
+events of a bucket and launches its all-reduce while the rest of backward is still
+running on the compute stream.  Adam waits for the last bucket.
+
+On CPU tensors (gloo; tests/test_dp.py) the same bucket plan runs synchronously.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+import torch.distributed as dist
+
+
+def plan_buckets(layer_ranges, bucket_elems):
+    """layer_ranges: [(lo, hi)] element ranges per layer in creation order (contiguous,
+    increasing).  Returns buckets [(lo, hi, [layer indices])] walking from the LAST layer
+    to the first, each at least ``bucket_elems`` long (except the final one)."""
+    buckets, cur = [], []
+    for l in range(len(layer_ranges) - 1, -1, -1):
+        cur.append(l)
+        lo, hi = layer_ranges[cur[-1]][0], layer_ranges[cur[0]][1]
+        if hi - lo >= bucket_elems:
+            buckets.append((lo, hi, list(cur)))
+            cur = []
+    if cur:
+        buckets.append((layer_ranges[cur[-1]][0], layer_ranges[cur[0]][1], list(cur)))
+    return buckets
+
+
+class GradientExchange(object):
+
+    def __init__(self, param_table, num_layers, flat, group=None, bucket_mb=16.0, average=False):
+        """param_table: OrderedDict name -> (shape, offset, count) in creation order (two
+        entries per layer: weights, beta); flat: the flat gradient accumulator tensor."""
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.average = bool(average)
+        self.flat = flat
+        items = list(param_table.values())
+        assert len(items) == 2 * num_layers
+        self.layer_ranges = []
+        for l in range(num_layers):
+            (_, wo, wc), (_, bo, bc) = items[2 * l], items[2 * l + 1]
+            hi = items[2 * l + 2][1] if l + 1 < num_layers else flat.numel()
+            self.layer_ranges.append((wo, hi))          # includes the alignment padding
+        self.buckets = plan_buckets(self.layer_ranges, int(bucket_mb * (1 << 20) / 4))
+        self.cuda = flat.is_cuda
+        self.expected_minibatches = 1
+        self._seen = 0
+        self._works = []
+        self._launched = False
+        if self.cuda:
+            self.comm_stream = torch.cuda.Stream(device=flat.device)
+            self.events = [torch.cuda.Event() for _ in range(num_layers)]
+            for e in self.events:                       # force creation of the CUDA handles
+                e.record()
+            self._ev_array = (C.c_void_p * num_layers)(*[C.c_void_p(e.cuda_event) for e in self.events])
+        else:
+            self.events, self._ev_array = None, None
+
+    # -- hooks called by ssnet_base ------------------------------------------------
+    def zeroed(self):
+        self._seen = 0
+        self._launched = False
+
+    def events_array(self):
+        """Event array for urn_backward, or None when this backward is not the last
+        minibatch of the step (gradients are still being accumulated locally)."""
+        if self.world == 1 or not self.cuda:
+            return None
+        return self._ev_array if self._seen + 1 >= self.expected_minibatches else None
+
+    def backward_enqueued(self):
+        """Called right after urn_backward returned (work is only enqueued): launch every
+        bucket's all-reduce on the communication stream behind that bucket's events."""
+        self._seen += 1
+        if self.world == 1 or not self.cuda or self._seen < self.expected_minibatches:
+            return
+        for lo, hi, layers in self.buckets:
+            for l in layers:
+                self.comm_stream.wait_event(self.events[l])
+            with torch.cuda.stream(self.comm_stream):
+                self._works.append(dist.all_reduce(self.flat[lo:hi], op=dist.ReduceOp.SUM,
+                                                   group=self.group, async_op=True))
+        self._launched = True
+
+    def finish(self, flat=None):
+        """Before the optimizer: make the compute stream wait for the exchange (or run it
+        now if it was not overlapped)."""
+        if self.world == 1:
+            return
+        if not self._launched:
+            for lo, hi, _ in self.buckets:
+                self._works.append(dist.all_reduce(self.flat[lo:hi], op=dist.ReduceOp.SUM,
+                                                   group=self.group, async_op=True))
+        for w in self._works:
+            w.wait()
+        self._works = []
+        self._launched = False
+        if self.average:
+            self.flat.mul_(1.0 / self.world)
+
+    def allreduce_scalars(self, values):
+        """Sum a small list of python floats over ranks (loss / accuracy counters)."""
+        if self.world == 1:
+            return list(values)
+        t = torch.tensor(list(values), dtype=torch.float64, device=self.flat.device)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        return [float(v) for v in t.cpu()]
+
+
+def attach(net, group=None, bucket_mb=16.0, average=False):
+    """Give a constructed, trainable ``uresnet`` a gradient exchange over ``group``."""
+    ex = GradientExchange(net._param_table, net._num_layers, net._accum, group=group,
+                          bucket_mb=bucket_mb, average=average)
+    net._exchange = ex
+    return ex
+
+
+def broadcast_variables(net, src=0, group=None):
+    """Make every replica start from rank ``src``'s variables."""
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.broadcast(net._params, src=src, group=group)

@@ -255,10 +255,14 @@ class ssnet_base(object):
 
     def zero_gradients(self, sess=None):
         self._accum.zero_()
+        if self._exchange is not None:
+            self._exchange.zeroed()
         return [None]
 
-    def accum_gradients(self, sess, input_data, input_label, input_weight=None):
-        """ssnet.py:103-115: one fused forward+backward, gradients ADDED to the accumulators."""
+    def accum_gradients(self, sess, input_data, input_label, input_weight=None, fetch=True):
+        """ssnet.py:103-115: one fused forward+backward, gradients ADDED to the accumulators.
+        Inputs may be host numpy arrays (staged through pinned memory) or CUDA tensors.
+        ``fetch=False`` skips the device->host read of the metrics (nothing synchronises)."""
         if not self._trainable:
             raise RuntimeError("network constructed with trainable=False")
         feed = self.feed_dict(input_data=input_data, input_label=input_label, input_weight=input_weight)
@@ -269,6 +273,8 @@ class ssnet_base(object):
                                            ws.data_ptr(), events, self._stream()))
         if self._exchange is not None:
             self._exchange.backward_enqueued()
+        if not fetch:
+            return [None, None, None, None], ['', 'loss', 'acc. all', 'acc. nonzero']
         loss, acc_all, acc_nz = self._metrics(batch)
         return [None, loss, acc_all, acc_nz], ['', 'loss', 'acc. all', 'acc. nonzero']
 
@@ -303,6 +309,31 @@ class ssnet_base(object):
         if input_label is not None:
             _, acc_all, acc_nz = self._metrics(batch)
             out += [acc_all, acc_nz]
+        return out
+
+    # ------------------------------------------------------------ measurement
+    PHASES = ("conv_fwd", "bn_stats", "bn_apply", "bn_bwd", "wgrad", "dgrad", "misc", "-")
+
+    def profile_enable(self, batch, on=True):
+        h, _ = self._handle(batch)
+        _capi.check(self._lib.urn_profile_enable(h, int(on)))
+
+    def profile_collect(self, batch):
+        """Returns (ms[layers,8], counts[layers,8]) accumulated since the last collect."""
+        h, _ = self._handle(batch)
+        n = self._num_layers * 8
+        ms, cnt = (C.c_double * n)(), (C.c_int64 * n)()
+        _capi.check(self._lib.urn_profile_collect(h, ms, cnt))
+        return (np.array(ms[:]).reshape(self._num_layers, 8), np.array(cnt[:]).reshape(self._num_layers, 8))
+
+    def layer_table(self, batch):
+        """[(scope, desc, is_transpose)] of the plan (for FLOP / byte accounting)."""
+        h, _ = self._handle(batch)
+        out = []
+        for i in range(self._num_layers):
+            scope, d, tr = C.c_char_p(), _capi.urn_conv_desc(), C.c_int()
+            _capi.check(self._lib.urn_layer_info(h, i, C.byref(scope), C.byref(d), C.byref(tr), None, None, None, None))
+            out.append((scope.value.decode(), d, bool(tr.value)))
         return out
 
     # ------------------------------------------------------------ conveniences
