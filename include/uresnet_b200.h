@@ -76,6 +76,15 @@ int urn_conv_dgrad(const urn_conv_desc* d, int dtype, int impl, const void* dy, 
                    const float* w, void* dx, int64_t ldx, int x_dtype, int accumulate,
                    void* stream);
 
+/* The same two operations on the tcgen05 tensor-core path (16-bit operands, fp32 accumulate;
+ * needs cx % 16 == 0 and cy % 16 == 0).  The f32 TF-layout filter is first packed to the
+ * operand dtype into `wpack` (caller scratch, >= 2*taps*cx*cy bytes); inside a network handle
+ * the packing happens once per step instead.  y_dtype/x_dtype: URN_F32 or URN_BF16. */
+int urn_conv_fwd_tc(const urn_conv_desc* d, int dtype, const void* x, int64_t ldx, const float* w,
+                    void* wpack, void* y, int64_t ldy, int y_dtype, int accumulate, void* stream);
+int urn_conv_dgrad_tc(const urn_conv_desc* d, int dtype, const void* dy, int64_t ldy, const float* w,
+                      void* wpack, void* dx, int64_t ldx, int x_dtype, int accumulate, void* stream);
+
 /* Conv*BackpropFilter: dw[t][cx][cy] (+)= sum_o x[o*s+t-pad][cx] * y[o][cy].
  * ws must hold urn_conv_wgrad_workspace(d) bytes. */
 int64_t urn_conv_wgrad_workspace(const urn_conv_desc* d);

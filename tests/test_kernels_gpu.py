@@ -105,6 +105,73 @@ def test_conv_fwd_dgrad_wgrad(lib, dt, nd, n, sp, cin, cout, k, s):
     assert relerr(host(dw), 2 * dwo.numpy()) < 4e-5
 
 
+TC_CASES = [
+    # nd, n, spatial, cin, cout, k, s
+    (2, 2, (32, 48), 16, 16, 3, 1),      # kc=16 (SWIZZLE_32B)
+    (2, 2, (24, 40), 32, 32, 3, 1),      # kc=32 (SWIZZLE_64B)
+    (2, 1, (20, 24), 64, 64, 3, 1),      # kc=64 (SWIZZLE_128B)
+    (2, 1, (16, 16), 128, 256, 3, 1),    # two K chunks, N=256
+    (2, 1, (8, 8), 256, 512, 3, 1),      # two N tiles
+    (2, 2, (32, 32), 16, 32, 3, 2),      # stride 2 via TMA elementStrides, asymmetric SAME pad
+    (2, 1, (17, 23), 32, 48, 3, 2),      # odd sizes (pad_before = 1), ragged tiles
+    (2, 2, (16, 16), 32, 64, 1, 2),      # 1x1 shortcut s2
+    (2, 1, (16, 24), 64, 32, 1, 1),
+    (3, 1, (12, 16, 20), 16, 16, 3, 1),  # 27 taps
+    (3, 1, (8, 8, 16), 32, 64, 3, 2),
+    (3, 1, (6, 6, 6), 64, 64, 3, 1),     # small grid: tile box larger than the grid
+    (3, 1, (8, 8, 8), 32, 64, 1, 2),
+]
+
+
+@pytest.mark.parametrize("dt", [F16, BF16])
+@pytest.mark.parametrize("nd,n,sp,cin,cout,k,s", TC_CASES)
+def test_conv_tcgen05_fwd_dgrad(lib, dt, nd, n, sp, cin, cout, k, s):
+    """The tcgen05 implicit-GEMM path against the oracle on bit-identical (pre-rounded) operands:
+    fp32 outputs must agree to accumulation-order noise."""
+    rng = np.random.default_rng(hash((nd, n, sp, cin, cout, k, s, 1)) % 2**32)
+    x = host(dev(rng.standard_normal((n,) + sp + (cin,)).astype(np.float32), dt))
+    w = (rng.standard_normal((k,) * nd + (cin, cout)) / np.sqrt(k**nd * cin)).astype(np.float32)
+    wq = host(dev(w, dt))                                     # operand rounding of the filter
+    d = _capi.conv_desc_same(nd, n, sp, cin, cout, k, s)
+    osp = (d.yd, d.yh, d.yw)[3 - nd:]
+    xt = torch.tensor(x, dtype=torch.float64, requires_grad=True)
+    yo = O.conv_same(xt.permute(0, nd + 1, *range(1, nd + 1)), torch.tensor(wq, dtype=torch.float64), s)
+    xd, wd = dev(x, dt), dev(w)
+    wpack = torch.empty(2 * w.size + 64, dtype=torch.uint8, device=DEV)
+    y = torch.full((n,) + osp + (cout,), 5.0, dtype=torch.float32, device=DEV)
+    _capi.check(lib.urn_conv_fwd_tc(C.byref(d), dt, xd.data_ptr(), cin, wd.data_ptr(), wpack.data_ptr(), y.data_ptr(), cout, F32, 0, st()))
+    assert relerr(host(y), cl(yo.detach())) < 2e-5
+    # input gradient: gradients are bf16 operands in both 16-bit modes
+    g_cl = host(dev(rng.standard_normal((n,) + osp + (cout,)).astype(np.float32), BF16))
+    wqb = host(dev(w, BF16))
+    yb = O.conv_same(xt.permute(0, nd + 1, *range(1, nd + 1)), torch.tensor(wqb, dtype=torch.float64), s)
+    (dxo,) = torch.autograd.grad(yb, xt, torch.tensor(np.moveaxis(g_cl, -1, 1), dtype=torch.float64))
+    gd = dev(g_cl, BF16)
+    dx = torch.full((n,) + sp + (cin,), 3.0, dtype=torch.float32, device=DEV)
+    _capi.check(lib.urn_conv_dgrad_tc(C.byref(d), BF16, gd.data_ptr(), cout, wd.data_ptr(), wpack.data_ptr(), dx.data_ptr(), cin, F32, 0, st()))
+    assert relerr(host(dx), dxo.numpy()) < 2e-5
+    _capi.check(lib.urn_conv_dgrad_tc(C.byref(d), BF16, gd.data_ptr(), cout, wd.data_ptr(), wpack.data_ptr(), dx.data_ptr(), cin, F32, 1, st()))
+    assert relerr(host(dx), 2 * dxo.numpy()) < 4e-5
+    dxb = torch.zeros((n,) + sp + (cin,), dtype=torch.bfloat16, device=DEV)
+    _capi.check(lib.urn_conv_dgrad_tc(C.byref(d), BF16, gd.data_ptr(), cout, wd.data_ptr(), wpack.data_ptr(), dxb.data_ptr(), cin, BF16, 0, st()))
+    assert relerr(host(dxb), dxo.numpy()) < 1e-2
+
+
+def test_conv_tcgen05_pitched_concat_view(lib):
+    """TMA reads a channel slice of a concat buffer (pitch 2C, offset C)."""
+    rng = np.random.default_rng(5)
+    n, sp, c = 1, (16, 16), 32
+    z = host(dev(rng.standard_normal((n,) + sp + (2 * c,)).astype(np.float32), F16))
+    w = rng.standard_normal((3, 3, c, c)).astype(np.float32) / 17
+    d = _capi.conv_desc_same(2, n, sp, c, c, 3, 1)
+    zd, wd = dev(z, F16), dev(w)
+    wpack = torch.empty(2 * w.size + 64, dtype=torch.uint8, device=DEV)
+    y = torch.empty((n,) + sp + (c,), dtype=torch.float32, device=DEV)
+    _capi.check(lib.urn_conv_fwd_tc(C.byref(d), F16, zd.data_ptr() + 2 * c, 2 * c, wd.data_ptr(), wpack.data_ptr(), y.data_ptr(), c, F32, 0, st()))
+    yo = cl(O.conv_same(cf(z[..., c:]), torch.tensor(host(dev(w, F16)), dtype=torch.float64), 1))
+    assert relerr(host(y), yo) < 2e-5
+
+
 @pytest.mark.parametrize("nd,n,sp,cin,cout", [(2, 2, (8, 12), 32, 16), (3, 1, (4, 6, 4), 32, 16), (2, 1, (5, 7), 8, 4)])
 def test_conv_transpose_forward(lib, nd, n, sp, cin, cout):
     """slim.conv*_transpose forward == urn_conv_dgrad on the deconv's base relation."""

@@ -1,6 +1,8 @@
 // C-ABI conv entry points: geometry -> generalised-conv launches (FFMA or tcgen05).
 #include <stdarg.h>
 
+#include <algorithm>
+
 #include "common.cuh"
 #include "gconv_tc.cuh"
 
@@ -144,4 +146,67 @@ extern "C" int urn_conv_wgrad(const urn_conv_desc* d, int dtype, int impl, const
   URN_CHECK(ldx >= d->cx && ldy >= d->cy, "urn_conv_wgrad: pitch smaller than channel count");
   URN_CHECK(impl != URN_IMPL_TC, "urn_conv_wgrad: tcgen05 path runs through the net handle");
   return wgrad_ffma_launch(*d, dtype, x, ldx, y_dtype, y, ldy, dw, accumulate, ws, (cudaStream_t)stream);
+}
+
+// ---------------- tcgen05 per-kernel entry points ----------------
+namespace {
+template <typename T>
+__global__ void pack_one_kernel(const float* __restrict__ w, int taps, int cx, int cy, int transpose,
+                                T* __restrict__ dst) {
+  const long long n = (long long)taps * cx * cy;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int y = (int)(i % cy);
+    const int x = (int)((i / cy) % cx);
+    const long long t = i / ((long long)cx * cy);
+    st1(dst + (transpose ? (t * cy + y) * cx + x : i), w[i]);
+  }
+}
+int pack_filter(const urn_conv_desc& d, int dtype, const float* w, void* wpack, bool gather, cudaStream_t st) {
+  const int taps = d.kd * d.kh * d.kw;
+  const long long n = (long long)taps * d.cx * d.cy;
+  const unsigned nb = (unsigned)std::min<long long>((n + 255) / 256, 148 * 4);
+  if (dispatch_dtype(dtype, [&](auto pt) {
+        using T = URN_T(pt);
+        pack_one_kernel<T><<<nb, 256, 0, st>>>(w, taps, d.cx, d.cy, gather ? 1 : 0, (T*)wpack);
+        return 0;
+      }))
+    return 1;
+  URN_LAUNCH_CHECK();
+  return 0;
+}
+}  // namespace
+
+extern "C" int urn_conv_fwd_tc(const urn_conv_desc* d, int dtype, const void* x, int64_t ldx,
+                               const float* w, void* wpack, void* y, int64_t ldy, int y_dtype,
+                               int accumulate, void* stream) {
+  if (check_desc(d)) return 1;
+  cudaStream_t st = (cudaStream_t)stream;
+  GConv g;
+  gconv_gather(*d, ldx, ldy, &g);
+  g.accumulate = accumulate;
+  URN_CHECK(gconv_tc_supported(g, dtype, y_dtype), "urn_conv_fwd_tc: shape/dtype not supported by the tcgen05 path");
+  if (pack_filter(*d, dtype, w, wpack, true, st)) return 1;
+  return gconv_tc_launch(g, dtype, x, wpack, y, y_dtype, st);
+}
+
+extern "C" int urn_conv_dgrad_tc(const urn_conv_desc* d, int dtype, const void* dy, int64_t ldy,
+                                 const float* w, void* wpack, void* dx, int64_t ldx, int x_dtype,
+                                 int accumulate, void* stream) {
+  if (check_desc(d)) return 1;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (pack_filter(*d, dtype, w, wpack, false, st)) return 1;
+  for (int pd = 0; pd < d->s; ++pd)
+    for (int ph = 0; ph < d->s; ++ph)
+      for (int pw = 0; pw < d->s; ++pw) {
+        GConv g;
+        if (!gconv_scatter_class(*d, ldy, ldx, pd, ph, pw, accumulate, &g)) continue;
+        if (g.ntaps == 0) {   // parity class without taps (1x1 stride-2): zeros, CUDA-core kernel
+          if (gconv_ffma_launch(g, dtype, dy, w, dx, x_dtype, st)) return 1;
+          continue;
+        }
+        URN_CHECK(gconv_tc_supported(g, dtype, x_dtype), "urn_conv_dgrad_tc: shape/dtype not supported by the tcgen05 path");
+        if (gconv_tc_launch(g, dtype, dy, wpack, dx, x_dtype, st)) return 1;
+      }
+  return 0;
 }

@@ -9,3 +9,8 @@ bool gconv_scatter_class(const urn_conv_desc& d, int64_t ldy, int64_t ldx, int p
                          int accumulate, GConv* g);
 int urn_softmax_only(const float* logits, int64_t ld, int64_t total, int c, float* softmax,
                      cudaStream_t st);
+
+// tcgen05 path (gconv_tc.cu).  wpack: 16-bit filter, same dtype as `in`, laid out [tap][cout][cin].
+bool gconv_tc_supported(const GConv& g, int in_dtype, int out_dtype);
+int gconv_tc_launch(const GConv& g, int in_dtype, const void* in, const void* wpack, void* out,
+                    int out_dtype, cudaStream_t st);

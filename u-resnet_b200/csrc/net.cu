@@ -103,6 +103,8 @@ struct urn_net {
   // 16-bit modes: fp32 copies of the parameters rounded to the activation-side operand type
   // (forward / wgrad) and to the gradient-side operand type (dgrad)
   int64_t wq_off = -1, wqg_off = -1;
+  // 16-bit packed filters for the tcgen05 path: gather form [tap][cy][cx], scatter form [tap][cx][cy]
+  int64_t wpg_off = -1, wps_off = -1;
   int TA = URN_F32, TG = URN_F32;   // activation / gradient storage dtypes
   int max_c = 0;
   // profiling (urn_profile_*): event pairs recorded around each (layer, phase) launch group
@@ -346,6 +348,10 @@ static int build_plan(urn_net& N) {
   if (T != URN_F32) {
     N.wq_off = b.alloc(N.param_total * 4);
     N.wqg_off = TG == T ? N.wq_off : b.alloc(N.param_total * 4);
+    if (c.impl != URN_IMPL_FFMA) {
+      N.wpg_off = b.alloc(N.param_total * 2);
+      N.wps_off = b.alloc(N.param_total * 2);
+    }
   }
 
   // ---- backward schedule ----
@@ -527,6 +533,33 @@ __global__ void round_params_kernel(const float* __restrict__ src, long long n, 
     if (dst_g != dst_a) dst_g[i] = dt_g == URN_F16 ? vh : vb;
   }
 }
+// One launch per layer: 16-bit copies of the filter in both contraction orders.
+//   gather form  Wg[t][cy][cx]  (conv forward / deconv input-gradient)
+//   scatter form Ws[t][cx][cy]  (conv input-gradient / deconv forward) == TF layout
+template <typename TGa, typename TSc>
+__global__ void pack_filter_kernel(const float* __restrict__ w, int taps, int cx, int cy,
+                                   TGa* __restrict__ wg, TSc* __restrict__ wsc) {
+  const long long n = (long long)taps * cx * cy;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int y = (int)(i % cy);
+    const int x = (int)((i / cy) % cx);
+    const long long t = i / ((long long)cx * cy);
+    const float v = w[i];
+    st1(wsc + i, v);
+    st1(wg + (t * cy + y) * cx + x, v);
+  }
+}
+inline bool tc_enabled(const urn_net* h) { return h->wpg_off >= 0; }
+
+// Generalised conv dispatch: tcgen05 when the shape allows, CUDA cores otherwise.
+inline int run_gconv(const urn_net* h, const GConv& g, int in_dtype, const void* in, const float* w_f32,
+                     const void* w_pack, void* out, int out_dtype, cudaStream_t st) {
+  if (tc_enabled(h) && gconv_tc_supported(g, in_dtype, out_dtype))
+    return gconv_tc_launch(g, in_dtype, in, w_pack, out, out_dtype, st);
+  return gconv_ffma_launch(g, in_dtype, in, w_f32, out, out_dtype, st);
+}
+
 // grad_side: the operand multiplies a gradient tensor (dgrad) rather than an activation
 inline const float* conv_weights(const urn_net* h, const Layer& L, const float* params, void* ws,
                                  bool grad_side = false) {
@@ -544,14 +577,14 @@ int run_conv_fwd(urn_net* h, int li, const float* params, void* ws, cudaStream_t
   if (!L.transpose) {
     GConv g;
     gconv_gather(L.d, in.ld, L.cout, &g);
-    if (gconv_ffma_launch(g, in.dtype, P(ws, in.off), w, raw, URN_F32, st)) return 1;
+    if (run_gconv(h, g, in.dtype, P(ws, in.off), w, P(ws, h->wpg_off + L.w_off * 2), raw, URN_F32, st)) return 1;
   } else {
     for (int pd = 0; pd < L.d.s; ++pd)
       for (int ph = 0; ph < L.d.s; ++ph)
         for (int pw = 0; pw < L.d.s; ++pw) {
           GConv g;
           if (!gconv_scatter_class(L.d, in.ld, L.cout, pd, ph, pw, 0, &g)) continue;
-          if (gconv_ffma_launch(g, in.dtype, P(ws, in.off), w, raw, URN_F32, st)) return 1;
+          if (run_gconv(h, g, in.dtype, P(ws, in.off), w, P(ws, h->wps_off + L.w_off * 2), raw, URN_F32, st)) return 1;
         }
   }
   }
@@ -583,6 +616,29 @@ extern "C" int urn_forward(urn_net* h, const float* params, const float* data, v
       round_params_kernel<<<nb2, 256, 0, st>>>(params, h->param_total, h->TA, (float*)P(ws, h->wq_off),
                                                h->TG, (float*)P(ws, h->wqg_off));
       URN_LAUNCH_CHECK();
+    }
+    if (tc_enabled(h)) {
+      for (const Layer& L : h->layers) {
+        if (L.d.cx % 16 || L.d.cy % 16) continue;       // stem / head stay on the CUDA cores
+        const int taps = L.d.kd * L.d.kh * L.d.kw;
+        const long long n = (long long)taps * L.d.cx * L.d.cy;
+        const unsigned nb3 = (unsigned)std::min<long long>((n + 255) / 256, 148 * 4);
+        const float* w = params + L.w_off;
+        void* wg = P(ws, h->wpg_off + L.w_off * 2);
+        void* wsc = P(ws, h->wps_off + L.w_off * 2);
+        // conv: gather multiplies activations (TA), scatter multiplies gradients (TG); deconv: swapped
+        const int dt_g = L.transpose ? h->TG : h->TA, dt_s = L.transpose ? h->TA : h->TG;
+        if (dispatch_dtype(dt_g, [&](auto pg) {
+              using TGa = URN_T(pg);
+              return dispatch_dtype(dt_s, [&](auto psc) {
+                using TSc = URN_T(psc);
+                pack_filter_kernel<TGa, TSc><<<nb3, 256, 0, st>>>(w, taps, L.d.cx, L.d.cy, (TGa*)wg, (TSc*)wsc);
+                return 0;
+              });
+            }))
+          return 1;
+        URN_LAUNCH_CHECK();
+      }
     }
   }
   for (const FStep& s : h->fwd) {
@@ -694,13 +750,13 @@ extern "C" int urn_backward(urn_net* h, const float* params, float* grads, int a
             for (int pw = 0; pw < L.d.s; ++pw) {
               GConv g;
               if (!gconv_scatter_class(L.d, L.cout, in.ld, pd, ph, pw, s.accumulate, &g)) continue;
-              if (gconv_ffma_launch(g, T, draw(L), w, gptr(in), T, st)) return 1;
+              if (run_gconv(h, g, T, draw(L), w, P(ws, h->wps_off + L.w_off * 2), gptr(in), T, st)) return 1;
             }
       } else {
         GConv g;
         gconv_gather(L.d, L.cout, in.ld, &g);
         g.accumulate = s.accumulate;
-        if (gconv_ffma_launch(g, T, draw(L), w, gptr(in), T, st)) return 1;
+        if (run_gconv(h, g, T, draw(L), w, P(ws, h->wpg_off + L.w_off * 2), gptr(in), T, st)) return 1;
       }
     }
     if (s.last_for_layer && ready_events && ready_events[s.layer]) {
