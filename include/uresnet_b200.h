@@ -103,12 +103,14 @@ int urn_bn_stats(const float* raw, int64_t ld, int64_t rows, int c, float eps, f
  * residual: res (dtype, pitch ldres) added as is (identity shortcut,
  * lib/resnet_module.py:22-23,68) or, if res_raw != NULL, BN(res_raw; res_stats,
  * res_beta) (conv shortcut, lib/resnet_module.py:25-33,68).  relu != 0 applies
- * tf.nn.relu.  out is out_dtype with pitch ldout. */
+ * tf.nn.relu.  out is out_dtype with pitch ldout.  out2 (may be NULL) receives the same values
+ * as bf16 with the same pitch: the copy the tcgen05 filter-gradient kernel multiplies with the
+ * bf16 gradients (kind::f16 needs both operands in one 16-bit format). */
 int urn_bn_apply(const float* raw, int64_t ld, int64_t rows, int c, const float* stats,
                  const float* beta, const void* res, int64_t ldres, int res_dtype,
                  const float* res_raw, int64_t ldres_raw, const float* res_stats,
                  const float* res_beta, int relu, void* out, int64_t ldout, int out_dtype,
-                 void* stream);
+                 void* out2, void* stream);
 
 /* K8  batch-norm (+ReLU, +residual fan-out) backward.
  * g = dout * (relu ? out>0 : 1);  dbeta = sum g;  draw = rstd*(g - mean(g) - xhat*mean(g*xhat)).

@@ -157,6 +157,27 @@ def test_conv_tcgen05_fwd_dgrad(lib, dt, nd, n, sp, cin, cout, k, s):
     assert relerr(host(dxb), dxo.numpy()) < 1e-2
 
 
+@pytest.mark.parametrize("xdt,ydt", [(BF16, BF16), (F16, F16)])   # kind::f16 needs one format for both operands
+@pytest.mark.parametrize("nd,n,sp,cin,cout,k,s", TC_CASES)
+def test_conv_tcgen05_wgrad(lib, xdt, ydt, nd, n, sp, cin, cout, k, s):
+    """Filter gradient on tcgen05 (MN-major operands, split-K, deterministic reduce)."""
+    rng = np.random.default_rng(hash((nd, n, sp, cin, cout, k, s, 2)) % 2**32)
+    x = host(dev(rng.standard_normal((n,) + sp + (cin,)).astype(np.float32), xdt))
+    d = _capi.conv_desc_same(nd, n, sp, cin, cout, k, s)
+    osp = (d.yd, d.yh, d.yw)[3 - nd:]
+    g_cl = host(dev(rng.standard_normal((n,) + osp + (cout,)).astype(np.float32), ydt))
+    wt = torch.zeros((k,) * nd + (cin, cout), dtype=torch.float64, requires_grad=True)
+    yo = O.conv_same(cf(x), wt, s)
+    (dwo,) = torch.autograd.grad(yo, wt, torch.tensor(np.moveaxis(g_cl, -1, 1), dtype=torch.float64))
+    xd, gd = dev(x, xdt), dev(g_cl, ydt)
+    ws = torch.empty(max(int(lib.urn_conv_wgrad_workspace(C.byref(d))), 16), dtype=torch.uint8, device=DEV)
+    dw = torch.full(tuple(wt.shape), 2.0, dtype=torch.float32, device=DEV)
+    _capi.check(lib.urn_conv_wgrad(C.byref(d), xdt, 2, xd.data_ptr(), cin, gd.data_ptr(), cout, ydt, dw.data_ptr(), 0, ws.data_ptr(), st()))
+    assert relerr(host(dw), dwo.numpy()) < 2e-5
+    _capi.check(lib.urn_conv_wgrad(C.byref(d), xdt, 2, xd.data_ptr(), cin, gd.data_ptr(), cout, ydt, dw.data_ptr(), 1, ws.data_ptr(), st()))
+    assert relerr(host(dw), 2 * dwo.numpy()) < 4e-5
+
+
 def test_conv_tcgen05_pitched_concat_view(lib):
     """TMA reads a channel slice of a concat buffer (pitch 2C, offset C)."""
     rng = np.random.default_rng(5)
@@ -217,17 +238,17 @@ def test_bn_stats_apply(lib, c, rows):
     for relu in (0, 1):
         out = torch.empty((rows, c), dtype=torch.float32, device=DEV)
         _capi.check(lib.urn_bn_apply(xd.data_ptr(), c, rows, c, stats.data_ptr(), bd.data_ptr(), None, 0, 0, None, 0,
-                                     None, None, relu, out.data_ptr(), c, F32, st()))
+                                     None, None, relu, out.data_ptr(), c, F32, None, st()))
         assert relerr(host(out), np.maximum(ref, 0) if relu else ref) < 2e-5
     # residual forms: identity tensor, and a second BN (conv shortcut)
     r = rng.standard_normal((rows, c)).astype(np.float32)
     out = torch.empty((rows, c), dtype=torch.float32, device=DEV)
     rd = dev(r)
     _capi.check(lib.urn_bn_apply(xd.data_ptr(), c, rows, c, stats.data_ptr(), bd.data_ptr(), rd.data_ptr(), c, F32,
-                                 None, 0, None, None, 1, out.data_ptr(), c, F32, st()))
+                                 None, 0, None, None, 1, out.data_ptr(), c, F32, None, st()))
     assert relerr(host(out), np.maximum(ref + r, 0)) < 2e-5
     _capi.check(lib.urn_bn_apply(xd.data_ptr(), c, rows, c, stats.data_ptr(), bd.data_ptr(), None, 0, 0,
-                                 xd.data_ptr(), c, stats.data_ptr(), bd.data_ptr(), 1, out.data_ptr(), c, F32, st()))
+                                 xd.data_ptr(), c, stats.data_ptr(), bd.data_ptr(), 1, out.data_ptr(), c, F32, None, st()))
     assert relerr(host(out), np.maximum(2 * ref, 0)) < 2e-5
 
 

@@ -50,7 +50,7 @@ SIGNATURES = {
     "urn_bn_workspace": (_i64, [_i]),
     "urn_bn_stats": (_i, [_vp, _i64, _i64, _i, _f, _vp, _vp, _vp]),
     "urn_bn_apply": (_i, [_vp, _i64, _i64, _i, _vp, _vp, _vp, _i64, _i, _vp, _i64, _vp, _vp, _i,
-                          _vp, _i64, _i, _vp]),
+                          _vp, _i64, _i, _vp, _vp]),
     "urn_bn_bwd": (_i, [_vp, _i64, _vp, _i64, _i, _i, _i, _i64, _i, _vp, _i64, _vp, _vp, _vp, _i64,
                         _vp, _i64, _vp, _vp, _vp, _i64, _vp, _i64, _i, _i, _vp, _vp]),
     "urn_loss_workspace": (_i64, [_i64]),

@@ -100,7 +100,8 @@ bn_apply_kernel(const float* __restrict__ raw, long long ld, long long rows, int
                 const float* __restrict__ stats, const float* __restrict__ beta,
                 const TR* __restrict__ res, long long ldres, const float* __restrict__ res_raw,
                 long long ldres_raw, const float* __restrict__ res_stats,
-                const float* __restrict__ res_beta, int relu, TO* __restrict__ out, long long ldout) {
+                const float* __restrict__ res_beta, int relu, TO* __restrict__ out, long long ldout,
+                bf16* __restrict__ out2) {
   const int cg = c / vec;
   const long long total = rows * cg;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -126,12 +127,14 @@ bn_apply_kernel(const float* __restrict__ raw, long long ld, long long rows, int
         y.x = fmaxf(y.x, 0.f); y.y = fmaxf(y.y, 0.f); y.z = fmaxf(y.z, 0.f); y.w = fmaxf(y.w, 0.f);
       }
       st4(out + r * ldout + ch, y);
+      if (out2) st4(out2 + r * ldout + ch, y);
     } else {
       float y = (raw[r * ld + ch] - stats[ch]) * stats[c + ch] + beta[ch];
       if (res_raw) y += (res_raw[r * ldres_raw + ch] - res_stats[ch]) * res_stats[c + ch] + res_beta[ch];
       else if (res) y += ld1(res + r * ldres + ch);
       if (relu) y = fmaxf(y, 0.f);
       st1(out + r * ldout + ch, y);
+      if (out2) st1(out2 + r * ldout + ch, y);
     }
   }
 }
@@ -335,13 +338,13 @@ template <typename TR, typename TO>
 static int bn_apply_t(const float* raw, int64_t ld, int64_t rows, int c, const float* stats,
                       const float* beta, const void* res, int64_t ldres, const float* res_raw,
                       int64_t ldres_raw, const float* res_stats, const float* res_beta, int relu,
-                      void* out, int64_t ldout, cudaStream_t st) {
+                      void* out, int64_t ldout, void* out2, cudaStream_t st) {
   bool al = aligned4(c, {ld, ldout, res ? ldres : 0, res_raw ? ldres_raw : 0});
   int vec = al ? 4 : 1;
   long long total = rows * (c / vec);
   bn_apply_kernel<TR, TO><<<ew_blocks(total), 256, 0, st>>>(
       raw, ld, rows, c, vec, stats, beta, (const TR*)res, ldres, res_raw, ldres_raw, res_stats,
-      res_beta, relu, (TO*)out, ldout);
+      res_beta, relu, (TO*)out, ldout, (bf16*)out2);
   URN_LAUNCH_CHECK();
   return 0;
 }
@@ -350,7 +353,7 @@ extern "C" int urn_bn_apply(const float* raw, int64_t ld, int64_t rows, int c, c
                             const float* beta, const void* res, int64_t ldres, int res_dtype,
                             const float* res_raw, int64_t ldres_raw, const float* res_stats,
                             const float* res_beta, int relu, void* out, int64_t ldout,
-                            int out_dtype, void* stream) {
+                            int out_dtype, void* out2, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   URN_CHECK(rows > 0 && c >= 1, "urn_bn_apply: empty input");
   if (!res) res_dtype = out_dtype;
@@ -359,7 +362,7 @@ extern "C" int urn_bn_apply(const float* raw, int64_t ld, int64_t rows, int c, c
     return dispatch_dtype(out_dtype, [&](auto po) {
       using TO = URN_T(po);
       return bn_apply_t<TR, TO>(raw, ld, rows, c, stats, beta, res, ldres, res_raw, ldres_raw,
-                                res_stats, res_beta, relu, out, ldout, st);
+                                res_stats, res_beta, relu, out, ldout, out2, st);
     });
   });
 }

@@ -136,7 +136,7 @@ extern "C" int urn_conv_dgrad(const urn_conv_desc* d, int dtype, int impl, const
 
 extern "C" int64_t urn_conv_wgrad_workspace(const urn_conv_desc* d) {
   if (check_desc(d)) return -1;
-  return wgrad_ffma_workspace(*d);
+  return std::max<int64_t>(wgrad_ffma_workspace(*d), wgrad_tc_workspace(*d));
 }
 
 extern "C" int urn_conv_wgrad(const urn_conv_desc* d, int dtype, int impl, const void* x, int64_t ldx,
@@ -144,7 +144,10 @@ extern "C" int urn_conv_wgrad(const urn_conv_desc* d, int dtype, int impl, const
                               void* ws, void* stream) {
   if (check_desc(d)) return 1;
   URN_CHECK(ldx >= d->cx && ldy >= d->cy, "urn_conv_wgrad: pitch smaller than channel count");
-  URN_CHECK(impl != URN_IMPL_TC, "urn_conv_wgrad: tcgen05 path runs through the net handle");
+  if (impl == URN_IMPL_TC) {
+    URN_CHECK(wgrad_tc_supported(*d, dtype, y_dtype, ldx, ldy), "urn_conv_wgrad: shape/dtype not supported by the tcgen05 path");
+    return wgrad_tc_launch(*d, dtype, x, ldx, y_dtype, y, ldy, dw, accumulate, ws, (cudaStream_t)stream);
+  }
   return wgrad_ffma_launch(*d, dtype, x, ldx, y_dtype, y, ldy, dw, accumulate, ws, (cudaStream_t)stream);
 }
 

@@ -15,6 +15,7 @@
 // tile's MMAs run.  Persistent CTAs, warp-specialised: warp0 = TMA producer, warp1 = MMA
 // issuer, warp2 = TMEM allocator, warps4-7 = epilogue.
 #include <cuda.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -362,6 +363,7 @@ int gconv_tc_launch(const GConv& g, int in_dtype, const void* in, const void* wp
   p.tx_bytes = p.a_bytes + p.n_tile * p.kc * 2;
   int stage_bytes = p.a_bytes + p.b_bytes;
   p.stages = std::max(2, std::min(kMaxStages, (160 * 1024) / stage_bytes));
+  if (const char* e = getenv("URN_TC_STAGES")) p.stages = std::max(1, std::min(p.stages, atoi(e)));
   const int fmt = in_dtype == URN_BF16 ? 1 : 0;
   p.idesc = (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)(p.n_tile >> 3) << 17) |
             ((uint32_t)(128 >> 4) << 24);
@@ -403,6 +405,318 @@ int gconv_tc_launch(const GConv& g, int in_dtype, const void* in, const void* wp
   long long nwork = p.ntiles * p.n_tiles;
   int grid = (int)std::min<long long>(nwork, num_sms());
   gconv_tc_kernel<<<grid, kThreads, smem, st>>>(map_a, map_b, p, out);
+  URN_LAUNCH_CHECK();
+  return 0;
+}
+
+// =====================================================================================
+// Filter gradient on tcgen05:  dW[t][cx][cy] = sum_pos X[pos*s + off_t][cx] * Y[pos][cy]
+//
+// GEMM view: M = (tap, cx) -- 128/AW groups of AW channels, each group one tap-shifted TMA box
+// of X; N = cy; K = output positions (a PD x PH x PW box of 64 positions per pipeline stage).
+// Both operands are MN-major (the channel axis is the contiguous one in NHWC), which the UMMA
+// shared-memory descriptor expresses directly: the TMA boxes [positions][channels] land as
+// swizzled K-rows and consecutive channel groups sit LBO bytes apart.  The positions are split
+// over CTAs (split-K); every CTA writes an fp32 partial [taps][cx][cy] that a second kernel
+// reduces in a fixed order (deterministic).  kind::f16 wants ONE 16-bit format for both
+// operands (a mixed fp16 x bf16 instruction descriptor raises an illegal-instruction fault on
+// B200), so in mix16 mode the activations enter through their bf16 shadow copy.
+// =====================================================================================
+namespace {
+
+constexpr int kWgP = 64;   // positions per pipeline stage
+
+struct WgParams {
+  int n, yd, yh, yw;          // small-side (Y) grid
+  int pd, ph, pw;             // position box per stage (pd*ph*pw == kWgP)
+  int nbd, nbh, nbw;          // boxes per dim
+  long long nkb;              // K blocks in total
+  int s;                      // stride (X sampling)
+  int pad_d, pad_h, pad_w, kd, kh, kw;
+  int cx, cy;
+  int aw, bw;                 // channel-group widths of A (X) and B (Y)
+  int gx;                     // cx / aw
+  int groups;                 // taps * gx   (M space in groups)
+  int gpt;                    // groups per M tile (128 / aw)
+  int m_tiles, n_tile, n_tiles, ksplit;
+  long long kb_per_split;
+  int stages, a_bytes, b_bytes;
+  uint32_t idesc;
+  uint64_t adesc_hi, bdesc_hi;
+  int tmem_cols;
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_y,
+                const __grid_constant__ WgParams p, float* __restrict__ partial) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + (size_t)p.stages * p.a_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + (size_t)p.stages * p.b_bytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + kMaxStages;
+  uint64_t* tfull = bars + 2 * kMaxStages;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long nwork = (long long)p.m_tiles * p.n_tiles * p.ksplit;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_x);
+    tma_prefetch_desc(&map_y);
+    for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)p.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // work item -> (m tile, n tile, k split); k split varies fastest so that the CTAs running
+  // concurrently stream disjoint positions
+  auto decode = [&](long long w, int& mt, int& nt, long long& kb0, long long& kb1) {
+    const int ks = (int)(w % p.ksplit);
+    long long t = w / p.ksplit;
+    nt = (int)(t % p.n_tiles);
+    mt = (int)(t / p.n_tiles);
+    kb0 = (long long)ks * p.kb_per_split;
+    kb1 = kb0 + p.kb_per_split;
+    if (kb1 > p.nkb) kb1 = p.nkb;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (long long w = blockIdx.x; w < nwork; w += gridDim.x) {
+        int mt, nt; long long kb0, kb1;
+        decode(w, mt, nt, kb0, kb1);
+        const int g0 = mt * p.gpt;
+        const int ng = min(p.gpt, p.groups - g0);
+        const int nb_groups = p.n_tile / p.bw;
+        const uint32_t tx = (uint32_t)(ng * kWgP * p.aw * 2 + nb_groups * kWgP * p.bw * 2);
+        for (long long kb = kb0; kb < kb1; ++kb, ++it) {
+          long long t = kb;
+          const int bw_ = (int)(t % p.nbw); t /= p.nbw;
+          const int bh_ = (int)(t % p.nbh); t /= p.nbh;
+          const int bd_ = (int)(t % p.nbd);
+          const int nn = (int)(t / p.nbd);
+          const int w0 = bw_ * p.pw, h0 = bh_ * p.ph, d0 = bd_ * p.pd;
+          const int s = it % p.stages;
+          mbar_wait(&empty[s], ((it / p.stages) & 1) ^ 1);
+          mbar_expect_tx(&full[s], tx);
+          uint8_t* a_dst = smem_a + (size_t)s * p.a_bytes;
+          for (int g = 0; g < ng; ++g) {
+            const int gi = g0 + g;
+            const int tap = gi / p.gx, cx0 = (gi % p.gx) * p.aw;
+            const int tw = tap % p.kw, th = (tap / p.kw) % p.kh, td = tap / (p.kw * p.kh);
+            tma_load_5d(a_dst + (size_t)g * kWgP * p.aw * 2, &map_x, &full[s], cx0, w0 * p.s + tw - p.pad_w,
+                        h0 * p.s + th - p.pad_h, d0 * p.s + td - p.pad_d, nn);
+          }
+          uint8_t* b_dst = smem_b + (size_t)s * p.b_bytes;
+          for (int g = 0; g < nb_groups; ++g)
+            tma_load_5d(b_dst + (size_t)g * kWgP * p.bw * 2, &map_y, &full[s], nt * p.n_tile + g * p.bw, w0, h0,
+                        d0, nn);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      uint32_t it = 0, wi = 0;
+      for (long long w = blockIdx.x; w < nwork; w += gridDim.x, ++wi) {
+        int mt, nt; long long kb0, kb1;
+        decode(w, mt, nt, kb0, kb1);
+        const uint32_t acc = wi & 1;
+        mbar_wait(&tempty[acc], ((wi >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * (uint32_t)p.n_tile;
+        uint32_t first = 1;
+        for (long long kb = kb0; kb < kb1; ++kb, ++it) {
+          const int s = it % p.stages;
+          mbar_wait(&full[s], (it / p.stages) & 1);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem_a + (size_t)s * p.a_bytes);
+          const uint32_t b_addr = smem_u32(smem_b + (size_t)s * p.b_bytes);
+          for (int k = 0; k < kWgP / 16; ++k) {
+            // 16 positions further = 16 K-rows of (group width * 2) bytes
+            const uint64_t adesc = p.adesc_hi | (uint64_t)(((a_addr + k * 16 * p.aw * 2) >> 4) & 0x3FFF);
+            const uint64_t bdesc = p.bdesc_hi | (uint64_t)(((b_addr + k * 16 * p.bw * 2) >> 4) & 0x3FFF);
+            umma_f16(d_tmem, adesc, bdesc, p.idesc, first ? 0u : 1u);
+            first = 0;
+          }
+          umma_commit(&empty[s]);
+        }
+        umma_commit(&tfull[acc]);
+      }
+    }
+  } else if (warp >= 4) {
+    const int q = warp & 3;
+    const int r = q * 32 + lane;                 // accumulator row = (group, channel in group)
+    uint32_t wi = 0;
+    const long long nw = (long long)p.kd * p.kh * p.kw * p.cx * p.cy;
+    for (long long w = blockIdx.x; w < nwork; w += gridDim.x, ++wi) {
+      int mt, nt; long long kb0, kb1;
+      decode(w, mt, nt, kb0, kb1);
+      const int ks = (int)(w % p.ksplit);
+      const uint32_t acc = wi & 1;
+      const int gi = mt * p.gpt + r / p.aw;
+      const bool valid = gi < p.groups;
+      const int tap = valid ? gi / p.gx : 0;
+      const int cx = valid ? (gi % p.gx) * p.aw + r % p.aw : 0;
+      float* dst = partial + (long long)ks * nw + ((long long)tap * p.cx + cx) * p.cy + nt * p.n_tile;
+      mbar_wait(&tfull[acc], (wi >> 1) & 1);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * (uint32_t)p.n_tile;
+      for (int c0 = 0; c0 < p.n_tile; c0 += 16) {
+        float v[16];
+        tmem_ld16(taddr + c0, v);
+        if (c0 + 16 >= p.n_tile) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty[acc]);
+        }
+        if (!valid) continue;
+        if (kb1 <= kb0) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = 0.f;   // empty split: nothing was accumulated
+        }
+#pragma unroll
+        for (int j = 0; j < 16; j += 4)
+          *reinterpret_cast<float4*>(dst + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols)
+                 : "memory");
+  }
+}
+
+int make_map_5d(CUtensorMap* map, int dtype, const void* base, int c, long long ld, int w, int h, int d, int n,
+                int box_c, int box_w, int box_h, int box_d, int stride) {
+  EncodeTiledFn enc = get_encode();
+  URN_CHECK(enc, "cuTensorMapEncodeTiled not available");
+  const CUtensorMapDataType dt = dtype == URN_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  const int bytes = box_c * 2;
+  const CUtensorMapSwizzle sw = bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+  cuuint64_t dims[5] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)d, (cuuint64_t)n};
+  cuuint64_t strides[4] = {(cuuint64_t)ld * 2, (cuuint64_t)ld * 2 * w, (cuuint64_t)ld * 2 * w * h, (cuuint64_t)ld * 2 * w * h * d};
+  cuuint32_t box[5] = {(cuuint32_t)box_c, (cuuint32_t)(box_w * stride), (cuuint32_t)(box_h * stride), (cuuint32_t)(box_d * stride), 1};
+  cuuint32_t estr[5] = {1, (cuuint32_t)stride, (cuuint32_t)stride, (cuuint32_t)stride, 1};
+  CUresult r = enc(map, dt, 5, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  URN_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed: %d", (int)r);
+  return 0;
+}
+
+__global__ void wgrad_tc_reduce_kernel(const float* __restrict__ partial, long long nw, int nsplit,
+                                       float* __restrict__ dw, int accumulate) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nw) return;
+  float s = 0.f;
+  for (int k = 0; k < nsplit; ++k) s += partial[(long long)k * nw + i];
+  dw[i] = accumulate ? dw[i] + s : s;
+}
+
+int wgrad_tc_plan(const urn_conv_desc& d, WgParams* pp) {
+  WgParams& p = *pp;
+  memset(&p, 0, sizeof(p));
+  if (d.cx % 16 || d.cy % 16) return 1;       // stem / head: CUDA-core kernel
+  p.n = d.n; p.yd = d.yd; p.yh = d.yh; p.yw = d.yw;
+  p.pw = std::min(pow2_ceil(d.yw), 16);
+  p.ph = std::min(pow2_ceil(d.yh), kWgP / p.pw);
+  p.pd = kWgP / (p.pw * p.ph);
+  if (p.pd > pow2_ceil(d.yd)) {
+    p.pd = pow2_ceil(d.yd);
+    p.ph = std::min(pow2_ceil(d.yh), kWgP / (p.pw * p.pd));
+    p.pw = kWgP / (p.ph * p.pd);
+  }
+  if (p.pw * p.ph * p.pd != kWgP || p.pw * d.s > 256 || p.ph * d.s > 256 || p.pd * d.s > 256) return 1;
+  p.nbw = (d.yw + p.pw - 1) / p.pw; p.nbh = (d.yh + p.ph - 1) / p.ph; p.nbd = (d.yd + p.pd - 1) / p.pd;
+  p.nkb = (long long)d.n * p.nbd * p.nbh * p.nbw;
+  p.s = d.s; p.pad_d = d.pad_d; p.pad_h = d.pad_h; p.pad_w = d.pad_w; p.kd = d.kd; p.kh = d.kh; p.kw = d.kw;
+  p.cx = d.cx; p.cy = d.cy;
+  p.aw = d.cx % 64 == 0 ? 64 : (d.cx % 32 == 0 ? 32 : 16);
+  p.bw = d.cy % 64 == 0 ? 64 : (d.cy % 32 == 0 ? 32 : 16);
+  p.gx = d.cx / p.aw;
+  p.groups = d.kd * d.kh * d.kw * p.gx;
+  p.gpt = 128 / p.aw;
+  p.m_tiles = (p.groups + p.gpt - 1) / p.gpt;
+  p.n_tile = d.cy <= 256 ? d.cy : (d.cy % 256 == 0 ? 256 : 128);
+  if (d.cy % p.n_tile) return 1;
+  p.n_tiles = d.cy / p.n_tile;
+  const long long tiles = (long long)p.m_tiles * p.n_tiles;
+  const long long nw = (long long)d.kd * d.kh * d.kw * d.cx * d.cy;
+  long long ks = std::max<long long>(1, (2ll * 148 + tiles - 1) / tiles);
+  ks = std::min<long long>(ks, std::max<long long>(1, p.nkb / 4));
+  ks = std::min<long long>(ks, std::max<long long>(1, (64ll << 20) / nw));      // partials <= 256 MB
+  p.kb_per_split = (p.nkb + ks - 1) / ks;
+  p.ksplit = (int)((p.nkb + p.kb_per_split - 1) / p.kb_per_split);
+  p.a_bytes = 128 * kWgP * 2;
+  p.b_bytes = ((p.n_tile * kWgP * 2 + 1023) / 1024) * 1024;
+  p.stages = std::max(2, std::min(kMaxStages, (160 * 1024) / (p.a_bytes + p.b_bytes)));
+  p.tmem_cols = std::max(32, pow2_ceil(2 * p.n_tile));
+  return 0;
+}
+
+}  // namespace
+
+bool wgrad_tc_supported(const urn_conv_desc& d, int x_dtype, int y_dtype, int64_t ldx, int64_t ldy) {
+  if ((x_dtype != URN_BF16 && x_dtype != URN_F16) || x_dtype != y_dtype) return false;
+  if (d.cx % 16 || d.cy % 16 || ldx % 8 || ldy % 8) return false;
+  WgParams p;
+  return wgrad_tc_plan(d, &p) == 0 && p.tmem_cols <= 512;
+}
+
+int64_t wgrad_tc_workspace(const urn_conv_desc& d) {
+  WgParams p;
+  if (wgrad_tc_plan(d, &p)) return 0;
+  return (int64_t)p.ksplit * d.kd * d.kh * d.kw * d.cx * d.cy * 4;
+}
+
+int wgrad_tc_launch(const urn_conv_desc& d, int x_dtype, const void* x, int64_t ldx, int y_dtype,
+                    const void* y, int64_t ldy, float* dw, int accumulate, void* ws, cudaStream_t st) {
+  WgParams p;
+  URN_CHECK(wgrad_tc_plan(d, &p) == 0, "wgrad_tc: unsupported geometry");
+  const int fa = x_dtype == URN_BF16 ? 1 : 0, fb = y_dtype == URN_BF16 ? 1 : 0;
+  p.idesc = (1u << 4) | ((uint32_t)fa << 7) | ((uint32_t)fb << 10) | (1u << 15) | (1u << 16) |
+            ((uint32_t)(p.n_tile >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  auto desc_hi = [](int gw_elems) {
+    const uint64_t bytes = (uint64_t)gw_elems * 2;
+    const uint64_t layout = bytes == 128 ? 2 : (bytes == 64 ? 4 : 6);
+    const uint64_t sbo = (8 * bytes) >> 4;                 // next 8 positions (K)
+    const uint64_t lbo = ((uint64_t)kWgP * bytes) >> 4;   // next channel group (MN)
+    return (layout << 61) | (1ull << 46) | (sbo << 32) | (lbo << 16);
+  };
+  p.adesc_hi = desc_hi(p.aw);
+  p.bdesc_hi = desc_hi(p.bw);
+  CUtensorMap map_x, map_y;
+  if (make_map_5d(&map_x, x_dtype, x, d.cx, ldx, d.xw, d.xh, d.xd, d.n, p.aw, p.pw, p.ph, p.pd, d.s)) return 1;
+  if (make_map_5d(&map_y, y_dtype, y, d.cy, ldy, d.yw, d.yh, d.yd, d.n, p.bw, p.pw, p.ph, p.pd, 1)) return 1;
+  const size_t smem = 1024 + (size_t)p.stages * (p.a_bytes + p.b_bytes) + 256;
+  static bool attr_set = false;
+  if (!attr_set) {
+    URN_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  const long long nwork = (long long)p.m_tiles * p.n_tiles * p.ksplit;
+  const int grid = (int)std::min<long long>(nwork, num_sms());
+  wgrad_tc_kernel<<<grid, kThreads, smem, st>>>(map_x, map_y, p, (float*)ws);
+  URN_LAUNCH_CHECK();
+  const long long nw = (long long)d.kd * d.kh * d.kw * d.cx * d.cy;
+  wgrad_tc_reduce_kernel<<<(unsigned)((nw + 255) / 256), 256, 0, st>>>((const float*)ws, nw, p.ksplit, dw, accumulate);
   URN_LAUNCH_CHECK();
   return 0;
 }

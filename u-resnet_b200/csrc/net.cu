@@ -28,6 +28,7 @@ struct Node {
   int64_t rows = 0;
   int dtype = URN_F32;
   int64_t off = 0;   // byte offset of element (row 0, channel 0) in the workspace
+  int64_t off2 = -1; // bf16 shadow copy (mix16 + tcgen05: operand of the filter-gradient MMA)
   int64_t ld = 0;    // element pitch
   int parent = -1;   // full buffer this node is a channel slice of
   int choff = 0;     // channel offset inside the parent
@@ -147,10 +148,12 @@ struct Builder {
     cur = align_up(cur + bytes, 256);
     return o;
   }
+  bool shadow = false;
   int new_node(int c, int64_t rows, int dtype) {
     Node n;
     n.c = c; n.rows = rows; n.dtype = dtype; n.ld = c;
     n.off = alloc(rows * c * esize(dtype));
+    if (shadow && dtype == URN_F16) n.off2 = alloc(rows * c * 2);
     N.nodes.push_back(n);
     return (int)N.nodes.size() - 1;
   }
@@ -158,6 +161,7 @@ struct Builder {
     Node n = N.nodes[parent];
     n.parent = parent; n.choff = choff; n.c = c;
     n.off = N.nodes[parent].off + (int64_t)choff * esize(n.dtype);
+    if (n.off2 >= 0) n.off2 = N.nodes[parent].off2 + (int64_t)choff * 2;
     N.nodes.push_back(n);
     return (int)N.nodes.size() - 1;
   }
@@ -223,6 +227,7 @@ static int build_plan(urn_net& N) {
   for (int i = 0; i < 3; ++i) URN_CHECK(N.sp[i] >= 1, "urn_create: bad spatial dims");
   const int T = N.TA, TG = N.TG, nd = c.nd, B = c.batch, F = c.base_filters, S = c.num_strides;
   Builder b(N);
+  b.shadow = (T == URN_F16 && TG == URN_BF16 && c.impl != URN_IMPL_FFMA && c.training);
 
   struct Cur { int node; int sp[3]; int ch; };
   int sp0[3] = {N.sp[0], N.sp[1], N.sp[2]};
@@ -343,7 +348,8 @@ static int build_plan(urn_net& N) {
   N.loss_ws_off = b.alloc(urn_loss_workspace(rows0));
   N.result_off = b.alloc(64);
   N.wgrad_ws_bytes = 0;
-  for (auto& L : N.layers) N.wgrad_ws_bytes = std::max<int64_t>(N.wgrad_ws_bytes, wgrad_ffma_workspace(L.d));
+  for (auto& L : N.layers)
+    N.wgrad_ws_bytes = std::max<int64_t>(N.wgrad_ws_bytes, std::max<int64_t>(wgrad_ffma_workspace(L.d), wgrad_tc_workspace(L.d)));
   N.wgrad_ws_off = b.alloc(N.wgrad_ws_bytes);
   if (T != URN_F32) {
     N.wq_off = b.alloc(N.param_total * 4);
@@ -511,10 +517,13 @@ extern "C" int urn_layer_info(const urn_net* h, int layer, const char** scope, u
 namespace {
 
 template <typename TT>
-__global__ void convert_in_kernel(const float* __restrict__ src, long long n, TT* __restrict__ dst) {
+__global__ void convert_in_kernel(const float* __restrict__ src, long long n, TT* __restrict__ dst,
+                                  bf16* __restrict__ dst2) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
-       i += (long long)gridDim.x * blockDim.x)
+       i += (long long)gridDim.x * blockDim.x) {
     st1(dst + i, src[i]);
+    if (dst2) st1(dst2 + i, src[i]);
+  }
 }
 
 inline char* P(void* ws, int64_t off) { return (char*)ws + off; }
@@ -606,7 +615,8 @@ extern "C" int urn_forward(urn_net* h, const float* params, const float* data, v
     unsigned nb = (unsigned)std::min<long long>((n + 255) / 256, 148 * 16);
     if (dispatch_dtype(dn.dtype, [&](auto pt) {
           using TT = URN_T(pt);
-          convert_in_kernel<TT><<<nb, 256, 0, st>>>(data, n, (TT*)P(ws, dn.off));
+          convert_in_kernel<TT><<<nb, 256, 0, st>>>(data, n, (TT*)P(ws, dn.off),
+                                                    dn.off2 >= 0 ? (bf16*)P(ws, dn.off2) : nullptr);
           return 0;
         }))
       return 1;
@@ -650,7 +660,8 @@ extern "C" int urn_forward(urn_net* h, const float* params, const float* data, v
       const Node& o = h->nodes[s.out_node];
       if (urn_bn_apply((const float*)P(ws, L.raw_off), L.cout, L.rows_out, L.cout,
                        (const float*)P(ws, L.stats_off), params + L.b_off, nullptr, 0, 0, nullptr,
-                       0, nullptr, nullptr, s.relu, P(ws, o.off), o.ld, o.dtype, st))
+                       0, nullptr, nullptr, s.relu, P(ws, o.off), o.ld, o.dtype,
+                       o.off2 >= 0 ? P(ws, o.off2) : nullptr, st))
         return 1;
     } else {  // F_MERGE: relu(BN(conv2) + shortcut)
       ProfScope ps(h, s.layer, PH_APPLY, st);
@@ -667,7 +678,8 @@ extern "C" int urn_forward(urn_net* h, const float* params, const float* data, v
       }
       if (urn_bn_apply((const float*)P(ws, L.raw_off), L.cout, L.rows_out, L.cout,
                        (const float*)P(ws, L.stats_off), params + L.b_off, res, ldres, rdt, res_raw,
-                       ldrr, res_stats, res_beta, 1, P(ws, o.off), o.ld, o.dtype, st))
+                       ldrr, res_stats, res_beta, 1, P(ws, o.off), o.ld, o.dtype,
+                       o.off2 >= 0 ? P(ws, o.off2) : nullptr, st))
         return 1;
     }
   }
@@ -733,13 +745,22 @@ extern "C" int urn_backward(urn_net* h, const float* params, float* grads, int a
         return 1;
     } else if (s.kind == B_WGRAD) {
       const Node& in = h->nodes[L.in_node];
+      // conv: big side = input activations, small side = d(raw); deconv: big side = d(raw)
+      // activations enter the tensor-core filter gradient through their bf16 shadow copy
+      const bool sh = in.off2 >= 0 && tc_enabled(h) && L.d.cx % 16 == 0 && L.d.cy % 16 == 0;
+      const void* act = P(ws, sh ? in.off2 : in.off);
+      const int adt = sh ? URN_BF16 : in.dtype;
+      const void* xp = L.transpose ? (const void*)draw(L) : act;
+      const void* yp = L.transpose ? act : (const void*)draw(L);
+      const int xdt = L.transpose ? T : adt, ydt = L.transpose ? adt : T;
+      const int64_t ldx = L.transpose ? L.cout : in.ld, ldy = L.transpose ? in.ld : L.cout;
       int rc;
-      if (!L.transpose)
-        rc = wgrad_ffma_launch(L.d, in.dtype, P(ws, in.off), in.ld, T, draw(L), L.cout,
-                               grads + L.w_off, accumulate, P(ws, h->wgrad_ws_off), st);
-      else  // deconv: big side = its output gradient, small side = its input
-        rc = wgrad_ffma_launch(L.d, T, draw(L), L.cout, in.dtype, P(ws, in.off), in.ld,
-                               grads + L.w_off, accumulate, P(ws, h->wgrad_ws_off), st);
+      if (tc_enabled(h) && wgrad_tc_supported(L.d, xdt, ydt, ldx, ldy))
+        rc = wgrad_tc_launch(L.d, xdt, xp, ldx, ydt, yp, ldy, grads + L.w_off, accumulate,
+                             P(ws, h->wgrad_ws_off), st);
+      else
+        rc = wgrad_ffma_launch(L.d, xdt, xp, ldx, ydt, yp, ldy, grads + L.w_off, accumulate,
+                               P(ws, h->wgrad_ws_off), st);
       if (rc) return 1;
     } else {  // B_DGRAD
       const Node& in = h->nodes[L.in_node];
