@@ -1,0 +1,104 @@
+"""CPU tests of the host-side mirror of the reference interface: config reader, synthetic IO
+source, bucket planning, class-level validation (no GPU, no compute calls)."""
+import os
+
+import numpy as np
+import pytest
+
+from uresnet_b200 import dp, synthetic_io as S
+from uresnet_b200.config import ssnet_config
+from uresnet_b200.uresnet import uresnet
+
+REF_CFG = "/root/reference/config"
+
+
+def write(tmp_path, text, name="a.cfg"):
+    p = tmp_path / name
+    p.write_text(text)
+    return str(p)
+
+
+def test_config_defaults_match_reference_schema():
+    c = ssnet_config()
+    assert (c.NUM_CLASS, c.BASE_NUM_FILTERS, c.MINIBATCH_SIZE, c.NUM_MINIBATCHES) == (3, 16, 10, 5)
+    assert c.LEARNING_RATE == -1 and c.TF_RANDOM_SEED == 1234 and c.USE_WEIGHTS is True
+    assert c.CHECKPOINT_NHOUR == 0.4 and c.KEYWORD_DATA == 'data'
+    ref_keys = {"NUM_CLASS", "BASE_NUM_FILTERS", "MAIN_INPUT_CONFIG", "TEST_INPUT_CONFIG", "ANA_OUTPUT_CONFIG",
+                "LOGDIR", "SAVE_FILE", "LOAD_FILE", "AVOID_LOAD_PARAMS", "LEARNING_RATE", "MINIBATCH_SIZE",
+                "NUM_MINIBATCHES", "TEST_BATCH_SIZE", "ITERATIONS", "TF_RANDOM_SEED", "TRAIN", "DEBUG",
+                "USE_WEIGHTS", "REPORT_STEPS", "SUMMARY_STEPS", "CHECKPOINT_STEPS", "CHECKPOINT_NMAX",
+                "CHECKPOINT_NHOUR", "KEYWORD_DATA", "KEYWORD_LABEL", "KEYWORD_WEIGHT", "KEYWORD_TEST_DATA",
+                "KEYWORD_TEST_LABEL", "KEYWORD_TEST_WEIGHT"}
+    assert ref_keys <= set(ssnet_config._keys())
+
+
+def test_config_override_rules(tmp_path, capsys):
+    c = ssnet_config()
+    c.override(write(tmp_path, "NUM_CLASS 4   # comment\nLEARNING_RATE 0.001\nthree tokens here\nUNKNOWN_KEY 1\n"
+                               "SAVE_FILE './w'\nAVOID_LOAD_PARAMS ['a:0']\n"))
+    assert c.NUM_CLASS == 4 and c.LEARNING_RATE == 0.001 and c.SAVE_FILE == './w' and c.AVOID_LOAD_PARAMS == ['a:0']
+    out = capsys.readouterr().out
+    assert "Ignoring a line: three tokens here" in out and "Ignoring a parameter in file: UNKNOWN_KEY" in out
+    with pytest.raises(TypeError):
+        c.override(write(tmp_path, "NUM_CLASS 4.5\n", "b.cfg"))        # type must match the default's
+    with pytest.raises(IOError):
+        c.override(str(tmp_path / "missing.cfg"))
+    with pytest.raises(TypeError):
+        c.override(write(tmp_path, "LOGDIR __import__('os')\n", "c.cfg"))   # literals only, no exec
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_CFG), reason="reference configs not present on this box")
+@pytest.mark.parametrize("name", ["train2d.cfg", "train3d.cfg", "ana2d.cfg", "ana3d.cfg", "default2d.cfg", "ana2d_no_out.cfg"])
+def test_reference_cfg_files_load(name):
+    c = ssnet_config()
+    c.override(os.path.join(REF_CFG, name))          # ana3d.cfg's unknown DUMP_IMAGE is tolerated
+    assert c.NUM_CLASS == 3
+
+
+def test_config_dump_format(capsys):
+    ssnet_config().dump()
+    lines = capsys.readouterr().out.splitlines()
+    assert lines[0] == "NUM_CLASS........... 3"
+
+
+def test_synthetic_source_interface():
+    io = S.synthetic_threadio()
+    io.configure({'filler_name': 'MainIO', 'verbosity': 0, 'filler_cfg': 'x.cfg', 'dims': [32, 32, 1],
+                  'keyword_data': 'main_data', 'keyword_label': 'main_label', 'keyword_weight': 'main_weight'})
+    io.start_manager(3)
+    io.next()
+    d = io.fetch_data('main_data')
+    assert d.dim() == [3, 32, 32, 1] and d.data().shape == (3, 1024) and d.data().dtype == np.float32
+    lab, w = io.fetch_data('main_label').data(), io.fetch_data('main_weight').data()
+    assert set(np.unique(lab)) <= {0.0, 1.0, 2.0} and (w > 0).all()
+    assert ((d.data() > 0) == (lab > 0)).all()              # nonzero pixels carry a class
+    first = d.data().copy()
+    io.next()
+    assert not np.array_equal(first, io.fetch_data('main_data').data())
+    assert list(io.fetch_entries()) == [3, 4, 5]
+    a = S.make_batch(2, [16, 16, 16, 1], seed=5)
+    b = S.make_batch(2, [16, 16, 16, 1], seed=5)
+    assert all(np.array_equal(x, y) for x, y in zip(a, b))  # deterministic
+
+
+def test_dims_validation_matches_reference():
+    with pytest.raises(NotImplementedError):       # ssnet.py:12-14
+        uresnet(dims=[32, 32], num_class=3)
+    with pytest.raises(NotImplementedError):
+        uresnet(dims=[2, 3, 4, 5, 6], num_class=3)
+    n = uresnet(dims=[64, 64, 1], num_class=3, num_strides=5, base_num_outputs=16, debug=True)
+    assert n._build(None) == dict(nd=2, spatial=[64, 64], in_channels=1, base_filters=16, num_strides=5)
+
+
+def test_bucket_plan_covers_everything_in_backward_order():
+    ranges, off = [], 0
+    for n in (100, 3000, 50, 70000, 10, 10, 500000, 64):
+        ranges.append((off, off + n))
+        off += n
+    buckets = dp.plan_buckets(ranges, 4000)
+    seen = [l for _, _, ls in buckets for l in ls]
+    assert seen == list(range(len(ranges) - 1, -1, -1))          # last layer first
+    assert buckets[0][1] == off and buckets[-1][0] == 0
+    for (lo, hi, ls), nxt in zip(buckets, buckets[1:]):
+        assert nxt[1] == lo                                        # contiguous, no gaps
+    assert all(hi - lo >= 4000 for lo, hi, _ in buckets[:-1])

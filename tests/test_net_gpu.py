@@ -246,3 +246,50 @@ def test_full_size_properties_2d():
     net2 = make_net(dims, 16, 5, 3, "mix16", use_weight=False, trainable=False)
     sm = net2.inference(None, data)[0]
     assert np.allclose(sm.sum(-1), 1.0, atol=1e-5)
+
+
+def test_trainval_driver_train_checkpoint_and_ana(tmp_path, capsys):
+    """The drop-in driver (lib/ssnet_trainval.py mirror): cfg override, train_step loop with the
+    reference's report format, npz checkpoint with TF variable names, LOAD_FILE / iteration from
+    the file-name suffix, ana_step result dictionary."""
+    from uresnet_b200.ssnet_trainval import ssnet_trainval
+    cfg = tmp_path / "train.cfg"
+    cfg.write_text("\n".join([
+        "NUM_CLASS 3", "BASE_NUM_FILTERS 4", "MAIN_INPUT_CONFIG 'config/input_train2d.cfg'",
+        "LOGDIR '%s'" % (tmp_path / "log"), "SAVE_FILE '%s'" % (tmp_path / "w" / "uresnet"),
+        "ITERATIONS 4", "MINIBATCH_SIZE 2", "NUM_MINIBATCHES 2", "TRAIN True", "USE_WEIGHTS True",
+        "CHECKPOINT_STEPS 2", "SUMMARY_STEPS 2", "REPORT_STEPS 1", "LEARNING_RATE 0.001",
+        "KEYWORD_DATA 'main_data'", "KEYWORD_LABEL 'main_label'", "KEYWORD_WEIGHT 'main_weight'",
+        "SYNTHETIC_DIMS [64,64,1]", "DTYPE 'f32'"]))
+    t = ssnet_trainval()
+    t.override_config(str(cfg))
+    t.initialize()
+    t.batch_process()
+    out = capsys.readouterr().out
+    assert "@ iteration 0 LR 0.001 Mem" in out and "Train set: loss=" in out and "acc. nonzero=" in out
+    assert t.current_iteration() == 3
+    ck = sorted((tmp_path / "w").glob("uresnet-*.npz"))
+    assert [p.name for p in ck] == ["uresnet-1.npz", "uresnet-3.npz"]
+    z = np.load(ck[-1])
+    assert z["UResNet/conv0/weights"].shape == (3, 3, 1, 4) and "UResNet/conv0/BatchNorm/moving_variance" in z
+    assert (tmp_path / "log" / "train" / "scalars.jsonl").read_text().count("\n") == 2
+    saved = t._net.get_variables()
+    t.reset()
+    # inference from the checkpoint
+    cfg2 = tmp_path / "ana.cfg"
+    cfg2.write_text("\n".join([
+        "NUM_CLASS 3", "BASE_NUM_FILTERS 4", "MAIN_INPUT_CONFIG 'config/input_ana2d.cfg'", "LOGDIR ''", "SAVE_FILE ''",
+        "LOAD_FILE '%s'" % str(ck[-1])[:-4], "AVOID_LOAD_PARAMS ['UResNet/conv2/BatchNorm/beta:0']",
+        "MINIBATCH_SIZE 2", "ITERATIONS 2", "TRAIN False", "USE_WEIGHTS False",
+        "KEYWORD_DATA 'main_data'", "KEYWORD_LABEL 'main_label'", "SYNTHETIC_DIMS [64,64,1]", "DTYPE 'f32'"]))
+    a = ssnet_trainval()
+    a.override_config(str(cfg2))
+    a.initialize()
+    assert a.current_iteration() == 3                       # recovered from the '-3' suffix
+    v = a._net.get_variables()
+    assert np.array_equal(v["UResNet/conv1/weights"], saved["UResNet/conv1/weights"])
+    assert np.all(v["UResNet/conv2/BatchNorm/beta"] == 0)   # skipped by AVOID_LOAD_PARAMS
+    res = a.ana_step()
+    assert res["softmax"].shape == (2, 64, 64, 3) and res["input"].shape == (2, 64, 64, 1)
+    assert 0.0 <= res["acc_all"] <= 1.0 and set(res) == {"entries", "input", "label", "softmax", "acc_all", "acc_nonzero"}
+    a.reset()
