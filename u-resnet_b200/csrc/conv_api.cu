@@ -190,7 +190,7 @@ extern "C" int urn_conv_fwd_tc(const urn_conv_desc* d, int dtype, const void* x,
   g.accumulate = accumulate;
   URN_CHECK(gconv_tc_supported(g, dtype, y_dtype), "urn_conv_fwd_tc: shape/dtype not supported by the tcgen05 path");
   if (pack_filter(*d, dtype, w, wpack, true, st)) return 1;
-  return gconv_tc_launch(g, dtype, x, wpack, y, y_dtype, st);
+  return gconv_tc_auto(g, dtype, x, wpack, y, y_dtype, st);
 }
 
 extern "C" int urn_conv_dgrad_tc(const urn_conv_desc* d, int dtype, const void* dy, int64_t ldy,
@@ -209,7 +209,7 @@ extern "C" int urn_conv_dgrad_tc(const urn_conv_desc* d, int dtype, const void* 
           continue;
         }
         URN_CHECK(gconv_tc_supported(g, dtype, x_dtype), "urn_conv_dgrad_tc: shape/dtype not supported by the tcgen05 path");
-        if (gconv_tc_launch(g, dtype, dy, wpack, dx, x_dtype, st)) return 1;
+        if (gconv_tc_auto(g, dtype, dy, wpack, dx, x_dtype, st)) return 1;
       }
   return 0;
 }

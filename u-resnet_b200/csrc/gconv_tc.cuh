@@ -18,3 +18,14 @@ bool wgrad_tc_supported(const urn_conv_desc& d, int x_dtype, int y_dtype, int64_
 int64_t wgrad_tc_workspace(const urn_conv_desc& d);
 int wgrad_tc_launch(const urn_conv_desc& d, int x_dtype, const void* x, int64_t ldx, int y_dtype,
                     const void* y, int64_t ldy, float* dw, int accumulate, void* ws, cudaStream_t st);
+
+// Halo-tile variant for narrow stride-1 3x3(x3) layers (gconv_halo.cu); same wpack layout.
+bool gconv_halo_supported(const GConv& g, int in_dtype, int out_dtype);
+int gconv_halo_launch(const GConv& g, int in_dtype, const void* in, const void* wpack, void* out,
+                      int out_dtype, cudaStream_t st);
+// Picks the best tensor-core kernel for the shape.
+static inline int gconv_tc_auto(const GConv& g, int in_dtype, const void* in, const void* wpack, void* out,
+                                int out_dtype, cudaStream_t st) {
+  if (gconv_halo_supported(g, in_dtype, out_dtype)) return gconv_halo_launch(g, in_dtype, in, wpack, out, out_dtype, st);
+  return gconv_tc_launch(g, in_dtype, in, wpack, out, out_dtype, st);
+}

@@ -565,7 +565,7 @@ inline bool tc_enabled(const urn_net* h) { return h->wpg_off >= 0; }
 inline int run_gconv(const urn_net* h, const GConv& g, int in_dtype, const void* in, const float* w_f32,
                      const void* w_pack, void* out, int out_dtype, cudaStream_t st) {
   if (tc_enabled(h) && gconv_tc_supported(g, in_dtype, out_dtype))
-    return gconv_tc_launch(g, in_dtype, in, w_pack, out, out_dtype, st);
+    return gconv_tc_auto(g, in_dtype, in, w_pack, out, out_dtype, st);
   return gconv_ffma_launch(g, in_dtype, in, w_f32, out, out_dtype, st);
 }
 
