@@ -7,7 +7,7 @@
 namespace {
 
 constexpr int BN_THREADS = 256;
-constexpr int BN_MAX_BLOCKS = 148 * 8;
+constexpr int BN_MAX_BLOCKS = 148 * 4;
 
 struct ColMap {
   int vec;     // 4 or 1
@@ -58,6 +58,7 @@ bn_stats_kernel(const float* __restrict__ raw, long long ld, long long rows, int
     // cancel catastrophically on nearly-constant channels.
     float K[4] = {0.f, 0.f, 0.f, 0.f};
     for (int v = 0; v < m.vec; ++v) K[v] = raw[g * m.vec + v];
+#pragma unroll 4
     for (long long r = (long long)blockIdx.x * m.lanes + lane; r < rows;
          r += (long long)gridDim.x * m.lanes) {
       const float* p = raw + r * ld + g * m.vec;
@@ -77,21 +78,44 @@ bn_stats_kernel(const float* __restrict__ raw, long long ld, long long rows, int
   block_col_reduce<2>(acc, m, c, partial);
 }
 
-__global__ void bn_stats_finalize_kernel(const double* __restrict__ partial, int nblocks, int c,
-                                         long long rows, float eps, const float* __restrict__ raw,
-                                         float* __restrict__ stats) {
-  int ch = blockIdx.x * blockDim.x + threadIdx.x;
-  if (ch >= c) return;
-  double s = 0.0, q = 0.0;
-  for (int b = 0; b < nblocks; ++b) {
-    s += partial[((long long)b * 2 + 0) * c + ch];
-    q += partial[((long long)b * 2 + 1) * c + ch];
+// Deterministic parallel second stage: one block per channel, thread t adds partials
+// t, t+128, ... in double, then a fixed-shape shared-memory tree.
+template <int K>
+__device__ __forceinline__ void channel_partial_sum(const double* __restrict__ partial, int nblocks, int c,
+                                                    int ch, double (&out)[K]) {
+  __shared__ double sh[K][128];
+  double acc[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) acc[k] = 0.0;
+  for (int b = threadIdx.x; b < nblocks; b += 128)
+#pragma unroll
+    for (int k = 0; k < K; ++k) acc[k] += partial[((long long)b * K + k) * c + ch];
+#pragma unroll
+  for (int k = 0; k < K; ++k) sh[k][threadIdx.x] = acc[k];
+  __syncthreads();
+  for (int o = 64; o > 0; o >>= 1) {
+    if (threadIdx.x < o)
+#pragma unroll
+      for (int k = 0; k < K; ++k) sh[k][threadIdx.x] += sh[k][threadIdx.x + o];
+    __syncthreads();
   }
-  double dm = s / (double)rows;                 // mean of (x - K)
-  double var = q / (double)rows - dm * dm;
-  if (var < 0.0) var = 0.0;
-  stats[ch] = (float)((double)raw[ch] + dm);
-  stats[c + ch] = (float)(1.0 / sqrt(var + (double)eps));
+#pragma unroll
+  for (int k = 0; k < K; ++k) out[k] = sh[k][0];
+}
+
+__global__ void __launch_bounds__(128)
+bn_stats_finalize_kernel(const double* __restrict__ partial, int nblocks, int c, long long rows,
+                         float eps, const float* __restrict__ raw, float* __restrict__ stats) {
+  const int ch = blockIdx.x;
+  double v[2];
+  channel_partial_sum<2>(partial, nblocks, c, ch, v);
+  if (threadIdx.x == 0) {
+    const double dm = v[0] / (double)rows;                 // mean of (x - K)
+    double var = v[1] / (double)rows - dm * dm;
+    if (var < 0.0) var = 0.0;
+    stats[ch] = (float)((double)raw[ch] + dm);
+    stats[c + ch] = (float)(1.0 / sqrt(var + (double)eps));
+  }
 }
 
 template <typename TR, typename TO>
@@ -104,6 +128,7 @@ bn_apply_kernel(const float* __restrict__ raw, long long ld, long long rows, int
                 bf16* __restrict__ out2) {
   const int cg = c / vec;
   const long long total = rows * cg;
+#pragma unroll 2
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const long long r = i / cg;
@@ -159,6 +184,7 @@ bn_bwd_reduce_kernel(const T* __restrict__ dout, long long lddout, const TA* __r
       rs[v] = stats[c + ch + v];
       if (raw2) { mu2[v] = stats2[ch + v]; rs2[v] = stats2[c + ch + v]; }
     }
+#pragma unroll 4
     for (long long r = (long long)blockIdx.x * m.lanes + lane; r < rows;
          r += (long long)gridDim.x * m.lanes) {
       float gv[4], xv[4], x2v[4] = {0, 0, 0, 0};
@@ -195,22 +221,19 @@ bn_bwd_reduce_kernel(const T* __restrict__ dout, long long lddout, const TA* __r
 }
 
 // sums[0..c) = sum g ; [c..2c) = sum g*xhat ; [2c..3c) = sum g*xhat2 ; also emits dbeta(2)
-__global__ void bn_bwd_finalize_kernel(const double* __restrict__ partial, int nblocks, int c,
-                                       float* __restrict__ sums, float* __restrict__ dbeta,
-                                       float* __restrict__ dbeta2, int acc_beta) {
-  int ch = blockIdx.x * blockDim.x + threadIdx.x;
-  if (ch >= c) return;
-  double s0 = 0.0, s1 = 0.0, s2 = 0.0;
-  for (int b = 0; b < nblocks; ++b) {
-    s0 += partial[((long long)b * 3 + 0) * c + ch];
-    s1 += partial[((long long)b * 3 + 1) * c + ch];
-    s2 += partial[((long long)b * 3 + 2) * c + ch];
+__global__ void __launch_bounds__(128)
+bn_bwd_finalize_kernel(const double* __restrict__ partial, int nblocks, int c, float* __restrict__ sums,
+                       float* __restrict__ dbeta, float* __restrict__ dbeta2, int acc_beta) {
+  const int ch = blockIdx.x;
+  double v[3];
+  channel_partial_sum<3>(partial, nblocks, c, ch, v);
+  if (threadIdx.x == 0) {
+    sums[ch] = (float)v[0];
+    sums[c + ch] = (float)v[1];
+    sums[2 * c + ch] = (float)v[2];
+    if (dbeta) dbeta[ch] = acc_beta ? dbeta[ch] + (float)v[0] : (float)v[0];
+    if (dbeta2) dbeta2[ch] = acc_beta ? dbeta2[ch] + (float)v[0] : (float)v[0];
   }
-  sums[ch] = (float)s0;
-  sums[c + ch] = (float)s1;
-  sums[2 * c + ch] = (float)s2;
-  if (dbeta) dbeta[ch] = acc_beta ? dbeta[ch] + (float)s0 : (float)s0;
-  if (dbeta2) dbeta2[ch] = acc_beta ? dbeta2[ch] + (float)s0 : (float)s0;
 }
 
 // ---- backward: pass 2, elementwise ----
@@ -226,6 +249,7 @@ bn_bwd_apply_kernel(const T* __restrict__ dout, long long lddout, const TA* __re
   const int cg = c / vec;
   const long long total = rows * cg;
   const float inv = 1.0f / (float)rows;
+#pragma unroll 2
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const long long r = i / cg;
@@ -329,7 +353,7 @@ extern "C" int urn_bn_stats(const float* raw, int64_t ld, int64_t rows, int c, f
   double* partial = (double*)ws;
   bn_stats_kernel<<<nb, BN_THREADS, 0, st>>>(raw, ld, rows, c, al, partial);
   URN_LAUNCH_CHECK();
-  bn_stats_finalize_kernel<<<(c + 127) / 128, 128, 0, st>>>(partial, nb, c, rows, eps, raw, stats);
+  bn_stats_finalize_kernel<<<c, 128, 0, st>>>(partial, nb, c, rows, eps, raw, stats);
   URN_LAUNCH_CHECK();
   return 0;
 }
@@ -385,7 +409,7 @@ static int bn_bwd_t(const void* dout, int64_t lddout, const void* out, int64_t l
                                                      relu, rows, c, al, raw, ldraw, stats, raw2,
                                                      ldraw2, stats2, partial);
   URN_LAUNCH_CHECK();
-  bn_bwd_finalize_kernel<<<(c + 127) / 128, 128, 0, st>>>(partial, nb, c, sums, dbeta,
+  bn_bwd_finalize_kernel<<<c, 128, 0, st>>>(partial, nb, c, sums, dbeta,
                                                           raw2 ? dbeta2 : nullptr, acc_beta);
   URN_LAUNCH_CHECK();
   int vec = al ? 4 : 1;

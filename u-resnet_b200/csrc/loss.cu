@@ -69,14 +69,23 @@ ce_kernel(const float* __restrict__ logits, long long ld, const float* __restric
   }
 }
 
-__global__ void ce_finalize_kernel(const double* __restrict__ partial, int nblocks, double inv_batch,
-                                   double* __restrict__ result) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) {
-    double l = 0.0, a = 0.0, b = 0.0, d = 0.0;
-    for (int i = 0; i < nblocks; ++i) {
-      l += partial[i * 4 + 0]; a += partial[i * 4 + 1]; b += partial[i * 4 + 2]; d += partial[i * 4 + 3];
-    }
-    result[0] = l * inv_batch; result[1] = a; result[2] = b; result[3] = d;
+__global__ void __launch_bounds__(128)
+ce_finalize_kernel(const double* __restrict__ partial, int nblocks, double inv_batch,
+                   double* __restrict__ result) {
+  // fixed-shape (deterministic) parallel sum of the per-block partials
+  __shared__ double sh[4][128];
+  double acc[4] = {0.0, 0.0, 0.0, 0.0};
+  for (int b = threadIdx.x; b < nblocks; b += 128)
+    for (int k = 0; k < 4; ++k) acc[k] += partial[b * 4 + k];
+  for (int k = 0; k < 4; ++k) sh[k][threadIdx.x] = acc[k];
+  __syncthreads();
+  for (int o = 64; o > 0; o >>= 1) {
+    if (threadIdx.x < o)
+      for (int k = 0; k < 4; ++k) sh[k][threadIdx.x] += sh[k][threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    result[0] = sh[0][0] * inv_batch; result[1] = sh[1][0]; result[2] = sh[2][0]; result[3] = sh[3][0];
   }
 }
 
@@ -149,7 +158,7 @@ extern "C" int urn_ce_fwd_bwd(const float* logits, int64_t ld, const float* labe
       }))
     return 1;
   URN_LAUNCH_CHECK();
-  ce_finalize_kernel<<<1, 32, 0, st>>>(partial, nb, 1.0 / (double)batch, result);
+  ce_finalize_kernel<<<1, 128, 0, st>>>(partial, nb, 1.0 / (double)batch, result);
   URN_LAUNCH_CHECK();
   return 0;
 }
