@@ -68,6 +68,32 @@ CONV_CASES = [
 @pytest.mark.parametrize("dt", [F32, BF16, F16])
 @pytest.mark.parametrize("nd,n,sp,cin,cout,k,s", CONV_CASES)
 def test_conv_fwd_dgrad_wgrad(lib, dt, nd, n, sp, cin, cout, k, s):
+    _conv_case(lib, dt, 1, nd, n, sp, cin, cout, k, s)
+
+
+STEM_HEAD_CASES = [
+    # dedicated stem (Cin = 1) / head (Cout <= 4) kernels of stemhead.cu, reached with impl = auto
+    (2, 2, (16, 24), 1, 16, 3, 1),
+    (2, 1, (9, 20), 1, 8, 3, 1),
+    (2, 3, (7, 36), 1, 16, 3, 1),        # rows not a multiple of the warp tile
+    (3, 1, (6, 5, 12), 1, 16, 3, 1),
+    (3, 2, (4, 4, 8), 1, 8, 3, 1),
+    (2, 2, (9, 14), 16, 3, 3, 1),
+    (2, 1, (12, 11), 8, 3, 3, 1),
+    (2, 1, (8, 8), 16, 2, 3, 1),
+    (2, 1, (8, 8), 16, 4, 3, 1),
+    (3, 1, (5, 6, 7), 16, 3, 3, 1),
+    (3, 2, (4, 6, 6), 8, 3, 3, 1),
+]
+
+
+@pytest.mark.parametrize("dt", [F32, BF16, F16])
+@pytest.mark.parametrize("nd,n,sp,cin,cout,k,s", STEM_HEAD_CASES)
+def test_stem_head_dedicated(lib, dt, nd, n, sp, cin, cout, k, s):
+    _conv_case(lib, dt, 0, nd, n, sp, cin, cout, k, s)
+
+
+def _conv_case(lib, dt, impl, nd, n, sp, cin, cout, k, s):
     rng = np.random.default_rng(hash((nd, n, sp, cin, cout, k, s)) % 2**32)
     x = rng.standard_normal((n,) + sp + (cin,)).astype(np.float32)
     w = (rng.standard_normal((k,) * nd + (cin, cout)) / np.sqrt(k**nd * cin)).astype(np.float32)
@@ -86,22 +112,22 @@ def test_conv_fwd_dgrad_wgrad(lib, dt, nd, n, sp, cin, cout, k, s):
     # forward
     xd, wd = dev(x, dt), dev(w)
     y = torch.empty((n,) + osp + (cout,), dtype=torch.float32, device=DEV)
-    _capi.check(lib.urn_conv_fwd(C.byref(d), dt, 1, xd.data_ptr(), cin, wd.data_ptr(), y.data_ptr(), cout, F32, st()))
+    _capi.check(lib.urn_conv_fwd(C.byref(d), dt, impl, xd.data_ptr(), cin, wd.data_ptr(), y.data_ptr(), cout, F32, st()))
     assert relerr(host(y), cl(yo.detach())) < 2e-5
     # dgrad (write, then accumulate)
     gd = dev(g_cl, gdt(dt))
     dx = torch.full((n,) + sp + (cin,), 7.0, dtype=TORCH_DT[gdt(dt)], device=DEV)
-    _capi.check(lib.urn_conv_dgrad(C.byref(d), gdt(dt), 1, gd.data_ptr(), cout, wd.data_ptr(), dx.data_ptr(), cin, gdt(dt), 0, st()))
+    _capi.check(lib.urn_conv_dgrad(C.byref(d), gdt(dt), impl, gd.data_ptr(), cout, wd.data_ptr(), dx.data_ptr(), cin, gdt(dt), 0, st()))
     assert relerr(host(dx), dxo.numpy()) < TOL[dt]
-    _capi.check(lib.urn_conv_dgrad(C.byref(d), gdt(dt), 1, gd.data_ptr(), cout, wd.data_ptr(), dx.data_ptr(), cin, gdt(dt), 1, st()))
+    _capi.check(lib.urn_conv_dgrad(C.byref(d), gdt(dt), impl, gd.data_ptr(), cout, wd.data_ptr(), dx.data_ptr(), cin, gdt(dt), 1, st()))
     assert relerr(host(dx), 2 * dxo.numpy()) < 2 * TOL[dt]
     # wgrad
     wsb = lib.urn_conv_wgrad_workspace(C.byref(d))
     ws = torch.empty(max(int(wsb), 16), dtype=torch.uint8, device=DEV)
     dw = torch.full(w.shape, 3.0, dtype=torch.float32, device=DEV)
-    _capi.check(lib.urn_conv_wgrad(C.byref(d), dt, 1, xd.data_ptr(), cin, gd.data_ptr(), cout, gdt(dt), dw.data_ptr(), 0, ws.data_ptr(), st()))
+    _capi.check(lib.urn_conv_wgrad(C.byref(d), dt, impl, xd.data_ptr(), cin, gd.data_ptr(), cout, gdt(dt), dw.data_ptr(), 0, ws.data_ptr(), st()))
     assert relerr(host(dw), dwo.numpy()) < 2e-5
-    _capi.check(lib.urn_conv_wgrad(C.byref(d), dt, 1, xd.data_ptr(), cin, gd.data_ptr(), cout, gdt(dt), dw.data_ptr(), 1, ws.data_ptr(), st()))
+    _capi.check(lib.urn_conv_wgrad(C.byref(d), dt, impl, xd.data_ptr(), cin, gd.data_ptr(), cout, gdt(dt), dw.data_ptr(), 1, ws.data_ptr(), st()))
     assert relerr(host(dw), 2 * dwo.numpy()) < 4e-5
 
 

@@ -113,6 +113,10 @@ extern "C" int urn_conv_fwd(const urn_conv_desc* d, int dtype, int impl, const v
   URN_CHECK(ldx >= d->cx && ldy >= d->cy, "urn_conv_fwd: pitch smaller than channel count");
   URN_CHECK(impl != URN_IMPL_TC, "urn_conv_fwd: the tcgen05 path runs through the net handle "
             "(packed bf16 filters); per-kernel entry is urn_tc_conv");
+  if (impl == URN_IMPL_AUTO && y_dtype == URN_F32) {     // dedicated stem / head kernels (stemhead.cu)
+    if (stem_supported(*d, ldx, ldy)) return stem_fwd_launch(*d, dtype, x, ldx, w, (float*)y, ldy, (cudaStream_t)stream);
+    if (head_supported(*d, ldx, ldy)) return head_fwd_launch(*d, dtype, x, ldx, w, (float*)y, ldy, (cudaStream_t)stream);
+  }
   GConv g;
   gconv_gather(*d, ldx, ldy, &g);
   return gconv_ffma_launch(g, dtype, x, w, y, y_dtype, (cudaStream_t)stream);
@@ -124,6 +128,8 @@ extern "C" int urn_conv_dgrad(const urn_conv_desc* d, int dtype, int impl, const
   if (check_desc(d)) return 1;
   URN_CHECK(ldx >= d->cx && ldy >= d->cy, "urn_conv_dgrad: pitch smaller than channel count");
   URN_CHECK(impl != URN_IMPL_TC, "urn_conv_dgrad: tcgen05 path runs through the net handle");
+  if (impl == URN_IMPL_AUTO && x_dtype == dtype && head_supported(*d, ldx, ldy) && ldx % 4 == 0)
+    return head_dgrad_launch(*d, dtype, dy, ldy, w, dx, ldx, accumulate, (cudaStream_t)stream);
   for (int pd = 0; pd < d->s; ++pd)
     for (int ph = 0; ph < d->s; ++ph)
       for (int pw = 0; pw < d->s; ++pw) {
@@ -136,7 +142,7 @@ extern "C" int urn_conv_dgrad(const urn_conv_desc* d, int dtype, int impl, const
 
 extern "C" int64_t urn_conv_wgrad_workspace(const urn_conv_desc* d) {
   if (check_desc(d)) return -1;
-  return std::max<int64_t>(wgrad_ffma_workspace(*d), wgrad_tc_workspace(*d));
+  return std::max<int64_t>(std::max<int64_t>(wgrad_ffma_workspace(*d), wgrad_tc_workspace(*d)), stemhead_wgrad_workspace(*d));
 }
 
 extern "C" int urn_conv_wgrad(const urn_conv_desc* d, int dtype, int impl, const void* x, int64_t ldx,
@@ -147,6 +153,12 @@ extern "C" int urn_conv_wgrad(const urn_conv_desc* d, int dtype, int impl, const
   if (impl == URN_IMPL_TC) {
     URN_CHECK(wgrad_tc_supported(*d, dtype, y_dtype, ldx, ldy), "urn_conv_wgrad: shape/dtype not supported by the tcgen05 path");
     return wgrad_tc_launch(*d, dtype, x, ldx, y_dtype, y, ldy, dw, accumulate, ws, (cudaStream_t)stream);
+  }
+  if (impl == URN_IMPL_AUTO) {
+    if (stem_supported(*d, ldx, d->cy) && ldy % 4 == 0)
+      return stem_wgrad_launch(*d, dtype, x, ldx, y_dtype, y, ldy, dw, accumulate, ws, (cudaStream_t)stream);
+    if (head_supported(*d, ldx, ldy))
+      return head_wgrad_launch(*d, dtype, x, ldx, y_dtype, y, ldy, dw, accumulate, ws, (cudaStream_t)stream);
   }
   return wgrad_ffma_launch(*d, dtype, x, ldx, y_dtype, y, ldy, dw, accumulate, ws, (cudaStream_t)stream);
 }

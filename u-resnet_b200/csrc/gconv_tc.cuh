@@ -29,3 +29,18 @@ static inline int gconv_tc_auto(const GConv& g, int in_dtype, const void* in, co
   if (gconv_halo_supported(g, in_dtype, out_dtype)) return gconv_halo_launch(g, in_dtype, in, wpack, out, out_dtype, st);
   return gconv_tc_launch(g, in_dtype, in, wpack, out, out_dtype, st);
 }
+
+// Dedicated CUDA-core kernels for the stem (Cin = 1) and the head (Cout <= 4) -- stemhead.cu.
+bool stem_supported(const urn_conv_desc& d, int64_t ldx, int64_t ldy);
+bool head_supported(const urn_conv_desc& d, int64_t ldx, int64_t ldy);
+int64_t stemhead_wgrad_workspace(const urn_conv_desc& d);
+int stem_fwd_launch(const urn_conv_desc& d, int x_dtype, const void* x, int64_t ldx, const float* w,
+                    float* y, int64_t ldy, cudaStream_t st);
+int stem_wgrad_launch(const urn_conv_desc& d, int x_dtype, const void* x, int64_t ldx, int g_dtype,
+                      const void* dy, int64_t ldy, float* dw, int accumulate, void* ws, cudaStream_t st);
+int head_fwd_launch(const urn_conv_desc& d, int x_dtype, const void* x, int64_t ldx, const float* w,
+                    float* y, int64_t ldy, cudaStream_t st);
+int head_dgrad_launch(const urn_conv_desc& d, int g_dtype, const void* dy, int64_t ldy, const float* w,
+                      void* dx, int64_t ldx, int accumulate, cudaStream_t st);
+int head_wgrad_launch(const urn_conv_desc& d, int x_dtype, const void* x, int64_t ldx, int g_dtype,
+                      const void* dy, int64_t ldy, float* dw, int accumulate, void* ws, cudaStream_t st);

@@ -349,7 +349,7 @@ static int build_plan(urn_net& N) {
   N.result_off = b.alloc(64);
   N.wgrad_ws_bytes = 0;
   for (auto& L : N.layers)
-    N.wgrad_ws_bytes = std::max<int64_t>(N.wgrad_ws_bytes, std::max<int64_t>(wgrad_ffma_workspace(L.d), wgrad_tc_workspace(L.d)));
+    N.wgrad_ws_bytes = std::max<int64_t>(N.wgrad_ws_bytes, std::max<int64_t>(std::max<int64_t>(wgrad_ffma_workspace(L.d), wgrad_tc_workspace(L.d)), stemhead_wgrad_workspace(L.d)));
   N.wgrad_ws_off = b.alloc(N.wgrad_ws_bytes);
   if (T != URN_F32) {
     N.wq_off = b.alloc(N.param_total * 4);
@@ -583,7 +583,12 @@ int run_conv_fwd(urn_net* h, int li, const float* params, void* ws, cudaStream_t
   const float* w = conv_weights(h, L, params, ws);
   {
   ProfScope ps(h, li, PH_CONV, st);
-  if (!L.transpose) {
+  const bool ded = h->cfg.impl != URN_IMPL_FFMA;     // dedicated stem / head kernels (stemhead.cu)
+  if (!L.transpose && ded && stem_supported(L.d, in.ld, L.cout)) {
+    if (stem_fwd_launch(L.d, in.dtype, P(ws, in.off), in.ld, w, raw, L.cout, st)) return 1;
+  } else if (!L.transpose && ded && head_supported(L.d, in.ld, L.cout)) {
+    if (head_fwd_launch(L.d, in.dtype, P(ws, in.off), in.ld, w, raw, L.cout, st)) return 1;
+  } else if (!L.transpose) {
     GConv g;
     gconv_gather(L.d, in.ld, L.cout, &g);
     if (run_gconv(h, g, in.dtype, P(ws, in.off), w, P(ws, h->wpg_off + L.w_off * 2), raw, URN_F32, st)) return 1;
@@ -755,7 +760,12 @@ extern "C" int urn_backward(urn_net* h, const float* params, float* grads, int a
       const int xdt = L.transpose ? T : adt, ydt = L.transpose ? adt : T;
       const int64_t ldx = L.transpose ? L.cout : in.ld, ldy = L.transpose ? in.ld : L.cout;
       int rc;
-      if (tc_enabled(h) && wgrad_tc_supported(L.d, xdt, ydt, ldx, ldy))
+      const bool ded = h->cfg.impl != URN_IMPL_FFMA && !L.transpose;
+      if (ded && stem_supported(L.d, ldx, L.cout) && ldy % 4 == 0)
+        rc = stem_wgrad_launch(L.d, xdt, xp, ldx, ydt, yp, ldy, grads + L.w_off, accumulate, P(ws, h->wgrad_ws_off), st);
+      else if (ded && head_supported(L.d, ldx, ldy))
+        rc = head_wgrad_launch(L.d, xdt, xp, ldx, ydt, yp, ldy, grads + L.w_off, accumulate, P(ws, h->wgrad_ws_off), st);
+      else if (tc_enabled(h) && wgrad_tc_supported(L.d, xdt, ydt, ldx, ldy))
         rc = wgrad_tc_launch(L.d, xdt, xp, ldx, ydt, yp, ldy, grads + L.w_off, accumulate,
                              P(ws, h->wgrad_ws_off), st);
       else
@@ -765,7 +775,9 @@ extern "C" int urn_backward(urn_net* h, const float* params, float* grads, int a
     } else {  // B_DGRAD
       const Node& in = h->nodes[L.in_node];
       const float* w = conv_weights(h, L, params, ws, true);   // rounded copy left by urn_forward
-      if (!L.transpose) {
+      if (!L.transpose && h->cfg.impl != URN_IMPL_FFMA && head_supported(L.d, in.ld, L.cout) && in.ld % 4 == 0) {
+        if (head_dgrad_launch(L.d, T, draw(L), L.cout, w, gptr(in), in.ld, s.accumulate, st)) return 1;
+      } else if (!L.transpose) {
         for (int pd = 0; pd < L.d.s; ++pd)
           for (int ph = 0; ph < L.d.s; ++ph)
             for (int pw = 0; pw < L.d.s; ++pw) {
