@@ -204,6 +204,47 @@ def test_conv_tcgen05_wgrad(lib, xdt, ydt, nd, n, sp, cin, cout, k, s):
     assert relerr(host(dw), 2 * dwo.numpy()) < 4e-5
 
 
+HALO_WGRAD_CASES = [
+    # nd, n, spatial, cin, cout, ldx factor  (stride-1 3x3(x3): the halo-tile filter-gradient kernel)
+    (2, 3, (40, 24), 16, 16, 1),         # several tiles per image, ragged in h
+    (2, 2, (33, 19), 16, 32, 1),         # ragged in both dims
+    (2, 1, (32, 16), 32, 16, 2),         # concat slice as X (pitch 2C)
+    (2, 2, (16, 24), 32, 32, 1),
+    (2, 1, (20, 12), 64, 32, 1),
+    (2, 1, (16, 8), 64, 64, 1),
+    (2, 1, (18, 10), 16, 64, 1),
+    (3, 1, (5, 20, 12), 16, 16, 1),
+    (3, 2, (3, 16, 8), 32, 32, 1),
+    (3, 1, (1, 16, 8), 16, 16, 1),       # depth 1: only the central depth tap sees data
+    (3, 1, (52, 16, 8), 16, 16, 1),      # two depth chunks
+    (3, 1, (4, 9, 9), 64, 32, 1),
+    (3, 1, (6, 16, 16), 32, 16, 2),
+]
+
+
+@pytest.mark.parametrize("xdt", [BF16, F16])
+@pytest.mark.parametrize("nd,n,sp,cin,cout,ldf", HALO_WGRAD_CASES)
+def test_conv_halo_wgrad(lib, xdt, nd, n, sp, cin, cout, ldf):
+    """Halo-tile tcgen05 filter gradient (wgrad_halo.cu) against the oracle on pre-rounded operands."""
+    rng = np.random.default_rng(hash((nd, n, sp, cin, cout, ldf, 3)) % 2**32)
+    z = host(dev(rng.standard_normal((n,) + sp + (ldf * cin,)).astype(np.float32), xdt))
+    off = (ldf - 1) * cin
+    x = np.ascontiguousarray(z[..., off:])
+    d = _capi.conv_desc_same(nd, n, sp, cin, cout, 3, 1)
+    g_cl = host(dev(rng.standard_normal((n,) + sp + (cout,)).astype(np.float32), xdt))
+    wt = torch.zeros((3,) * nd + (cin, cout), dtype=torch.float64, requires_grad=True)
+    yo = O.conv_same(cf(x), wt, 1)
+    (dwo,) = torch.autograd.grad(yo, wt, torch.tensor(np.moveaxis(g_cl, -1, 1), dtype=torch.float64))
+    zd, gd = dev(z, xdt), dev(g_cl, xdt)
+    ws = torch.empty(max(int(lib.urn_conv_wgrad_workspace(C.byref(d))), 16), dtype=torch.uint8, device=DEV)
+    dw = torch.full(tuple(wt.shape), 2.0, dtype=torch.float32, device=DEV)
+    _capi.check(lib.urn_conv_wgrad(C.byref(d), xdt, 2, zd.data_ptr() + 2 * off, ldf * cin, gd.data_ptr(), cout, xdt, dw.data_ptr(), 0, ws.data_ptr(), st()))
+    assert relerr(host(dw), dwo.numpy()) < 2e-5
+    _capi.check(lib.urn_conv_wgrad(C.byref(d), xdt, 2, zd.data_ptr() + 2 * off, ldf * cin, gd.data_ptr(), cout, xdt, dw.data_ptr(), 1, ws.data_ptr(), st()))
+    assert relerr(host(dw), 2 * dwo.numpy()) < 4e-5
+    torch.cuda.synchronize()
+
+
 def test_conv_tcgen05_pitched_concat_view(lib):
     """TMA reads a channel slice of a concat buffer (pitch 2C, offset C)."""
     rng = np.random.default_rng(5)

@@ -142,7 +142,7 @@ extern "C" int urn_conv_dgrad(const urn_conv_desc* d, int dtype, int impl, const
 
 extern "C" int64_t urn_conv_wgrad_workspace(const urn_conv_desc* d) {
   if (check_desc(d)) return -1;
-  return std::max<int64_t>(std::max<int64_t>(wgrad_ffma_workspace(*d), wgrad_tc_workspace(*d)), stemhead_wgrad_workspace(*d));
+  return wgrad_any_workspace(*d);
 }
 
 extern "C" int urn_conv_wgrad(const urn_conv_desc* d, int dtype, int impl, const void* x, int64_t ldx,
@@ -152,7 +152,7 @@ extern "C" int urn_conv_wgrad(const urn_conv_desc* d, int dtype, int impl, const
   URN_CHECK(ldx >= d->cx && ldy >= d->cy, "urn_conv_wgrad: pitch smaller than channel count");
   if (impl == URN_IMPL_TC) {
     URN_CHECK(wgrad_tc_supported(*d, dtype, y_dtype, ldx, ldy), "urn_conv_wgrad: shape/dtype not supported by the tcgen05 path");
-    return wgrad_tc_launch(*d, dtype, x, ldx, y_dtype, y, ldy, dw, accumulate, ws, (cudaStream_t)stream);
+    return wgrad_tc_auto(*d, dtype, x, ldx, y_dtype, y, ldy, dw, accumulate, ws, (cudaStream_t)stream);
   }
   if (impl == URN_IMPL_AUTO) {
     if (stem_supported(*d, ldx, d->cy) && ldy % 4 == 0)

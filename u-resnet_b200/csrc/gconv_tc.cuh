@@ -44,3 +44,21 @@ int head_dgrad_launch(const urn_conv_desc& d, int g_dtype, const void* dy, int64
                       void* dx, int64_t ldx, int accumulate, cudaStream_t st);
 int head_wgrad_launch(const urn_conv_desc& d, int x_dtype, const void* x, int64_t ldx, int g_dtype,
                       const void* dy, int64_t ldy, float* dw, int accumulate, void* ws, cudaStream_t st);
+
+// Halo-tile filter gradient for narrow stride-1 3x3(x3) layers (wgrad_halo.cu).
+bool wgrad_halo_supported(const urn_conv_desc& d, int x_dtype, int y_dtype, int64_t ldx, int64_t ldy);
+int64_t wgrad_halo_workspace(const urn_conv_desc& d);
+int wgrad_halo_launch(const urn_conv_desc& d, int x_dtype, const void* x, int64_t ldx, int y_dtype,
+                      const void* y, int64_t ldy, float* dw, int accumulate, void* ws, cudaStream_t st);
+// Best tensor-core filter-gradient kernel for the shape.
+static inline int wgrad_tc_auto(const urn_conv_desc& d, int x_dtype, const void* x, int64_t ldx, int y_dtype,
+                                const void* y, int64_t ldy, float* dw, int accumulate, void* ws, cudaStream_t st) {
+  if (wgrad_halo_supported(d, x_dtype, y_dtype, ldx, ldy))
+    return wgrad_halo_launch(d, x_dtype, x, ldx, y_dtype, y, ldy, dw, accumulate, ws, st);
+  return wgrad_tc_launch(d, x_dtype, x, ldx, y_dtype, y, ldy, dw, accumulate, ws, st);
+}
+static inline int64_t wgrad_any_workspace(const urn_conv_desc& d) {
+  int64_t a = wgrad_ffma_workspace(d), b = wgrad_tc_workspace(d), c = wgrad_halo_workspace(d), e = stemhead_wgrad_workspace(d);
+  a = a > b ? a : b; c = c > e ? c : e;
+  return a > c ? a : c;
+}

@@ -349,7 +349,7 @@ static int build_plan(urn_net& N) {
   N.result_off = b.alloc(64);
   N.wgrad_ws_bytes = 0;
   for (auto& L : N.layers)
-    N.wgrad_ws_bytes = std::max<int64_t>(N.wgrad_ws_bytes, std::max<int64_t>(std::max<int64_t>(wgrad_ffma_workspace(L.d), wgrad_tc_workspace(L.d)), stemhead_wgrad_workspace(L.d)));
+    N.wgrad_ws_bytes = std::max<int64_t>(N.wgrad_ws_bytes, wgrad_any_workspace(L.d));
   N.wgrad_ws_off = b.alloc(N.wgrad_ws_bytes);
   if (T != URN_F32) {
     N.wq_off = b.alloc(N.param_total * 4);
@@ -766,7 +766,7 @@ extern "C" int urn_backward(urn_net* h, const float* params, float* grads, int a
       else if (ded && head_supported(L.d, ldx, ldy))
         rc = head_wgrad_launch(L.d, xdt, xp, ldx, ydt, yp, ldy, grads + L.w_off, accumulate, P(ws, h->wgrad_ws_off), st);
       else if (tc_enabled(h) && wgrad_tc_supported(L.d, xdt, ydt, ldx, ldy))
-        rc = wgrad_tc_launch(L.d, xdt, xp, ldx, ydt, yp, ldy, grads + L.w_off, accumulate,
+        rc = wgrad_tc_auto(L.d, xdt, xp, ldx, ydt, yp, ldy, grads + L.w_off, accumulate,
                              P(ws, h->wgrad_ws_off), st);
       else
         rc = wgrad_ffma_launch(L.d, xdt, xp, ldx, ydt, yp, ldy, grads + L.w_off, accumulate,

@@ -1,0 +1,401 @@
+// Halo-tile tcgen05 filter gradient for the narrow stride-1 3x3 / 3x3x3 layers
+// (cx, cy in {16, 32, 64}):   dW[t][cx][cy] = sum_p X[p + t - 1][cx] * dY[p][cy].
+//
+// Why: the tap-box kernel (wgrad_tc_kernel) issues one TMA box per (tap, channel group) and
+// K block, i.e. it re-reads every activation 9 / 27 times through TMA rows of only 32-64 bytes
+// and is bound by the TMA box-row rate (0.85 ms per 2D C=16 layer, 7-26 ms in 3D).  Here each
+// X plane of a 16x8 tile is staged ONCE (with its halo, 16-byte cp.async, zero fill = TF 'same'
+// padding) into the same (hy, kw, w)-ordered swizzled layout the forward halo kernel uses; the
+// 9 in-plane taps are then descriptor views 8 rows apart, which is exactly the MN-group stride
+// (LBO) of an MN-major UMMA operand: ONE tcgen05.mma with M = 128 covers 128/cx taps.
+//   GEMM view   M = (tap, cx)   N = cy   K = 128 positions of the tile (8 MMAs of K = 16)
+//   A = X views (MN-major, SBO = 24 rows = next image row, LBO = 8 rows = next tap)
+//   B = dY tile (MN-major, rows = positions)
+// In 3D a CTA walks a column of planes: X plane z meets dY planes z+1, z, z-1 (depth taps
+// -1, 0, +1), each pair accumulating into its own TMEM accumulator, so X and dY are read once
+// per depth chunk.  Accumulators stay in TMEM for the CTA's whole range of tiles; at the end
+// every CTA writes one fp32 partial [tap][cx][cy] and a fixed-order second stage sums the
+// <= 148 partials (deterministic).
+//   warps 0-7 : cp.async producers (X plane + dY tile per step)   warp 8 : TMEM alloc, MMA issue
+//   warps 9-12: final epilogue (tcgen05.ld -> fp32 partial)
+#include <cuda.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+#include "gconv_tc.cuh"
+#include "halo_common.cuh"
+
+namespace {
+
+constexpr int kWThreads = 416;
+constexpr int kWProdWarps = 8, kWProdThreads = kWProdWarps * 32;
+constexpr int kWMmaWarp = kWProdWarps, kWEpiWarp0 = kWProdWarps + 1;
+constexpr int kWTH = 16, kWTW = 8;
+constexpr int kWHaloRows = (kWTH + 2) * 3 * kWTW;     // 432 rows per staged X plane
+constexpr int kWMaxStages = 8;
+constexpr int kYMaxStages = 8;                         // dY ring: 3 planes live + the producers' look-ahead
+
+struct WHParams {
+  int n, D, H, W;
+  int cx, cy;
+  long long ldx, ldy;
+  int nkd, LA;               // depth taps (1 / 3); dY look-ahead in planes (0 / 1)
+  int DC, ndc;               // planes per depth chunk, number of chunks
+  int ntw, nth;
+  long long nunits;          // (n, depth chunk, tile row, tile column)
+  int stages, ystages, pf;   // X ring, dY ring (power of two), cp.async groups in flight
+  int xplane_bytes, yplane_bytes;
+  int tpm, nM;               // taps per MMA (128 / cx), MMAs per depth tap
+  uint32_t idesc;
+  uint64_t adesc_hi, bdesc_hi;
+  int tmem_cols;
+  int ntaps;
+};
+
+struct UnitIter {
+  int nn, dc, ht, wt;
+  __device__ __forceinline__ void init(const WHParams& p, long long u) {
+    wt = (int)(u % p.ntw); u /= p.ntw;
+    ht = (int)(u % p.nth); u /= p.nth;
+    dc = (int)(u % p.ndc);
+    nn = (int)(u / p.ndc);
+  }
+  __device__ __forceinline__ void next(const WHParams& p) {
+    if (++wt == p.ntw) { wt = 0; if (++ht == p.nth) { ht = 0; if (++dc == p.ndc) { dc = 0; ++nn; } } }
+  }
+};
+
+template <int NCH>   // 16-byte X chunks per producer thread and plane: 4 / 7 / 14 for cx 16 / 32 / 64
+__global__ void __launch_bounds__(kWThreads, 1)
+wgrad_halo_kernel(const __grid_constant__ WHParams p, const void* __restrict__ x, const void* __restrict__ dy,
+                  float* __restrict__ partial) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_x = smem;
+  const int x_bytes = ((p.stages * p.xplane_bytes + 1023) / 1024) * 1024;
+  uint8_t* smem_y = smem + x_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_y + (size_t)p.ystages * p.yplane_bytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + kWMaxStages;
+  uint64_t* yempty = bars + 2 * kWMaxStages;
+  uint64_t* tfull = yempty + kYMaxStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull + 1);
+  uint32_t* touched_slot = tmem_slot + 1;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long u_begin = p.nunits * (long long)blockIdx.x / gridDim.x;
+  const long long u_end = p.nunits * (long long)(blockIdx.x + 1) / gridDim.x;
+  const int my_units = (int)(u_end - u_begin);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) { h_mbar_init(&full[s], kWProdWarps); h_mbar_init(&empty[s], 1); }
+    for (int s = 0; s < p.ystages; ++s) h_mbar_init(&yempty[s], 1);
+    h_mbar_init(tfull, 2);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == kWMmaWarp) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(h_smem_u32(tmem_slot)),
+                 "r"((uint32_t)p.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  h_fence_before();
+  __syncthreads();
+  h_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < kWProdWarps) {
+    // ===================== producers =====================
+    const int t = threadIdx.x;
+    const int pitch = p.cx * 2, cpr = pitch / 16;
+    const int total = kWHaloRows * cpr;
+    const int cpr_log2 = cpr == 8 ? 3 : (cpr == 4 ? 2 : 1);
+    const int sw_shift = cpr == 8 ? 0 : (cpr == 4 ? 1 : 2);
+    const int sw_mask = cpr == 8 ? 7 : (cpr == 4 ? 3 : 1);
+    uint32_t desc[NCH];
+#pragma unroll
+    for (int j = 0; j < NCH; ++j) {
+      const int idx = t + j * kWProdThreads;
+      const int row = idx >> cpr_log2, c = idx & (cpr - 1);
+      const int hy = (row * 2731) >> 16;                       // row / 24, exact for row < 432
+      const int rem = row - hy * 24;
+      const int dx = rem - 7 * (rem >> 3);                     // kw + w
+      const int sw = (row >> sw_shift) & sw_mask;
+      const uint32_t dst16 = (uint32_t)(row * (pitch >> 4) + (c ^ sw));
+      desc[j] = idx < total ? (dst16 | ((uint32_t)hy << 12) | ((uint32_t)dx << 17) | ((uint32_t)c << 21) | (1u << 31)) : 0u;
+    }
+    // dY tile: 128 rows (h, w) of cy*2 bytes
+    const int ypitch = p.cy * 2, ycpr = ypitch / 16;
+    const int ycpr_log2 = ycpr == 8 ? 3 : (ycpr == 4 ? 2 : 1);
+    const int ysw_shift = ycpr == 8 ? 0 : (ycpr == 4 ? 1 : 2);
+    const int ysw_mask = ycpr == 8 ? 7 : (ycpr == 4 ? 3 : 1);
+    const int ytotal = 128 * ycpr;                             // 256 / 512 / 1024 chunks
+    const char* x_base = reinterpret_cast<const char*>(x);
+    const char* y_base = reinterpret_cast<const char*>(dy);
+    const int xpix = (int)(p.ldx * 2), xrow = xpix * p.W;
+    const int ypix = (int)(p.ldy * 2), yrow = ypix * p.W;
+    UnitIter ui; ui.init(p, u_begin);
+    Ring st, ar, yr; st.init(p.stages); ar.init(p.stages); yr.init(p.ystages);
+    uint32_t issued = 0;
+    const int pf = p.pf;
+    for (int k = 0; k < my_units; ++k, ui.next(p)) {
+      const int d0 = ui.dc * p.DC, d1 = min(d0 + p.DC, p.D);
+      const int y0 = ui.ht * kWTH, x0 = ui.wt * kWTW;
+      for (int z = d0 - p.LA; z <= d1 - 1 + p.LA; ++z) {
+        const bool xvalid = z >= 0 && z < p.D;
+        const int yp = z + p.LA;
+        const bool yvalid = yp < d1;
+        h_mbar_wait_warp(&empty[st.idx], st.phase ^ 1);
+        if (yvalid) h_mbar_wait_warp(&yempty[yr.idx], yr.phase ^ 1);
+        if (xvalid) {
+          const uint32_t dst_base = h_smem_u32(smem_x + (size_t)st.idx * p.xplane_bytes);
+          const char* plane = x_base + ((long long)ui.nn * p.D + z) * p.H * (long long)xrow;
+#pragma unroll
+          for (int j = 0; j < NCH; ++j) {
+            const uint32_t dsc = desc[j];
+            if (!(dsc >> 31)) continue;
+            const int yy = y0 - 1 + (int)((dsc >> 12) & 31), xx = x0 - 1 + (int)((dsc >> 17) & 15);
+            const bool ok = (unsigned)yy < (unsigned)p.H && (unsigned)xx < (unsigned)p.W;
+            const char* src = ok ? plane + (yy * xrow + xx * xpix + (int)((dsc >> 21) & 7) * 16) : x_base;
+            cp_async16_zfill(dst_base + ((dsc & 0xFFFu) << 4), src, ok ? 16u : 0u);
+          }
+        }
+        if (yvalid) {
+          const uint32_t dst_base = h_smem_u32(smem_y + (size_t)yr.idx * p.yplane_bytes);
+          const char* plane = y_base + ((long long)ui.nn * p.D + yp) * p.H * (long long)yrow;
+          for (int idx = t; idx < ytotal; idx += kWProdThreads) {
+            const int row = idx >> ycpr_log2, c = idx & (ycpr - 1);
+            const int yy = y0 + (row >> 3), xx = x0 + (row & 7);
+            const bool ok = yy < p.H && xx < p.W;
+            const char* src = ok ? plane + (yy * yrow + xx * ypix + c * 16) : y_base;
+            const int sw = (row >> ysw_shift) & ysw_mask;
+            cp_async16_zfill(dst_base + (uint32_t)((row * ycpr + (c ^ sw)) << 4), src, ok ? 16u : 0u);
+          }
+          yr.next();
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        if (issued >= (uint32_t)pf) {
+          if (pf >= 4) asm volatile("cp.async.wait_group 4;" ::: "memory");
+          else if (pf == 3) asm volatile("cp.async.wait_group 3;" ::: "memory");
+          else if (pf == 2) asm volatile("cp.async.wait_group 2;" ::: "memory");
+          else asm volatile("cp.async.wait_group 1;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) h_mbar_arrive(&full[ar.idx]);
+          ar.next();
+        }
+        ++issued;
+        st.next();
+      }
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncwarp();
+    if (lane == 0)
+      for (uint32_t j = (issued > (uint32_t)pf ? issued - pf : 0); j < issued; ++j) { h_mbar_arrive(&full[ar.idx]); ar.next(); }
+  } else if (warp == kWMmaWarp) {
+    // ===================== MMA issue (warp-uniform loop, one elected lane issues) =====================
+    const uint32_t a_hi = (uint32_t)(p.adesc_hi >> 32), b_hi = (uint32_t)(p.bdesc_hi >> 32);
+    const uint32_t a_lo_base = (uint32_t)p.adesc_hi, b_lo_base = (uint32_t)p.bdesc_hi;
+    const uint32_t pitch = (uint32_t)p.cx * 2;
+    const uint32_t a_mstep = ((uint32_t)p.tpm * 8u * pitch) >> 4;      // next M tile: tpm taps further
+    const uint32_t a_kstep = (48u * pitch) >> 4;                        // 16 positions = 2 image rows = 48 staged rows
+    const uint32_t b_kstep = (16u * (uint32_t)p.cy * 2u) >> 4;
+    const uint32_t y_lo0 = h_smem_u32(smem_y) >> 4, y_stage = (uint32_t)p.yplane_bytes >> 4;
+    UnitIter ui; ui.init(p, u_begin);
+    Ring st; st.init(p.stages);
+    uint32_t yseq0 = 0, touched = 0;
+    const uint32_t ymask = (uint32_t)p.ystages - 1u;
+    for (int k = 0; k < my_units; ++k, ui.next(p)) {
+      const int d0 = ui.dc * p.DC, d1 = min(d0 + p.DC, p.D);
+      for (int z = d0 - p.LA; z <= d1 - 1 + p.LA; ++z) {
+        const bool xvalid = z >= 0 && z < p.D;
+        h_mbar_wait(&full[st.idx], st.phase);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // cp.async (generic proxy) -> UMMA (async proxy)
+        h_fence_after();
+        if (xvalid) {
+          const uint32_t a_lo0 = a_lo_base | (h_smem_u32(smem_x + (size_t)st.idx * p.xplane_bytes) >> 4);
+          for (int oi = 0; oi < p.nkd; ++oi) {
+            const int pl = z - (oi - p.LA);                    // dY plane paired with depth tap oi
+            if (pl < d0 || pl >= d1) continue;
+            const uint32_t ys = (yseq0 + (uint32_t)(pl - d0)) & ymask;
+            const uint32_t b_lo0 = b_lo_base | (y_lo0 + ys * y_stage);
+            for (int mi = 0; mi < p.nM; ++mi) {
+              const int ai = oi * p.nM + mi;
+              const uint32_t d_tmem = tmem_base + (uint32_t)(ai * p.cy);
+              const uint32_t accf = (touched >> ai) & 1u;
+              touched |= 1u << ai;
+              const uint32_t a_lo = a_lo0 + (uint32_t)mi * a_mstep;
+              if (h_elect_one()) {
+#pragma unroll
+                for (int kk = 0; kk < 8; ++kk)
+                  h_umma2(d_tmem, a_lo + (uint32_t)kk * a_kstep, a_hi, b_lo0 + (uint32_t)kk * b_kstep, b_hi, p.idesc,
+                          kk == 0 ? accf : 1u);
+              }
+              __syncwarp();
+            }
+          }
+        }
+        const int rel = z - p.LA;                              // last use of dY plane `rel` was this step
+        if (h_elect_one()) {
+          h_commit(&empty[st.idx]);
+          if (rel >= d0 && rel < d1) h_commit(&yempty[(yseq0 + (uint32_t)(rel - d0)) & ymask]);
+        }
+        __syncwarp();
+        st.next();
+      }
+      yseq0 += (uint32_t)(d1 - d0);
+    }
+    if (lane == 0) {
+      *touched_slot = touched;
+      h_mbar_arrive(tfull);
+    }
+    __syncwarp();
+    if (h_elect_one()) h_commit(tfull);
+    __syncwarp();
+  } else {
+    // ===================== final epilogue =====================
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    h_mbar_wait_warp(tfull, 0);
+    h_fence_after();
+    const uint32_t touched = *reinterpret_cast<volatile uint32_t*>(touched_slot);
+    const int tl = r / p.cx, ci = r - tl * p.cx;
+    for (int oi = 0; oi < p.nkd; ++oi)
+      for (int mi = 0; mi < p.nM; ++mi) {
+        const int ai = oi * p.nM + mi;
+        const int tap_local = mi * p.tpm + tl;
+        const bool valid = tap_local < 9;
+        const bool have = (touched >> ai) & 1u;
+        float* dst = partial + (((long long)blockIdx.x * p.ntaps + (oi * 9 + tap_local)) * p.cx + ci) * p.cy;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ai * p.cy);
+        for (int c0 = 0; c0 < p.cy; c0 += 16) {
+          float v[16];
+          h_tmem_ld16(taddr + c0, v);
+          if (!valid) continue;
+          if (!have) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = 0.f;
+          }
+#pragma unroll
+          for (int j = 0; j < 16; j += 4)
+            *reinterpret_cast<float4*>(dst + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        }
+      }
+  }
+
+  h_fence_before();
+  __syncthreads();
+  if (warp == kWMmaWarp) {
+    h_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols)
+                 : "memory");
+  }
+}
+
+// fixed-order sum of the per-CTA partials
+__global__ void wgrad_halo_reduce_kernel(const float* __restrict__ partial, int nw, int nsplit,
+                                         float* __restrict__ dw, int accumulate) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nw) return;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  int k = 0;
+  for (; k + 4 <= nsplit; k += 4) {
+    s0 += partial[(long long)(k + 0) * nw + i];
+    s1 += partial[(long long)(k + 1) * nw + i];
+    s2 += partial[(long long)(k + 2) * nw + i];
+    s3 += partial[(long long)(k + 3) * nw + i];
+  }
+  for (; k < nsplit; ++k) s0 += partial[(long long)k * nw + i];
+  const float s = (s0 + s1) + (s2 + s3);
+  dw[i] = accumulate ? dw[i] + s : s;
+}
+
+bool wh_plan(const urn_conv_desc& d, int x_dtype, int y_dtype, int64_t ldx, int64_t ldy, WHParams* pp) {
+  WHParams& p = *pp;
+  memset(&p, 0, sizeof(p));
+  if (getenv("URN_NO_HALO_WGRAD")) return false;
+  if ((x_dtype != URN_BF16 && x_dtype != URN_F16) || x_dtype != y_dtype) return false;
+  if (d.s != 1 || d.kh != 3 || d.kw != 3 || (d.kd != 1 && d.kd != 3)) return false;
+  if (d.xd != d.yd || d.xh != d.yh || d.xw != d.yw) return false;
+  if (d.pad_h != 1 || d.pad_w != 1 || d.pad_d != (d.kd == 3 ? 1 : 0)) return false;
+  if (d.cx != 16 && d.cx != 32 && d.cx != 64) return false;
+  if (d.cy != 16 && d.cy != 32 && d.cy != 64) return false;
+  if (ldx % 8 || ldy % 8) return false;
+  p.n = d.n; p.D = d.xd; p.H = d.xh; p.W = d.xw; p.cx = d.cx; p.cy = d.cy; p.ldx = ldx; p.ldy = ldy;
+  if ((long long)p.H * p.W * std::max(ldx, ldy) * 2 >= (1ll << 31)) return false;   // 32-bit in-plane offsets
+  p.nkd = d.kd; p.LA = d.kd == 3 ? 1 : 0;
+  p.ntaps = 9 * p.nkd;
+  p.ndc = (p.D + 47) / 48;
+  p.DC = (p.D + p.ndc - 1) / p.ndc;
+  p.ndc = (p.D + p.DC - 1) / p.DC;
+  p.ntw = (p.W + kWTW - 1) / kWTW; p.nth = (p.H + kWTH - 1) / kWTH;
+  p.nunits = (long long)p.n * p.ndc * p.nth * p.ntw;
+  if (p.nunits >= (1ll << 31)) return false;
+  p.xplane_bytes = kWHaloRows * p.cx * 2;
+  p.yplane_bytes = 128 * p.cy * 2;
+  p.tpm = 128 / p.cx;
+  p.nM = (9 + p.tpm - 1) / p.tpm;
+  const int cols = p.nkd * p.nM * p.cy;
+  if (cols > 512) return false;
+  p.tmem_cols = std::max(32, pow2c(cols));
+  // Producers run `pf` cp.async groups ahead of the full-barrier arrival; the dY slot of plane z+1
+  // frees two steps after its previous tenant's last use, so the dY ring needs >= pf + 3 slots
+  // (and the X ring >= pf + 1) or producers and MMA warp would wait on each other.
+  const int budget = 200 * 1024;
+  p.pf = 0;
+  for (int pf : {4, 2, 1}) {
+    const int ys = pf == 1 ? 4 : 8;
+    const int st = std::min(kWMaxStages, (budget - ys * p.yplane_bytes) / p.xplane_bytes);
+    if (st >= 2 * pf) { p.pf = pf; p.ystages = ys; p.stages = st; break; }
+  }
+  if (!p.pf) return false;
+  const int fmt = x_dtype == URN_BF16 ? 1 : 0;
+  p.idesc = (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | (1u << 15) | (1u << 16) |
+            ((uint32_t)(p.cy >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  auto layout_of = [](uint64_t bytes) -> uint64_t { return bytes == 128 ? 2 : (bytes == 64 ? 4 : 6); };
+  const uint64_t xp = (uint64_t)p.cx * 2, yp = (uint64_t)p.cy * 2;
+  // MN-major: SBO = next 8 positions (K), LBO = next channel group (MN)
+  p.adesc_hi = (layout_of(xp) << 61) | (1ull << 46) | (((24 * xp) >> 4) << 32) | (((8 * xp) >> 4) << 16);
+  p.bdesc_hi = (layout_of(yp) << 61) | (1ull << 46) | (((8 * yp) >> 4) << 32) | (((128 * yp) >> 4) << 16);
+  return true;
+}
+
+}  // namespace
+
+bool wgrad_halo_supported(const urn_conv_desc& d, int x_dtype, int y_dtype, int64_t ldx, int64_t ldy) {
+  WHParams p;
+  return wh_plan(d, x_dtype, y_dtype, ldx, ldy, &p);
+}
+
+int64_t wgrad_halo_workspace(const urn_conv_desc& d) {
+  WHParams p;
+  if (!wh_plan(d, URN_BF16, URN_BF16, 64, 64, &p)) return 0;
+  return (int64_t)num_sms() * p.ntaps * d.cx * d.cy * 4;
+}
+
+int wgrad_halo_launch(const urn_conv_desc& d, int x_dtype, const void* x, int64_t ldx, int y_dtype,
+                      const void* y, int64_t ldy, float* dw, int accumulate, void* ws, cudaStream_t st) {
+  WHParams p;
+  URN_CHECK(wh_plan(d, x_dtype, y_dtype, ldx, ldy, &p), "wgrad_halo: unsupported shape/dtype");
+  const int x_bytes = ((p.stages * p.xplane_bytes + 1023) / 1024) * 1024;
+  const size_t smem = 1024 + (size_t)x_bytes + (size_t)p.ystages * p.yplane_bytes + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    URN_CUDA(cudaFuncSetAttribute(wgrad_halo_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    URN_CUDA(cudaFuncSetAttribute(wgrad_halo_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    URN_CUDA(cudaFuncSetAttribute(wgrad_halo_kernel<14>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  const int grid = (int)std::min<long long>(p.nunits, num_sms());
+  float* partial = (float*)ws;
+  if (d.cx == 16) wgrad_halo_kernel<4><<<grid, kWThreads, smem, st>>>(p, x, y, partial);
+  else if (d.cx == 32) wgrad_halo_kernel<7><<<grid, kWThreads, smem, st>>>(p, x, y, partial);
+  else wgrad_halo_kernel<14><<<grid, kWThreads, smem, st>>>(p, x, y, partial);
+  URN_LAUNCH_CHECK();
+  const int nw = p.ntaps * d.cx * d.cy;
+  wgrad_halo_reduce_kernel<<<(nw + 127) / 128, 128, 0, st>>>(partial, nw, grid, dw, accumulate);
+  URN_LAUNCH_CHECK();
+  return 0;
+}
