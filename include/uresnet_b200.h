@@ -127,6 +127,19 @@ int urn_bn_bwd(const void* dout, int64_t lddout, const void* out, int64_t ldo, i
                void* dres, int64_t lddres, int dres_accumulate, int acc_beta,
                void* ws, void* stream);
 
+/* Same as urn_bn_bwd, told the layer's beta (f32[c]).  With beta the fast path needs fewer
+ * bytes: for BN without ReLU the forward output is xhat + beta, so xhat = out - beta and raw is
+ * not read; for BN -> ReLU without residual the mask is recomputed from raw as
+ * fma(raw - mean, rstd, beta) > 0 and `out` is not read.  beta == NULL behaves as urn_bn_bwd. */
+int urn_bn_bwd_beta(const void* dout, int64_t lddout, const void* out, int64_t ldo, int dtype,
+                    int out_dtype, int relu, int64_t rows, int c,
+                    const float* raw, int64_t ldraw, const float* stats, const float* beta,
+                    float* dbeta, void* draw, int64_t lddraw,
+                    const float* raw2, int64_t ldraw2, const float* stats2, float* dbeta2,
+                    void* draw2, int64_t lddraw2,
+                    void* dres, int64_t lddres, int dres_accumulate, int acc_beta,
+                    void* ws, void* stream);
+
 /* K9/K10/K11  tf.nn.sparse_softmax_cross_entropy_with_logits + weight + per-image
  * sum + batch mean, argmax accuracies, softmax (lib/ssnet.py:57-71).
  * logits f32 [batch*pixels, c]; label/weight/data f32 [batch*pixels] (weight may be

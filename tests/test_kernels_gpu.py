@@ -321,8 +321,13 @@ def test_bn_stats_apply(lib, c, rows):
 
 @pytest.mark.parametrize("dt", [F32, BF16, F16])
 @pytest.mark.parametrize("c,rows,relu,mode", [(16, 3000, 1, "conv_sc"), (16, 3000, 1, "identity"), (3, 500, 0, "plain"),
-                                              (64, 129, 1, "plain"), (256, 40, 0, "plain")])
+                                              (64, 129, 1, "plain"), (256, 40, 0, "plain"),
+                                              (16, 70001, 1, "plain"), (32, 5003, 0, "plain"), (8, 999, 1, "identity"),
+                                              (512, 33, 1, "conv_sc"), (16, 3000, 1, "plain+beta"), (32, 4099, 0, "plain+beta"),
+                                              (128, 300, 1, "plain+beta")])
 def test_bn_backward(lib, dt, c, rows, relu, mode):
+    with_beta = mode.endswith("+beta")      # urn_bn_bwd_beta: xhat from out / mask from raw
+    mode = mode.split("+")[0]
     rng = np.random.default_rng(rows + c)
     x = rng.standard_normal((rows, c)).astype(np.float32) * 2 + 0.5
     x2 = rng.standard_normal((rows, c)).astype(np.float32)
@@ -356,6 +361,11 @@ def test_bn_backward(lib, dt, c, rows, relu, mode):
     xd, s1 = stats_of(x)
     x2d, s2 = stats_of(x2)
     outd = dev(out.detach().numpy(), dt)
+    if with_beta:     # the fast path recomputes mask / xhat from what the forward kernel stored
+        bd = dev(beta)
+        outd = torch.empty((rows, c), dtype=TORCH_DT[dt], device=DEV)
+        _capi.check(lib.urn_bn_apply(xd.data_ptr(), c, rows, c, s1.data_ptr(), bd.data_ptr(), None, 0, 0, None, 0,
+                                     None, None, relu, outd.data_ptr(), c, dt, None, st()))
     doutd = dev(dout, gdt(dt))
     tdt = TORCH_DT[gdt(dt)]
     draw = torch.empty((rows, c), dtype=tdt, device=DEV)
@@ -363,8 +373,10 @@ def test_bn_backward(lib, dt, c, rows, relu, mode):
     dres = torch.ones((rows, c), dtype=tdt, device=DEV)
     dbeta = torch.zeros(c, dtype=torch.float32, device=DEV)
     dbeta2 = torch.zeros(c, dtype=torch.float32, device=DEV)
-    _capi.check(lib.urn_bn_bwd(
-        doutd.data_ptr(), c, outd.data_ptr(), c, gdt(dt), dt, relu, rows, c, xd.data_ptr(), c, s1.data_ptr(), dbeta.data_ptr(),
+    fn = lib.urn_bn_bwd_beta if with_beta else lib.urn_bn_bwd
+    extra = (bd.data_ptr(),) if with_beta else ()
+    _capi.check(fn(
+        doutd.data_ptr(), c, outd.data_ptr(), c, gdt(dt), dt, relu, rows, c, xd.data_ptr(), c, s1.data_ptr(), *extra, dbeta.data_ptr(),
         draw.data_ptr(), c,
         x2d.data_ptr() if mode == "conv_sc" else None, c, s2.data_ptr() if mode == "conv_sc" else None,
         dbeta2.data_ptr() if mode == "conv_sc" else None, draw2.data_ptr() if mode == "conv_sc" else None, c,

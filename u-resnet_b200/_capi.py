@@ -53,6 +53,8 @@ SIGNATURES = {
                           _vp, _i64, _i, _vp, _vp]),
     "urn_bn_bwd": (_i, [_vp, _i64, _vp, _i64, _i, _i, _i, _i64, _i, _vp, _i64, _vp, _vp, _vp, _i64,
                         _vp, _i64, _vp, _vp, _vp, _i64, _vp, _i64, _i, _i, _vp, _vp]),
+    "urn_bn_bwd_beta": (_i, [_vp, _i64, _vp, _i64, _i, _i, _i, _i64, _i, _vp, _i64, _vp, _vp, _vp, _vp, _i64,
+                             _vp, _i64, _vp, _vp, _vp, _i64, _vp, _i64, _i, _i, _vp, _vp]),
     "urn_loss_workspace": (_i64, [_i64]),
     "urn_ce_fwd_bwd": (_i, [_vp, _i64, _vp, _vp, _vp, _i64, _i64, _i, _vp, _i64, _i, _vp, _vp, _vp,
                             _vp]),

@@ -3,6 +3,7 @@
 // access over [rows, c] channel-last tensors, fp32 math, per-block partials reduced
 // in a fixed order (deterministic) in double.
 #include "common.cuh"
+#include "bn_fast.cuh"
 
 namespace {
 
@@ -346,6 +347,13 @@ extern "C" int urn_bn_stats(const float* raw, int64_t ld, int64_t rows, int c, f
   URN_CHECK(c >= 1 && c <= 1024, "urn_bn_stats: c=%d out of range", c);
   URN_CHECK(rows > 0, "urn_bn_stats: empty input");
   cudaStream_t st = (cudaStream_t)stream;
+  if (bn_fast_shape(c, {ld}, {raw})) {
+    int nbf = 0;
+    if (bn_stats_fast_launch(raw, ld, rows, c, (double*)ws, &nbf, st)) return 1;
+    bn_stats_finalize_kernel<<<c, 128, 0, st>>>((const double*)ws, nbf, c, rows, eps, raw, stats);
+    URN_LAUNCH_CHECK();
+    return 0;
+  }
   bool al = aligned4(c, {ld}) && ((uintptr_t)raw % 16 == 0);
   ColMap m = col_map(c, al);
   URN_CHECK(m.cg <= BN_THREADS, "urn_bn_stats: c=%d needs 4-aligned pitch", c);
@@ -380,6 +388,9 @@ extern "C" int urn_bn_apply(const float* raw, int64_t ld, int64_t rows, int c, c
                             int out_dtype, void* out2, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   URN_CHECK(rows > 0 && c >= 1, "urn_bn_apply: empty input");
+  if (bn_fast_shape(c, {ld, ldout, res ? ldres : 0, res_raw ? ldres_raw : 0}, {raw, out, out2, res, res_raw}))
+    return bn_apply_fast_launch(raw, ld, rows, c, stats, beta, res, ldres, res_dtype, res_raw, ldres_raw,
+                                res_stats, res_beta, relu, out, ldout, out_dtype, out2, st);
   if (!res) res_dtype = out_dtype;
   return dispatch_dtype(res_dtype, [&](auto pr) {
     using TR = URN_T(pr);
@@ -427,9 +438,48 @@ extern "C" int urn_bn_bwd(const void* dout, int64_t lddout, const void* out, int
                           int64_t lddraw, const float* raw2, int64_t ldraw2, const float* stats2,
                           float* dbeta2, void* draw2, int64_t lddraw2, void* dres, int64_t lddres,
                           int dres_accumulate, int acc_beta, void* ws, void* stream) {
-  cudaStream_t st = (cudaStream_t)stream;
+  return bn_bwd_full(dout, lddout, out, ldo, dtype, out_dtype, relu, rows, c, raw, ldraw, stats, nullptr, dbeta,
+                     draw, lddraw, raw2, ldraw2, stats2, dbeta2, draw2, lddraw2, dres, lddres, dres_accumulate,
+                     acc_beta, ws, (cudaStream_t)stream);
+}
+
+extern "C" int urn_bn_bwd_beta(const void* dout, int64_t lddout, const void* out, int64_t ldo, int dtype,
+                               int out_dtype, int relu, int64_t rows, int c, const float* raw,
+                               int64_t ldraw, const float* stats, const float* beta, float* dbeta,
+                               void* draw, int64_t lddraw, const float* raw2, int64_t ldraw2,
+                               const float* stats2, float* dbeta2, void* draw2, int64_t lddraw2,
+                               void* dres, int64_t lddres, int dres_accumulate, int acc_beta, void* ws,
+                               void* stream) {
+  return bn_bwd_full(dout, lddout, out, ldo, dtype, out_dtype, relu, rows, c, raw, ldraw, stats, beta, dbeta,
+                     draw, lddraw, raw2, ldraw2, stats2, dbeta2, draw2, lddraw2, dres, lddres, dres_accumulate,
+                     acc_beta, ws, (cudaStream_t)stream);
+}
+
+int bn_bwd_full(const void* dout, int64_t lddout, const void* out, int64_t ldo, int dtype, int out_dtype,
+                int relu, int64_t rows, int c, const float* raw, int64_t ldraw, const float* stats,
+                const float* beta, float* dbeta, void* draw, int64_t lddraw, const float* raw2,
+                int64_t ldraw2, const float* stats2, float* dbeta2, void* draw2, int64_t lddraw2, void* dres,
+                int64_t lddres, int dres_accumulate, int acc_beta, void* ws, cudaStream_t st) {
   URN_CHECK(rows > 0 && c >= 1 && c <= 1024, "urn_bn_bwd: bad shape");
   URN_CHECK(!relu || out, "urn_bn_bwd: relu needs the forward output");
+  const bool pair_ok = (dtype == URN_F32 && out_dtype == URN_F32) || (dtype == URN_BF16 && out_dtype != URN_F32);
+  if (pair_ok && out &&
+      bn_fast_shape(c, {lddout, ldo, ldraw, lddraw, raw2 ? ldraw2 : 0, raw2 ? lddraw2 : 0, dres ? lddres : 0},
+                    {dout, out, raw, draw, raw2, draw2, dres})) {
+    double* partial = (double*)ws;
+    const int64_t pb = ((int64_t)BN_MAX_BLOCKS * 3 * c * 8 + 255) / 256 * 256;
+    float* sums = (float*)((char*)ws + pb);
+    int nb = 0;
+    if (bn_bwd_fast_launch(0, dout, lddout, out, ldo, dtype, out_dtype, relu, rows, c, raw, ldraw, stats, beta,
+                           draw, lddraw, raw2, ldraw2, stats2, draw2, lddraw2, dres, lddres, dres_accumulate,
+                           partial, sums, &nb, st))
+      return 1;
+    bn_bwd_finalize_kernel<<<c, 128, 0, st>>>(partial, nb, c, sums, dbeta, raw2 ? dbeta2 : nullptr, acc_beta);
+    URN_LAUNCH_CHECK();
+    return bn_bwd_fast_launch(1, dout, lddout, out, ldo, dtype, out_dtype, relu, rows, c, raw, ldraw, stats, beta,
+                              draw, lddraw, raw2, ldraw2, stats2, draw2, lddraw2, dres, lddres, dres_accumulate,
+                              partial, sums, &nb, st);
+  }
 #define URN_BB(GD, AD, TG, TAA)                                                                   \
   if (dtype == GD && out_dtype == AD)                                                             \
     return bn_bwd_t<TG, TAA>(dout, lddout, out, ldo, relu, rows, c, raw, ldraw, stats, dbeta, draw, \

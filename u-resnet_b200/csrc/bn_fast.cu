@@ -1,0 +1,413 @@
+// Fast paths of the batch-norm kernels for the shapes the network
+// actually has: power-of-two channel counts >= 8, pitches that are multiples of 8 elements and
+// 16-byte aligned views.  Every thread owns ONE group of 8 channels for its whole life (the grid
+// stride is a multiple of the groups per row), so the per-channel constants live in registers,
+// all index arithmetic is shifts, every global access is a 16-byte vector, and U independent
+// rows are in flight per thread.  Reductions keep the fixed-order, double-precision second
+// stage of bn.cu (deterministic).
+//
+// Backward byte diet (16 B/elem instead of 18, 10 instead of 14):
+//   * BN without ReLU (resnet_conv1, /root/reference/lib/resnet_module.py:43-51): the stored
+//     forward output IS xhat + beta, so xhat = out - beta and the fp32 raw tensor is not read;
+//   * BN -> ReLU without residual (conv0, deconv, conv1): the mask out > 0 is recomputed from
+//     raw with the forward's exact expression fma(x - mean, rstd, beta), so `out` is not read.
+#include <algorithm>
+
+#include "common.cuh"
+#include "bn_fast.cuh"
+
+namespace {
+
+constexpr int BF_T = 256;
+
+__device__ __forceinline__ void load_params8(const float* p, float* v) {
+  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+
+// Sum K per-thread vectors of 8 channels over all threads of the block that own the same
+// channel group; thread ch < c then writes partial[(block*K + k)*c + ch] as double.
+template <int K>
+__device__ __forceinline__ void block_group_reduce(float (&acc)[K][8], int cg, int c, double* __restrict__ partial) {
+  __shared__ float red[BF_T * 8];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = tid & (cg - 1);
+  int nl, slot;
+  if (cg < 32) {
+#pragma unroll
+    for (int k = 0; k < K; ++k)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float v = acc[k][j];
+        for (int o = 16; o >= cg; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        acc[k][j] = v;
+      }
+    nl = BF_T / 32;
+    slot = lane < cg ? warp * cg + g : -1;
+  } else {
+    nl = BF_T / cg;
+    slot = tid;                        // == (tid / cg) * cg + g
+  }
+  for (int k = 0; k < K; ++k) {
+    __syncthreads();
+    if (slot >= 0) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) red[slot * 8 + j] = acc[k][j];
+    }
+    __syncthreads();
+    for (int ch = tid; ch < c; ch += BF_T) {
+      double s = 0.0;
+      for (int l = 0; l < nl; ++l) s += (double)red[(l * cg + (ch >> 3)) * 8 + (ch & 7)];
+      partial[((long long)blockIdx.x * K + k) * c + ch] = s;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// forward statistics (shifted sums, see bn.cu)
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(BF_T)
+bn_stats_fast_kernel(const float* __restrict__ raw, long long ld, long long rows, int c, int lg,
+                     double* __restrict__ partial) {
+  constexpr int U = 4;
+  const int cg = c >> 3;
+  const long long tid = (long long)blockIdx.x * BF_T + threadIdx.x;
+  const int ch = (int)(tid & (cg - 1)) * 8;
+  const long long rstride = ((long long)gridDim.x * BF_T) >> lg;
+  float K[8];
+  load_params8(raw + ch, K);
+  float acc[2][8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[0][j] = acc[1][j] = 0.f;
+  for (long long r = tid >> lg; r < rows; r += rstride * U) {
+    float x[U][8];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long rr = r + u * rstride;
+      if (rr < rows) load8(raw + rr * ld + ch, x[u]);
+      else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) x[u][j] = K[j];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float v = x[u][j] - K[j];
+        acc[0][j] += v;
+        acc[1][j] = fmaf(v, v, acc[1][j]);
+      }
+  }
+  block_group_reduce<2>(acc, cg, c, partial);
+}
+
+// ---------------------------------------------------------------------------------------
+// forward apply: out = act(BN(raw) [+ res | + BN(res_raw)])
+// ---------------------------------------------------------------------------------------
+template <typename TR, typename TO, int RES, bool RELU, bool SHADOW>
+__global__ void __launch_bounds__(BF_T)
+bn_apply_fast_kernel(const float* __restrict__ raw, long long ld, long long rows, int c, int lg,
+                     const float* __restrict__ stats, const float* __restrict__ beta,
+                     const TR* __restrict__ res, long long ldres, const float* __restrict__ res_raw,
+                     long long ldres_raw, const float* __restrict__ res_stats,
+                     const float* __restrict__ res_beta, TO* __restrict__ out, long long ldout,
+                     bf16* __restrict__ out2) {
+  constexpr int U = RES == 2 ? 2 : 4;
+  const int cg = c >> 3;
+  const long long tid = (long long)blockIdx.x * BF_T + threadIdx.x;
+  const int ch = (int)(tid & (cg - 1)) * 8;
+  const long long rstride = ((long long)gridDim.x * BF_T) >> lg;
+  float mu[8], rs[8], be[8], mu2[8], rs2[8], be2[8];
+  load_params8(stats + ch, mu); load_params8(stats + c + ch, rs); load_params8(beta + ch, be);
+  if (RES == 2) { load_params8(res_stats + ch, mu2); load_params8(res_stats + c + ch, rs2); load_params8(res_beta + ch, be2); }
+  for (long long r = tid >> lg; r < rows; r += rstride * U) {
+    float x[U][8], x2[U][8];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long rr = r + u * rstride;
+      if (rr < rows) {
+        load8(raw + rr * ld + ch, x[u]);
+        if (RES == 2) load8(res_raw + rr * ldres_raw + ch, x2[u]);
+        if (RES == 1) load8(res + rr * ldres + ch, x2[u]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long rr = r + u * rstride;
+      if (rr >= rows) continue;
+      float y[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float v = fmaf(x[u][j] - mu[j], rs[j], be[j]);
+        if (RES == 2) v += fmaf(x2[u][j] - mu2[j], rs2[j], be2[j]);
+        if (RES == 1) v += x2[u][j];
+        y[j] = RELU ? fmaxf(v, 0.f) : v;
+      }
+      store8(out + rr * ldout + ch, y);
+      if (SHADOW) store8(out2 + rr * ldout + ch, y);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// backward pass 1: per-channel sums of g, g*xhat (and g*xhat2)
+//   XMODE 0: xhat from raw; 1: xhat = out - beta (no ReLU); 2: xhat and the ReLU mask from raw
+// ---------------------------------------------------------------------------------------
+template <typename TG, typename TA, bool RELU, bool DUAL, int XMODE>
+__global__ void __launch_bounds__(BF_T)
+bn_bwd_reduce_fast_kernel(const TG* __restrict__ dout, long long lddout, const TA* __restrict__ outp,
+                          long long ldo, long long rows, int c, int lg, const float* __restrict__ raw,
+                          long long ldraw, const float* __restrict__ stats, const float* __restrict__ beta,
+                          const float* __restrict__ raw2, long long ldraw2,
+                          const float* __restrict__ stats2, double* __restrict__ partial) {
+  constexpr int U = DUAL ? 2 : 4;
+  constexpr bool NEED_OUT = (RELU && XMODE != 2) || XMODE == 1;
+  constexpr bool NEED_RAW = XMODE != 1;
+  const int cg = c >> 3;
+  const long long tid = (long long)blockIdx.x * BF_T + threadIdx.x;
+  const int ch = (int)(tid & (cg - 1)) * 8;
+  const long long rstride = ((long long)gridDim.x * BF_T) >> lg;
+  float mu[8], rs[8], be[8], mu2[8], rs2[8];
+  load_params8(stats + ch, mu); load_params8(stats + c + ch, rs);
+  if (XMODE != 0) load_params8(beta + ch, be);
+  if (DUAL) { load_params8(stats2 + ch, mu2); load_params8(stats2 + c + ch, rs2); }
+  float acc[3][8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[0][j] = acc[1][j] = acc[2][j] = 0.f;
+  for (long long r = tid >> lg; r < rows; r += rstride * U) {
+    float g[U][8], o[U][8], x[U][8], x2[U][8];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long rr = r + u * rstride;
+      if (rr < rows) {
+        load8(dout + rr * lddout + ch, g[u]);
+        if (NEED_OUT) load8(outp + rr * ldo + ch, o[u]);
+        if (NEED_RAW) load8(raw + rr * ldraw + ch, x[u]);
+        if (DUAL) load8(raw2 + rr * ldraw2 + ch, x2[u]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { g[u][j] = 0.f; o[u][j] = 1.f; x[u][j] = 0.f; x2[u][j] = 0.f; }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float gv = g[u][j], xh;
+        if (XMODE == 1) xh = o[u][j] - be[j];
+        else xh = (x[u][j] - mu[j]) * rs[j];
+        if (RELU) {
+          if (XMODE == 2) { if (!(fmaf(x[u][j] - mu[j], rs[j], be[j]) > 0.f)) gv = 0.f; }
+          else if (!(o[u][j] > 0.f)) gv = 0.f;
+        }
+        acc[0][j] += gv;
+        acc[1][j] = fmaf(gv, xh, acc[1][j]);
+        if (DUAL) acc[2][j] = fmaf(gv, (x2[u][j] - mu2[j]) * rs2[j], acc[2][j]);
+      }
+  }
+  block_group_reduce<3>(acc, cg, c, partial);
+}
+
+// ---------------------------------------------------------------------------------------
+// backward pass 2: d(raw) = rstd*(g - mean(g) - xhat*mean(g*xhat))  (+ dual BN, + residual fan-out)
+//   DRES 0: none, 1: write g, 2: accumulate g
+// ---------------------------------------------------------------------------------------
+template <typename TG, typename TA, bool RELU, bool DUAL, int DRES, int XMODE>
+__global__ void __launch_bounds__(BF_T)
+bn_bwd_apply_fast_kernel(const TG* __restrict__ dout, long long lddout, const TA* __restrict__ outp,
+                         long long ldo, long long rows, int c, int lg, const float* __restrict__ raw,
+                         long long ldraw, const float* __restrict__ stats, const float* __restrict__ beta,
+                         TG* __restrict__ draw, long long lddraw, const float* __restrict__ raw2,
+                         long long ldraw2, const float* __restrict__ stats2, TG* __restrict__ draw2,
+                         long long lddraw2, TG* __restrict__ dres, long long lddres,
+                         const float* __restrict__ sums) {
+  constexpr int U = 2;
+  constexpr bool NEED_OUT = (RELU && XMODE != 2) || XMODE == 1;
+  constexpr bool NEED_RAW = XMODE != 1;
+  const int cg = c >> 3;
+  const long long tid = (long long)blockIdx.x * BF_T + threadIdx.x;
+  const int ch = (int)(tid & (cg - 1)) * 8;
+  const long long rstride = ((long long)gridDim.x * BF_T) >> lg;
+  const float inv = 1.0f / (float)rows;
+  float mu[8], rs[8], be[8], mg[8], mgx[8], mu2[8], rs2[8], mgx2[8];
+  load_params8(stats + ch, mu); load_params8(stats + c + ch, rs);
+  load_params8(sums + ch, mg); load_params8(sums + c + ch, mgx);
+  if (XMODE != 0) load_params8(beta + ch, be);
+  if (DUAL) { load_params8(stats2 + ch, mu2); load_params8(stats2 + c + ch, rs2); load_params8(sums + 2 * c + ch, mgx2); }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { mg[j] *= inv; mgx[j] *= inv; if (DUAL) mgx2[j] *= inv; }
+  for (long long r = tid >> lg; r < rows; r += rstride * U) {
+    float g[U][8], o[U][8], x[U][8], x2[U][8], dr[U][8];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long rr = r + u * rstride;
+      if (rr < rows) {
+        load8(dout + rr * lddout + ch, g[u]);
+        if (NEED_OUT) load8(outp + rr * ldo + ch, o[u]);
+        if (NEED_RAW) load8(raw + rr * ldraw + ch, x[u]);
+        if (DUAL) load8(raw2 + rr * ldraw2 + ch, x2[u]);
+        if (DRES == 2) load8(dres + rr * lddres + ch, dr[u]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long rr = r + u * rstride;
+      if (rr >= rows) continue;
+      float o1[8], o2[8], gg[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float gv = g[u][j], xh;
+        if (XMODE == 1) xh = o[u][j] - be[j];
+        else xh = (x[u][j] - mu[j]) * rs[j];
+        if (RELU) {
+          if (XMODE == 2) { if (!(fmaf(x[u][j] - mu[j], rs[j], be[j]) > 0.f)) gv = 0.f; }
+          else if (!(o[u][j] > 0.f)) gv = 0.f;
+        }
+        o1[j] = rs[j] * (gv - mg[j] - xh * mgx[j]);
+        if (DUAL) o2[j] = rs2[j] * (gv - mg[j] - (x2[u][j] - mu2[j]) * rs2[j] * mgx2[j]);
+        gg[j] = DRES == 2 ? gv + dr[u][j] : gv;
+      }
+      store8(draw + rr * lddraw + ch, o1);
+      if (DUAL) store8(draw2 + rr * lddraw2 + ch, o2);
+      if (DRES) store8(dres + rr * lddres + ch, gg);
+    }
+  }
+}
+
+inline int ilog2(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
+inline bool al16(const void* p) { return ((uintptr_t)p & 15) == 0; }
+
+// grid: a multiple of the SM count; grid*256 is always a multiple of c/8 <= 64
+inline int fast_grid(long long rows, int c, int per_sm) {
+  const long long items = rows * (c >> 3);
+  long long b = (items + BF_T - 1) / BF_T;
+  const long long cap = (long long)num_sms() * per_sm;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+}  // namespace
+
+bool bn_fast_shape(int c, std::initializer_list<long long> lds, std::initializer_list<const void*> ptrs) {
+  if (c < 8 || c > 512 || (c & (c - 1))) return false;
+  for (long long l : lds)
+    if (l % 8) return false;
+  for (const void* p : ptrs)
+    if (p && !al16(p)) return false;
+  return true;
+}
+
+int bn_stats_fast_launch(const float* raw, long long ld, long long rows, int c, double* partial, int* nblocks,
+                         cudaStream_t st) {
+  const int nb = std::min(fast_grid(rows, c, 4), 148 * 4);      // partial buffer: BN_MAX_BLOCKS entries
+  bn_stats_fast_kernel<<<nb, BF_T, 0, st>>>(raw, ld, rows, c, ilog2(c >> 3), partial);
+  URN_LAUNCH_CHECK();
+  *nblocks = nb;
+  return 0;
+}
+
+template <typename TR, typename TO>
+static int bn_apply_fast_t(const float* raw, long long ld, long long rows, int c, const float* stats,
+                           const float* beta, const void* res, long long ldres, const float* res_raw,
+                           long long ldres_raw, const float* res_stats, const float* res_beta, int relu,
+                           void* out, long long ldout, void* out2, cudaStream_t st) {
+  const int nb = fast_grid(rows, c, 8), lg = ilog2(c >> 3);
+  const int resk = res_raw ? 2 : (res ? 1 : 0);
+#define BF_APPLY(RESV, RELUV, SHV)                                                                     \
+  bn_apply_fast_kernel<TR, TO, RESV, RELUV, SHV><<<nb, BF_T, 0, st>>>(raw, ld, rows, c, lg, stats, beta, \
+      (const TR*)res, ldres, res_raw, ldres_raw, res_stats, res_beta, (TO*)out, ldout, (bf16*)out2)
+#define BF_APPLY_SH(RESV, RELUV) do { if (out2) BF_APPLY(RESV, RELUV, true); else BF_APPLY(RESV, RELUV, false); } while (0)
+  if (resk == 0) { if (relu) BF_APPLY_SH(0, true); else BF_APPLY_SH(0, false); }
+  else if (resk == 1) { if (relu) BF_APPLY_SH(1, true); else BF_APPLY_SH(1, false); }
+  else { if (relu) BF_APPLY_SH(2, true); else BF_APPLY_SH(2, false); }
+#undef BF_APPLY_SH
+#undef BF_APPLY
+  URN_LAUNCH_CHECK();
+  return 0;
+}
+
+int bn_apply_fast_launch(const float* raw, long long ld, long long rows, int c, const float* stats,
+                         const float* beta, const void* res, long long ldres, int res_dtype,
+                         const float* res_raw, long long ldres_raw, const float* res_stats,
+                         const float* res_beta, int relu, void* out, long long ldout, int out_dtype,
+                         void* out2, cudaStream_t st) {
+  if (!res) res_dtype = out_dtype;
+  return dispatch_dtype(res_dtype, [&](auto pr) {
+    using TR = URN_T(pr);
+    return dispatch_dtype(out_dtype, [&](auto po) {
+      using TO = URN_T(po);
+      return bn_apply_fast_t<TR, TO>(raw, ld, rows, c, stats, beta, res, ldres, res_raw, ldres_raw, res_stats,
+                                     res_beta, relu, out, ldout, out2, st);
+    });
+  });
+}
+
+template <typename TG, typename TA>
+static int bn_bwd_fast_t(const void* dout, long long lddout, const void* out, long long ldo, int relu,
+                         long long rows, int c, const float* raw, long long ldraw, const float* stats,
+                         const float* beta, void* draw, long long lddraw, const float* raw2, long long ldraw2,
+                         const float* stats2, void* draw2, long long lddraw2, void* dres, long long lddres,
+                         int dres_acc, double* partial, const float* sums, int phase, int* nblocks,
+                         cudaStream_t st) {
+  const int lg = ilog2(c >> 3);
+  const bool dual = raw2 != nullptr;
+  // xhat source: plain BN (no ReLU, no second BN, no residual fan-out) -> from `out`;
+  // BN -> ReLU without residual -> mask from raw; everything else -> classic
+  int xmode = 0;
+  if (beta && !dual && !dres) xmode = relu ? 2 : 1;
+  if (phase == 0) {
+    const int nb = std::min(fast_grid(rows, c, 4), 148 * 4);
+    *nblocks = nb;
+#define BF_RED(RELUV, DUALV, XM)                                                                        \
+  bn_bwd_reduce_fast_kernel<TG, TA, RELUV, DUALV, XM><<<nb, BF_T, 0, st>>>((const TG*)dout, lddout,      \
+      (const TA*)out, ldo, rows, c, lg, raw, ldraw, stats, beta, raw2, ldraw2, stats2, partial)
+    if (xmode == 1) BF_RED(false, false, 1);
+    else if (xmode == 2) BF_RED(true, false, 2);
+    else if (dual) { if (relu) BF_RED(true, true, 0); else BF_RED(false, true, 0); }
+    else { if (relu) BF_RED(true, false, 0); else BF_RED(false, false, 0); }
+#undef BF_RED
+    URN_LAUNCH_CHECK();
+    return 0;
+  }
+  const int nb = fast_grid(rows, c, 8);
+  const int dr = dres ? (dres_acc ? 2 : 1) : 0;
+#define BF_APP(RELUV, DUALV, DRESV, XM)                                                                  \
+  bn_bwd_apply_fast_kernel<TG, TA, RELUV, DUALV, DRESV, XM><<<nb, BF_T, 0, st>>>((const TG*)dout, lddout, \
+      (const TA*)out, ldo, rows, c, lg, raw, ldraw, stats, beta, (TG*)draw, lddraw, raw2, ldraw2, stats2,  \
+      (TG*)draw2, lddraw2, (TG*)dres, lddres, sums)
+#define BF_APP_DR(RELUV, DUALV)                                         \
+  do {                                                                  \
+    if (dr == 0) BF_APP(RELUV, DUALV, 0, 0);                            \
+    else if (dr == 1) BF_APP(RELUV, DUALV, 1, 0);                       \
+    else BF_APP(RELUV, DUALV, 2, 0);                                    \
+  } while (0)
+  if (xmode == 1) BF_APP(false, false, 0, 1);
+  else if (xmode == 2) BF_APP(true, false, 0, 2);
+  else if (dual) { if (relu) BF_APP_DR(true, true); else BF_APP_DR(false, true); }
+  else { if (relu) BF_APP_DR(true, false); else BF_APP_DR(false, false); }
+#undef BF_APP_DR
+#undef BF_APP
+  URN_LAUNCH_CHECK();
+  return 0;
+}
+
+int bn_bwd_fast_launch(int phase, const void* dout, long long lddout, const void* out, long long ldo, int dtype,
+                       int out_dtype, int relu, long long rows, int c, const float* raw, long long ldraw,
+                       const float* stats, const float* beta, void* draw, long long lddraw, const float* raw2,
+                       long long ldraw2, const float* stats2, void* draw2, long long lddraw2, void* dres,
+                       long long lddres, int dres_acc, double* partial, const float* sums, int* nblocks,
+                       cudaStream_t st) {
+#define URN_BBF(GD, AD, TGT, TAT)                                                                        \
+  if (dtype == GD && out_dtype == AD)                                                                    \
+    return bn_bwd_fast_t<TGT, TAT>(dout, lddout, out, ldo, relu, rows, c, raw, ldraw, stats, beta, draw,  \
+                                   lddraw, raw2, ldraw2, stats2, draw2, lddraw2, dres, lddres, dres_acc, \
+                                   partial, sums, phase, nblocks, st);
+  URN_BBF(URN_F32, URN_F32, float, float)
+  URN_BBF(URN_BF16, URN_BF16, bf16, bf16)
+  URN_BBF(URN_BF16, URN_F16, bf16, f16)
+#undef URN_BBF
+  urn_set_error("bn_bwd_fast: unsupported dtype pair (grad %d, act %d)", dtype, out_dtype);
+  return 1;
+}

@@ -15,6 +15,7 @@
 
 #include "common.cuh"
 #include "gconv_tc.cuh"
+#include "bn_fast.cuh"
 
 namespace {
 
@@ -743,10 +744,10 @@ extern "C" int urn_backward(urn_net* h, const float* params, float* grads, int a
       }
       void* dres = nullptr; int64_t lddres = 0;
       if (s.dres_node >= 0) { const Node& r = h->nodes[s.dres_node]; dres = gptr(r); lddres = r.ld; }
-      if (urn_bn_bwd(gptr(dn), dn.ld, P(ws, dn.off), dn.ld, T, dn.dtype, s.relu, L.rows_out, L.cout,
-                     (const float*)P(ws, L.raw_off), L.cout, (const float*)P(ws, L.stats_off),
-                     grads + L.b_off, draw(L), L.cout, raw2, ld2, stats2, dbeta2, draw2, ld2, dres,
-                     lddres, s.accumulate, accumulate, P(ws, h->bn_ws_off), st))
+      if (bn_bwd_full(gptr(dn), dn.ld, P(ws, dn.off), dn.ld, T, dn.dtype, s.relu, L.rows_out, L.cout,
+                      (const float*)P(ws, L.raw_off), L.cout, (const float*)P(ws, L.stats_off),
+                      params + L.b_off, grads + L.b_off, draw(L), L.cout, raw2, ld2, stats2, dbeta2, draw2,
+                      ld2, dres, lddres, s.accumulate, accumulate, P(ws, h->bn_ws_off), st))
         return 1;
     } else if (s.kind == B_WGRAD) {
       const Node& in = h->nodes[L.in_node];

@@ -216,30 +216,6 @@ __device__ __forceinline__ void load_vec(const T* p, float (&v)[N]) {
     v[i] = f.x; v[i + 1] = f.y; v[i + 2] = f.z; v[i + 3] = f.w;
   }
 }
-// 8 x 16-bit in one 16-byte load
-__device__ __forceinline__ void load8(const f16* p, float* v) {
-  const uint4 u = *reinterpret_cast<const uint4*>(p);
-  const uint32_t r[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&r[i]));
-    v[2 * i] = f.x; v[2 * i + 1] = f.y;
-  }
-}
-__device__ __forceinline__ void load8(const bf16* p, float* v) {
-  const uint4 u = *reinterpret_cast<const uint4*>(p);
-  const uint32_t r[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    v[2 * i] = __uint_as_float(r[i] << 16);
-    v[2 * i + 1] = __uint_as_float(r[i] & 0xffff0000u);
-  }
-}
-__device__ __forceinline__ void load8(const float* p, float* v) {
-  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
-  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-}
-
 template <typename TI, int KD, int CI, int NC>
 __global__ void __launch_bounds__(SH_T)
 head_fwd_kernel(const TI* __restrict__ x, long long ldx, const float* __restrict__ w,
