@@ -3,13 +3,17 @@
 //
 // Why: the tap-per-TMA-box kernel (gconv_tc.cu) issues 9 (2D) or 27 (3D) tap-shifted boxes of
 // 128 rows per tile and is bound by the TMA box-row rate when the rows are only 32-64 B.  Here
-// each input plane of a tile is staged ONCE, by four producer warps with 16-byte cp.async
+// each input plane of a tile is staged ONCE, by eight producer warps with 16-byte cp.async
 // (zero-fill for TF 'same' padding), into a swizzled K-major shared-memory layout whose rows
-// are ordered (hy, kw, w): for every halo row hy the three horizontally shifted 8-pixel groups
-// kw = 0,1,2 sit next to each other.  The operand of tap (kh,kw) is then just a descriptor
-// view -- start (kh*3+kw)*8 rows, 8-row groups 24 rows apart -- so all 9 in-plane taps (and in
-// 3D the 3 depth taps, which accumulate into different TMEM accumulators of a TD-plane tile)
-// reuse the same staged plane.  Filters for all taps stay resident in shared memory.
+// are ordered (hy, kw, w): for every halo row hy the three horizontally shifted pixel runs
+// kw = 0,1,2 sit next to each other.  The operand of tap (kh,kw) for the 16x8 sub-tile j is then
+// just a descriptor view -- start kh*RW + kw*8*KS + j*8 rows, 8-row groups RW rows apart -- so all
+// 9 in-plane taps (and in 3D the 3 depth taps, which accumulate into different TMEM accumulators
+// of a TD-plane tile) reuse the same staged plane.  Filters for all taps stay resident in smem.
+// A tile is a SUPER-tile of KS = 4/2/1 sub-tiles (16 x 32/16/8 positions, ~55 KB per staged
+// plane): the per-tile costs that bound the first version of this kernel (mbarrier round trips,
+// proxy fences, commits, ~1300 cycles per 128 positions, measured with URN_HALO_TIMELINE) are
+// paid once per 512 positions and the halo overhead drops from 1.41x to 1.20x.
 //   warps 0-7 : cp.async producers          warp 8 : TMEM alloc, filter TMA, MMA issue
 //   warps 9-12: epilogue (tcgen05.ld -> fp32 raw output / bf16 gradient, accumulate flag)
 // Every CTA owns a contiguous range of tiles; ring indices and tile coordinates advance
@@ -30,15 +34,17 @@ constexpr int kHThreads = 416;       // 13 warps: 8 producers, 1 MMA, 4 epilogue
 constexpr int kHMaxStages = 8;
 constexpr int kMaxAcc = 8;           // TMEM accumulator ring (hides the MMA<->epilogue hand-off latency)
 constexpr int kMaxPF = 4;            // cp.async groups kept in flight per producer thread (<= stages-1)
-constexpr int kTH = 16, kTW = 8;     // 128 positions per plane tile
-constexpr int kHaloRows = (kTH + 2) * 3 * kTW;   // 432 rows per staged plane
+constexpr int kTH = 16, kTW = 8;     // 128 positions per sub-tile
+constexpr int kNCH = 14;             // 16-byte chunks per producer thread and plane (<= 55 KB planes)
 
 struct HaloParams {
   int n, D, H, W;
   int cin, cout;
+  int cout_store;            // channels actually written (< cout when the filter was zero-padded)
   long long ldin, ldout;
   int nkd;                   // 1 (2D) or 3 (3D)
   int TD;                    // output planes per tile
+  int ks, rw;                // sub-tiles per tile (along w); staged rows per halo row = 24 * ks
   int ntw, nth, ntd;
   long long ntiles;
   int stages, plane_bytes, w_tap_bytes, ntaps_w;
@@ -69,9 +75,13 @@ constexpr int kNumProducerWarps = 8;
 constexpr int kProducerThreads = kNumProducerWarps * 32;
 constexpr int kMmaWarp = kNumProducerWarps;            // warp 8
 constexpr int kEpiWarp0 = kNumProducerWarps + 1;       // warps 9..12
-constexpr int kMaxChunks = (kHaloRows * 8 + kProducerThreads - 1) / kProducerThreads;   // cin = 64
 
-template <int NCH>   // 16-byte chunks staged per producer thread and plane: 4 / 7 / 14 for Cin 16 / 32 / 64
+// NKD: depth taps (1 / 3).  OUT_F32: fp32 raw output (else bf16 gradient).  MODE: 0 vector
+// store, 1 vector accumulate, 2 partial scalar store (zero-padded filter).  Template parameters
+// instead of runtime switches keep each instantiation's code small: the first version's 92 KB of
+// SASS (all variants, fully unrolled tap loops) did not fit the instruction cache and the three
+// role loops evicted one another (SMs far from the L2 slice holding the code ran 1.7x slower).
+template <int NKD, bool OUT_F32, int MODE>
 __global__ void __launch_bounds__(kHThreads, 1)
 gconv_halo_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ HaloParams p,
                   const void* __restrict__ in, void* __restrict__ out, long long* __restrict__ tl) {
@@ -90,10 +100,11 @@ gconv_halo_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_consta
   uint64_t* wfull = tempty + kMaxAcc;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wfull + 1);
 
+  const long long tl_t0 = tl ? clock64() : 0;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int pitch = p.cin * 2;                  // bytes per staged row
   const int cpr = pitch / 16;                   // 16-byte chunks per row
-  const int od_lo = p.nkd == 3 ? -1 : 0, od_hi = p.nkd == 3 ? 1 : 0;
+  constexpr int od_lo = NKD == 3 ? -1 : 0, od_hi = NKD == 3 ? 1 : 0;
   // contiguous tile range of this CTA
   const long long t_begin = p.ntiles * (long long)blockIdx.x / gridDim.x;
   const long long t_end = p.ntiles * (long long)(blockIdx.x + 1) / gridDim.x;
@@ -118,59 +129,76 @@ gconv_halo_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_consta
 
   if (warp < kNumProducerWarps) {
     // ===================== producers: stage one input plane per pipeline slot =====================
-    // Per-thread chunk descriptors are tile-invariant: dst offset (16 B units), halo row, halo
-    // column and chunk-in-row, packed into one register each.
+    // Per-thread chunk tables are tile-invariant and live in registers: byte offset of the chunk
+    // from the tile's halo origin in global memory, byte offset of its swizzled slot in the
+    // stage, and (halo row, halo column) for the border test.  Slots beyond the plane's chunk
+    // count replicate slot 0 (the same 16 bytes are copied twice), so the copy loop has no
+    // validity branch; interior tiles skip the border test altogether.  (The first version
+    // decoded a packed descriptor per chunk behind a `continue`: ~25 dependent instructions and
+    // a divergence region per 16 bytes, 150 cycles per chunk -- it bounded the whole kernel.)
     const int t = threadIdx.x;
-    const int total = kHaloRows * cpr;
+    const int total = (kTH + 2) * p.rw * cpr;
     const int cpr_log2 = cpr == 8 ? 3 : (cpr == 4 ? 2 : 1);
     const int sw_shift = cpr == 8 ? 0 : (cpr == 4 ? 1 : 2);
     const int sw_mask = cpr == 8 ? 7 : (cpr == 4 ? 3 : 1);
-    uint32_t desc[NCH];
-#pragma unroll
-    for (int j = 0; j < NCH; ++j) {
-      const int idx = t + j * kProducerThreads;
-      const int row = idx >> cpr_log2, c = idx & (cpr - 1);
-      const int hy = (row * 2731) >> 16;                       // row / 24, exact for row < 432
-      const int rem = row - hy * 24;
-      const int dx = rem - 7 * (rem >> 3);                     // kw + w
-      const int sw = (row >> sw_shift) & sw_mask;              // K-major SW128 / SW64 / SW32 chunk swizzle
-      const uint32_t dst16 = (uint32_t)(row * (pitch >> 4) + (c ^ sw));
-      desc[j] = idx < total ? (dst16 | ((uint32_t)hy << 12) | ((uint32_t)dx << 17) | ((uint32_t)c << 21) | (1u << 31)) : 0u;
-    }
+    const int run = 8 * p.ks;                                  // pixels per (hy, kw) run
     const char* src_base = reinterpret_cast<const char*>(in);
     const int pix_bytes = (int)(p.ldin * 2);        // one plane is < 2 GB: 32-bit offsets inside it
     const int row_bytes = pix_bytes * p.W;
+    const int H = p.H, W = p.W;
+    int soff[kNCH], hyv[kNCH], dxv[kNCH];
+    uint32_t doff[kNCH];
+#pragma unroll
+    for (int j = 0; j < kNCH; ++j) {
+      int idx = t + j * kProducerThreads;
+      if (idx >= total) idx = t;                               // replicate slot 0
+      const int row = idx >> cpr_log2, c = idx & (cpr - 1);
+      const int hy = row / p.rw;
+      const int rem = row - hy * p.rw;
+      const int kw = rem / run;
+      const int dx = kw + (rem - kw * run);                    // halo column of this row
+      const int sw = (row >> sw_shift) & sw_mask;              // K-major SW128 / SW64 / SW32 chunk swizzle
+      doff[j] = (uint32_t)(row * (pitch >> 4) + (c ^ sw)) << 4;
+      soff[j] = hy * row_bytes + dx * pix_bytes + c * 16;
+      hyv[j] = hy; dxv[j] = dx;
+    }
     TileIter ti; ti.init(p, t_begin);
     Ring st, ar; st.init(p.stages); ar.init(p.stages);
     uint32_t issued = 0;
     const int pf = max(1, min(kMaxPF, p.stages / 2));
+    const bool no_load = (p.dbg & 2) != 0;
     for (int k = 0; k < my_tiles; ++k, ti.next(p)) {
       const int d0 = ti.dt * p.TD;
-      const int ybase = ti.ht * kTH - 1, xbase = ti.wt * kTW - 1;
+      const int ybase = ti.ht * kTH - 1, xbase = ti.wt * kTW * p.ks - 1;
+      const bool interior = ybase >= 0 && ybase + kTH + 1 < H && xbase >= 0 && xbase + run + 1 < W;
+      const long long org_off = (long long)ybase * row_bytes + (long long)xbase * pix_bytes;
       const int zhi = min(d0 + p.TD, p.D) - 1 + od_hi;
       for (int z = d0 + od_lo; z <= zhi; ++z) {
         if (z < 0 || z >= p.D) continue;                 // a plane of zeros contributes nothing
         h_mbar_wait_warp(&empty[st.idx], st.phase ^ 1);
         if (t == 0) TL(0, k, 0);
         const uint32_t dst_base = h_smem_u32(smem_a + (size_t)st.idx * p.plane_bytes);
-        const char* plane_ptr = src_base + ((long long)ti.nn * p.D + z) * p.H * (long long)row_bytes;
+        const char* origin = src_base + ((long long)ti.nn * p.D + z) * H * (long long)row_bytes + org_off;
+        if (no_load) {
+        } else if (interior) {
 #pragma unroll
-        for (int j = 0; j < NCH; ++j) {
-          const uint32_t dsc = desc[j];
-          if (!(dsc >> 31)) continue;
-          const int y = ybase + (int)((dsc >> 12) & 31), x = xbase + (int)((dsc >> 17) & 15);
-          const bool ok = (unsigned)y < (unsigned)p.H && (unsigned)x < (unsigned)p.W;
-          const char* src = ok ? plane_ptr + (y * row_bytes + x * pix_bytes + (int)((dsc >> 21) & 7) * 16) : src_base;
-          if (!(p.dbg & 2)) cp_async16_zfill(dst_base + ((dsc & 0xFFFu) << 4), src, ok ? 16u : 0u);
+          for (int j = 0; j < kNCH; ++j) cp_async16_zfill(dst_base + doff[j], origin + soff[j], 16u);
+        } else {
+#pragma unroll
+          for (int j = 0; j < kNCH; ++j) {
+            const bool ok = (unsigned)(ybase + hyv[j]) < (unsigned)H && (unsigned)(xbase + dxv[j]) < (unsigned)W;
+            cp_async16_zfill(dst_base + doff[j], ok ? origin + soff[j] : src_base, ok ? 16u : 0u);
+          }
         }
         // One barrier arrival per WARP (256 per-thread arrivals on one mbarrier word serialise
         // for ~2 us per stage): each thread waits until its copies of the stage issued kPF stages
         // ago have landed, the warp converges, lane 0 arrives.  The consumer issues the
         // generic->async proxy fence after its barrier wait.
-        asm volatile("cp.async.commit_group;" ::: "memory");
+        if (!(p.dbg & 4096)) asm volatile("cp.async.commit_group;" ::: "memory");
         if (t == 0) TL(0, k, 1);
         if (issued >= (uint32_t)pf) {
-          if (pf >= 4) asm volatile("cp.async.wait_group 4;" ::: "memory");
+          if (p.dbg & 4096) {}
+          else if (pf >= 4) asm volatile("cp.async.wait_group 4;" ::: "memory");
           else if (pf == 3) asm volatile("cp.async.wait_group 3;" ::: "memory");
           else if (pf == 2) asm volatile("cp.async.wait_group 2;" ::: "memory");
           else asm volatile("cp.async.wait_group 1;" ::: "memory");
@@ -208,62 +236,67 @@ gconv_halo_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_consta
     const uint32_t w_lo0 = h_smem_u32(smem_w) >> 4;
     const uint32_t b_hi = (uint32_t)(p.bdesc_hi >> 32), a_hi = (uint32_t)(p.adesc_hi >> 32);
     const uint32_t b_lo_base = (uint32_t)p.bdesc_hi, a_lo_base = (uint32_t)p.adesc_hi;
-    uint32_t boff[27];
-#pragma unroll
-    for (int i = 0; i < 27; ++i)
-      boff[i] = b_lo_base | (w_lo0 + (uint32_t)((p.tapw[i] < 0 ? 0 : p.tapw[i]) * (p.w_tap_bytes >> 4)));
-    const uint32_t a_step = (uint32_t)(8 * pitch) >> 4;        // one (kh,kw) view further
-    const int ksteps = p.cin >> 4;
+    const uint32_t b_base = b_lo_base | w_lo0;
+    const uint32_t w_tap16 = (uint32_t)p.w_tap_bytes >> 4;
+    // tap view (kh,kw) of sub-tile j starts at staged row kh*RW + kw*8*KS + j*8
+    const uint32_t row16 = (uint32_t)pitch >> 4;                  // 16-byte units per staged row
+    const uint32_t a_kw = (uint32_t)(8 * p.ks) * row16, a_kh = (uint32_t)p.rw * row16, a_sub = 8u * row16;
+    const bool k2 = p.cin >= 32;                                   // two K steps per tap
     const bool no_mma = (p.dbg & 4) != 0;
-    h_mbar_wait(wfull, 0);     // all lanes poll: keeps the warp converged and its values in the uniform datapath
+    h_mbar_wait_warp(wfull, 0);
     TileIter ti; ti.init(p, t_begin);
     Ring st, ac; st.init(p.stages); ac.init(p.nacc);
+    const uint32_t acc_cols = (uint32_t)(p.TD * p.ks * p.cout);
     for (int k = 0; k < my_tiles; ++k, ti.next(p)) {
       const int d0 = ti.dt * p.TD;
       if (lane == 0) TL(1, k, 0);
-      h_mbar_wait(&tempty[ac.idx], ac.phase ^ 1);
+      h_mbar_wait_warp(&tempty[ac.idx], ac.phase ^ 1);
       h_fence_after();
       if (lane == 0) TL(1, k, 1);
-      uint32_t touched = 0;                              // bit dd: accumulator of plane dd written
+      uint32_t touched = 0;                              // bit dd: accumulators of plane dd written
       const int nd_out = min(d0 + p.TD, p.D) - d0;       // output planes of this tile
-      const uint32_t d_tmem0 = tmem_base + (uint32_t)(ac.idx * p.TD * p.cout);
+      const int nsub = min(p.ks, (p.W - ti.wt * kTW * p.ks + kTW - 1) / kTW);   // sub-tiles inside the image
+      const uint32_t d_tmem0 = tmem_base + (uint32_t)ac.idx * acc_cols;
       const int zhi = d0 + nd_out - 1 + od_hi;
       for (int z = d0 + od_lo; z <= zhi; ++z) {
         if (z < 0 || z >= p.D) continue;
-        h_mbar_wait(&full[st.idx], st.phase);
+        h_mbar_wait_warp(&full[st.idx], st.phase);
         if (lane == 0) TL(1, k, 2);
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // cp.async (generic proxy) -> UMMA (async proxy)
+        if (!(p.dbg & 2048)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // cp.async (generic proxy) -> UMMA (async proxy)
         h_fence_after();
         if (lane == 0) TL(1, k, 3);
         const uint32_t a_lo0 = a_lo_base | (h_smem_u32(smem_a + (size_t)st.idx * p.plane_bytes) >> 4);
-#pragma unroll
-        for (int oi = 0; oi < 3; ++oi) {
-          if (p.nkd == 1 && oi != 1) continue;
+#pragma unroll 1
+        for (int oi = (NKD == 3 ? 0 : 1); oi < (NKD == 3 ? 3 : 2); ++oi) {
           const int dd = z - (oi - 1) - d0;              // od = oi - 1
           if (dd < 0 || dd >= nd_out) continue;
-          const uint32_t d_tmem = d_tmem0 + (uint32_t)(dd * p.cout);
           const uint32_t accf = (touched >> dd) & 1u;
           touched |= 1u << dd;
           if (!no_mma && h_elect_one()) {
+#pragma unroll 1
+            for (int sj = 0; sj < nsub; ++sj) {
+              const uint32_t d_tmem = d_tmem0 + (uint32_t)((dd * p.ks + sj) * p.cout);
+              const uint32_t a_sj = a_lo0 + (uint32_t)sj * a_sub;
 #pragma unroll
-            for (int j = 0; j < 9; ++j) {
-              const uint32_t a_lo = a_lo0 + (uint32_t)j * a_step, b_lo = boff[oi * 9 + j];
-              h_umma2(d_tmem, a_lo, a_hi, b_lo, b_hi, p.idesc, j == 0 ? accf : 1u);
-              if (ksteps > 1) h_umma2(d_tmem, a_lo + 2, a_hi, b_lo + 2, b_hi, p.idesc, 1u);
-              if (ksteps > 2) {
-                h_umma2(d_tmem, a_lo + 4, a_hi, b_lo + 4, b_hi, p.idesc, 1u);
-                h_umma2(d_tmem, a_lo + 6, a_hi, b_lo + 6, b_hi, p.idesc, 1u);
+              for (int kh = 0; kh < 3; ++kh) {
+#pragma unroll
+                for (int kw = 0; kw < 3; ++kw) {
+                  const uint32_t a_lo = a_sj + (uint32_t)kh * a_kh + (uint32_t)kw * a_kw;
+                  const uint32_t b_lo = b_base + (uint32_t)p.tapw[oi * 9 + kh * 3 + kw] * w_tap16;
+                  h_umma2(d_tmem, a_lo, a_hi, b_lo, b_hi, p.idesc, (kh | kw) == 0 ? accf : 1u);
+                  if (k2) h_umma2(d_tmem, a_lo + 2, a_hi, b_lo + 2, b_hi, p.idesc, 1u);
+                }
               }
             }
           }
           __syncwarp();
         }
         if (lane == 0) TL(1, k, 4);
-        if (h_elect_one()) h_commit(&empty[st.idx]);
+        if (h_elect_one()) { if (p.dbg & 1024) h_mbar_arrive(&empty[st.idx]); else h_commit(&empty[st.idx]); }
         __syncwarp();
         st.next();
       }
-      if (h_elect_one()) h_commit(&tfull[ac.idx]);
+      if (h_elect_one()) { if (p.dbg & 1024) h_mbar_arrive(&tfull[ac.idx]); else h_commit(&tfull[ac.idx]); }
       __syncwarp();
       if (lane == 0) TL(1, k, 5);
       ac.next();
@@ -275,10 +308,11 @@ gconv_halo_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_consta
     const int lh = r >> 3, lw = r & 7;
     TileIter ti; ti.init(p, t_begin);
     Ring ac; ac.init(p.nacc);
+    const uint32_t acc_cols = (uint32_t)(p.TD * p.ks * p.cout);
     for (int k = 0; k < my_tiles; ++k, ti.next(p)) {
       const int d0 = ti.dt * p.TD;
-      const int y = ti.ht * kTH + lh, x = ti.wt * kTW + lw;
-      const bool valid_hw = y < p.H && x < p.W;
+      const int y = ti.ht * kTH + lh, x0 = ti.wt * kTW * p.ks + lw;
+      const int nsub = min(p.ks, (p.W - ti.wt * kTW * p.ks + kTW - 1) / kTW);
       const int dmax = min(d0 + p.TD, p.D);
       if (warp == kEpiWarp0 && lane == 0) TL(2, k, 0);
       h_mbar_wait_warp(&tfull[ac.idx], ac.phase);
@@ -286,34 +320,55 @@ gconv_halo_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_consta
       if (warp == kEpiWarp0 && lane == 0) TL(2, k, 1);
       for (int dd = 0; dd < p.TD; ++dd) {
         const int d = d0 + dd;
-        if (d >= dmax) continue;                       // warp-uniform: accumulator never written
-        const long long opix = (((long long)ti.nn * p.D + d) * p.H + y) * p.W + x;
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((ac.idx * p.TD + dd) * p.cout);
-        for (int c0 = 0; c0 < p.cout; c0 += 16) {
-          float v[16];
-          h_tmem_ld16(taddr + c0, v);
-          if (!valid_hw || (p.dbg & 1)) continue;
-          if (p.out_dtype == URN_F32) {
-            float* o = reinterpret_cast<float*>(out) + opix * p.ldout + c0;
+        if (d >= dmax) continue;                       // warp-uniform: accumulators never written
+        const long long opix0 = (((long long)ti.nn * p.D + d) * p.H + y) * p.W + x0;
+        const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)ac.idx * acc_cols +
+                                (uint32_t)(dd * p.ks * p.cout);
+        for (int c0 = 0; c0 < p.cout_store; c0 += 16) {
+          // all sub-tiles' TMEM loads in flight, one wait, then the stores
+          float v[4][16];
 #pragma unroll
-            for (int j = 0; j < 16; j += 4) {
-              float4 xx = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-              if (p.accumulate) {
-                float4 yy = *reinterpret_cast<float4*>(o + j);
-                xx.x += yy.x; xx.y += yy.y; xx.z += yy.z; xx.w += yy.w;
-              }
-              *reinterpret_cast<float4*>(o + j) = xx;
-            }
-          } else {
-            bf16* o = reinterpret_cast<bf16*>(out) + opix * p.ldout + c0;
+          for (int sj = 0; sj < 4; ++sj)
+            if (sj < nsub && !(p.dbg & 512)) h_tmem_ld16_nowait(taddr0 + (uint32_t)(sj * p.cout + c0), v[sj]);
+          if (!(p.dbg & 512)) h_tmem_wait_ld();
 #pragma unroll
-            for (int j = 0; j < 16; j += 4) {
-              float4 xx = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-              if (p.accumulate) {
-                float4 yy = ld4(o + j);
-                xx.x += yy.x; xx.y += yy.y; xx.z += yy.z; xx.w += yy.w;
+          for (int sj = 0; sj < 4; ++sj) {
+            if (sj >= nsub) continue;
+            const int x = x0 + sj * kTW;
+            if (!(y < p.H && x < p.W) || (p.dbg & 1)) continue;
+            const long long opix = opix0 + sj * kTW;
+            if (MODE == 2) {                           // zero-padded filter: only cout_store channels exist
+              if (OUT_F32) {
+                float* o = reinterpret_cast<float*>(out) + opix * p.ldout + c0;
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                  if (c0 + j < p.cout_store) o[j] = p.accumulate ? o[j] + v[sj][j] : v[sj][j];
+              } else {
+                bf16* o = reinterpret_cast<bf16*>(out) + opix * p.ldout + c0;
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                  if (c0 + j < p.cout_store) st1(o + j, p.accumulate ? ld1(o + j) + v[sj][j] : v[sj][j]);
               }
-              st4(o + j, xx);
+            } else if (OUT_F32) {
+              float* o = reinterpret_cast<float*>(out) + opix * p.ldout + c0;
+#pragma unroll
+              for (int j = 0; j < 16; j += 4) {
+                float4 xx = make_float4(v[sj][j], v[sj][j + 1], v[sj][j + 2], v[sj][j + 3]);
+                if (MODE == 1) {
+                  float4 yy = *reinterpret_cast<float4*>(o + j);
+                  xx.x += yy.x; xx.y += yy.y; xx.z += yy.z; xx.w += yy.w;
+                }
+                *reinterpret_cast<float4*>(o + j) = xx;
+              }
+            } else {
+              bf16* o = reinterpret_cast<bf16*>(out) + opix * p.ldout + c0;
+              if (MODE == 1) {
+                float old[16];
+                load8(o, old); load8(o + 8, old + 8);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[sj][j] += old[j];
+              }
+              store8(o, v[sj]); store8(o + 8, v[sj] + 8);
             }
           }
         }
@@ -327,6 +382,11 @@ gconv_halo_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_consta
     }
   }
 
+  if (tl && threadIdx.x == 0) {
+    uint32_t smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    tl[3 * 64 * 8 + blockIdx.x] = ((clock64() - tl_t0) << 8) | (long long)(smid & 255);
+  }
   h_fence_before();
   __syncthreads();
   if (warp == kMmaWarp) {
@@ -336,7 +396,7 @@ gconv_halo_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_consta
   }
 }
 
-bool halo_plan(const GConv& g, int in_dtype, int out_dtype, HaloParams* pp) {
+bool halo_plan(const GConv& g, int in_dtype, int out_dtype, int cout_store, HaloParams* pp) {
   HaloParams& p = *pp;
   memset(&p, 0, sizeof(p));
   if (getenv("URN_NO_HALO")) return false;
@@ -346,7 +406,10 @@ bool halo_plan(const GConv& g, int in_dtype, int out_dtype, HaloParams* pp) {
   if (g.id != g.od || g.ih != g.oh || g.iw != g.ow || g.gd != g.od || g.gh != g.oh || g.gw != g.ow) return false;
   if (g.cin != 16 && g.cin != 32) return false;   // at Cin=64 the tap-box kernel (128 B TMA rows) is as fast
   if (g.cout % 16 || g.cout > 64) return false;
-  if (g.ldin % 8 || g.ldout % 4) return false;
+  if (cout_store <= 0) cout_store = g.cout;
+  if (cout_store > g.cout) return false;
+  if (g.ldin % 8 || g.ldout < cout_store) return false;
+  if (cout_store % 16 == 0 && g.ldout % (out_dtype == URN_F32 ? 4 : 8)) return false;   // 16-byte vector stores
   if (g.ntaps != 9 && g.ntaps != 27) return false;
   for (int i = 0; i < 27; ++i) p.tapw[i] = -1;
   bool has_d = false;
@@ -363,16 +426,25 @@ bool halo_plan(const GConv& g, int in_dtype, int out_dtype, HaloParams* pp) {
   if (has_d != (g.ntaps == 27)) return false;
   p.nkd = has_d ? 3 : 1;
   p.n = g.n; p.D = g.od; p.H = g.oh; p.W = g.ow;
-  p.cin = g.cin; p.cout = g.cout; p.ldin = g.ldin; p.ldout = g.ldout;
-  p.TD = has_d ? (g.cout <= 32 ? 4 : 2) : 1;
+  p.cin = g.cin; p.cout = g.cout; p.cout_store = cout_store; p.ldin = g.ldin; p.ldout = g.ldout;
+  if ((long long)p.H * p.W * g.ldin * 2 >= (1ll << 31)) return false;     // 32-bit offsets inside a plane
+  // super-tile: ~55 KB staged planes; narrower for images that would leave sub-tiles empty
+  p.ks = g.cin == 16 ? 4 : 2;
+  if (const char* e = getenv("URN_HALO_KS")) p.ks = std::max(1, std::min(p.ks, atoi(e)));
+  while (p.ks > 1 && (p.W + kTW - 1) / kTW <= p.ks / 2) p.ks /= 2;
+  p.rw = 24 * p.ks;
+  p.TD = has_d ? 4 : 1;
+  while (p.TD > 1 && p.TD * p.ks * g.cout * 2 > 512) p.TD /= 2;
+  if (p.TD * p.ks * g.cout * 2 > 512) return false;
   if (has_d && p.D < p.TD) p.TD = std::max(1, p.D);
-  p.ntw = (p.W + kTW - 1) / kTW; p.nth = (p.H + kTH - 1) / kTH; p.ntd = (p.D + p.TD - 1) / p.TD;
+  p.ntw = (p.W + kTW * p.ks - 1) / (kTW * p.ks); p.nth = (p.H + kTH - 1) / kTH; p.ntd = (p.D + p.TD - 1) / p.TD;
   p.ntiles = (long long)p.n * p.ntd * p.nth * p.ntw;
-  p.plane_bytes = kHaloRows * g.cin * 2;
+  p.plane_bytes = (kTH + 2) * p.rw * g.cin * 2;
+  if ((kTH + 2) * p.rw * (g.cin * 2 / 16) > kNCH * 256) return false;
   p.w_tap_bytes = g.cout * g.cin * 2;
   p.ntaps_w = maxw + 1;
   const int w_bytes = ((p.ntaps_w * p.w_tap_bytes + 1023) / 1024) * 1024;
-  const int budget = 198 * 1024 - w_bytes;
+  const int budget = 224 * 1024 - w_bytes;
   p.stages = std::min(kHMaxStages, budget / p.plane_bytes);
   if (p.stages < 2) return false;
   if (p.ntiles >= (1ll << 31)) return false;
@@ -382,11 +454,11 @@ bool halo_plan(const GConv& g, int in_dtype, int out_dtype, HaloParams* pp) {
             ((uint32_t)(128 >> 4) << 24);
   const uint64_t pitch = (uint64_t)g.cin * 2;
   const uint64_t layout = pitch == 128 ? 2 : (pitch == 64 ? 4 : 6);
-  p.adesc_hi = (layout << 61) | (1ull << 46) | (((24 * pitch) >> 4) << 32) | (1ull << 16);   // 8-row groups 24 rows apart
+  p.adesc_hi = (layout << 61) | (1ull << 46) | ((((uint64_t)p.rw * pitch) >> 4) << 32) | (1ull << 16);   // 8-row groups RW rows apart
   p.bdesc_hi = (layout << 61) | (1ull << 46) | (((8 * pitch) >> 4) << 32) | (1ull << 16);
-  p.nacc = std::max(2, std::min(kMaxAcc, 512 / (p.TD * g.cout)));
+  p.nacc = std::max(2, std::min(kMaxAcc, 512 / (p.TD * p.ks * g.cout)));
   if (const char* e = getenv("URN_HALO_NACC")) p.nacc = std::max(2, std::min(p.nacc, atoi(e)));
-  p.tmem_cols = std::max(32, pow2c(p.nacc * p.TD * g.cout));
+  p.tmem_cols = std::max(32, pow2c(p.nacc * p.TD * p.ks * g.cout));
   if (p.tmem_cols > 512) return false;
   if (const char* e = getenv("URN_HALO_DBG")) p.dbg = atoi(e);
   return true;
@@ -396,14 +468,19 @@ bool halo_plan(const GConv& g, int in_dtype, int out_dtype, HaloParams* pp) {
 
 bool gconv_halo_supported(const GConv& g, int in_dtype, int out_dtype) {
   HaloParams p;
-  return halo_plan(g, in_dtype, out_dtype, &p);
+  return halo_plan(g, in_dtype, out_dtype, 0, &p);
+}
+bool gconv_halo_supported_padded(const GConv& g, int in_dtype, int out_dtype, int cout_store) {
+  HaloParams p;
+  return halo_plan(g, in_dtype, out_dtype, cout_store, &p);
 }
 
-// wpack: 16-bit filter (dtype of `in`) laid out [tap][cout][cin]
-int gconv_halo_launch(const GConv& g, int in_dtype, const void* in, const void* wpack, void* out,
-                      int out_dtype, cudaStream_t st) {
+// wpack: 16-bit filter (dtype of `in`) laid out [tap][cout][cin].  cout_store (0 = all): only the
+// first cout_store output channels are written (the filter was zero-padded to a multiple of 16).
+int gconv_halo_launch_padded(const GConv& g, int in_dtype, const void* in, const void* wpack, void* out,
+                             int out_dtype, int cout_store, cudaStream_t st) {
   HaloParams p;
-  URN_CHECK(halo_plan(g, in_dtype, out_dtype, &p), "gconv_halo: unsupported shape/dtype");
+  URN_CHECK(halo_plan(g, in_dtype, out_dtype, cout_store, &p), "gconv_halo: unsupported shape/dtype");
   if (p.ntiles == 0) return 0;
   EncodeTiledFnH enc = get_encode_h();
   URN_CHECK(enc, "gconv_halo: cuTensorMapEncodeTiled not available");
@@ -421,19 +498,35 @@ int gconv_halo_launch(const GConv& g, int in_dtype, const void* in, const void* 
   }
   const int w_bytes = ((p.ntaps_w * p.w_tap_bytes + 1023) / 1024) * 1024;
   const size_t smem = 1024 + (size_t)w_bytes + (size_t)p.stages * p.plane_bytes + 1024;
-  static bool attr_set = false;
-  if (!attr_set) {
-    URN_CUDA(cudaFuncSetAttribute(gconv_halo_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    URN_CUDA(cudaFuncSetAttribute(gconv_halo_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    URN_CUDA(cudaFuncSetAttribute(gconv_halo_kernel<14>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
-  }
   const int grid = (int)std::min<long long>(p.ntiles, num_sms());
   long long* tl = nullptr;
   if (const char* e = getenv("URN_HALO_TIMELINE")) tl = (long long*)strtoull(e, nullptr, 0);
-  if (g.cin == 16) gconv_halo_kernel<4><<<grid, kHThreads, smem, st>>>(map_w, p, in, out, tl);
-  else if (g.cin == 32) gconv_halo_kernel<7><<<grid, kHThreads, smem, st>>>(map_w, p, in, out, tl);
-  else gconv_halo_kernel<14><<<grid, kHThreads, smem, st>>>(map_w, p, in, out, tl);
+  const int mode = (p.cout_store & 15) ? 2 : (p.accumulate ? 1 : 0);
+#define HALO_GO(NKD, F32, MODE)                                                                               \
+  do {                                                                                                        \
+    static bool attr_set = false;                                                                             \
+    if (!attr_set) {                                                                                          \
+      URN_CUDA(cudaFuncSetAttribute(gconv_halo_kernel<NKD, F32, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                    227 * 1024));                                                             \
+      attr_set = true;                                                                                        \
+    }                                                                                                         \
+    gconv_halo_kernel<NKD, F32, MODE><<<grid, kHThreads, smem, st>>>(map_w, p, in, out, tl);                  \
+  } while (0)
+#define HALO_GO_M(NKD, F32)                          \
+  do {                                               \
+    if (mode == 0) HALO_GO(NKD, F32, 0);             \
+    else if (mode == 1) HALO_GO(NKD, F32, 1);        \
+    else HALO_GO(NKD, F32, 2);                       \
+  } while (0)
+  if (p.nkd == 3) { if (out_dtype == URN_F32) HALO_GO_M(3, true); else HALO_GO_M(3, false); }
+  else { if (out_dtype == URN_F32) HALO_GO_M(1, true); else HALO_GO_M(1, false); }
+#undef HALO_GO_M
+#undef HALO_GO
   URN_LAUNCH_CHECK();
   return 0;
+}
+
+int gconv_halo_launch(const GConv& g, int in_dtype, const void* in, const void* wpack, void* out,
+                      int out_dtype, cudaStream_t st) {
+  return gconv_halo_launch_padded(g, in_dtype, in, wpack, out, out_dtype, 0, st);
 }

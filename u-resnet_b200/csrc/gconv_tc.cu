@@ -140,10 +140,8 @@ __device__ __forceinline__ bool elect_one() {
       : "=r"(pred));
   return pred != 0;
 }
-__device__ __forceinline__ void mbar_wait_lane0(uint64_t* bar, uint32_t parity) {
-  if ((threadIdx.x & 31) == 0) mbar_wait(bar, parity);
-  __syncwarp();
-}
+// All lanes wait: a lane-0 poll + __syncwarp costs 3-6x more per hand-off (tools/probe/pingpong.cu).
+__device__ __forceinline__ void mbar_wait_lane0(uint64_t* bar, uint32_t parity) { mbar_wait(bar, parity); }
 // descriptors passed as 32-bit halves (the high halves are loop invariants)
 __device__ __forceinline__ void umma_f16_2(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
                                            uint32_t idesc, uint32_t accumulate) {

@@ -23,6 +23,10 @@ int wgrad_tc_launch(const urn_conv_desc& d, int x_dtype, const void* x, int64_t 
 bool gconv_halo_supported(const GConv& g, int in_dtype, int out_dtype);
 int gconv_halo_launch(const GConv& g, int in_dtype, const void* in, const void* wpack, void* out,
                       int out_dtype, cudaStream_t st);
+// Zero-padded filter variant: g.cout is the padded width, only cout_store channels are written.
+bool gconv_halo_supported_padded(const GConv& g, int in_dtype, int out_dtype, int cout_store);
+int gconv_halo_launch_padded(const GConv& g, int in_dtype, const void* in, const void* wpack, void* out,
+                             int out_dtype, int cout_store, cudaStream_t st);
 // Picks the best tensor-core kernel for the shape.
 static inline int gconv_tc_auto(const GConv& g, int in_dtype, const void* in, const void* wpack, void* out,
                                 int out_dtype, cudaStream_t st) {

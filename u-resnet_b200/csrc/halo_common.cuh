@@ -23,26 +23,26 @@ __device__ __forceinline__ void h_mbar_expect_tx(uint64_t* bar, uint32_t bytes) 
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(h_smem_u32(bar)), "r"(bytes)
                : "memory");
 }
+// mbarrier wait: ALL lanes of the warp call try_wait.  Measured on B200 with tools/probe/pingpong.cu
+// (round trip of a two-barrier hand-off between warps of one CTA): all lanes try_wait 109 cycles
+// (123 with 8 waiting warps); lane 0 polling + __syncwarp 324 cycles (692 with 8 waiting warps, the
+// divergence/reconvergence around the poll loop dominates); test_wait spin 352 / 417.
 __device__ __forceinline__ void h_mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0, ok = 0;
+  const uint32_t addr = h_smem_u32(bar);
   while (true) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
-        : "r"(h_smem_u32(bar)), "r"(parity)
+        : "r"(addr), "r"(parity)
         : "memory");
     if (ok) break;
     if (++spins > kSpin) __trap();
   }
 }
-// Warp-level wait: ONE lane polls (32 lanes x 8 warps polling the same mbarrier word serialise
-// in the shared-memory pipe for ~1000 cycles per wait), then the warp reconverges.
-__device__ __forceinline__ void h_mbar_wait_warp(uint64_t* bar, uint32_t parity) {
-  if ((threadIdx.x & 31) == 0) h_mbar_wait(bar, parity);
-  __syncwarp();
-}
+__device__ __forceinline__ void h_mbar_wait_warp(uint64_t* bar, uint32_t parity) { h_mbar_wait(bar, parity); }
 __device__ __forceinline__ void h_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void h_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void h_umma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
@@ -93,8 +93,22 @@ __device__ __forceinline__ void h_tmem_ld16(uint32_t taddr, float (&v)[16]) {
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
+// Issue-only variant: several loads in flight, one h_tmem_wait_ld() before the values are used.
+__device__ __forceinline__ void h_tmem_ld16_nowait(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]),
+        "=r"(r[15])
+      : "r"(taddr));
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void h_tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void cp_async16_zfill(uint32_t dst, const void* src, uint32_t src_bytes) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
 
 struct Ring {
