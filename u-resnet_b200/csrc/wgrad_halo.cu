@@ -34,7 +34,8 @@ constexpr int kWThreads = 416;
 constexpr int kWProdWarps = 8, kWProdThreads = kWProdWarps * 32;
 constexpr int kWMmaWarp = kWProdWarps, kWEpiWarp0 = kWProdWarps + 1;
 constexpr int kWTH = 16, kWTW = 8;
-constexpr int kWHaloRows = (kWTH + 2) * 3 * kWTW;     // 432 rows per staged X plane
+constexpr int kWNCH = 14;                              // 16-byte X chunks per producer thread and plane
+constexpr int kWYCH = 4;                               // 16-byte dY chunks per producer thread and tile
 constexpr int kWMaxStages = 8;
 constexpr int kYMaxStages = 8;                         // dY ring: 3 planes live + the producers' look-ahead
 
@@ -44,6 +45,8 @@ struct WHParams {
   long long ldx, ldy;
   int nkd, LA;               // depth taps (1 / 3); dY look-ahead in planes (0 / 1)
   int DC, ndc;               // planes per depth chunk, number of chunks
+  int ks, rw;                // sub-tiles (16x8 positions) per super-tile along w; staged rows per halo row = 24*ks
+  uint32_t idesc_last;       // instruction descriptor of the last M tile (M = 64 when only one 16-channel tap is live)
   int ntw, nth;
   long long nunits;          // (n, depth chunk, tile row, tile column)
   int stages, ystages, pf;   // X ring, dY ring (power of two), cp.async groups in flight
@@ -68,7 +71,6 @@ struct UnitIter {
   }
 };
 
-template <int NCH>   // 16-byte X chunks per producer thread and plane: 4 / 7 / 14 for cx 16 / 32 / 64
 __global__ void __launch_bounds__(kWThreads, 1)
 wgrad_halo_kernel(const __grid_constant__ WHParams p, const void* __restrict__ x, const void* __restrict__ dy,
                   float* __restrict__ partial) {
@@ -109,41 +111,66 @@ wgrad_halo_kernel(const __grid_constant__ WHParams p, const void* __restrict__ x
 
   if (warp < kWProdWarps) {
     // ===================== producers =====================
+    // Register-resident chunk tables (see gconv_halo.cu): byte offset from the tile's halo origin,
+    // swizzled slot in the stage, halo row / column for the border test; surplus slots replicate
+    // slot 0; interior tiles skip the border test.
     const int t = threadIdx.x;
     const int pitch = p.cx * 2, cpr = pitch / 16;
-    const int total = kWHaloRows * cpr;
+    const int total = (kWTH + 2) * p.rw * cpr;
     const int cpr_log2 = cpr == 8 ? 3 : (cpr == 4 ? 2 : 1);
     const int sw_shift = cpr == 8 ? 0 : (cpr == 4 ? 1 : 2);
     const int sw_mask = cpr == 8 ? 7 : (cpr == 4 ? 3 : 1);
-    uint32_t desc[NCH];
-#pragma unroll
-    for (int j = 0; j < NCH; ++j) {
-      const int idx = t + j * kWProdThreads;
-      const int row = idx >> cpr_log2, c = idx & (cpr - 1);
-      const int hy = (row * 2731) >> 16;                       // row / 24, exact for row < 432
-      const int rem = row - hy * 24;
-      const int dx = rem - 7 * (rem >> 3);                     // kw + w
-      const int sw = (row >> sw_shift) & sw_mask;
-      const uint32_t dst16 = (uint32_t)(row * (pitch >> 4) + (c ^ sw));
-      desc[j] = idx < total ? (dst16 | ((uint32_t)hy << 12) | ((uint32_t)dx << 17) | ((uint32_t)c << 21) | (1u << 31)) : 0u;
-    }
-    // dY tile: 128 rows (h, w) of cy*2 bytes
-    const int ypitch = p.cy * 2, ycpr = ypitch / 16;
-    const int ycpr_log2 = ycpr == 8 ? 3 : (ycpr == 4 ? 2 : 1);
-    const int ysw_shift = ycpr == 8 ? 0 : (ycpr == 4 ? 1 : 2);
-    const int ysw_mask = ycpr == 8 ? 7 : (ycpr == 4 ? 3 : 1);
-    const int ytotal = 128 * ycpr;                             // 256 / 512 / 1024 chunks
+    const int run = 8 * p.ks;
     const char* x_base = reinterpret_cast<const char*>(x);
     const char* y_base = reinterpret_cast<const char*>(dy);
     const int xpix = (int)(p.ldx * 2), xrow = xpix * p.W;
     const int ypix = (int)(p.ldy * 2), yrow = ypix * p.W;
+    const int H = p.H, W = p.W;
+    int soff[kWNCH], hyv[kWNCH], dxv[kWNCH];
+    uint32_t doff[kWNCH];
+#pragma unroll
+    for (int j = 0; j < kWNCH; ++j) {
+      int idx = t + j * kWProdThreads;
+      if (idx >= total) idx = t;
+      const int row = idx >> cpr_log2, c = idx & (cpr - 1);
+      const int hy = row / p.rw;
+      const int rem = row - hy * p.rw;
+      const int kw = rem / run;
+      const int dx = kw + (rem - kw * run);
+      const int sw = (row >> sw_shift) & sw_mask;
+      doff[j] = (uint32_t)(row * (pitch >> 4) + (c ^ sw)) << 4;
+      soff[j] = hy * xrow + dx * xpix + c * 16;
+      hyv[j] = hy; dxv[j] = dx;
+    }
+    // dY tile: rows ordered (sub-tile, h, w8), cy*2 bytes each
+    const int ypitch = p.cy * 2, ycpr = ypitch / 16;
+    const int ycpr_log2 = ycpr == 8 ? 3 : (ycpr == 4 ? 2 : 1);
+    const int ysw_shift = ycpr == 8 ? 0 : (ycpr == 4 ? 1 : 2);
+    const int ysw_mask = ycpr == 8 ? 7 : (ycpr == 4 ? 3 : 1);
+    const int ytotal = p.ks * 128 * ycpr;
+    int ysoff[kWYCH], yhv[kWYCH], yxv[kWYCH];
+    uint32_t ydoff[kWYCH];
+#pragma unroll
+    for (int j = 0; j < kWYCH; ++j) {
+      int idx = t + j * kWProdThreads;
+      if (idx >= ytotal) idx = t;
+      const int row = idx >> ycpr_log2, c = idx & (ycpr - 1);
+      const int sj = row >> 7, h = (row >> 3) & 15, w = row & 7;
+      const int sw = (row >> ysw_shift) & ysw_mask;
+      ydoff[j] = (uint32_t)(row * ycpr + (c ^ sw)) << 4;
+      yhv[j] = h; yxv[j] = sj * 8 + w;
+      ysoff[j] = h * yrow + (sj * 8 + w) * ypix + c * 16;
+    }
     UnitIter ui; ui.init(p, u_begin);
     Ring st, ar, yr; st.init(p.stages); ar.init(p.stages); yr.init(p.ystages);
     uint32_t issued = 0;
     const int pf = p.pf;
     for (int k = 0; k < my_units; ++k, ui.next(p)) {
       const int d0 = ui.dc * p.DC, d1 = min(d0 + p.DC, p.D);
-      const int y0 = ui.ht * kWTH, x0 = ui.wt * kWTW;
+      const int y0 = ui.ht * kWTH, x0 = ui.wt * kWTW * p.ks;
+      const bool interior = y0 >= 1 && y0 + kWTH < H && x0 >= 1 && x0 + run < W;
+      const long long xorg = (long long)(y0 - 1) * xrow + (long long)(x0 - 1) * xpix;
+      const long long yorg = (long long)y0 * yrow + (long long)x0 * ypix;
       for (int z = d0 - p.LA; z <= d1 - 1 + p.LA; ++z) {
         const bool xvalid = z >= 0 && z < p.D;
         const int yp = z + p.LA;
@@ -152,27 +179,30 @@ wgrad_halo_kernel(const __grid_constant__ WHParams p, const void* __restrict__ x
         if (yvalid) h_mbar_wait_warp(&yempty[yr.idx], yr.phase ^ 1);
         if (xvalid) {
           const uint32_t dst_base = h_smem_u32(smem_x + (size_t)st.idx * p.xplane_bytes);
-          const char* plane = x_base + ((long long)ui.nn * p.D + z) * p.H * (long long)xrow;
+          const char* origin = x_base + ((long long)ui.nn * p.D + z) * H * (long long)xrow + xorg;
+          if (interior) {
 #pragma unroll
-          for (int j = 0; j < NCH; ++j) {
-            const uint32_t dsc = desc[j];
-            if (!(dsc >> 31)) continue;
-            const int yy = y0 - 1 + (int)((dsc >> 12) & 31), xx = x0 - 1 + (int)((dsc >> 17) & 15);
-            const bool ok = (unsigned)yy < (unsigned)p.H && (unsigned)xx < (unsigned)p.W;
-            const char* src = ok ? plane + (yy * xrow + xx * xpix + (int)((dsc >> 21) & 7) * 16) : x_base;
-            cp_async16_zfill(dst_base + ((dsc & 0xFFFu) << 4), src, ok ? 16u : 0u);
+            for (int j = 0; j < kWNCH; ++j) cp_async16_zfill(dst_base + doff[j], origin + soff[j], 16u);
+          } else {
+#pragma unroll
+            for (int j = 0; j < kWNCH; ++j) {
+              const bool ok = (unsigned)(y0 - 1 + hyv[j]) < (unsigned)H && (unsigned)(x0 - 1 + dxv[j]) < (unsigned)W;
+              cp_async16_zfill(dst_base + doff[j], ok ? origin + soff[j] : x_base, ok ? 16u : 0u);
+            }
           }
         }
         if (yvalid) {
           const uint32_t dst_base = h_smem_u32(smem_y + (size_t)yr.idx * p.yplane_bytes);
-          const char* plane = y_base + ((long long)ui.nn * p.D + yp) * p.H * (long long)yrow;
-          for (int idx = t; idx < ytotal; idx += kWProdThreads) {
-            const int row = idx >> ycpr_log2, c = idx & (ycpr - 1);
-            const int yy = y0 + (row >> 3), xx = x0 + (row & 7);
-            const bool ok = yy < p.H && xx < p.W;
-            const char* src = ok ? plane + (yy * yrow + xx * ypix + c * 16) : y_base;
-            const int sw = (row >> ysw_shift) & ysw_mask;
-            cp_async16_zfill(dst_base + (uint32_t)((row * ycpr + (c ^ sw)) << 4), src, ok ? 16u : 0u);
+          const char* origin = y_base + ((long long)ui.nn * p.D + yp) * H * (long long)yrow + yorg;
+          if (interior) {
+#pragma unroll
+            for (int j = 0; j < kWYCH; ++j) cp_async16_zfill(dst_base + ydoff[j], origin + ysoff[j], 16u);
+          } else {
+#pragma unroll
+            for (int j = 0; j < kWYCH; ++j) {
+              const bool ok = y0 + yhv[j] < H && x0 + yxv[j] < W;
+              cp_async16_zfill(dst_base + ydoff[j], ok ? origin + ysoff[j] : y_base, ok ? 16u : 0u);
+            }
           }
           yr.next();
         }
@@ -199,9 +229,11 @@ wgrad_halo_kernel(const __grid_constant__ WHParams p, const void* __restrict__ x
     const uint32_t a_hi = (uint32_t)(p.adesc_hi >> 32), b_hi = (uint32_t)(p.bdesc_hi >> 32);
     const uint32_t a_lo_base = (uint32_t)p.adesc_hi, b_lo_base = (uint32_t)p.bdesc_hi;
     const uint32_t pitch = (uint32_t)p.cx * 2;
-    const uint32_t a_mstep = ((uint32_t)p.tpm * 8u * pitch) >> 4;      // next M tile: tpm taps further
-    const uint32_t a_kstep = (48u * pitch) >> 4;                        // 16 positions = 2 image rows = 48 staged rows
+    const uint32_t a_mstep = ((uint32_t)(p.tpm * 8 * p.ks) * pitch) >> 4;   // next M tile: tpm taps further (taps are 8*KS rows apart)
+    const uint32_t a_kstep = ((uint32_t)(2 * p.rw) * pitch) >> 4;           // 16 positions = 2 image rows
+    const uint32_t a_sub = (8u * pitch) >> 4;                               // next sub-tile: 8 pixels further in the run
     const uint32_t b_kstep = (16u * (uint32_t)p.cy * 2u) >> 4;
+    const uint32_t b_sub = (128u * (uint32_t)p.cy * 2u) >> 4;
     const uint32_t y_lo0 = h_smem_u32(smem_y) >> 4, y_stage = (uint32_t)p.yplane_bytes >> 4;
     UnitIter ui; ui.init(p, u_begin);
     Ring st; st.init(p.stages);
@@ -209,6 +241,7 @@ wgrad_halo_kernel(const __grid_constant__ WHParams p, const void* __restrict__ x
     const uint32_t ymask = (uint32_t)p.ystages - 1u;
     for (int k = 0; k < my_units; ++k, ui.next(p)) {
       const int d0 = ui.dc * p.DC, d1 = min(d0 + p.DC, p.D);
+      const int nsub = min(p.ks, (p.W - ui.wt * kWTW * p.ks + kWTW - 1) / kWTW);   // sub-tiles inside the image
       for (int z = d0 - p.LA; z <= d1 - 1 + p.LA; ++z) {
         const bool xvalid = z >= 0 && z < p.D;
         h_mbar_wait(&full[st.idx], st.phase);
@@ -216,22 +249,29 @@ wgrad_halo_kernel(const __grid_constant__ WHParams p, const void* __restrict__ x
         h_fence_after();
         if (xvalid) {
           const uint32_t a_lo0 = a_lo_base | (h_smem_u32(smem_x + (size_t)st.idx * p.xplane_bytes) >> 4);
+#pragma unroll 1
           for (int oi = 0; oi < p.nkd; ++oi) {
             const int pl = z - (oi - p.LA);                    // dY plane paired with depth tap oi
             if (pl < d0 || pl >= d1) continue;
             const uint32_t ys = (yseq0 + (uint32_t)(pl - d0)) & ymask;
             const uint32_t b_lo0 = b_lo_base | (y_lo0 + ys * y_stage);
+#pragma unroll 1
             for (int mi = 0; mi < p.nM; ++mi) {
               const int ai = oi * p.nM + mi;
               const uint32_t d_tmem = tmem_base + (uint32_t)(ai * p.cy);
               const uint32_t accf = (touched >> ai) & 1u;
               touched |= 1u << ai;
               const uint32_t a_lo = a_lo0 + (uint32_t)mi * a_mstep;
+              const uint32_t idesc = mi == p.nM - 1 ? p.idesc_last : p.idesc;
               if (h_elect_one()) {
+#pragma unroll 1
+                for (int sj = 0; sj < nsub; ++sj) {
 #pragma unroll
-                for (int kk = 0; kk < 8; ++kk)
-                  h_umma2(d_tmem, a_lo + (uint32_t)kk * a_kstep, a_hi, b_lo0 + (uint32_t)kk * b_kstep, b_hi, p.idesc,
-                          kk == 0 ? accf : 1u);
+                  for (int kk = 0; kk < 8; ++kk)
+                    h_umma2(d_tmem, a_lo + (uint32_t)sj * a_sub + (uint32_t)kk * a_kstep, a_hi,
+                            b_lo0 + (uint32_t)sj * b_sub + (uint32_t)kk * b_kstep, b_hi, idesc,
+                            (sj | kk) == 0 ? accf : 1u);
+                }
               }
               __syncwarp();
             }
@@ -330,34 +370,45 @@ bool wh_plan(const urn_conv_desc& d, int x_dtype, int y_dtype, int64_t ldx, int6
   p.ndc = (p.D + 47) / 48;
   p.DC = (p.D + p.ndc - 1) / p.ndc;
   p.ndc = (p.D + p.DC - 1) / p.DC;
-  p.ntw = (p.W + kWTW - 1) / kWTW; p.nth = (p.H + kWTH - 1) / kWTH;
-  p.nunits = (long long)p.n * p.ndc * p.nth * p.ntw;
-  if (p.nunits >= (1ll << 31)) return false;
-  p.xplane_bytes = kWHaloRows * p.cx * 2;
-  p.yplane_bytes = 128 * p.cy * 2;
   p.tpm = 128 / p.cx;
   p.nM = (9 + p.tpm - 1) / p.tpm;
   const int cols = p.nkd * p.nM * p.cy;
   if (cols > 512) return false;
   p.tmem_cols = std::max(32, pow2c(cols));
+  // super-tile: KS sub-tiles share one staged X plane (~55 KB) and one barrier round trip
+  p.ks = p.cx == 16 ? 4 : (p.cx == 32 ? 2 : 1);
+  if (const char* e = getenv("URN_WHALO_KS")) p.ks = std::max(1, std::min(p.ks, atoi(e)));
+  while (p.ks > 1 && (p.W + kWTW - 1) / kWTW <= p.ks / 2) p.ks /= 2;
+  while (p.ks > 1 && p.ks * 128 * (p.cy * 2 / 16) > kWYCH * kWProdThreads) p.ks /= 2;
+  p.rw = 24 * p.ks;
+  p.ntw = (p.W + kWTW * p.ks - 1) / (kWTW * p.ks); p.nth = (p.H + kWTH - 1) / kWTH;
+  p.nunits = (long long)p.n * p.ndc * p.nth * p.ntw;
+  if (p.nunits >= (1ll << 31)) return false;
+  p.xplane_bytes = (kWTH + 2) * p.rw * p.cx * 2;
+  p.yplane_bytes = p.ks * 128 * p.cy * 2;
+  if ((kWTH + 2) * p.rw * (p.cx * 2 / 16) > kWNCH * kWProdThreads) return false;
   // Producers run `pf` cp.async groups ahead of the full-barrier arrival; the dY slot of plane z+1
   // frees two steps after its previous tenant's last use, so the dY ring needs >= pf + 3 slots
   // (and the X ring >= pf + 1) or producers and MMA warp would wait on each other.
-  const int budget = 200 * 1024;
+  const int budget = 222 * 1024;
   p.pf = 0;
   for (int pf : {4, 2, 1}) {
-    const int ys = pf == 1 ? 4 : 8;
+    const int ys = pow2c(pf + (p.nkd == 3 ? 3 : 1));
     const int st = std::min(kWMaxStages, (budget - ys * p.yplane_bytes) / p.xplane_bytes);
-    if (st >= 2 * pf) { p.pf = pf; p.ystages = ys; p.stages = st; break; }
+    if (st >= std::max(2, pf + 1)) { p.pf = pf; p.ystages = ys; p.stages = st; break; }
   }
   if (!p.pf) return false;
   const int fmt = x_dtype == URN_BF16 ? 1 : 0;
-  p.idesc = (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | (1u << 15) | (1u << 16) |
-            ((uint32_t)(p.cy >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  const uint32_t idesc0 = (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | (1u << 15) | (1u << 16) |
+                          ((uint32_t)(p.cy >> 3) << 17);
+  p.idesc = idesc0 | ((uint32_t)(128 >> 4) << 24);
+  // cx = 16: the last M tile holds one live tap (accumulator rows 0..15 = TMEM lanes 0..15 in the
+  // M = 64 layout too): a half-height MMA reads half the shared memory.
+  p.idesc_last = (p.cx == 16 && !getenv("URN_WHALO_NO_M64")) ? (idesc0 | ((uint32_t)(64 >> 4) << 24)) : p.idesc;
   auto layout_of = [](uint64_t bytes) -> uint64_t { return bytes == 128 ? 2 : (bytes == 64 ? 4 : 6); };
   const uint64_t xp = (uint64_t)p.cx * 2, yp = (uint64_t)p.cy * 2;
   // MN-major: SBO = next 8 positions (K), LBO = next channel group (MN)
-  p.adesc_hi = (layout_of(xp) << 61) | (1ull << 46) | (((24 * xp) >> 4) << 32) | (((8 * xp) >> 4) << 16);
+  p.adesc_hi = (layout_of(xp) << 61) | (1ull << 46) | ((((uint64_t)p.rw * xp) >> 4) << 32) | ((((uint64_t)(8 * p.ks) * xp) >> 4) << 16);
   p.bdesc_hi = (layout_of(yp) << 61) | (1ull << 46) | (((8 * yp) >> 4) << 32) | (((128 * yp) >> 4) << 16);
   return true;
 }
@@ -383,16 +434,12 @@ int wgrad_halo_launch(const urn_conv_desc& d, int x_dtype, const void* x, int64_
   const size_t smem = 1024 + (size_t)x_bytes + (size_t)p.ystages * p.yplane_bytes + 1024;
   static bool attr_set = false;
   if (!attr_set) {
-    URN_CUDA(cudaFuncSetAttribute(wgrad_halo_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    URN_CUDA(cudaFuncSetAttribute(wgrad_halo_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    URN_CUDA(cudaFuncSetAttribute(wgrad_halo_kernel<14>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    URN_CUDA(cudaFuncSetAttribute(wgrad_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
   const int grid = (int)std::min<long long>(p.nunits, num_sms());
   float* partial = (float*)ws;
-  if (d.cx == 16) wgrad_halo_kernel<4><<<grid, kWThreads, smem, st>>>(p, x, y, partial);
-  else if (d.cx == 32) wgrad_halo_kernel<7><<<grid, kWThreads, smem, st>>>(p, x, y, partial);
-  else wgrad_halo_kernel<14><<<grid, kWThreads, smem, st>>>(p, x, y, partial);
+  wgrad_halo_kernel<<<grid, kWThreads, smem, st>>>(p, x, y, partial);
   URN_LAUNCH_CHECK();
   const int nw = p.ntaps * d.cx * d.cy;
   wgrad_halo_reduce_kernel<<<(nw + 127) / 128, 128, 0, st>>>(partial, nw, grid, dw, accumulate);
