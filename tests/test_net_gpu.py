@@ -293,3 +293,37 @@ def test_trainval_driver_train_checkpoint_and_ana(tmp_path, capsys):
     assert res["softmax"].shape == (2, 64, 64, 3) and res["input"].shape == (2, 64, 64, 1)
     assert 0.0 <= res["acc_all"] <= 1.0 and set(res) == {"entries", "input", "label", "softmax", "acc_all", "acc_nonzero"}
     a.reset()
+
+
+@pytest.mark.parametrize("dims,B", [([32, 64, 1], 2), ([8, 16, 16, 1], 1)])
+def test_padded_head_matches_cuda_core_head(dims, B, monkeypatch):
+    """The head conv2 (Cout = 3) runs on the tensor cores with its filter zero-padded to 16 output
+    channels (forward stores 3; d(raw) is kept at pitch 16 with zero pad channels so that dgrad /
+    wgrad are plain 16 -> 16 halo launches).  It must reproduce the dedicated CUDA-core head
+    kernels (URN_NO_PADDED_HEAD=1) on the same 16-bit operands: logits to accumulation-order noise,
+    every gradient to bf16 storage precision."""
+    F, St = 16, 2
+    nd = len(dims) - 1
+    data, label, weight = S.make_batch(B, dims, seed=21)
+    weight /= weight.sum(axis=1, keepdims=True)
+    P = O.init_params(nd, base=F, num_strides=St, seed=3)
+    out = {}
+    for tag, env in (("cuda_core", "1"), ("padded", None)):
+        if env:
+            monkeypatch.setenv("URN_NO_PADDED_HEAD", env)
+        else:
+            monkeypatch.delenv("URN_NO_PADDED_HEAD", raising=False)
+        net = make_net(dims, F, St, 3, "mix16")
+        net.set_variables(P)
+        net.zero_gradients(None)
+        res, _ = net.accum_gradients(None, data, label, weight)
+        out[tag] = (net.logits(B).cpu().numpy(), res, net.get_variables("grads"))
+    la, ra, ga = out["cuda_core"]
+    lb, rb, gb = out["padded"]
+    assert relerr(lb, la) < 1e-5
+    assert abs(ra[1] - rb[1]) <= 1e-5 * abs(ra[1])
+    for k in ga:
+        assert relerr(gb[k], ga[k]) < 2e-2, (k, relerr(gb[k], ga[k]))
+    # the tensor-core filter gradient multiplies the bf16 shadow of the activations (2^-9 rounding),
+    # the CUDA-core one their fp16 copy
+    assert relerr(gb["UResNet/conv2/weights"], ga["UResNet/conv2/weights"]) < 8e-3

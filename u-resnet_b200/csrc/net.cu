@@ -49,6 +49,11 @@ struct Layer {
   int draw_gbuf = -1;
   int out_node = -1;     // node produced by this layer's own BN-apply (-1: merged later)
   int relu = 0;
+  // Head (Cout = num_class < 16) on the tensor cores: the filter is zero-padded to `cpad` output
+  // channels (forward stores only cout of them) and d(raw) is kept with a pitch of cpad, pad
+  // channels zero, so that dgrad / wgrad are ordinary 16 -> 16 halo-tile launches.
+  int cpad = 0;
+  int64_t wpg_pad_off = -1, wps_pad_off = -1, dw_pad_off = -1;
 };
 
 struct GBuf {
@@ -351,15 +356,33 @@ static int build_plan(urn_net& N) {
   N.wgrad_ws_bytes = 0;
   for (auto& L : N.layers)
     N.wgrad_ws_bytes = std::max<int64_t>(N.wgrad_ws_bytes, wgrad_any_workspace(L.d));
-  N.wgrad_ws_off = b.alloc(N.wgrad_ws_bytes);
   if (T != URN_F32) {
     N.wq_off = b.alloc(N.param_total * 4);
     N.wqg_off = TG == T ? N.wq_off : b.alloc(N.param_total * 4);
     if (c.impl != URN_IMPL_FFMA) {
       N.wpg_off = b.alloc(N.param_total * 2);
       N.wps_off = b.alloc(N.param_total * 2);
+      for (auto& L : N.layers) {
+        if (L.transpose || L.d.cy >= 16 || L.d.cx % 16 || !c.training || getenv("URN_NO_PADDED_HEAD")) continue;
+        urn_conv_desc dp = L.d;
+        dp.cy = 16;
+        const Node& in = N.nodes[L.in_node];
+        GConv g;
+        gconv_gather(dp, in.ld, L.cout, &g);
+        if ((N.TA != N.TG && in.off2 < 0) || !gconv_halo_supported_padded(g, in.dtype, URN_F32, L.cout) ||
+            !wgrad_halo_supported(dp, URN_BF16, URN_BF16, in.ld, 16))
+          continue;
+        L.cpad = 16;
+        const int64_t taps = (int64_t)dp.kd * dp.kh * dp.kw;
+        L.wpg_pad_off = b.alloc(taps * dp.cx * 16 * 2);
+        L.wps_pad_off = b.alloc(taps * dp.cx * 16 * 2);
+        L.dw_pad_off = b.alloc(taps * dp.cx * 16 * 4);
+        N.wgrad_ws_bytes = std::max<int64_t>(N.wgrad_ws_bytes, wgrad_any_workspace(dp));
+      }
     }
   }
+
+  N.wgrad_ws_off = b.alloc(N.wgrad_ws_bytes);
 
   // ---- backward schedule ----
   if (c.training) {
@@ -373,7 +396,7 @@ static int build_plan(urn_net& N) {
     }
     for (auto& n : N.nodes)
       if (n.parent >= 0) n.gbuf = N.nodes[n.parent].gbuf;
-    for (auto& L : N.layers) L.draw_gbuf = new_gbuf(L.rows_out * L.cout * esize(TG));
+    for (auto& L : N.layers) L.draw_gbuf = new_gbuf(L.rows_out * (L.cpad ? L.cpad : L.cout) * esize(TG));
 
     auto mark_write = [&](int node) -> int {   // returns accumulate flag
       Node& n = N.nodes[node];
@@ -560,6 +583,29 @@ __global__ void pack_filter_kernel(const float* __restrict__ w, int taps, int cx
     st1(wg + (t * cy + y) * cx + x, v);
   }
 }
+// Zero-padded variant for the head: cy -> cpad output channels.
+template <typename TGa, typename TSc>
+__global__ void pack_filter_padded_kernel(const float* __restrict__ w, int taps, int cx, int cy, int cpad,
+                                          TGa* __restrict__ wg, TSc* __restrict__ wsc) {
+  const long long n = (long long)taps * cx * cpad;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int y = (int)(i % cpad);
+    const int x = (int)((i / cpad) % cx);
+    const long long t = i / ((long long)cx * cpad);
+    const float v = y < cy ? w[(t * cx + x) * cy + y] : 0.f;
+    st1(wsc + i, v);
+    st1(wg + (t * cpad + y) * cx + x, v);
+  }
+}
+// grads[t][cx][cy] (+)= dw_pad[t][cx][cpad]
+__global__ void extract_padded_dw_kernel(const float* __restrict__ dwp, long long n, int cy, int cpad,
+                                         float* __restrict__ dw, int accumulate) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float v = dwp[(i / cy) * cpad + (i % cy)];
+  dw[i] = accumulate ? dw[i] + v : v;
+}
 inline bool tc_enabled(const urn_net* h) { return h->wpg_off >= 0; }
 
 // Generalised conv dispatch: tcgen05 when the shape allows, CUDA cores otherwise.
@@ -585,7 +631,13 @@ int run_conv_fwd(urn_net* h, int li, const float* params, void* ws, cudaStream_t
   {
   ProfScope ps(h, li, PH_CONV, st);
   const bool ded = h->cfg.impl != URN_IMPL_FFMA;     // dedicated stem / head kernels (stemhead.cu)
-  if (!L.transpose && ded && stem_supported(L.d, in.ld, L.cout)) {
+  if (L.cpad) {
+    urn_conv_desc dp = L.d;
+    dp.cy = L.cpad;
+    GConv g;
+    gconv_gather(dp, in.ld, L.cout, &g);
+    if (gconv_halo_launch_padded(g, in.dtype, P(ws, in.off), P(ws, L.wpg_pad_off), raw, URN_F32, L.cout, st)) return 1;
+  } else if (!L.transpose && ded && stem_supported(L.d, in.ld, L.cout)) {
     if (stem_fwd_launch(L.d, in.dtype, P(ws, in.off), in.ld, w, raw, L.cout, st)) return 1;
   } else if (!L.transpose && ded && head_supported(L.d, in.ld, L.cout)) {
     if (head_fwd_launch(L.d, in.dtype, P(ws, in.off), in.ld, w, raw, L.cout, st)) return 1;
@@ -635,6 +687,24 @@ extern "C" int urn_forward(urn_net* h, const float* params, const float* data, v
     }
     if (tc_enabled(h)) {
       for (const Layer& L : h->layers) {
+        if (L.cpad) {
+          const int taps = L.d.kd * L.d.kh * L.d.kw;
+          const long long n = (long long)taps * L.d.cx * L.cpad;
+          const unsigned nbp = (unsigned)std::min<long long>((n + 255) / 256, 148 * 4);
+          // gather form multiplies activations (TA), scatter form multiplies gradients (TG)
+          if (dispatch_dtype(h->TA, [&](auto pg) {
+                using TGa = URN_T(pg);
+                return dispatch_dtype(h->TG, [&](auto psc) {
+                  using TSc = URN_T(psc);
+                  pack_filter_padded_kernel<TGa, TSc><<<nbp, 256, 0, st>>>(params + L.w_off, taps, L.d.cx, L.d.cy, L.cpad,
+                                                                        (TGa*)P(ws, L.wpg_pad_off), (TSc*)P(ws, L.wps_pad_off));
+                  return 0;
+                });
+              }))
+            return 1;
+          URN_LAUNCH_CHECK();
+          continue;
+        }
         if (L.d.cx % 16 || L.d.cy % 16) continue;       // stem / head stay on the CUDA cores
         const int taps = L.d.kd * L.d.kh * L.d.kw;
         const long long n = (long long)taps * L.d.cx * L.d.cy;
@@ -744,16 +814,18 @@ extern "C" int urn_backward(urn_net* h, const float* params, float* grads, int a
       }
       void* dres = nullptr; int64_t lddres = 0;
       if (s.dres_node >= 0) { const Node& r = h->nodes[s.dres_node]; dres = gptr(r); lddres = r.ld; }
+      const int64_t lddraw = L.cpad ? L.cpad : L.cout;
+      if (L.cpad) URN_CUDA(cudaMemsetAsync(draw(L), 0, (size_t)L.rows_out * L.cpad * esize(T), st));   // pad channels = 0
       if (bn_bwd_full(gptr(dn), dn.ld, P(ws, dn.off), dn.ld, T, dn.dtype, s.relu, L.rows_out, L.cout,
                       (const float*)P(ws, L.raw_off), L.cout, (const float*)P(ws, L.stats_off),
-                      params + L.b_off, grads + L.b_off, draw(L), L.cout, raw2, ld2, stats2, dbeta2, draw2,
+                      params + L.b_off, grads + L.b_off, draw(L), lddraw, raw2, ld2, stats2, dbeta2, draw2,
                       ld2, dres, lddres, s.accumulate, accumulate, P(ws, h->bn_ws_off), st))
         return 1;
     } else if (s.kind == B_WGRAD) {
       const Node& in = h->nodes[L.in_node];
       // conv: big side = input activations, small side = d(raw); deconv: big side = d(raw)
       // activations enter the tensor-core filter gradient through their bf16 shadow copy
-      const bool sh = in.off2 >= 0 && tc_enabled(h) && L.d.cx % 16 == 0 && L.d.cy % 16 == 0;
+      const bool sh = in.off2 >= 0 && tc_enabled(h) && L.d.cx % 16 == 0 && (L.d.cy % 16 == 0 || L.cpad);
       const void* act = P(ws, sh ? in.off2 : in.off);
       const int adt = sh ? URN_BF16 : in.dtype;
       const void* xp = L.transpose ? (const void*)draw(L) : act;
@@ -762,7 +834,17 @@ extern "C" int urn_backward(urn_net* h, const float* params, float* grads, int a
       const int64_t ldx = L.transpose ? L.cout : in.ld, ldy = L.transpose ? in.ld : L.cout;
       int rc;
       const bool ded = h->cfg.impl != URN_IMPL_FFMA && !L.transpose;
-      if (ded && stem_supported(L.d, ldx, L.cout) && ldy % 4 == 0)
+      if (L.cpad) {
+        urn_conv_desc dp = L.d;
+        dp.cy = L.cpad;
+        float* dwp = (float*)P(ws, L.dw_pad_off);
+        rc = wgrad_halo_launch(dp, xdt, xp, ldx, ydt, yp, L.cpad, dwp, 0, P(ws, h->wgrad_ws_off), st);
+        if (!rc) {
+          const long long n = (long long)L.w_count;
+          extract_padded_dw_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(dwp, n, L.d.cy, L.cpad, grads + L.w_off, accumulate);
+          URN_LAUNCH_CHECK();
+        }
+      } else if (ded && stem_supported(L.d, ldx, L.cout) && ldy % 4 == 0)
         rc = stem_wgrad_launch(L.d, xdt, xp, ldx, ydt, yp, ldy, grads + L.w_off, accumulate, P(ws, h->wgrad_ws_off), st);
       else if (ded && head_supported(L.d, ldx, ldy))
         rc = head_wgrad_launch(L.d, xdt, xp, ldx, ydt, yp, ldy, grads + L.w_off, accumulate, P(ws, h->wgrad_ws_off), st);
@@ -776,7 +858,13 @@ extern "C" int urn_backward(urn_net* h, const float* params, float* grads, int a
     } else {  // B_DGRAD
       const Node& in = h->nodes[L.in_node];
       const float* w = conv_weights(h, L, params, ws, true);   // rounded copy left by urn_forward
-      if (!L.transpose && h->cfg.impl != URN_IMPL_FFMA && head_supported(L.d, in.ld, L.cout) && in.ld % 4 == 0) {
+      if (L.cpad) {
+        urn_conv_desc dp = L.d;
+        dp.cy = L.cpad;
+        GConv g;
+        gconv_scatter_class(dp, L.cpad, in.ld, 0, 0, 0, s.accumulate, &g);
+        if (gconv_halo_launch(g, T, draw(L), P(ws, L.wps_pad_off), gptr(in), T, st)) return 1;
+      } else if (!L.transpose && h->cfg.impl != URN_IMPL_FFMA && head_supported(L.d, in.ld, L.cout) && in.ld % 4 == 0) {
         if (head_dgrad_launch(L.d, T, draw(L), L.cout, w, gptr(in), in.ld, s.accumulate, st)) return 1;
       } else if (!L.transpose) {
         for (int pd = 0; pd < L.d.s; ++pd)
