@@ -7,11 +7,10 @@ OUT=gpurun_out
 CMD="python bench.py --workload $WL --steps 1 --warmup 3 --no-cpu-baseline"
 $CMD > $OUT/plain_$TAG.log 2>&1 || { echo "plain run failed"; tail -5 $OUT/plain_$TAG.log; exit 1; }
 tail -1 $OUT/plain_$TAG.log | cut -c1-300
-ncu --metrics gpu__time_duration.sum --clock-control none -s 1500 -c 700 --csv --log-file $OUT/launches_${TAG}_$WL.csv $CMD > $OUT/ncu_launch_$TAG.log 2>&1
+# the timed step: skip the 3 warm-up steps (~650 launches each)
+ncu --metrics gpu__time_duration.sum --clock-control none -s 1950 -c 660 --csv --log-file $OUT/launches_${TAG}_$WL.csv $CMD > $OUT/ncu_launch_$TAG.log 2>&1
 echo "launch list rc=$?"
-ncu --set full --clock-control none --import-source on -k regex:gconv_tc_kernel -s 40 -c 2 -o $OUT/prof_conv_${TAG}_$WL -f $CMD > $OUT/ncu_full1_$TAG.log 2>&1
-echo "full conv rc=$?"
-ncu --set full --clock-control none --import-source on -k regex:wgrad_tc_kernel -s 40 -c 2 -o $OUT/prof_wgrad_${TAG}_$WL -f $CMD > $OUT/ncu_full2_$TAG.log 2>&1
-echo "full wgrad rc=$?"
-ncu --set full --clock-control none --import-source on -k regex:bn_bwd_apply_kernel -s 40 -c 1 -o $OUT/prof_bnbwd_${TAG}_$WL -f $CMD > $OUT/ncu_full3_$TAG.log 2>&1
-echo "full bn rc=$?"
+for K in gconv_halo_kernel wgrad_halo_kernel gconv_tc_kernel wgrad_tc_kernel bn_bwd_apply_fast_kernel bn_apply_fast_kernel; do
+  ncu --set full --clock-control none --import-source on -k regex:$K -s 30 -c 2 -o $OUT/prof_${K}_${TAG}_$WL -f $CMD > $OUT/ncu_full_${K}_$TAG.log 2>&1
+  echo "full $K rc=$?"
+done

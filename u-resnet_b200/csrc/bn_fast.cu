@@ -11,6 +11,8 @@
 //     forward output IS xhat + beta, so xhat = out - beta and the fp32 raw tensor is not read;
 //   * BN -> ReLU without residual (conv0, deconv, conv1): the mask out > 0 is recomputed from
 //     raw with the forward's exact expression fma(x - mean, rstd, beta), so `out` is not read.
+#include <stdlib.h>
+
 #include <algorithm>
 
 #include "common.cuh"
@@ -154,14 +156,13 @@ bn_apply_fast_kernel(const float* __restrict__ raw, long long ld, long long rows
 // backward pass 1: per-channel sums of g, g*xhat (and g*xhat2)
 //   XMODE 0: xhat from raw; 1: xhat = out - beta (no ReLU); 2: xhat and the ReLU mask from raw
 // ---------------------------------------------------------------------------------------
-template <typename TG, typename TA, bool RELU, bool DUAL, int XMODE>
+template <typename TG, typename TA, bool RELU, bool DUAL, int XMODE, int U>
 __global__ void __launch_bounds__(BF_T)
 bn_bwd_reduce_fast_kernel(const TG* __restrict__ dout, long long lddout, const TA* __restrict__ outp,
                           long long ldo, long long rows, int c, int lg, const float* __restrict__ raw,
                           long long ldraw, const float* __restrict__ stats, const float* __restrict__ beta,
                           const float* __restrict__ raw2, long long ldraw2,
                           const float* __restrict__ stats2, double* __restrict__ partial) {
-  constexpr int U = DUAL ? 2 : 4;
   constexpr bool NEED_OUT = (RELU && XMODE != 2) || XMODE == 1;
   constexpr bool NEED_RAW = XMODE != 1;
   const int cg = c >> 3;
@@ -360,9 +361,16 @@ static int bn_bwd_fast_t(const void* dout, long long lddout, const void* out, lo
   if (phase == 0) {
     const int nb = std::min(fast_grid(rows, c, 4), 148 * 4);
     *nblocks = nb;
+    static const int uenv = getenv("URN_BN_U") ? atoi(getenv("URN_BN_U")) : 4;
 #define BF_RED(RELUV, DUALV, XM)                                                                        \
-  bn_bwd_reduce_fast_kernel<TG, TA, RELUV, DUALV, XM><<<nb, BF_T, 0, st>>>((const TG*)dout, lddout,      \
-      (const TA*)out, ldo, rows, c, lg, raw, ldraw, stats, beta, raw2, ldraw2, stats2, partial)
+  do {                                                                                                  \
+    if (uenv == 8) bn_bwd_reduce_fast_kernel<TG, TA, RELUV, DUALV, XM, 8><<<nb, BF_T, 0, st>>>((const TG*)dout, lddout, \
+      (const TA*)out, ldo, rows, c, lg, raw, ldraw, stats, beta, raw2, ldraw2, stats2, partial);        \
+    else if (uenv == 2) bn_bwd_reduce_fast_kernel<TG, TA, RELUV, DUALV, XM, 2><<<nb, BF_T, 0, st>>>((const TG*)dout, lddout, \
+      (const TA*)out, ldo, rows, c, lg, raw, ldraw, stats, beta, raw2, ldraw2, stats2, partial);        \
+    else bn_bwd_reduce_fast_kernel<TG, TA, RELUV, DUALV, XM, 4><<<nb, BF_T, 0, st>>>((const TG*)dout, lddout, \
+      (const TA*)out, ldo, rows, c, lg, raw, ldraw, stats, beta, raw2, ldraw2, stats2, partial);        \
+  } while (0)
     if (xmode == 1) BF_RED(false, false, 1);
     else if (xmode == 2) BF_RED(true, false, 2);
     else if (dual) { if (relu) BF_RED(true, true, 0); else BF_RED(false, true, 0); }
