@@ -95,6 +95,27 @@ def conv_flops(layer_table):
     return f
 
 
+def hbm_bytes(layer_table, elt_act=2, elt_grad=2):
+    """Algorithmic HBM bytes of one training step (every logical tensor counted once per
+    kernel that must touch it): conv fwd (in + fp32 raw out), BN statistics (raw), BN apply (raw in,
+    activation + bf16 shadow out), BN backward (two passes over dout and out/raw, d(raw) out),
+    dgrad (d(raw) in, dX out), wgrad (X + d(raw) in).  Residual / concat extras are left out, so
+    this is a lower bound of what the step has to move."""
+    tot = 0.0
+    for scope, d, tr in layer_table:
+        big = float(d.n) * d.xd * d.xh * d.xw * d.cx      # X side elements
+        small = float(d.n) * d.yd * d.yh * d.yw * d.cy    # Y side elements
+        ein, eout = (small, big) if tr else (big, small)
+        tot += ein * elt_act + eout * 4                    # conv forward
+        tot += eout * 4                                    # BN statistics
+        tot += eout * 4 + eout * 2 * elt_act               # BN apply (+ shadow)
+        tot += 2 * (eout * elt_grad + eout * 4) + eout * elt_grad   # BN backward, 2 passes
+        if scope != "conv0":
+            tot += eout * elt_grad + ein * elt_grad        # dgrad
+        tot += ein * elt_act + eout * elt_grad             # wgrad
+    return tot
+
+
 # ------------------------------------------------------------------------------------------
 # reference arm: the CPU oracle on the host cores
 # ------------------------------------------------------------------------------------------
@@ -271,6 +292,9 @@ def main():
                          "achieved": achieved, "peak": pk["tf_sus"], "unit": "TFLOP/s", "frac": achieved / pk["tf_sus"],
                          "peak_source": pk["src"] + " (sustained bf16)", "traffic": None,
                          "share_of_step": conv_ms / ms if ms > 0 else None},
+            "roofline_hbm": {"bound": "hbm", "kernel": "whole step (all kernels), algorithmic bytes lower bound",
+                             "achieved": hbm_bytes(net.layer_table(B)) / (ms * 1e-3) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
+                             "frac": hbm_bytes(net.layer_table(B)) / (ms * 1e-3) / 1e9 / pk["hbm"], "peak_source": pk["src"]},
             "phases_ms_per_step": {k: round(v, 3) for k, v in ph.items() if k != "-"},
             "loss": float(res[1]),
         }
