@@ -95,6 +95,9 @@ class ssnet_base(object):
         self._result = torch.zeros(4, dtype=torch.float64, device=dev)
         self._result_host = torch.zeros(4, dtype=torch.float64).pin_memory()
         self._staging = {}
+        self._copy_stream = None          # side stream for label / weight H2D copies
+        self._side_pending = []
+        self._step_start = None
         self._exchange = None              # set by dp.attach(): gradient allreduce hook
         self._constructed = True
 
@@ -190,22 +193,65 @@ class ssnet_base(object):
             feed["weight"] = self._to_device("weight", input_weight, self._label_size, batch)
         return feed
 
-    def _to_device(self, key, arr, row, batch=None):
+    def _to_device(self, key, arr, row, batch=None, side=False):
+        """Host array -> pinned staging buffer -> device (async).  With ``side=True`` the copy is
+        enqueued on the copy stream so that it (and the host-side memcpy into pinned memory that
+        precedes it) overlaps the forward pass already running on the compute stream; the
+        compute stream is made to wait for it by ``_join_side_copies``."""
         if isinstance(arr, torch.Tensor) and arr.is_cuda:
             t = arr.to(torch.float32).reshape(-1, row)
         else:
-            a = np.ascontiguousarray(np.asarray(arr, dtype=np.float32)).reshape(-1, row)
+            a = np.asarray(arr, dtype=np.float32).reshape(-1, row)
             st = self._staging.get(key)
             if st is None or st[0].shape != a.shape:
-                st = (torch.empty(a.shape, dtype=torch.float32).pin_memory(),
-                      torch.empty(a.shape, dtype=torch.float32, device=self._device))
+                st = [torch.empty(a.shape, dtype=torch.float32).pin_memory(),
+                      torch.empty(a.shape, dtype=torch.float32, device=self._device), None]
                 self._staging[key] = st
-            st[0].numpy()[...] = a
-            st[1].copy_(st[0], non_blocking=True)
+            if st[2] is not None:
+                st[2].synchronize()                 # previous H2D out of this pinned buffer is done
+            st[0].copy_(torch.from_numpy(np.ascontiguousarray(a)))     # multi-threaded host copy
+            if side:
+                if self._copy_stream is None:
+                    self._copy_stream = torch.cuda.Stream(device=self._device)
+                with torch.cuda.stream(self._copy_stream):
+                    if self._step_start is not None:
+                        self._copy_stream.wait_event(self._step_start)   # earlier consumers of st[1] are done
+                    st[1].copy_(st[0], non_blocking=True)
+                    st[2] = torch.cuda.Event()
+                    st[2].record(self._copy_stream)
+                self._side_pending.append(st[2])
+            else:
+                st[1].copy_(st[0], non_blocking=True)
+                st[2] = torch.cuda.Event()
+                st[2].record(torch.cuda.current_stream(self._device))
             t = st[1]
         if batch is not None and t.shape[0] != batch:
             raise ValueError("batch mismatch between data and %s" % key)
         return t
+
+    def _join_side_copies(self):
+        cur = torch.cuda.current_stream(self._device)
+        for ev in self._side_pending:
+            cur.wait_event(ev)
+        self._side_pending = []
+
+    def _feed_overlapped(self, input_data, input_label, input_weight):
+        """feed_dict for the hot entry points: data first, forward enqueued, THEN label / weight
+        are staged while the GPU is busy (they are only needed by the loss kernel)."""
+        if input_weight is None and self._use_weight:
+            sys.stderr.write('Network configured to use loss pixel-weighting. Cannot run w/ input_weight=None...\n')
+            raise TypeError
+        feed = {"data": self._to_device("data", input_data, self._data_size)}
+        batch = feed["data"].shape[0]
+        self._step_start = torch.cuda.Event()
+        self._step_start.record(torch.cuda.current_stream(self._device))
+        h, ws, batch = self._forward(feed)
+        if input_label is not None:
+            feed["label"] = self._to_device("label", input_label, self._label_size, batch, side=True)
+        if input_weight is not None:
+            feed["weight"] = self._to_device("weight", input_weight, self._label_size, batch, side=True)
+        self._join_side_copies()
+        return feed, h, ws, batch
 
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self._device).cuda_stream)
@@ -265,8 +311,7 @@ class ssnet_base(object):
         ``fetch=False`` skips the device->host read of the metrics (nothing synchronises)."""
         if not self._trainable:
             raise RuntimeError("network constructed with trainable=False")
-        feed = self.feed_dict(input_data=input_data, input_label=input_label, input_weight=input_weight)
-        h, ws, batch = self._forward(feed)
+        feed, h, ws, batch = self._feed_overlapped(input_data, input_label, input_weight)
         self._loss_metrics(h, ws, feed, want_grad=True, want_softmax=False)
         events = self._exchange.events_array() if self._exchange is not None else None
         _capi.check(self._lib.urn_backward(h, self._params.data_ptr(), self._accum.data_ptr(), 1,
@@ -291,8 +336,7 @@ class ssnet_base(object):
         return [None]
 
     def run_test(self, sess, input_data, input_label, input_weight=None):
-        feed = self.feed_dict(input_data=input_data, input_label=input_label, input_weight=input_weight)
-        h, ws, batch = self._forward(feed)
+        feed, h, ws, batch = self._feed_overlapped(input_data, input_label, input_weight)
         self._loss_metrics(h, ws, feed, want_grad=False, want_softmax=False)
         loss, acc_all, acc_nz = self._metrics(batch)
         return [loss, acc_all, acc_nz], ['loss', 'acc. all', 'acc. nonzero']
