@@ -27,6 +27,40 @@ __device__ __forceinline__ void load_params8(const float* p, float* v) {
   v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
 }
 
+// 8 consecutive elements kept PACKED while their loads are in flight (4 registers per 16 bytes):
+// U rows x several tensors can be outstanding per thread without the unpacked fp32 copies
+// inflating the register footprint (reads need ~100 KB in flight per SM to saturate HBM3e; the
+// first version unpacked at the load and topped out at 3.3 TB/s of read traffic).
+template <typename T> struct Raw8 { uint4 a; };
+template <> struct Raw8<float> { uint4 a, b; };
+template <typename T> __device__ __forceinline__ Raw8<T> ldraw8(const T* p) {
+  Raw8<T> r; r.a = *reinterpret_cast<const uint4*>(p); return r;
+}
+template <> __device__ __forceinline__ Raw8<float> ldraw8<float>(const float* p) {
+  Raw8<float> r; r.a = *reinterpret_cast<const uint4*>(p); r.b = *reinterpret_cast<const uint4*>(p + 4); return r;
+}
+template <typename T> __device__ __forceinline__ Raw8<T> zero8() { Raw8<T> r; r.a = make_uint4(0, 0, 0, 0); return r; }
+template <> __device__ __forceinline__ Raw8<float> zero8<float>() {
+  Raw8<float> r; r.a = make_uint4(0, 0, 0, 0); r.b = r.a; return r;
+}
+__device__ __forceinline__ void unpack8(const Raw8<f16>& r, float* v) {
+  const uint32_t w[4] = {r.a.x, r.a.y, r.a.z, r.a.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+    v[2 * i] = f.x; v[2 * i + 1] = f.y;
+  }
+}
+__device__ __forceinline__ void unpack8(const Raw8<bf16>& r, float* v) {
+  const uint32_t w[4] = {r.a.x, r.a.y, r.a.z, r.a.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { v[2 * i] = __uint_as_float(w[i] << 16); v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u); }
+}
+__device__ __forceinline__ void unpack8(const Raw8<float>& r, float* v) {
+  v[0] = __uint_as_float(r.a.x); v[1] = __uint_as_float(r.a.y); v[2] = __uint_as_float(r.a.z); v[3] = __uint_as_float(r.a.w);
+  v[4] = __uint_as_float(r.b.x); v[5] = __uint_as_float(r.b.y); v[6] = __uint_as_float(r.b.z); v[7] = __uint_as_float(r.b.w);
+}
+
 // Sum K per-thread vectors of 8 channels over all threads of the block that own the same
 // channel group; thread ch < c then writes partial[(block*K + k)*c + ch] as double.
 template <int K>
@@ -157,7 +191,7 @@ bn_apply_fast_kernel(const float* __restrict__ raw, long long ld, long long rows
 //   XMODE 0: xhat from raw; 1: xhat = out - beta (no ReLU); 2: xhat and the ReLU mask from raw
 // ---------------------------------------------------------------------------------------
 template <typename TG, typename TA, bool RELU, bool DUAL, int XMODE, int U>
-__global__ void __launch_bounds__(BF_T)
+__global__ void __launch_bounds__(BF_T, DUAL ? 2 : 3)
 bn_bwd_reduce_fast_kernel(const TG* __restrict__ dout, long long lddout, const TA* __restrict__ outp,
                           long long ldo, long long rows, int c, int lg, const float* __restrict__ raw,
                           long long ldraw, const float* __restrict__ stats, const float* __restrict__ beta,
@@ -177,35 +211,39 @@ bn_bwd_reduce_fast_kernel(const TG* __restrict__ dout, long long lddout, const T
 #pragma unroll
   for (int j = 0; j < 8; ++j) acc[0][j] = acc[1][j] = acc[2][j] = 0.f;
   for (long long r = tid >> lg; r < rows; r += rstride * U) {
-    float g[U][8], o[U][8], x[U][8], x2[U][8];
+    Raw8<TG> gb[U];
+    Raw8<TA> ob[NEED_OUT ? U : 1];
+    Raw8<float> xb[NEED_RAW ? U : 1], x2b[DUAL ? U : 1];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const long long rr = r + u * rstride;
-      if (rr < rows) {
-        load8(dout + rr * lddout + ch, g[u]);
-        if (NEED_OUT) load8(outp + rr * ldo + ch, o[u]);
-        if (NEED_RAW) load8(raw + rr * ldraw + ch, x[u]);
-        if (DUAL) load8(raw2 + rr * ldraw2 + ch, x2[u]);
-      } else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) { g[u][j] = 0.f; o[u][j] = 1.f; x[u][j] = 0.f; x2[u][j] = 0.f; }
-      }
+      const bool ok = rr < rows;
+      gb[u] = ok ? ldraw8(dout + rr * lddout + ch) : zero8<TG>();
+      if (NEED_OUT) ob[u] = ok ? ldraw8(outp + rr * ldo + ch) : zero8<TA>();
+      if (NEED_RAW) xb[u] = ok ? ldraw8(raw + rr * ldraw + ch) : zero8<float>();
+      if (DUAL) x2b[u] = ok ? ldraw8(raw2 + rr * ldraw2 + ch) : zero8<float>();
     }
 #pragma unroll
-    for (int u = 0; u < U; ++u)
+    for (int u = 0; u < U; ++u) {
+      float g[8], o[8], x[8], x2[8];
+      unpack8(gb[u], g);
+      if (NEED_OUT) unpack8(ob[u], o);
+      if (NEED_RAW) unpack8(xb[u], x);
+      if (DUAL) unpack8(x2b[u], x2);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        float gv = g[u][j], xh;
-        if (XMODE == 1) xh = o[u][j] - be[j];
-        else xh = (x[u][j] - mu[j]) * rs[j];
+        float gv = g[j], xh;
+        if (XMODE == 1) xh = o[j] - be[j];
+        else xh = (x[j] - mu[j]) * rs[j];
         if (RELU) {
-          if (XMODE == 2) { if (!(fmaf(x[u][j] - mu[j], rs[j], be[j]) > 0.f)) gv = 0.f; }
-          else if (!(o[u][j] > 0.f)) gv = 0.f;
+          if (XMODE == 2) { if (!(fmaf(x[j] - mu[j], rs[j], be[j]) > 0.f)) gv = 0.f; }
+          else if (!(o[j] > 0.f)) gv = 0.f;
         }
         acc[0][j] += gv;
         acc[1][j] = fmaf(gv, xh, acc[1][j]);
-        if (DUAL) acc[2][j] = fmaf(gv, (x2[u][j] - mu2[j]) * rs2[j], acc[2][j]);
+        if (DUAL) acc[2][j] = fmaf(gv, (x2[j] - mu2[j]) * rs2[j], acc[2][j]);
       }
+    }
   }
   block_group_reduce<3>(acc, cg, c, partial);
 }
@@ -223,7 +261,7 @@ bn_bwd_apply_fast_kernel(const TG* __restrict__ dout, long long lddout, const TA
                          long long ldraw2, const float* __restrict__ stats2, TG* __restrict__ draw2,
                          long long lddraw2, TG* __restrict__ dres, long long lddres,
                          const float* __restrict__ sums) {
-  constexpr int U = 2;
+  constexpr int U = DUAL ? 2 : 4;
   constexpr bool NEED_OUT = (RELU && XMODE != 2) || XMODE == 1;
   constexpr bool NEED_RAW = XMODE != 1;
   const int cg = c >> 3;
@@ -239,35 +277,42 @@ bn_bwd_apply_fast_kernel(const TG* __restrict__ dout, long long lddout, const TA
 #pragma unroll
   for (int j = 0; j < 8; ++j) { mg[j] *= inv; mgx[j] *= inv; if (DUAL) mgx2[j] *= inv; }
   for (long long r = tid >> lg; r < rows; r += rstride * U) {
-    float g[U][8], o[U][8], x[U][8], x2[U][8], dr[U][8];
+    Raw8<TG> gb[U], drb[DRES == 2 ? U : 1];
+    Raw8<TA> ob[NEED_OUT ? U : 1];
+    Raw8<float> xb[NEED_RAW ? U : 1], x2b[DUAL ? U : 1];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const long long rr = r + u * rstride;
       if (rr < rows) {
-        load8(dout + rr * lddout + ch, g[u]);
-        if (NEED_OUT) load8(outp + rr * ldo + ch, o[u]);
-        if (NEED_RAW) load8(raw + rr * ldraw + ch, x[u]);
-        if (DUAL) load8(raw2 + rr * ldraw2 + ch, x2[u]);
-        if (DRES == 2) load8(dres + rr * lddres + ch, dr[u]);
+        gb[u] = ldraw8(dout + rr * lddout + ch);
+        if (NEED_OUT) ob[u] = ldraw8(outp + rr * ldo + ch);
+        if (NEED_RAW) xb[u] = ldraw8(raw + rr * ldraw + ch);
+        if (DUAL) x2b[u] = ldraw8(raw2 + rr * ldraw2 + ch);
+        if (DRES == 2) drb[u] = ldraw8(dres + rr * lddres + ch);
       }
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const long long rr = r + u * rstride;
       if (rr >= rows) continue;
-      float o1[8], o2[8], gg[8];
+      float g[8], o[8], x[8], x2[8], dr[8], o1[8], o2[8], gg[8];
+      unpack8(gb[u], g);
+      if (NEED_OUT) unpack8(ob[u], o);
+      if (NEED_RAW) unpack8(xb[u], x);
+      if (DUAL) unpack8(x2b[u], x2);
+      if (DRES == 2) unpack8(drb[u], dr);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        float gv = g[u][j], xh;
-        if (XMODE == 1) xh = o[u][j] - be[j];
-        else xh = (x[u][j] - mu[j]) * rs[j];
+        float gv = g[j], xh;
+        if (XMODE == 1) xh = o[j] - be[j];
+        else xh = (x[j] - mu[j]) * rs[j];
         if (RELU) {
-          if (XMODE == 2) { if (!(fmaf(x[u][j] - mu[j], rs[j], be[j]) > 0.f)) gv = 0.f; }
-          else if (!(o[u][j] > 0.f)) gv = 0.f;
+          if (XMODE == 2) { if (!(fmaf(x[j] - mu[j], rs[j], be[j]) > 0.f)) gv = 0.f; }
+          else if (!(o[j] > 0.f)) gv = 0.f;
         }
         o1[j] = rs[j] * (gv - mg[j] - xh * mgx[j]);
-        if (DUAL) o2[j] = rs2[j] * (gv - mg[j] - (x2[u][j] - mu2[j]) * rs2[j] * mgx2[j]);
-        gg[j] = DRES == 2 ? gv + dr[u][j] : gv;
+        if (DUAL) o2[j] = rs2[j] * (gv - mg[j] - (x2[j] - mu2[j]) * rs2[j] * mgx2[j]);
+        gg[j] = DRES == 2 ? gv + dr[j] : gv;
       }
       store8(draw + rr * lddraw + ch, o1);
       if (DUAL) store8(draw2 + rr * lddraw2 + ch, o2);
@@ -359,7 +404,8 @@ static int bn_bwd_fast_t(const void* dout, long long lddout, const void* out, lo
   int xmode = 0;
   if (beta && !dual && !dres) xmode = relu ? 2 : 1;
   if (phase == 0) {
-    const int nb = std::min(fast_grid(rows, c, 4), 148 * 4);
+    static const int psm = getenv("URN_BN_PSM") ? atoi(getenv("URN_BN_PSM")) : (dual ? 2 : 3);
+    const int nb = std::min(fast_grid(rows, c, psm), 148 * 4);
     *nblocks = nb;
     static const int uenv = getenv("URN_BN_U") ? atoi(getenv("URN_BN_U")) : 4;
 #define BF_RED(RELUV, DUALV, XM)                                                                        \
