@@ -1,5 +1,7 @@
-// Halo-tile tcgen05 convolution for the narrow layers (Cin in {16,32,64}, Cout <= 64,
-// stride 1, 3x3 / 3x3x3 taps, forward and input-gradient).
+// Halo-tile tcgen05 convolution for the narrow layers (Cin in {16,32,64}, Cout <= 64): any
+// generalised-conv launch whose tap offsets form a box -- 3x3(x3) stride 1 (forward, input
+// gradient), stride-2 forward (input sampled with stride 2), 1x1 shortcuts, and the parity
+// classes of stride-2 input gradients / conv-transposes (1-8 taps, output placed with stride 2).
 //
 // Why: the tap-per-TMA-box kernel (gconv_tc.cu) issues 9 (2D) or 27 (3D) tap-shifted boxes of
 // 128 rows per tile and is bound by the TMA box-row rate when the rows are only 32-64 B.  Here
@@ -38,17 +40,23 @@ constexpr int kTH = 16, kTW = 8;     // 128 positions per sub-tile
 constexpr int kNCH = 14;             // 16-byte chunks per producer thread and plane (<= 55 KB planes)
 
 struct HaloParams {
-  int n, D, H, W;
+  int n, D, H, W;            // INPUT tensor dims
+  int OD, OH, OW;            // full OUTPUT tensor dims
+  int gd, gh, gw;            // output sub-grid of this launch (outputs per dim)
+  int is, os;                // input sampling stride, output placement stride
+  int ood, ooh, oow;         // output placement offset (parity class)
+  int nkd, nkh, nkw;         // tap box extents
+  int od0, oh0, ow0;         // smallest tap offset per dim
+  int hr;                    // staged halo rows per plane = (kTH-1)*is + nkh
   int cin, cout;
   int cout_store;            // channels actually written (< cout when the filter was zero-padded)
   long long ldin, ldout;
-  int nkd;                   // 1 (2D) or 3 (3D)
   int TD;                    // output planes per tile
-  int ks, rw;                // sub-tiles per tile (along w); staged rows per halo row = 24 * ks
+  int ks, rw;                // sub-tiles per tile (along w); staged rows per halo row = nkw * 8 * ks
   int ntw, nth, ntd;
   long long ntiles;
   int stages, plane_bytes, w_tap_bytes, ntaps_w;
-  int tapw[27];              // packed-filter tap index for offset (od+1,oh+1,ow+1); -1 = absent
+  int tapw[27];              // packed-filter tap index of box position (kd_i*9 + kh_i*3 + kw_i)
   int accumulate, out_dtype, in_dtype;
   uint32_t idesc;
   uint64_t adesc_hi, bdesc_hi;
@@ -76,12 +84,22 @@ constexpr int kProducerThreads = kNumProducerWarps * 32;
 constexpr int kMmaWarp = kNumProducerWarps;            // warp 8
 constexpr int kEpiWarp0 = kNumProducerWarps + 1;       // warps 9..12
 
-// NKD: depth taps (1 / 3).  OUT_F32: fp32 raw output (else bf16 gradient).  MODE: 0 vector
+// Does any depth tap of the tile's output planes [d0, d0+nd_out) read input plane z?
+__device__ __forceinline__ bool plane_used(const HaloParams& p, int z, int d0, int nd_out) {
+  if (p.is == 1) return true;
+  for (int kdi = 0; kdi < p.nkd; ++kdi) {
+    const int tt = z - p.od0 - kdi;
+    if (tt < 0 || (tt & 1)) continue;
+    const int dd = (tt >> 1) - d0;
+    if (dd >= 0 && dd < nd_out) return true;
+  }
+  return false;
+}
+
+// OUT_F32: fp32 raw output (else bf16 gradient).  MODE: 0 vector
 // store, 1 vector accumulate, 2 partial scalar store (zero-padded filter).  Template parameters
-// instead of runtime switches keep each instantiation's code small: the first version's 92 KB of
-// SASS (all variants, fully unrolled tap loops) did not fit the instruction cache and the three
-// role loops evicted one another (SMs far from the L2 slice holding the code ran 1.7x slower).
-template <int NKD, bool OUT_F32, int MODE>
+// instead of runtime switches keep each instantiation's code small.
+template <bool OUT_F32, int MODE, bool FULL3>   // FULL3: the in-plane tap box is 3x3 (compile-time unrolled issue loop)
 __global__ void __launch_bounds__(kHThreads, 1)
 gconv_halo_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ HaloParams p,
                   const void* __restrict__ in, void* __restrict__ out, long long* __restrict__ tl) {
@@ -104,7 +122,6 @@ gconv_halo_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_consta
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int pitch = p.cin * 2;                  // bytes per staged row
   const int cpr = pitch / 16;                   // 16-byte chunks per row
-  constexpr int od_lo = NKD == 3 ? -1 : 0, od_hi = NKD == 3 ? 1 : 0;
   // contiguous tile range of this CTA
   const long long t_begin = p.ntiles * (long long)blockIdx.x / gridDim.x;
   const long long t_end = p.ntiles * (long long)(blockIdx.x + 1) / gridDim.x;
@@ -137,7 +154,7 @@ gconv_halo_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_consta
     // decoded a packed descriptor per chunk behind a `continue`: ~25 dependent instructions and
     // a divergence region per 16 bytes, 150 cycles per chunk -- it bounded the whole kernel.)
     const int t = threadIdx.x;
-    const int total = (kTH + 2) * p.rw * cpr;
+    const int total = p.hr * p.rw * cpr;
     const int cpr_log2 = cpr == 8 ? 3 : (cpr == 4 ? 2 : 1);
     const int sw_shift = cpr == 8 ? 0 : (cpr == 4 ? 1 : 2);
     const int sw_mask = cpr == 8 ? 7 : (cpr == 4 ? 3 : 1);
@@ -156,7 +173,7 @@ gconv_halo_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_consta
       const int hy = row / p.rw;
       const int rem = row - hy * p.rw;
       const int kw = rem / run;
-      const int dx = kw + (rem - kw * run);                    // halo column of this row
+      const int dx = kw + (rem - kw * run) * p.is;             // input column of this row, relative to the tile origin
       const int sw = (row >> sw_shift) & sw_mask;              // K-major SW128 / SW64 / SW32 chunk swizzle
       doff[j] = (uint32_t)(row * (pitch >> 4) + (c ^ sw)) << 4;
       soff[j] = hy * row_bytes + dx * pix_bytes + c * 16;
@@ -169,12 +186,14 @@ gconv_halo_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_consta
     const bool no_load = (p.dbg & 2) != 0;
     for (int k = 0; k < my_tiles; ++k, ti.next(p)) {
       const int d0 = ti.dt * p.TD;
-      const int ybase = ti.ht * kTH - 1, xbase = ti.wt * kTW * p.ks - 1;
-      const bool interior = ybase >= 0 && ybase + kTH + 1 < H && xbase >= 0 && xbase + run + 1 < W;
+      const int ybase = ti.ht * kTH * p.is + p.oh0, xbase = ti.wt * kTW * p.ks * p.is + p.ow0;
+      const bool interior = ybase >= 0 && ybase + p.hr <= H && xbase >= 0 && xbase + (run - 1) * p.is + p.nkw <= W;
       const long long org_off = (long long)ybase * row_bytes + (long long)xbase * pix_bytes;
-      const int zhi = min(d0 + p.TD, p.D) - 1 + od_hi;
-      for (int z = d0 + od_lo; z <= zhi; ++z) {
+      const int nd_out = min(d0 + p.TD, p.gd) - d0;
+      const int zlo = d0 * p.is + p.od0, zhi = (d0 + nd_out - 1) * p.is + p.od0 + p.nkd - 1;
+      for (int z = zlo; z <= zhi; ++z) {
         if (z < 0 || z >= p.D) continue;                 // a plane of zeros contributes nothing
+        if (!plane_used(p, z, d0, nd_out)) continue;     // stride 2: no tap of this tile reads the plane
         h_mbar_wait_warp(&empty[st.idx], st.phase ^ 1);
         if (t == 0) TL(0, k, 0);
         const uint32_t dst_base = h_smem_u32(smem_a + (size_t)st.idx * p.plane_bytes);
@@ -240,8 +259,8 @@ gconv_halo_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_consta
     const uint32_t w_tap16 = (uint32_t)p.w_tap_bytes >> 4;
     // tap view (kh,kw) of sub-tile j starts at staged row kh*RW + kw*8*KS + j*8
     const uint32_t row16 = (uint32_t)pitch >> 4;                  // 16-byte units per staged row
-    const uint32_t a_kw = (uint32_t)(8 * p.ks) * row16, a_kh = (uint32_t)p.rw * row16, a_sub = 8u * row16;
-    const bool k2 = p.cin >= 32;                                   // two K steps per tap
+    const uint32_t a_kw = (uint32_t)(8 * p.ks) * row16, a_kh = (uint32_t)p.rw * row16, a_sub = 8u * row16;   // a_kh: next tap ROW offset (one halo row)
+    const int ksteps = p.cin >> 4;                                 // K = 16 per MMA
     const bool no_mma = (p.dbg & 4) != 0;
     h_mbar_wait_warp(wfull, 0);
     TileIter ti; ti.init(p, t_begin);
@@ -254,12 +273,13 @@ gconv_halo_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_consta
       h_fence_after();
       if (lane == 0) TL(1, k, 1);
       uint32_t touched = 0;                              // bit dd: accumulators of plane dd written
-      const int nd_out = min(d0 + p.TD, p.D) - d0;       // output planes of this tile
-      const int nsub = min(p.ks, (p.W - ti.wt * kTW * p.ks + kTW - 1) / kTW);   // sub-tiles inside the image
+      const int nd_out = min(d0 + p.TD, p.gd) - d0;      // output planes of this tile
+      const int nsub = min(p.ks, (p.gw - ti.wt * kTW * p.ks + kTW - 1) / kTW);   // sub-tiles inside the sub-grid
       const uint32_t d_tmem0 = tmem_base + (uint32_t)ac.idx * acc_cols;
-      const int zhi = d0 + nd_out - 1 + od_hi;
-      for (int z = d0 + od_lo; z <= zhi; ++z) {
+      const int zlo = d0 * p.is + p.od0, zhi = (d0 + nd_out - 1) * p.is + p.od0 + p.nkd - 1;
+      for (int z = zlo; z <= zhi; ++z) {
         if (z < 0 || z >= p.D) continue;
+        if (!plane_used(p, z, d0, nd_out)) continue;
         h_mbar_wait_warp(&full[st.idx], st.phase);
         if (lane == 0) TL(1, k, 2);
         if (!(p.dbg & 2048)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // cp.async (generic proxy) -> UMMA (async proxy)
@@ -267,8 +287,10 @@ gconv_halo_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_consta
         if (lane == 0) TL(1, k, 3);
         const uint32_t a_lo0 = a_lo_base | (h_smem_u32(smem_a + (size_t)st.idx * p.plane_bytes) >> 4);
 #pragma unroll 1
-        for (int oi = (NKD == 3 ? 0 : 1); oi < (NKD == 3 ? 3 : 2); ++oi) {
-          const int dd = z - (oi - 1) - d0;              // od = oi - 1
+        for (int kdi = 0; kdi < p.nkd; ++kdi) {
+          const int tt = z - p.od0 - kdi;                // = dd_global * is
+          if (tt < 0 || (p.is == 2 && (tt & 1))) continue;
+          const int dd = (p.is == 2 ? tt >> 1 : tt) - d0;
           if (dd < 0 || dd >= nd_out) continue;
           const uint32_t accf = (touched >> dd) & 1u;
           touched |= 1u << dd;
@@ -277,14 +299,23 @@ gconv_halo_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_consta
             for (int sj = 0; sj < nsub; ++sj) {
               const uint32_t d_tmem = d_tmem0 + (uint32_t)((dd * p.ks + sj) * p.cout);
               const uint32_t a_sj = a_lo0 + (uint32_t)sj * a_sub;
+              uint32_t acc = accf;
+              const int nkh = FULL3 ? 3 : p.nkh, nkw = FULL3 ? 3 : p.nkw;
 #pragma unroll
               for (int kh = 0; kh < 3; ++kh) {
+                if (!FULL3 && kh >= nkh) break;
 #pragma unroll
                 for (int kw = 0; kw < 3; ++kw) {
+                  if (!FULL3 && kw >= nkw) break;
                   const uint32_t a_lo = a_sj + (uint32_t)kh * a_kh + (uint32_t)kw * a_kw;
-                  const uint32_t b_lo = b_base + (uint32_t)p.tapw[oi * 9 + kh * 3 + kw] * w_tap16;
-                  h_umma2(d_tmem, a_lo, a_hi, b_lo, b_hi, p.idesc, (kh | kw) == 0 ? accf : 1u);
-                  if (k2) h_umma2(d_tmem, a_lo + 2, a_hi, b_lo + 2, b_hi, p.idesc, 1u);
+                  const uint32_t b_lo = b_base + (uint32_t)p.tapw[kdi * 9 + kh * 3 + kw] * w_tap16;
+                  h_umma2(d_tmem, a_lo, a_hi, b_lo, b_hi, p.idesc, acc);
+                  acc = 1u;
+                  if (ksteps > 1) h_umma2(d_tmem, a_lo + 2, a_hi, b_lo + 2, b_hi, p.idesc, 1u);
+                  if (ksteps > 2) {
+                    h_umma2(d_tmem, a_lo + 4, a_hi, b_lo + 4, b_hi, p.idesc, 1u);
+                    h_umma2(d_tmem, a_lo + 6, a_hi, b_lo + 6, b_hi, p.idesc, 1u);
+                  }
                 }
               }
             }
@@ -312,8 +343,8 @@ gconv_halo_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_consta
     for (int k = 0; k < my_tiles; ++k, ti.next(p)) {
       const int d0 = ti.dt * p.TD;
       const int y = ti.ht * kTH + lh, x0 = ti.wt * kTW * p.ks + lw;
-      const int nsub = min(p.ks, (p.W - ti.wt * kTW * p.ks + kTW - 1) / kTW);
-      const int dmax = min(d0 + p.TD, p.D);
+      const int nsub = min(p.ks, (p.gw - ti.wt * kTW * p.ks + kTW - 1) / kTW);
+      const int dmax = min(d0 + p.TD, p.gd);
       if (warp == kEpiWarp0 && lane == 0) TL(2, k, 0);
       h_mbar_wait_warp(&tfull[ac.idx], ac.phase);
       h_fence_after();
@@ -321,7 +352,8 @@ gconv_halo_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_consta
       for (int dd = 0; dd < p.TD; ++dd) {
         const int d = d0 + dd;
         if (d >= dmax) continue;                       // warp-uniform: accumulators never written
-        const long long opix0 = (((long long)ti.nn * p.D + d) * p.H + y) * p.W + x0;
+        const long long opix0 = (((long long)ti.nn * p.OD + (d * p.os + p.ood)) * p.OH + (y * p.os + p.ooh)) * p.OW +
+                                (x0 * p.os + p.oow);
         const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)ac.idx * acc_cols +
                                 (uint32_t)(dd * p.ks * p.cout);
         for (int c0 = 0; c0 < p.cout_store; c0 += 16) {
@@ -335,8 +367,8 @@ gconv_halo_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_consta
           for (int sj = 0; sj < 4; ++sj) {
             if (sj >= nsub) continue;
             const int x = x0 + sj * kTW;
-            if (!(y < p.H && x < p.W) || (p.dbg & 1)) continue;
-            const long long opix = opix0 + sj * kTW;
+            if (!(y < p.gh && x < p.gw) || (p.dbg & 1)) continue;
+            const long long opix = opix0 + sj * kTW * p.os;
             if (MODE == 2) {                           // zero-padded filter: only cout_store channels exist
               if (OUT_F32) {
                 float* o = reinterpret_cast<float*>(out) + opix * p.ldout + c0;
@@ -402,45 +434,59 @@ bool halo_plan(const GConv& g, int in_dtype, int out_dtype, int cout_store, Halo
   if (getenv("URN_NO_HALO")) return false;
   if (in_dtype != URN_BF16 && in_dtype != URN_F16) return false;
   if (out_dtype != URN_F32 && out_dtype != URN_BF16) return false;
-  if (g.is != 1 || g.os != 1 || g.ood || g.ooh || g.oow) return false;
-  if (g.id != g.od || g.ih != g.oh || g.iw != g.ow || g.gd != g.od || g.gh != g.oh || g.gw != g.ow) return false;
-  if (g.cin != 16 && g.cin != 32) return false;   // at Cin=64 the tap-box kernel (128 B TMA rows) is as fast
+  if ((g.is != 1 && g.is != 2) || (g.os != 1 && g.os != 2) || (g.is == 2 && g.os == 2)) return false;
+  if (g.cin != 16 && g.cin != 32 && g.cin != 64) return false;
   if (g.cout % 16 || g.cout > 64) return false;
   if (cout_store <= 0) cout_store = g.cout;
   if (cout_store > g.cout) return false;
   if (g.ldin % 8 || g.ldout < cout_store) return false;
   if (cout_store % 16 == 0 && g.ldout % (out_dtype == URN_F32 ? 4 : 8)) return false;   // 16-byte vector stores
-  if (g.ntaps != 9 && g.ntaps != 27) return false;
+  if (g.ntaps < 1 || g.ntaps > 27 || g.gd < 1 || g.gh < 1 || g.gw < 1) return false;
+  // the tap offsets must form a full box [o0, o0+n) per dim
+  int lo[3] = {1 << 20, 1 << 20, 1 << 20}, hi[3] = {-(1 << 20), -(1 << 20), -(1 << 20)};
+  for (int t = 0; t < g.ntaps; ++t) {
+    const int o[3] = {g.taps[t].od, g.taps[t].oh, g.taps[t].ow};
+    for (int k = 0; k < 3; ++k) { lo[k] = std::min(lo[k], o[k]); hi[k] = std::max(hi[k], o[k]); }
+  }
+  p.nkd = hi[0] - lo[0] + 1; p.nkh = hi[1] - lo[1] + 1; p.nkw = hi[2] - lo[2] + 1;
+  if (p.nkd > 3 || p.nkh > 3 || p.nkw > 3 || p.nkd * p.nkh * p.nkw != g.ntaps) return false;
+  p.od0 = lo[0]; p.oh0 = lo[1]; p.ow0 = lo[2];
   for (int i = 0; i < 27; ++i) p.tapw[i] = -1;
-  bool has_d = false;
   int maxw = 0;
   for (int t = 0; t < g.ntaps; ++t) {
-    const GTap& tp = g.taps[t];
-    if (tp.od < -1 || tp.od > 1 || tp.oh < -1 || tp.oh > 1 || tp.ow < -1 || tp.ow > 1) return false;
-    if (tp.od != 0) has_d = true;
-    int& slot = p.tapw[(tp.od + 1) * 9 + (tp.oh + 1) * 3 + (tp.ow + 1)];
+    int& slot = p.tapw[(g.taps[t].od - lo[0]) * 9 + (g.taps[t].oh - lo[1]) * 3 + (g.taps[t].ow - lo[2])];
     if (slot >= 0) return false;
-    slot = tp.widx;
-    maxw = std::max(maxw, tp.widx);
+    slot = g.taps[t].widx;
+    maxw = std::max(maxw, g.taps[t].widx);
   }
-  if (has_d != (g.ntaps == 27)) return false;
-  p.nkd = has_d ? 3 : 1;
-  p.n = g.n; p.D = g.od; p.H = g.oh; p.W = g.ow;
+  p.n = g.n; p.D = g.id; p.H = g.ih; p.W = g.iw;
+  p.OD = g.od; p.OH = g.oh; p.OW = g.ow;
+  p.gd = g.gd; p.gh = g.gh; p.gw = g.gw;
+  p.is = g.is; p.os = g.os; p.ood = g.ood; p.ooh = g.ooh; p.oow = g.oow;
+  // every output needs one tap that is always inside the input (so that each TMEM accumulator of
+  // a tile is written at least once): offset 0 in the box and the last sample inside the input
+  const int gs[3] = {g.gd, g.gh, g.gw}, ins[3] = {g.id, g.ih, g.iw};
+  for (int k = 0; k < 3; ++k)
+    if (lo[k] > 0 || hi[k] < 0 || (gs[k] - 1) * g.is > ins[k] - 1) return false;
   p.cin = g.cin; p.cout = g.cout; p.cout_store = cout_store; p.ldin = g.ldin; p.ldout = g.ldout;
   if ((long long)p.H * p.W * g.ldin * 2 >= (1ll << 31)) return false;     // 32-bit offsets inside a plane
-  // super-tile: ~55 KB staged planes; narrower for images that would leave sub-tiles empty
-  p.ks = g.cin == 16 ? 4 : 2;
+  p.hr = (kTH - 1) * g.is + p.nkh;
+  const int cpr = g.cin * 2 / 16;
+  // super-tile width: the widest whose staged plane fits kNCH chunks per producer thread
+  p.ks = 4;
   if (const char* e = getenv("URN_HALO_KS")) p.ks = std::max(1, std::min(p.ks, atoi(e)));
-  while (p.ks > 1 && (p.W + kTW - 1) / kTW <= p.ks / 2) p.ks /= 2;
-  p.rw = 24 * p.ks;
+  while (p.ks > 1 && (p.gw + kTW - 1) / kTW <= p.ks / 2) p.ks /= 2;
+  while (p.ks > 1 && p.hr * p.nkw * 8 * p.ks * cpr > kNCH * 256) p.ks /= 2;
+  p.rw = p.nkw * 8 * p.ks;
+  if (p.hr * p.rw * cpr > kNCH * 256) return false;
+  const bool has_d = g.gd > 1 || p.nkd > 1;
   p.TD = has_d ? 4 : 1;
   while (p.TD > 1 && p.TD * p.ks * g.cout * 2 > 512) p.TD /= 2;
   if (p.TD * p.ks * g.cout * 2 > 512) return false;
-  if (has_d && p.D < p.TD) p.TD = std::max(1, p.D);
-  p.ntw = (p.W + kTW * p.ks - 1) / (kTW * p.ks); p.nth = (p.H + kTH - 1) / kTH; p.ntd = (p.D + p.TD - 1) / p.TD;
+  if (p.gd < p.TD) p.TD = std::max(1, p.gd);
+  p.ntw = (p.gw + kTW * p.ks - 1) / (kTW * p.ks); p.nth = (p.gh + kTH - 1) / kTH; p.ntd = (p.gd + p.TD - 1) / p.TD;
   p.ntiles = (long long)p.n * p.ntd * p.nth * p.ntw;
-  p.plane_bytes = (kTH + 2) * p.rw * g.cin * 2;
-  if ((kTH + 2) * p.rw * (g.cin * 2 / 16) > kNCH * 256) return false;
+  p.plane_bytes = p.hr * p.rw * g.cin * 2;
   p.w_tap_bytes = g.cout * g.cin * 2;
   p.ntaps_w = maxw + 1;
   const int w_bytes = ((p.ntaps_w * p.w_tap_bytes + 1023) / 1024) * 1024;
@@ -454,13 +500,18 @@ bool halo_plan(const GConv& g, int in_dtype, int out_dtype, int cout_store, Halo
             ((uint32_t)(128 >> 4) << 24);
   const uint64_t pitch = (uint64_t)g.cin * 2;
   const uint64_t layout = pitch == 128 ? 2 : (pitch == 64 ? 4 : 6);
-  p.adesc_hi = (layout << 61) | (1ull << 46) | ((((uint64_t)p.rw * pitch) >> 4) << 32) | (1ull << 16);   // 8-row groups RW rows apart
+  // 8-row groups (consecutive output rows of the sub-tile) are is*RW staged rows apart
+  p.adesc_hi = (layout << 61) | (1ull << 46) | ((((uint64_t)(g.is * p.rw) * pitch) >> 4) << 32) | (1ull << 16);
   p.bdesc_hi = (layout << 61) | (1ull << 46) | (((8 * pitch) >> 4) << 32) | (1ull << 16);
   p.nacc = std::max(2, std::min(kMaxAcc, 512 / (p.TD * p.ks * g.cout)));
   if (const char* e = getenv("URN_HALO_NACC")) p.nacc = std::max(2, std::min(p.nacc, atoi(e)));
   p.tmem_cols = std::max(32, pow2c(p.nacc * p.TD * p.ks * g.cout));
   if (p.tmem_cols > 512) return false;
   if (const char* e = getenv("URN_HALO_DBG")) p.dbg = atoi(e);
+  // shapes the tap-box kernel handles as well or better unless asked for (URN_HALO_ALL=1):
+  // Cin = 64 (128-byte TMA rows)
+  if (g.cin == 64 && !getenv("URN_HALO_ALL")) return false;
+  if (getenv("URN_HALO_ONLY3X3") && !(g.is == 1 && g.os == 1 && p.nkh == 3 && p.nkw == 3)) return false;
   return true;
 }
 
@@ -502,24 +553,25 @@ int gconv_halo_launch_padded(const GConv& g, int in_dtype, const void* in, const
   long long* tl = nullptr;
   if (const char* e = getenv("URN_HALO_TIMELINE")) tl = (long long*)strtoull(e, nullptr, 0);
   const int mode = (p.cout_store & 15) ? 2 : (p.accumulate ? 1 : 0);
-#define HALO_GO(NKD, F32, MODE)                                                                               \
+  const bool full3 = p.nkh == 3 && p.nkw == 3;
+#define HALO_GO(F32, MODE, F3)                                                                                \
   do {                                                                                                        \
     static bool attr_set = false;                                                                             \
     if (!attr_set) {                                                                                          \
-      URN_CUDA(cudaFuncSetAttribute(gconv_halo_kernel<NKD, F32, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+      URN_CUDA(cudaFuncSetAttribute(gconv_halo_kernel<F32, MODE, F3>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                     227 * 1024));                                                             \
       attr_set = true;                                                                                        \
     }                                                                                                         \
-    gconv_halo_kernel<NKD, F32, MODE><<<grid, kHThreads, smem, st>>>(map_w, p, in, out, tl);                  \
+    gconv_halo_kernel<F32, MODE, F3><<<grid, kHThreads, smem, st>>>(map_w, p, in, out, tl);                   \
   } while (0)
-#define HALO_GO_M(NKD, F32)                          \
-  do {                                               \
-    if (mode == 0) HALO_GO(NKD, F32, 0);             \
-    else if (mode == 1) HALO_GO(NKD, F32, 1);        \
-    else HALO_GO(NKD, F32, 2);                       \
+#define HALO_GO_M(F32)                                                               \
+  do {                                                                               \
+    if (mode == 0) { if (full3) HALO_GO(F32, 0, true); else HALO_GO(F32, 0, false); } \
+    else if (mode == 1) { if (full3) HALO_GO(F32, 1, true); else HALO_GO(F32, 1, false); } \
+    else HALO_GO(F32, 2, true);                                                      \
   } while (0)
-  if (p.nkd == 3) { if (out_dtype == URN_F32) HALO_GO_M(3, true); else HALO_GO_M(3, false); }
-  else { if (out_dtype == URN_F32) HALO_GO_M(1, true); else HALO_GO_M(1, false); }
+  URN_CHECK(mode != 2 || full3, "gconv_halo: padded filters only with 3x3 taps");
+  if (out_dtype == URN_F32) HALO_GO_M(true); else HALO_GO_M(false);
 #undef HALO_GO_M
 #undef HALO_GO
   URN_LAUNCH_CHECK();
