@@ -508,9 +508,8 @@ bool halo_plan(const GConv& g, int in_dtype, int out_dtype, int cout_store, Halo
   p.tmem_cols = std::max(32, pow2c(p.nacc * p.TD * p.ks * g.cout));
   if (p.tmem_cols > 512) return false;
   if (const char* e = getenv("URN_HALO_DBG")) p.dbg = atoi(e);
-  // shapes the tap-box kernel handles as well or better unless asked for (URN_HALO_ALL=1):
-  // Cin = 64 (128-byte TMA rows)
-  if (g.cin == 64 && !getenv("URN_HALO_ALL")) return false;
+  // Cin = 64 with 1-4 taps: the tap-box kernel (128-byte TMA rows, few boxes) is as fast or faster
+  if (g.cin == 64 && !(p.nkh == 3 && p.nkw == 3) && !getenv("URN_HALO_ALL")) return false;
   if (getenv("URN_HALO_ONLY3X3") && !(g.is == 1 && g.os == 1 && p.nkh == 3 && p.nkw == 3)) return false;
   return true;
 }
