@@ -245,6 +245,36 @@ def test_conv_halo_wgrad(lib, xdt, nd, n, sp, cin, cout, ldf):
     torch.cuda.synchronize()
 
 
+@pytest.mark.parametrize("nd,n,sp,cin,cout,k,s", [
+    (2, 3, (40, 72), 16, 16, 3, 1), (2, 2, (33, 19), 16, 32, 3, 1), (2, 1, (64, 64), 32, 64, 3, 1),
+    (2, 2, (32, 48), 16, 32, 3, 2), (2, 2, (16, 40), 32, 16, 1, 1), (3, 1, (9, 20, 12), 16, 16, 3, 1),
+    (3, 1, (8, 16, 16), 16, 32, 3, 2)])
+def test_conv_fused_bn_statistics(lib, nd, n, sp, cin, cout, k, s):
+    """BN statistics fused into the conv epilogue (per-warp butterfly + Chan merges) against
+    float64 mean / biased variance of the kernel's own fp32 output."""
+    rng = np.random.default_rng(hash((nd, n, sp, cin, cout, k, s, 9)) % 2**32)
+    x = host(dev(rng.standard_normal((n,) + sp + (cin,)).astype(np.float32) + 0.7, F16))
+    w = (rng.standard_normal((k,) * nd + (cin, cout)) / np.sqrt(k**nd * cin)).astype(np.float32)
+    w[..., 0] *= 1e-3                       # a nearly constant channel: variance << mean^2 + eps matters
+    d = _capi.conv_desc_same(nd, n, sp, cin, cout, k, s)
+    osp = (d.yd, d.yh, d.yw)[3 - nd:]
+    xd, wd = dev(x, F16), dev(w)
+    wpack = torch.empty(2 * w.size + 64, dtype=torch.uint8, device=DEV)
+    y = torch.empty((n,) + osp + (cout,), dtype=torch.float32, device=DEV)
+    stats = torch.empty(2 * cout, dtype=torch.float32, device=DEV)
+    ws = torch.empty(int(lib.urn_bn_workspace(cout)), dtype=torch.uint8, device=DEV)
+    _capi.check(lib.urn_conv_fwd_tc_stats(C.byref(d), F16, xd.data_ptr(), cin, wd.data_ptr(), wpack.data_ptr(),
+                                          y.data_ptr(), cout, 1e-3, stats.data_ptr(), ws.data_ptr(), st()))
+    yh = host(y).reshape(-1, cout).astype(np.float64)
+    mu, var = yh.mean(0), yh.var(0)
+    np.testing.assert_allclose(host(stats)[:cout], mu, rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(host(stats)[cout:], 1 / np.sqrt(var + 1e-3), rtol=2e-5)
+    # and the separate-pass kernel agrees
+    stats2 = torch.empty(2 * cout, dtype=torch.float32, device=DEV)
+    _capi.check(lib.urn_bn_stats(y.data_ptr(), cout, yh.shape[0], cout, 1e-3, stats2.data_ptr(), ws.data_ptr(), st()))
+    np.testing.assert_allclose(host(stats), host(stats2), rtol=2e-5, atol=1e-6)
+
+
 def test_conv_tcgen05_pitched_concat_view(lib):
     """TMA reads a channel slice of a concat buffer (pitch 2C, offset C)."""
     rng = np.random.default_rng(5)

@@ -45,6 +45,7 @@ SIGNATURES = {
     "urn_conv_dgrad": (_i, [_descp, _i, _i, _vp, _i64, _vp, _vp, _i64, _i, _i, _vp]),
     "urn_conv_fwd_tc": (_i, [_descp, _i, _vp, _i64, _vp, _vp, _vp, _i64, _i, _i, _vp]),
     "urn_conv_dgrad_tc": (_i, [_descp, _i, _vp, _i64, _vp, _vp, _vp, _i64, _i, _i, _vp]),
+    "urn_conv_fwd_tc_stats": (_i, [_descp, _i, _vp, _i64, _vp, _vp, _vp, _i64, _f, _vp, _vp, _vp]),
     "urn_conv_wgrad_workspace": (_i64, [_descp]),
     "urn_conv_wgrad": (_i, [_descp, _i, _i, _vp, _i64, _vp, _i64, _i, _vp, _i, _vp, _vp]),
     "urn_bn_workspace": (_i64, [_i]),

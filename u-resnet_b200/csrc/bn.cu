@@ -4,6 +4,7 @@
 // in a fixed order (deterministic) in double.
 #include "common.cuh"
 #include "bn_fast.cuh"
+#include "gconv_tc.cuh"
 
 namespace {
 
@@ -115,6 +116,42 @@ bn_stats_finalize_kernel(const double* __restrict__ partial, int nblocks, int c,
     double var = v[1] / (double)rows - dm * dm;
     if (var < 0.0) var = 0.0;
     stats[ch] = (float)((double)raw[ch] + dm);
+    stats[c + ch] = (float)(1.0 / sqrt(var + (double)eps));
+  }
+}
+
+// Merge of (n, mean, M2) partials produced by the conv epilogues (gconv_halo.cu): Chan's parallel
+// update in double, thread t takes parts t, t+128, ... then a fixed-shape tree (deterministic).
+__device__ __forceinline__ void chan_merge(double& n, double& mean, double& m2, double nb, double mb, double m2b) {
+  if (nb <= 0.0) return;
+  const double nn = n + nb, delta = mb - mean;
+  mean += delta * (nb / nn);
+  m2 += m2b + delta * delta * (n * nb / nn);
+  n = nn;
+}
+__global__ void __launch_bounds__(128)
+bn_stats_merge_kernel(const float* __restrict__ parts, int nparts, int c_stride, float eps,
+                      float* __restrict__ stats, int c) {
+  __shared__ double sh[3][128];
+  const int ch = blockIdx.x;
+  double n = 0.0, mean = 0.0, m2 = 0.0;
+  for (int pi = threadIdx.x; pi < nparts; pi += 128) {
+    const float* q = parts + ((long long)pi * c_stride + ch) * 3;
+    chan_merge(n, mean, m2, (double)q[0], (double)q[1], (double)q[2]);
+  }
+  sh[0][threadIdx.x] = n; sh[1][threadIdx.x] = mean; sh[2][threadIdx.x] = m2;
+  __syncthreads();
+  for (int o = 64; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      double a = sh[0][threadIdx.x], b = sh[1][threadIdx.x], c2 = sh[2][threadIdx.x];
+      chan_merge(a, b, c2, sh[0][threadIdx.x + o], sh[1][threadIdx.x + o], sh[2][threadIdx.x + o]);
+      sh[0][threadIdx.x] = a; sh[1][threadIdx.x] = b; sh[2][threadIdx.x] = c2;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const double var = sh[0][0] > 0.0 ? sh[2][0] / sh[0][0] : 0.0;
+    stats[ch] = (float)sh[1][0];
     stats[c + ch] = (float)(1.0 / sqrt(var + (double)eps));
   }
 }
@@ -334,6 +371,14 @@ inline bool aligned4(int c, std::initializer_list<long long> lds) {
 }
 
 }  // namespace
+
+int bn_stats_merge_launch(const float* parts, int nparts, int c_stride, int c, long long rows, float eps,
+                          float* stats, cudaStream_t st) {
+  (void)rows;
+  bn_stats_merge_kernel<<<c, 128, 0, st>>>(parts, nparts, c_stride, eps, stats, c);
+  URN_LAUNCH_CHECK();
+  return 0;
+}
 
 extern "C" int64_t urn_bn_workspace(int c) {
   // partials [BN_MAX_BLOCKS][3][c] doubles + sums [3][c] floats (256 B aligned)

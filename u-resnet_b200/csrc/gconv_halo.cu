@@ -62,6 +62,7 @@ struct HaloParams {
   uint64_t adesc_hi, bdesc_hi;
   int tmem_cols;
   int nacc;                  // accumulator buffers in the TMEM ring
+  float* stats_part;         // fused BN statistics: per (CTA, epilogue warp, channel) (n, mean, M2) partials, or NULL
   int dbg;                   // URN_HALO_DBG bitmask (perf experiments): 1 no stores, 2 no loads, 4 no MMA
 };
 
@@ -84,6 +85,51 @@ constexpr int kProducerThreads = kNumProducerWarps * 32;
 constexpr int kMmaWarp = kNumProducerWarps;            // warp 8
 constexpr int kEpiWarp0 = kNumProducerWarps + 1;       // warps 9..12
 
+// Fused BN statistics (SURVEY 8a K5 'stats fused into the conv epilogue').  A warp holds 32
+// positions x 16 channels of fp32 accumulator values.  Per channel the sum and the sum of squares
+// over the 32 positions are formed with a halving butterfly (16 shuffles per quantity: after the
+// xor-16/8/4/2 steps each lane holds one channel, the xor-1 step completes it), turned into the
+// chunk's (mean, M2) and merged into the lane's running (n, mean, M2) with Chan's update -- so no
+// E[x^2]-E[x]^2 cancellation over more than 128 values (one tile plane) ever happens in fp32.  Lane L owns channel
+// c0 + (L >> 1).  Invalid positions (tile overhang) contribute zeros and are not counted.
+__device__ __forceinline__ float butterfly16(float (&v)[16], int lane) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const bool hi = lane & 16;
+    const float send = hi ? v[i] : v[i + 8], keep = hi ? v[i + 8] : v[i];
+    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const bool hi = lane & 8;
+    const float send = hi ? v[i] : v[i + 4], keep = hi ? v[i + 4] : v[i];
+    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const bool hi = lane & 4;
+    const float send = hi ? v[i] : v[i + 2], keep = hi ? v[i + 2] : v[i];
+    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+  {
+    const bool hi = lane & 2;
+    const float send = hi ? v[0] : v[1], keep = hi ? v[1] : v[0];
+    v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  }
+  return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+struct RunStat { float n, mean, m2; };
+__device__ __forceinline__ void stat_merge(RunStat& r, float (&a)[16], float (&b)[16], unsigned nv, int lane) {
+  if (nv == 0) return;                                   // warp-uniform
+  const float s1 = butterfly16(a, lane), s2 = butterfly16(b, lane);
+  const float cn = (float)nv, cm = s1 / cn;
+  const float cm2 = fmaxf(s2 - s1 * cm, 0.f);
+  const float nn = r.n + cn, delta = cm - r.mean;
+  r.mean += delta * (cn / nn);
+  r.m2 += cm2 + delta * delta * (r.n * cn / nn);
+  r.n = nn;
+}
+
 // Does any depth tap of the tile's output planes [d0, d0+nd_out) read input plane z?
 __device__ __forceinline__ bool plane_used(const HaloParams& p, int z, int d0, int nd_out) {
   if (p.is == 1) return true;
@@ -99,7 +145,7 @@ __device__ __forceinline__ bool plane_used(const HaloParams& p, int z, int d0, i
 // OUT_F32: fp32 raw output (else bf16 gradient).  MODE: 0 vector
 // store, 1 vector accumulate, 2 partial scalar store (zero-padded filter).  Template parameters
 // instead of runtime switches keep each instantiation's code small.
-template <bool OUT_F32, int MODE, bool FULL3>   // FULL3: the in-plane tap box is 3x3 (compile-time unrolled issue loop)
+template <bool OUT_F32, int MODE, bool FULL3, bool STATS>   // FULL3: 3x3 in-plane tap box (unrolled issue loop); STATS: fused BN statistics
 __global__ void __launch_bounds__(kHThreads, 1)
 gconv_halo_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ HaloParams p,
                   const void* __restrict__ in, void* __restrict__ out, long long* __restrict__ tl) {
@@ -340,6 +386,10 @@ gconv_halo_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_consta
     TileIter ti; ti.init(p, t_begin);
     Ring ac; ac.init(p.nacc);
     const uint32_t acc_cols = (uint32_t)(p.TD * p.ks * p.cout);
+    constexpr bool do_stats = STATS;
+    RunStat rs[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { rs[i].n = 0.f; rs[i].mean = 0.f; rs[i].m2 = 0.f; }
     for (int k = 0; k < my_tiles; ++k, ti.next(p)) {
       const int d0 = ti.dt * p.TD;
       const int y = ti.ht * kTH + lh, x0 = ti.wt * kTW * p.ks + lw;
@@ -357,51 +407,77 @@ gconv_halo_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_consta
         const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)ac.idx * acc_cols +
                                 (uint32_t)(dd * p.ks * p.cout);
         for (int c0 = 0; c0 < p.cout_store; c0 += 16) {
-          // all sub-tiles' TMEM loads in flight, one wait, then the stores
-          float v[4][16];
+          // TMEM loads of a group of sub-tiles in flight, one wait, then statistics + stores.  With
+          // fused statistics the group is 2 sub-tiles (the running sums need the registers).
+          constexpr int G = STATS ? 2 : 4;
+          float sa[16], sb[16];
+          unsigned nv = 0;
+          if (STATS) {
 #pragma unroll
-          for (int sj = 0; sj < 4; ++sj)
-            if (sj < nsub && !(p.dbg & 512)) h_tmem_ld16_nowait(taddr0 + (uint32_t)(sj * p.cout + c0), v[sj]);
-          if (!(p.dbg & 512)) h_tmem_wait_ld();
+            for (int j = 0; j < 16; ++j) { sa[j] = 0.f; sb[j] = 0.f; }
+          }
 #pragma unroll
-          for (int sj = 0; sj < 4; ++sj) {
-            if (sj >= nsub) continue;
-            const int x = x0 + sj * kTW;
-            if (!(y < p.gh && x < p.gw) || (p.dbg & 1)) continue;
-            const long long opix = opix0 + sj * kTW * p.os;
-            if (MODE == 2) {                           // zero-padded filter: only cout_store channels exist
-              if (OUT_F32) {
+          for (int s0 = 0; s0 < 4; s0 += G) {
+            if (s0 >= nsub) break;
+            float v[G][16];
+#pragma unroll
+            for (int g = 0; g < G; ++g)
+              if (s0 + g < nsub) h_tmem_ld16_nowait(taddr0 + (uint32_t)((s0 + g) * p.cout + c0), v[g]);
+            h_tmem_wait_ld();
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+              const int sj = s0 + g;
+              if (sj >= nsub) continue;
+              const int x = x0 + sj * kTW;
+              const bool valid = y < p.gh && x < p.gw;
+              if (STATS) {
+                nv += __popc(__ballot_sync(0xffffffffu, valid));
+                if (valid) {
+#pragma unroll
+                  for (int j = 0; j < 16; ++j) { sa[j] += v[g][j]; sb[j] = fmaf(v[g][j], v[g][j], sb[j]); }
+                }
+              }
+              if (!valid || (p.dbg & 1)) continue;
+              const long long opix = opix0 + sj * kTW * p.os;
+              if (MODE == 2) {                           // zero-padded filter: only cout_store channels exist
+                if (OUT_F32) {
+                  float* o = reinterpret_cast<float*>(out) + opix * p.ldout + c0;
+#pragma unroll
+                  for (int j = 0; j < 16; ++j)
+                    if (c0 + j < p.cout_store) o[j] = p.accumulate ? o[j] + v[g][j] : v[g][j];
+                } else {
+                  bf16* o = reinterpret_cast<bf16*>(out) + opix * p.ldout + c0;
+#pragma unroll
+                  for (int j = 0; j < 16; ++j)
+                    if (c0 + j < p.cout_store) st1(o + j, p.accumulate ? ld1(o + j) + v[g][j] : v[g][j]);
+                }
+              } else if (OUT_F32) {
                 float* o = reinterpret_cast<float*>(out) + opix * p.ldout + c0;
 #pragma unroll
-                for (int j = 0; j < 16; ++j)
-                  if (c0 + j < p.cout_store) o[j] = p.accumulate ? o[j] + v[sj][j] : v[sj][j];
+                for (int j = 0; j < 16; j += 4) {
+                  float4 xx = make_float4(v[g][j], v[g][j + 1], v[g][j + 2], v[g][j + 3]);
+                  if (MODE == 1) {
+                    float4 yy = *reinterpret_cast<float4*>(o + j);
+                    xx.x += yy.x; xx.y += yy.y; xx.z += yy.z; xx.w += yy.w;
+                  }
+                  *reinterpret_cast<float4*>(o + j) = xx;
+                }
               } else {
                 bf16* o = reinterpret_cast<bf16*>(out) + opix * p.ldout + c0;
-#pragma unroll
-                for (int j = 0; j < 16; ++j)
-                  if (c0 + j < p.cout_store) st1(o + j, p.accumulate ? ld1(o + j) + v[sj][j] : v[sj][j]);
-              }
-            } else if (OUT_F32) {
-              float* o = reinterpret_cast<float*>(out) + opix * p.ldout + c0;
-#pragma unroll
-              for (int j = 0; j < 16; j += 4) {
-                float4 xx = make_float4(v[sj][j], v[sj][j + 1], v[sj][j + 2], v[sj][j + 3]);
                 if (MODE == 1) {
-                  float4 yy = *reinterpret_cast<float4*>(o + j);
-                  xx.x += yy.x; xx.y += yy.y; xx.z += yy.z; xx.w += yy.w;
-                }
-                *reinterpret_cast<float4*>(o + j) = xx;
-              }
-            } else {
-              bf16* o = reinterpret_cast<bf16*>(out) + opix * p.ldout + c0;
-              if (MODE == 1) {
-                float old[16];
-                load8(o, old); load8(o + 8, old + 8);
+                  float old[16];
+                  load8(o, old); load8(o + 8, old + 8);
 #pragma unroll
-                for (int j = 0; j < 16; ++j) v[sj][j] += old[j];
+                  for (int j = 0; j < 16; ++j) v[g][j] += old[j];
+                }
+                store8(o, v[g]); store8(o + 8, v[g] + 8);
               }
-              store8(o, v[sj]); store8(o + 8, v[sj] + 8);
             }
+          }
+          if (STATS) {
+#pragma unroll
+            for (int ci = 0; ci < 4; ++ci)
+              if (ci * 16 == c0) stat_merge(rs[ci], sa, sb, nv, lane);
           }
         }
       }
@@ -411,6 +487,15 @@ gconv_halo_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_consta
       if (lane == 0) h_mbar_arrive(&tempty[ac.idx]);
       if (warp == kEpiWarp0 && lane == 0) TL(2, k, 3);
       ac.next();
+    }
+    if (do_stats && !(lane & 1)) {
+      // partial[(cta*4 + q)][channel][3]
+      float* dst = p.stats_part + ((long long)(blockIdx.x * 4 + q) * p.cout) * 3;
+#pragma unroll
+      for (int ci = 0; ci < 4; ++ci) {
+        const int ch = ci * 16 + (lane >> 1);
+        if (ci * 16 < p.cout_store) { dst[ch * 3 + 0] = rs[ci].n; dst[ch * 3 + 1] = rs[ci].mean; dst[ch * 3 + 2] = rs[ci].m2; }
+      }
     }
   }
 
@@ -527,11 +612,19 @@ bool gconv_halo_supported_padded(const GConv& g, int in_dtype, int out_dtype, in
 
 // wpack: 16-bit filter (dtype of `in`) laid out [tap][cout][cin].  cout_store (0 = all): only the
 // first cout_store output channels are written (the filter was zero-padded to a multiple of 16).
-int gconv_halo_launch_padded(const GConv& g, int in_dtype, const void* in, const void* wpack, void* out,
-                             int out_dtype, int cout_store, cudaStream_t st) {
+int gconv_halo_launch_stats(const GConv& g, int in_dtype, const void* in, const void* wpack, void* out,
+                            int out_dtype, int cout_store, float* stats_part, int* nparts, cudaStream_t st) {
   HaloParams p;
   URN_CHECK(halo_plan(g, in_dtype, out_dtype, cout_store, &p), "gconv_halo: unsupported shape/dtype");
+  if (nparts) *nparts = 0;
   if (p.ntiles == 0) return 0;
+  const int grid_ = (int)std::min<long long>(p.ntiles, num_sms());
+  // statistics only when this single launch produces the whole raw tensor, freshly written
+  if (stats_part && nparts && out_dtype == URN_F32 && !g.accumulate && g.os == 1 && g.gd == g.od && g.gh == g.oh &&
+      g.gw == g.ow && !getenv("URN_NO_FUSED_STATS")) {
+    p.stats_part = stats_part;
+    *nparts = grid_ * 4;
+  }
   EncodeTiledFnH enc = get_encode_h();
   URN_CHECK(enc, "gconv_halo: cuTensorMapEncodeTiled not available");
   CUtensorMap map_w;
@@ -553,30 +646,42 @@ int gconv_halo_launch_padded(const GConv& g, int in_dtype, const void* in, const
   if (const char* e = getenv("URN_HALO_TIMELINE")) tl = (long long*)strtoull(e, nullptr, 0);
   const int mode = (p.cout_store & 15) ? 2 : (p.accumulate ? 1 : 0);
   const bool full3 = p.nkh == 3 && p.nkw == 3;
-#define HALO_GO(F32, MODE, F3)                                                                                \
+  const bool stats = p.stats_part != nullptr;
+#define HALO_GO(F32, MODE, F3, ST)                                                                            \
   do {                                                                                                        \
     static bool attr_set = false;                                                                             \
     if (!attr_set) {                                                                                          \
-      URN_CUDA(cudaFuncSetAttribute(gconv_halo_kernel<F32, MODE, F3>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+      URN_CUDA(cudaFuncSetAttribute(gconv_halo_kernel<F32, MODE, F3, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                     227 * 1024));                                                             \
       attr_set = true;                                                                                        \
     }                                                                                                         \
-    gconv_halo_kernel<F32, MODE, F3><<<grid, kHThreads, smem, st>>>(map_w, p, in, out, tl);                   \
-  } while (0)
-#define HALO_GO_M(F32)                                                               \
-  do {                                                                               \
-    if (mode == 0) { if (full3) HALO_GO(F32, 0, true); else HALO_GO(F32, 0, false); } \
-    else if (mode == 1) { if (full3) HALO_GO(F32, 1, true); else HALO_GO(F32, 1, false); } \
-    else HALO_GO(F32, 2, true);                                                      \
+    gconv_halo_kernel<F32, MODE, F3, ST><<<grid, kHThreads, smem, st>>>(map_w, p, in, out, tl);               \
   } while (0)
   URN_CHECK(mode != 2 || full3, "gconv_halo: padded filters only with 3x3 taps");
-  if (out_dtype == URN_F32) HALO_GO_M(true); else HALO_GO_M(false);
-#undef HALO_GO_M
+  URN_CHECK(!stats || (out_dtype == URN_F32 && mode != 1), "gconv_halo: statistics need a freshly written f32 output");
+  if (out_dtype == URN_F32) {
+    if (mode == 0) {
+      if (stats) { if (full3) HALO_GO(true, 0, true, true); else HALO_GO(true, 0, false, true); }
+      else { if (full3) HALO_GO(true, 0, true, false); else HALO_GO(true, 0, false, false); }
+    } else if (mode == 1) {
+      if (full3) HALO_GO(true, 1, true, false); else HALO_GO(true, 1, false, false);
+    } else {
+      if (stats) HALO_GO(true, 2, true, true); else HALO_GO(true, 2, true, false);
+    }
+  } else {
+    if (mode == 0) { if (full3) HALO_GO(false, 0, true, false); else HALO_GO(false, 0, false, false); }
+    else if (mode == 1) { if (full3) HALO_GO(false, 1, true, false); else HALO_GO(false, 1, false, false); }
+    else HALO_GO(false, 2, true, false);
+  }
 #undef HALO_GO
   URN_LAUNCH_CHECK();
   return 0;
 }
 
+int gconv_halo_launch_padded(const GConv& g, int in_dtype, const void* in, const void* wpack, void* out,
+                             int out_dtype, int cout_store, cudaStream_t st) {
+  return gconv_halo_launch_stats(g, in_dtype, in, wpack, out, out_dtype, cout_store, nullptr, nullptr, st);
+}
 int gconv_halo_launch(const GConv& g, int in_dtype, const void* in, const void* wpack, void* out,
                       int out_dtype, cudaStream_t st) {
   return gconv_halo_launch_padded(g, in_dtype, in, wpack, out, out_dtype, 0, st);

@@ -27,6 +27,13 @@ int gconv_halo_launch(const GConv& g, int in_dtype, const void* in, const void* 
 bool gconv_halo_supported_padded(const GConv& g, int in_dtype, int out_dtype, int cout_store);
 int gconv_halo_launch_padded(const GConv& g, int in_dtype, const void* in, const void* wpack, void* out,
                              int out_dtype, int cout_store, cudaStream_t st);
+// Same, with the BN statistics of the fp32 output fused into the epilogue: stats_part receives
+// *nparts (n, mean, M2) float triples per channel ([part][cout][3]); *nparts = 0 if not fused.
+int gconv_halo_launch_stats(const GConv& g, int in_dtype, const void* in, const void* wpack, void* out,
+                            int out_dtype, int cout_store, float* stats_part, int* nparts, cudaStream_t st);
+// Chan merge of the partials -> stats (mean | rstd), deterministic (bn.cu).
+int bn_stats_merge_launch(const float* parts, int nparts, int c_stride, int c, long long rows, float eps,
+                          float* stats, cudaStream_t st);
 // Picks the best tensor-core kernel for the shape.
 static inline int gconv_tc_auto(const GConv& g, int in_dtype, const void* in, const void* wpack, void* out,
                                 int out_dtype, cudaStream_t st) {

@@ -628,6 +628,8 @@ int run_conv_fwd(urn_net* h, int li, const float* params, void* ws, cudaStream_t
   const Node& in = h->nodes[L.in_node];
   float* raw = (float*)P(ws, L.raw_off);
   const float* w = conv_weights(h, L, params, ws);
+  int nparts = 0;                                   // > 0: BN statistics came out of the conv epilogue
+  float* parts = (float*)P(ws, h->bn_ws_off);
   {
   ProfScope ps(h, li, PH_CONV, st);
   const bool ded = h->cfg.impl != URN_IMPL_FFMA;     // dedicated stem / head kernels (stemhead.cu)
@@ -636,7 +638,7 @@ int run_conv_fwd(urn_net* h, int li, const float* params, void* ws, cudaStream_t
     dp.cy = L.cpad;
     GConv g;
     gconv_gather(dp, in.ld, L.cout, &g);
-    if (gconv_halo_launch_padded(g, in.dtype, P(ws, in.off), P(ws, L.wpg_pad_off), raw, URN_F32, L.cout, st)) return 1;
+    if (gconv_halo_launch_stats(g, in.dtype, P(ws, in.off), P(ws, L.wpg_pad_off), raw, URN_F32, L.cout, parts, &nparts, st)) return 1;
   } else if (!L.transpose && ded && stem_supported(L.d, in.ld, L.cout)) {
     if (stem_fwd_launch(L.d, in.dtype, P(ws, in.off), in.ld, w, raw, L.cout, st)) return 1;
   } else if (!L.transpose && ded && head_supported(L.d, in.ld, L.cout)) {
@@ -644,7 +646,9 @@ int run_conv_fwd(urn_net* h, int li, const float* params, void* ws, cudaStream_t
   } else if (!L.transpose) {
     GConv g;
     gconv_gather(L.d, in.ld, L.cout, &g);
-    if (run_gconv(h, g, in.dtype, P(ws, in.off), w, P(ws, h->wpg_off + L.w_off * 2), raw, URN_F32, st)) return 1;
+    if (tc_enabled(h) && gconv_halo_supported(g, in.dtype, URN_F32)) {
+      if (gconv_halo_launch_stats(g, in.dtype, P(ws, in.off), P(ws, h->wpg_off + L.w_off * 2), raw, URN_F32, 0, parts, &nparts, st)) return 1;
+    } else if (run_gconv(h, g, in.dtype, P(ws, in.off), w, P(ws, h->wpg_off + L.w_off * 2), raw, URN_F32, st)) return 1;
   } else {
     for (int pd = 0; pd < L.d.s; ++pd)
       for (int ph = 0; ph < L.d.s; ++ph)
@@ -656,6 +660,9 @@ int run_conv_fwd(urn_net* h, int li, const float* params, void* ws, cudaStream_t
   }
   }
   ProfScope ps(h, li, PH_STATS, st);
+  if (nparts > 0)
+    return bn_stats_merge_launch(parts, nparts, L.cpad ? L.cpad : L.cout, L.cout, L.rows_out, kBnEps,
+                                 (float*)P(ws, L.stats_off), st);
   return urn_bn_stats(raw, L.cout, L.rows_out, L.cout, kBnEps, (float*)P(ws, L.stats_off),
                       P(ws, h->bn_ws_off), st);
 }
