@@ -62,6 +62,10 @@ struct HaloParams {
   uint64_t adesc_hi, bdesc_hi;
   int tmem_cols;
   int nacc;                  // accumulator buffers in the TMEM ring
+  int concat;                // 3x3x3 stride 1: the 3 depth taps of a staged plane are ONE MMA with N = 3*cout
+  int zero_bytes;            // shared-memory zero block (accumulator clearing MMAs), 0 if !concat
+  uint32_t idesc_n[3];       // instruction descriptors for N = 1,2,3 x cout
+  uint32_t idesc_zero;       // N = TD*cout
   float* stats_part;         // fused BN statistics: per (CTA, epilogue warp, channel) (n, mean, M2) partials, or NULL
   int dbg;                   // URN_HALO_DBG bitmask (perf experiments): 1 no stores, 2 no loads, 4 no MMA
 };
@@ -155,7 +159,8 @@ gconv_halo_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_consta
   // optional timeline (URN_HALO_TIMELINE): CTA 0 records clock64() at role checkpoints of its first 64 tiles
 #define TL(role, k, pt) do { if (tl && blockIdx.x == 0 && (k) < 64) tl[((role) * 64 + (k)) * 8 + (pt)] = clock64(); } while (0)
   const int w_bytes = ((p.ntaps_w * p.w_tap_bytes + 1023) / 1024) * 1024;
-  uint8_t* smem_a = smem + w_bytes;                                   // staged planes
+  uint8_t* smem_zero = smem + w_bytes;                                // zeros (B operand of the accumulator-clearing MMAs)
+  uint8_t* smem_a = smem_zero + p.zero_bytes;                         // staged planes
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_a + (size_t)p.stages * p.plane_bytes);
   uint64_t* full = bars;
   uint64_t* empty = bars + kHMaxStages;
@@ -285,16 +290,24 @@ gconv_halo_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_consta
     // The WHOLE warp runs this loop with warp-uniform values (so the address arithmetic lives in
     // the uniform datapath and no lane-0 branch serialises it); only the tcgen05 instructions
     // themselves are issued by one elected lane.
+    // Filter slots: tap widx goes to slot widx, or -- concat mode -- the three depth taps of each
+    // (kh,kw) are placed next to each other in DESCENDING kd order: they form one [3*cout][cin]
+    // B tile whose N blocks line up with the ascending output planes z-1, z, z+1 of input plane z.
+    for (int i = lane * 16; i < p.zero_bytes; i += 32 * 16) *reinterpret_cast<uint4*>(smem_zero + i) = make_uint4(0, 0, 0, 0);
     if (h_elect_one()) {
-      h_mbar_expect_tx(wfull, (uint32_t)(p.ntaps_w * p.w_tap_bytes));
-      for (int tp = 0; tp < p.ntaps_w; ++tp) {
-        asm volatile(
-            "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes"
-            " [%0], [%1, {%3, %4, %5}], [%2];"
-            ::"r"(h_smem_u32(smem_w + (size_t)tp * p.w_tap_bytes)), "l"(reinterpret_cast<uint64_t>(&map_w)),
-            "r"(h_smem_u32(wfull)), "r"(0), "r"(0), "r"(tp)
-            : "memory");
-      }
+      h_mbar_expect_tx(wfull, (uint32_t)(p.nkd * p.nkh * p.nkw * p.w_tap_bytes));
+      for (int kd = 0; kd < p.nkd; ++kd)
+        for (int kh = 0; kh < p.nkh; ++kh)
+          for (int kw = 0; kw < p.nkw; ++kw) {
+            const int tp = p.tapw[kd * 9 + kh * 3 + kw];
+            const int slot = p.concat ? ((kh * 3 + kw) * 3 + (2 - kd)) : tp;
+            asm volatile(
+                "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes"
+                " [%0], [%1, {%3, %4, %5}], [%2];"
+                ::"r"(h_smem_u32(smem_w + (size_t)slot * p.w_tap_bytes)), "l"(reinterpret_cast<uint64_t>(&map_w)),
+                "r"(h_smem_u32(wfull)), "r"(0), "r"(0), "r"(tp)
+                : "memory");
+          }
     }
     __syncwarp();
     // filter descriptor low words of the 27 (od,kh,kw) taps (all present in this kernel)
@@ -332,6 +345,37 @@ gconv_halo_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_consta
         h_fence_after();
         if (lane == 0) TL(1, k, 3);
         const uint32_t a_lo0 = a_lo_base | (h_smem_u32(smem_a + (size_t)st.idx * p.plane_bytes) >> 4);
+        if (p.concat) {
+          // output planes fed by input plane z: z-1-d0 .. z+1-d0 (depth taps kd = 2, 1, 0), clipped to the tile
+          const int dlo = max(0, z - 1 - d0), dhi = min(nd_out - 1, z + 1 - d0);
+          const int skip = dlo - (z - 1 - d0);
+          const uint32_t idn = p.idesc_n[dhi - dlo];
+          if (!no_mma && dhi >= dlo && h_elect_one()) {
+#pragma unroll 1
+            for (int sj = 0; sj < nsub; ++sj) {
+              const uint32_t a_sj = a_lo0 + (uint32_t)sj * a_sub;
+              if (!touched)      // first plane of the tile: clear all TD accumulators of this sub-tile (D = A * 0)
+                h_umma2(d_tmem0 + (uint32_t)(sj * p.TD * p.cout), a_sj, a_hi, b_lo_base | (h_smem_u32(smem_zero) >> 4), b_hi,
+                        p.idesc_zero, 0u);
+              const uint32_t d_tmem = d_tmem0 + (uint32_t)((sj * p.TD + dlo) * p.cout);
+#pragma unroll
+              for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+                for (int kw = 0; kw < 3; ++kw) {
+                  const uint32_t a_lo = a_sj + (uint32_t)kh * a_kh + (uint32_t)kw * a_kw;
+                  const uint32_t b_lo = b_base + (uint32_t)((kh * 3 + kw) * 3 + skip) * w_tap16;
+                  h_umma2(d_tmem, a_lo, a_hi, b_lo, b_hi, idn, 1u);
+                  if (ksteps > 1) h_umma2(d_tmem, a_lo + 2, a_hi, b_lo + 2, b_hi, idn, 1u);
+                  if (ksteps > 2) {
+                    h_umma2(d_tmem, a_lo + 4, a_hi, b_lo + 4, b_hi, idn, 1u);
+                    h_umma2(d_tmem, a_lo + 6, a_hi, b_lo + 6, b_hi, idn, 1u);
+                  }
+                }
+            }
+          }
+          __syncwarp();
+          touched = 1u;
+        } else
 #pragma unroll 1
         for (int kdi = 0; kdi < p.nkd; ++kdi) {
           const int tt = z - p.od0 - kdi;                // = dd_global * is
@@ -404,8 +448,10 @@ gconv_halo_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_consta
         if (d >= dmax) continue;                       // warp-uniform: accumulators never written
         const long long opix0 = (((long long)ti.nn * p.OD + (d * p.os + p.ood)) * p.OH + (y * p.os + p.ooh)) * p.OW +
                                 (x0 * p.os + p.oow);
+        // accumulator columns: [dd][sj][cout], or [sj][dd][cout] in concat mode
         const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)ac.idx * acc_cols +
-                                (uint32_t)(dd * p.ks * p.cout);
+                                (uint32_t)((p.concat ? dd : dd * p.ks) * p.cout);
+        const uint32_t sj_cols = (uint32_t)((p.concat ? p.TD : 1) * p.cout);
         for (int c0 = 0; c0 < p.cout_store; c0 += 16) {
           // TMEM loads of a group of sub-tiles in flight, one wait, then statistics + stores.  With
           // fused statistics the group is 2 sub-tiles (the running sums need the registers).
@@ -422,7 +468,7 @@ gconv_halo_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_consta
             float v[G][16];
 #pragma unroll
             for (int g = 0; g < G; ++g)
-              if (s0 + g < nsub) h_tmem_ld16_nowait(taddr0 + (uint32_t)((s0 + g) * p.cout + c0), v[g]);
+              if (s0 + g < nsub) h_tmem_ld16_nowait(taddr0 + (uint32_t)(s0 + g) * sj_cols + (uint32_t)c0, v[g]);
             h_tmem_wait_ld();
 #pragma unroll
             for (int g = 0; g < G; ++g) {
@@ -588,6 +634,17 @@ bool halo_plan(const GConv& g, int in_dtype, int out_dtype, int cout_store, Halo
   // 8-row groups (consecutive output rows of the sub-tile) are is*RW staged rows apart
   p.adesc_hi = (layout << 61) | (1ull << 46) | ((((uint64_t)(g.is * p.rw) * pitch) >> 4) << 32) | (1ull << 16);
   p.bdesc_hi = (layout << 61) | (1ull << 46) | (((8 * pitch) >> 4) << 32) | (1ull << 16);
+  // concat mode: 3x3x3 stride-1 convs; the zero block is one B tile of N = TD*cout rows
+  p.concat = (p.nkd == 3 && p.nkh == 3 && p.nkw == 3 && g.is == 1 && g.os == 1 && 3 * g.cout <= 256 && p.TD >= 2 &&
+              !getenv("URN_HALO_NO_CONCAT")) ? 1 : 0;
+  if (p.concat) {
+    p.zero_bytes = ((p.TD * g.cout * (int)pitch + 1023) / 1024) * 1024;
+    const uint32_t id0 = (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)(128 >> 4) << 24);
+    for (int i = 0; i < 3; ++i) p.idesc_n[i] = id0 | ((uint32_t)(((i + 1) * g.cout) >> 3) << 17);
+    p.idesc_zero = id0 | ((uint32_t)((p.TD * g.cout) >> 3) << 17);
+    p.stages = std::min(kHMaxStages, (budget - p.zero_bytes) / p.plane_bytes);
+    if (p.stages < 2) { p.concat = 0; p.zero_bytes = 0; p.stages = std::min(kHMaxStages, budget / p.plane_bytes); }
+  }
   p.nacc = std::max(2, std::min(kMaxAcc, 512 / (p.TD * p.ks * g.cout)));
   if (const char* e = getenv("URN_HALO_NACC")) p.nacc = std::max(2, std::min(p.nacc, atoi(e)));
   p.tmem_cols = std::max(32, pow2c(p.nacc * p.TD * p.ks * g.cout));
@@ -640,7 +697,7 @@ int gconv_halo_launch_stats(const GConv& g, int in_dtype, const void* in, const 
     URN_CHECK(r == CUDA_SUCCESS, "gconv_halo: cuTensorMapEncodeTiled(W) failed: %d", (int)r);
   }
   const int w_bytes = ((p.ntaps_w * p.w_tap_bytes + 1023) / 1024) * 1024;
-  const size_t smem = 1024 + (size_t)w_bytes + (size_t)p.stages * p.plane_bytes + 1024;
+  const size_t smem = 1024 + (size_t)w_bytes + (size_t)p.zero_bytes + (size_t)p.stages * p.plane_bytes + 1024;
   const int grid = (int)std::min<long long>(p.ntiles, num_sms());
   long long* tl = nullptr;
   if (const char* e = getenv("URN_HALO_TIMELINE")) tl = (long long*)strtoull(e, nullptr, 0);
