@@ -47,6 +47,8 @@ struct WHParams {
   int DC, ndc;               // planes per depth chunk, number of chunks
   int ks, rw;                // sub-tiles (16x8 positions) per super-tile along w; staged rows per halo row = 24*ks
   uint32_t idesc_last;       // instruction descriptor of the last M tile (M = 64 when only one 16-channel tap is live)
+  uint32_t idesc_n[2][3];    // [last M tile][N blocks - 1]: N = 1,2,3 x cy (3D: depth taps concatenated along N)
+  int ymirror;               // dY ring slots 0,1 are mirrored at physical slots ystages, ystages+1 (no window wrap)
   int ntw, nth;
   long long nunits;          // (n, depth chunk, tile row, tile column)
   int stages, ystages, pf;   // X ring, dY ring (power of two), cp.async groups in flight
@@ -79,7 +81,7 @@ wgrad_halo_kernel(const __grid_constant__ WHParams p, const void* __restrict__ x
   uint8_t* smem_x = smem;
   const int x_bytes = ((p.stages * p.xplane_bytes + 1023) / 1024) * 1024;
   uint8_t* smem_y = smem + x_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_y + (size_t)p.ystages * p.yplane_bytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_y + (size_t)(p.ystages + p.ymirror) * p.yplane_bytes);
   uint64_t* full = bars;
   uint64_t* empty = bars + kWMaxStages;
   uint64_t* yempty = bars + 2 * kWMaxStages;
@@ -194,14 +196,20 @@ wgrad_halo_kernel(const __grid_constant__ WHParams p, const void* __restrict__ x
         if (yvalid) {
           const uint32_t dst_base = h_smem_u32(smem_y + (size_t)yr.idx * p.yplane_bytes);
           const char* origin = y_base + ((long long)ui.nn * p.D + yp) * H * (long long)yrow + yorg;
-          if (interior) {
+          // ring slots 0 and 1 are also written to their mirrors behind the ring, so that the
+          // three-plane window of the MMA warp never wraps
+          const int ncopy = (p.ymirror && yr.idx < p.ymirror) ? 2 : 1;
+          for (int cpy = 0; cpy < ncopy; ++cpy) {
+            const uint32_t dstb = dst_base + (uint32_t)(cpy * p.ystages * p.yplane_bytes);
+            if (interior) {
 #pragma unroll
-            for (int j = 0; j < kWYCH; ++j) cp_async16_zfill(dst_base + ydoff[j], origin + ysoff[j], 16u);
-          } else {
+              for (int j = 0; j < kWYCH; ++j) cp_async16_zfill(dstb + ydoff[j], origin + ysoff[j], 16u);
+            } else {
 #pragma unroll
-            for (int j = 0; j < kWYCH; ++j) {
-              const bool ok = y0 + yhv[j] < H && x0 + yxv[j] < W;
-              cp_async16_zfill(dst_base + ydoff[j], ok ? origin + ysoff[j] : y_base, ok ? 16u : 0u);
+              for (int j = 0; j < kWYCH; ++j) {
+                const bool ok = y0 + yhv[j] < H && x0 + yxv[j] < W;
+                cp_async16_zfill(dstb + ydoff[j], ok ? origin + ysoff[j] : y_base, ok ? 16u : 0u);
+              }
             }
           }
           yr.next();
@@ -249,31 +257,61 @@ wgrad_halo_kernel(const __grid_constant__ WHParams p, const void* __restrict__ x
         h_fence_after();
         if (xvalid) {
           const uint32_t a_lo0 = a_lo_base | (h_smem_u32(smem_x + (size_t)st.idx * p.xplane_bytes) >> 4);
+          // dY planes paired with this X plane: z-1 .. z+1 (depth taps kd = 2, 1, 0), clipped to the
+          // chunk; consecutive planes sit in consecutive ring slots, so the whole window is ONE B
+          // operand of N = (#planes)*cy (LBO = slot stride) and the three depth taps share one
+          // read of the X views.  Accumulator columns of M tile mi: [(mi*3 + g)*cy], g = plane-(z-1).
+          const int pa = max(d0, z - p.LA), pb = min(d1 - 1, z + p.LA);
+          if (pa <= pb) {
+            const int g0 = pa - (z - p.LA);
+            const uint32_t s0 = (yseq0 + (uint32_t)(pa - d0)) & ymask;            // ring slot of plane pa
+            int nseg = 1, len0 = pb - pa + 1;
+            if (!p.ymirror && (int)s0 + len0 > p.ystages) { len0 = p.ystages - (int)s0; nseg = 2; }
 #pragma unroll 1
-          for (int oi = 0; oi < p.nkd; ++oi) {
-            const int pl = z - (oi - p.LA);                    // dY plane paired with depth tap oi
-            if (pl < d0 || pl >= d1) continue;
-            const uint32_t ys = (yseq0 + (uint32_t)(pl - d0)) & ymask;
-            const uint32_t b_lo0 = b_lo_base | (y_lo0 + ys * y_stage);
+            for (int sg = 0; sg < nseg; ++sg) {
+              const int gs = sg == 0 ? g0 : g0 + len0;
+              const int len = sg == 0 ? len0 : (pb - pa + 1) - len0;
+              const uint32_t slot = sg == 0 ? s0 : 0u;
+              const uint32_t b_lo0 = b_lo_base | (y_lo0 + slot * y_stage);
 #pragma unroll 1
-            for (int mi = 0; mi < p.nM; ++mi) {
-              const int ai = oi * p.nM + mi;
-              const uint32_t d_tmem = tmem_base + (uint32_t)(ai * p.cy);
-              const uint32_t accf = (touched >> ai) & 1u;
-              touched |= 1u << ai;
-              const uint32_t a_lo = a_lo0 + (uint32_t)mi * a_mstep;
-              const uint32_t idesc = mi == p.nM - 1 ? p.idesc_last : p.idesc;
-              if (h_elect_one()) {
+              for (int mi = 0; mi < p.nM; ++mi) {
+                const uint32_t d_tmem = tmem_base + (uint32_t)((mi * p.nkd + gs) * p.cy);
+                // first write of these accumulator columns?
+                uint32_t bits = ((1u << len) - 1u) << (mi * p.nkd + gs);
+                const uint32_t accf = (touched & bits) == bits ? 1u : 0u;
+                const bool mixed = (touched & bits) != 0u && !accf;
+                const uint32_t a_lo = a_lo0 + (uint32_t)mi * a_mstep;
+                const int last = mi == p.nM - 1 ? 1 : 0;
+                if (mixed) {
+                  // some columns new, some not (chunk edges): one MMA per plane
+                  for (int gi = 0; gi < len; ++gi) {
+                    const uint32_t bit1 = 1u << (mi * p.nkd + gs + gi);
+                    const uint32_t af = (touched & bit1) ? 1u : 0u;
+                    if (h_elect_one()) {
 #pragma unroll 1
-                for (int sj = 0; sj < nsub; ++sj) {
+                      for (int sj = 0; sj < nsub; ++sj)
 #pragma unroll
-                  for (int kk = 0; kk < 8; ++kk)
-                    h_umma2(d_tmem, a_lo + (uint32_t)sj * a_sub + (uint32_t)kk * a_kstep, a_hi,
-                            b_lo0 + (uint32_t)sj * b_sub + (uint32_t)kk * b_kstep, b_hi, idesc,
-                            (sj | kk) == 0 ? accf : 1u);
+                        for (int kk = 0; kk < 8; ++kk)
+                          h_umma2(d_tmem + (uint32_t)(gi * p.cy), a_lo + (uint32_t)sj * a_sub + (uint32_t)kk * a_kstep, a_hi,
+                                  b_lo0 + (uint32_t)gi * y_stage + (uint32_t)sj * b_sub + (uint32_t)kk * b_kstep, b_hi,
+                                  p.idesc_n[last][0], (sj | kk) == 0 ? af : 1u);
+                    }
+                    __syncwarp();
+                  }
+                } else {
+                  if (h_elect_one()) {
+#pragma unroll 1
+                    for (int sj = 0; sj < nsub; ++sj)
+#pragma unroll
+                      for (int kk = 0; kk < 8; ++kk)
+                        h_umma2(d_tmem, a_lo + (uint32_t)sj * a_sub + (uint32_t)kk * a_kstep, a_hi,
+                                b_lo0 + (uint32_t)sj * b_sub + (uint32_t)kk * b_kstep, b_hi, p.idesc_n[last][len - 1],
+                                (sj | kk) == 0 ? accf : 1u);
+                  }
+                  __syncwarp();
                 }
+                touched |= bits;
               }
-              __syncwarp();
             }
           }
         }
@@ -304,7 +342,7 @@ wgrad_halo_kernel(const __grid_constant__ WHParams p, const void* __restrict__ x
     const int tl = r / p.cx, ci = r - tl * p.cx;
     for (int oi = 0; oi < p.nkd; ++oi)
       for (int mi = 0; mi < p.nM; ++mi) {
-        const int ai = oi * p.nM + mi;
+        const int ai = mi * p.nkd + (p.nkd - 1 - oi);          // column block g = plane - (z-1) = 2 - oi
         const int tap_local = mi * p.tpm + tl;
         const bool valid = tap_local < 9;
         const bool have = (touched >> ai) & 1u;
@@ -392,9 +430,10 @@ bool wh_plan(const urn_conv_desc& d, int x_dtype, int y_dtype, int64_t ldx, int6
   // (and the X ring >= pf + 1) or producers and MMA warp would wait on each other.
   const int budget = 222 * 1024;
   p.pf = 0;
+  p.ymirror = p.nkd == 3 ? 2 : 0;
   for (int pf : {4, 2, 1}) {
     const int ys = pow2c(pf + (p.nkd == 3 ? 3 : 1));
-    const int st = std::min(kWMaxStages, (budget - ys * p.yplane_bytes) / p.xplane_bytes);
+    const int st = std::min(kWMaxStages, (budget - (ys + p.ymirror) * p.yplane_bytes) / p.xplane_bytes);
     if (st >= std::max(2, pf + 1)) { p.pf = pf; p.ystages = ys; p.stages = st; break; }
   }
   if (!p.pf) return false;
@@ -405,11 +444,22 @@ bool wh_plan(const urn_conv_desc& d, int x_dtype, int y_dtype, int64_t ldx, int6
   // cx = 16: the last M tile holds one live tap (accumulator rows 0..15 = TMEM lanes 0..15 in the
   // M = 64 layout too): a half-height MMA reads half the shared memory.
   p.idesc_last = (p.cx == 16 && !getenv("URN_WHALO_NO_M64")) ? (idesc0 | ((uint32_t)(64 >> 4) << 24)) : p.idesc;
+  {
+    const uint32_t idm = (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | (1u << 15) | (1u << 16);
+    const uint32_t m_last = (p.cx == 16 && !getenv("URN_WHALO_NO_M64")) ? 64u : 128u;
+    for (int nb = 0; nb < 3; ++nb) {
+      const uint32_t nfield = (uint32_t)(((nb + 1) * p.cy) >> 3) << 17;
+      p.idesc_n[0][nb] = idm | nfield | ((128u >> 4) << 24);
+      p.idesc_n[1][nb] = idm | nfield | ((m_last >> 4) << 24);
+    }
+  }
   auto layout_of = [](uint64_t bytes) -> uint64_t { return bytes == 128 ? 2 : (bytes == 64 ? 4 : 6); };
   const uint64_t xp = (uint64_t)p.cx * 2, yp = (uint64_t)p.cy * 2;
   // MN-major: SBO = next 8 positions (K), LBO = next channel group (MN)
   p.adesc_hi = (layout_of(xp) << 61) | (1ull << 46) | ((((uint64_t)p.rw * xp) >> 4) << 32) | ((((uint64_t)(8 * p.ks) * xp) >> 4) << 16);
-  p.bdesc_hi = (layout_of(yp) << 61) | (1ull << 46) | (((8 * yp) >> 4) << 32) | (((128 * yp) >> 4) << 16);
+  // B: N groups of cy channels = consecutive dY ring slots (LBO = slot stride)
+  p.bdesc_hi = (layout_of(yp) << 61) | (1ull << 46) | (((8 * yp) >> 4) << 32) | ((((uint64_t)p.yplane_bytes) >> 4) << 16);
+  if (((uint64_t)p.yplane_bytes >> 4) >= (1u << 14)) return false;
   return true;
 }
 
@@ -431,7 +481,7 @@ int wgrad_halo_launch(const urn_conv_desc& d, int x_dtype, const void* x, int64_
   WHParams p;
   URN_CHECK(wh_plan(d, x_dtype, y_dtype, ldx, ldy, &p), "wgrad_halo: unsupported shape/dtype");
   const int x_bytes = ((p.stages * p.xplane_bytes + 1023) / 1024) * 1024;
-  const size_t smem = 1024 + (size_t)x_bytes + (size_t)p.ystages * p.yplane_bytes + 1024;
+  const size_t smem = 1024 + (size_t)x_bytes + (size_t)(p.ystages + p.ymirror) * p.yplane_bytes + 1024;
   static bool attr_set = false;
   if (!attr_set) {
     URN_CUDA(cudaFuncSetAttribute(wgrad_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
