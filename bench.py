@@ -235,10 +235,21 @@ def main():
     for _ in range(args.warmup):
         step_device()
     barrier()
+    # per-layer / per-phase CUDA-event profile of the same step (roofline numerator times), taken
+    # right before the timed region on the same stream: the event pairs cost ~1 % of a step and
+    # keep the launch sequence out of a CUDA graph, so they are not left inside it
+    prof_steps = max(1, min(args.steps, 3))
+    launches0 = lib.urn_launch_count()
     net.profile_enable(B, True)
+    for _ in range(prof_steps):
+        step_device()
+    prof_ms, prof_cnt = net.profile_collect(B)
+    net.profile_enable(B, False)
+    launches_per_step = (lib.urn_launch_count() - launches0) // prof_steps
+    for _ in range(3):          # graph capture happens on the third un-profiled call of each sequence
+        step_device()
     sampler = ClockSampler(local)
     sampler.start()
-    launches0 = lib.urn_launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record()
@@ -247,14 +258,13 @@ def main():
     ev1.record()
     barrier()
     sampler.stop_flag = True
-    launches = lib.urn_launch_count() - launches0
+    launches = launches_per_step * args.steps      # kernels executed in the timed region (graph replays included)
     ms = ev0.elapsed_time(ev1) / args.steps
-    prof_ms, prof_cnt = net.profile_collect(B)
-    net.profile_enable(B, False)
 
     # end to end through the public API with host buffers
     e2e_steps = max(2, min(args.steps, 5))
-    step_e2e()
+    for _ in range(3):        # warm-up: staging buffers, graph capture for the staged-input pointers
+        step_e2e()
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
@@ -270,11 +280,11 @@ def main():
     if rank == 0:
         pk = peaks()
         flops = conv_flops(net.layer_table(B))
-        ph = {n: float(prof_ms[:, i].sum()) / args.steps for i, n in enumerate(net.PHASES)}      # ms per step
+        ph = {n: float(prof_ms[:, i].sum()) / prof_steps for i, n in enumerate(net.PHASES)}      # ms per step
         conv_ms = ph["conv_fwd"] + ph["dgrad"] + ph["wgrad"]
         conv_fl = flops["conv_fwd"] + flops["dgrad"] + flops["wgrad"]
         achieved = conv_fl / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
-        n_conv_launch_groups = int(prof_cnt[:, [0, 4, 5]].sum() / args.steps)
+        n_conv_launch_groups = int(prof_cnt[:, [0, 4, 5]].sum() / prof_steps)
         clocks = sampler.summary()
         line = {
             "metric": "train images/sec", "value": world * B / (ms * 1e-3), "unit": "images/s", "n_gpus": world,
@@ -283,7 +293,8 @@ def main():
             "data": "synthetic",
             "config": {"workload": wl["name"], "per_gpu_batch": B, "global_batch": world * B, "kernel_impl": args.kimpl,
                        "l2": "inputs larger than L2 (%.1f GB of activations per step)" % (net.workspace_bytes(B) / 1e9),
-                       "parallelism": "dp%d" % world},
+                       "parallelism": "dp%d" % world,
+                       "cuda_graphs": ("forward+backward" if net._exchange is None else "forward") if net._use_graphs else "off"},
             "clocks": clocks,
             "e2e": {"value": world * B / t_e2e, "unit": "images/s", "h2d_bytes_per_step": int(data.nbytes + label.nbytes + weight.nbytes),
                     "d2h_bytes_per_step": 32, "steps": e2e_steps},
@@ -291,7 +302,7 @@ def main():
             "roofline": {"bound": "tensor", "kernel": "conv fwd + dgrad + wgrad launches (%d launch groups/step)" % n_conv_launch_groups,
                          "achieved": achieved, "peak": pk["tf_sus"], "unit": "TFLOP/s", "frac": achieved / pk["tf_sus"],
                          "peak_source": pk["src"] + " (sustained bf16)", "traffic": None,
-                         "share_of_step": conv_ms / ms if ms > 0 else None},
+                         "share_of_step": conv_ms / ms if ms > 0 else None, "profiled_steps": prof_steps},
             "roofline_hbm": {"bound": "hbm", "kernel": "whole step (all kernels), algorithmic bytes lower bound",
                              "achieved": hbm_bytes(net.layer_table(B)) / (ms * 1e-3) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
                              "frac": hbm_bytes(net.layer_table(B)) / (ms * 1e-3) / 1e9 / pk["hbm"], "peak_source": pk["src"]},
@@ -310,7 +321,7 @@ def main():
             with open(args.per_layer, "w") as f:
                 f.write("layer,scope," + ",".join(net.PHASES[:7]) + "\n")
                 for i, (scope, d, tr) in enumerate(tab):
-                    f.write("%d,%s,%s\n" % (i, scope, ",".join("%.4f" % (prof_ms[i, j] / args.steps) for j in range(7))))
+                    f.write("%d,%s,%s\n" % (i, scope, ",".join("%.4f" % (prof_ms[i, j] / prof_steps) for j in range(7))))
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -95,6 +95,10 @@ class ssnet_base(object):
         self._result = torch.zeros(4, dtype=torch.float64, device=dev)
         self._result_host = torch.zeros(4, dtype=torch.float64).pin_memory()
         self._staging = {}
+        self._graphs = {}                 # CUDA graphs of the forward / loss+backward launch sequences
+        self._graph_calls = {}
+        self._use_graphs = os.environ.get("URESNET_B200_GRAPHS", "1") != "0"
+        self._profiling = False
         self._copy_stream = None          # side stream for label / weight H2D copies
         self._side_pending = []
         self._step_start = None
@@ -256,11 +260,40 @@ class ssnet_base(object):
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self._device).cuda_stream)
 
+    def _graphed(self, key, launch, dp_safe=False):
+        """Run `launch()` (a sequence of library launches on the current stream with fixed
+        pointers) -- eagerly the first two times for a key, then captured once into a CUDA graph
+        and replayed: ~300 kernel launches become one cudaGraphLaunch.  The backward sequence stays
+        eager in data-parallel runs (it records the per-layer events the gradient exchange waits
+        on); nothing is captured while the per-layer profiler records."""
+        if not self._use_graphs or (self._exchange is not None and not dp_safe) or self._profiling:
+            return launch()
+        g = self._graphs.get(key)
+        if g is not None:
+            g.replay()
+            return
+        n = self._graph_calls.get(key, 0) + 1
+        self._graph_calls[key] = n
+        if n <= 2:
+            return launch()
+        try:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                launch()
+        except Exception as e:                      # capture not possible: stay eager, say so once
+            sys.stderr.write("uresnet_b200: CUDA graph capture failed (%r); running eagerly\n" % (e,))
+            self._use_graphs = False
+            torch.cuda.synchronize(self._device)
+            return launch()
+        self._graphs[key] = g
+        g.replay()
+
     def _forward(self, feed):
         batch = feed["data"].shape[0]
         h, ws = self._handle(batch)
-        _capi.check(self._lib.urn_forward(h, self._params.data_ptr(), feed["data"].data_ptr(),
-                                          ws.data_ptr(), self._stream()))
+        dptr, pptr, wptr = feed["data"].data_ptr(), self._params.data_ptr(), ws.data_ptr()
+        self._graphed(("fwd", batch, dptr, wptr),
+                      lambda: _capi.check(self._lib.urn_forward(h, pptr, dptr, wptr, self._stream())), dp_safe=True)
         return h, ws, batch
 
     def _loss_metrics(self, h, ws, feed, want_grad, want_softmax):
@@ -312,10 +345,15 @@ class ssnet_base(object):
         if not self._trainable:
             raise RuntimeError("network constructed with trainable=False")
         feed, h, ws, batch = self._feed_overlapped(input_data, input_label, input_weight)
-        self._loss_metrics(h, ws, feed, want_grad=True, want_softmax=False)
         events = self._exchange.events_array() if self._exchange is not None else None
-        _capi.check(self._lib.urn_backward(h, self._params.data_ptr(), self._accum.data_ptr(), 1,
-                                           ws.data_ptr(), events, self._stream()))
+
+        def loss_and_backward():
+            self._loss_metrics(h, ws, feed, want_grad=True, want_softmax=False)
+            _capi.check(self._lib.urn_backward(h, self._params.data_ptr(), self._accum.data_ptr(), 1,
+                                               ws.data_ptr(), events, self._stream()))
+        key = ("bwd", batch, feed["data"].data_ptr(), feed["label"].data_ptr(),
+               feed["weight"].data_ptr() if (self._use_weight and "weight" in feed) else 0, ws.data_ptr())
+        self._graphed(key, loss_and_backward)
         if self._exchange is not None:
             self._exchange.backward_enqueued()
         if not fetch:
@@ -359,6 +397,7 @@ class ssnet_base(object):
     PHASES = ("conv_fwd", "bn_stats", "bn_apply", "bn_bwd", "wgrad", "dgrad", "misc", "-")
 
     def profile_enable(self, batch, on=True):
+        self._profiling = bool(on)
         h, _ = self._handle(batch)
         _capi.check(self._lib.urn_profile_enable(h, int(on)))
 
