@@ -186,6 +186,12 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
 
+    # stdout must carry exactly ONE JSON line: libraries (NCCL prints its version banner) write to
+    # fd 1 directly, so fd 1 is pointed at stderr for the run and the line goes to the saved fd
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
     import torch
     import torch.distributed as dist
     from uresnet_b200 import _capi, dp, synthetic_io as S
@@ -198,6 +204,9 @@ def main():
         raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, world))
     torch.cuda.set_device(local)
     if world > 1:
+        # torchrun pins OMP_NUM_THREADS=1; the host-side staging copies of the e2e path are
+        # multi-threaded torch copies: give every rank its share of the host cores
+        torch.set_num_threads(max(1, (os.cpu_count() or 1) // world))
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     wl = WORKLOADS[args.workload]
     dims, B = wl["dims"], (args.batch or wl["batch"])
@@ -322,7 +331,8 @@ def main():
                 f.write("layer,scope," + ",".join(net.PHASES[:7]) + "\n")
                 for i, (scope, d, tr) in enumerate(tab):
                     f.write("%d,%s,%s\n" % (i, scope, ",".join("%.4f" % (prof_ms[i, j] / prof_steps) for j in range(7))))
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 
