@@ -227,6 +227,10 @@ extern "C" int urn_conv_dgrad_tc(const urn_conv_desc* d, int dtype, const void* 
   if (check_desc(d)) return 1;
   cudaStream_t st = (cudaStream_t)stream;
   if (pack_filter(*d, dtype, w, wpack, false, st)) return 1;
+  if (d->s == 2 && d->kh == 3) {          // all parity classes in one launch when the halo kernel takes them
+    const int rc = gconv_scatter_tc(*d, ldy, ldx, accumulate, dtype, dy, wpack, dx, x_dtype, st);
+    if (rc >= 0) return rc;
+  }
   for (int pd = 0; pd < d->s; ++pd)
     for (int ph = 0; ph < d->s; ++ph)
       for (int pw = 0; pw < d->s; ++pw) {

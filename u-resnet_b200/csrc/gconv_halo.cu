@@ -62,6 +62,9 @@ struct HaloParams {
   uint64_t adesc_hi, bdesc_hi;
   int tmem_cols;
   int nacc;                  // accumulator buffers in the TMEM ring
+  int ncls;                  // output parity classes computed by this launch (1, or 4 / 8 for stride-2 scatter)
+  int coff[8][3];            // output placement offset (d,h,w) per class
+  int ctapw[8][27];          // per class: packed-filter tap of box position, -1 = the class has no such tap
   int concat;                // 3x3x3 stride 1: the 3 depth taps of a staged plane are ONE MMA with N = 3*cout
   int zero_bytes;            // shared-memory zero block (accumulator clearing MMAs), 0 if !concat
   uint32_t idesc_n[3];       // instruction descriptors for N = 1,2,3 x cout
@@ -294,7 +297,18 @@ gconv_halo_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_consta
     // (kh,kw) are placed next to each other in DESCENDING kd order: they form one [3*cout][cin]
     // B tile whose N blocks line up with the ascending output planes z-1, z, z+1 of input plane z.
     for (int i = lane * 16; i < p.zero_bytes; i += 32 * 16) *reinterpret_cast<uint4*>(smem_zero + i) = make_uint4(0, 0, 0, 0);
-    if (h_elect_one()) {
+    if (p.ncls > 1) {
+      if (h_elect_one()) {
+        h_mbar_expect_tx(wfull, (uint32_t)(p.ntaps_w * p.w_tap_bytes));
+        for (int tp = 0; tp < p.ntaps_w; ++tp)
+          asm volatile(
+              "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes"
+              " [%0], [%1, {%3, %4, %5}], [%2];"
+              ::"r"(h_smem_u32(smem_w + (size_t)tp * p.w_tap_bytes)), "l"(reinterpret_cast<uint64_t>(&map_w)),
+              "r"(h_smem_u32(wfull)), "r"(0), "r"(0), "r"(tp)
+              : "memory");
+      }
+    } else if (h_elect_one()) {
       h_mbar_expect_tx(wfull, (uint32_t)(p.nkd * p.nkh * p.nkw * p.w_tap_bytes));
       for (int kd = 0; kd < p.nkd; ++kd)
         for (int kh = 0; kh < p.nkh; ++kh)
@@ -324,7 +338,7 @@ gconv_halo_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_consta
     h_mbar_wait_warp(wfull, 0);
     TileIter ti; ti.init(p, t_begin);
     Ring st, ac; st.init(p.stages); ac.init(p.nacc);
-    const uint32_t acc_cols = (uint32_t)(p.TD * p.ks * p.cout);
+    const uint32_t acc_cols = (uint32_t)(p.ncls * p.TD * p.ks * p.cout);
     for (int k = 0; k < my_tiles; ++k, ti.next(p)) {
       const int d0 = ti.dt * p.TD;
       if (lane == 0) TL(1, k, 0);
@@ -345,7 +359,50 @@ gconv_halo_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_consta
         h_fence_after();
         if (lane == 0) TL(1, k, 3);
         const uint32_t a_lo0 = a_lo_base | (h_smem_u32(smem_a + (size_t)st.idx * p.plane_bytes) >> 4);
-        if (p.concat) {
+        if (p.ncls > 1) {
+          // Parity classes of a stride-2 scatter (conv input gradient / conv-transpose): the staged
+          // plane of the SMALL side feeds every class; class c owns the accumulators
+          // [(c*TD + dd)*ks + sj] and the subset of the 2x2(x2) tap box its parity allows.
+#pragma unroll 1
+          for (int kdi = 0; kdi < p.nkd; ++kdi) {
+            const int dd = z - p.od0 - kdi - d0;
+            if (dd < 0 || dd >= nd_out) continue;
+#pragma unroll 1
+            for (int c = 0; c < p.ncls; ++c) {
+              int any = 0;
+              for (int j = 0; j < 9; ++j) any |= (p.ctapw[c][kdi * 9 + j] >= 0);
+              if (!any) continue;
+              const uint32_t bit = (uint32_t)(c * p.TD + dd);
+              const uint32_t accf = (touched >> bit) & 1u;
+              touched |= 1u << bit;
+              if (!no_mma && h_elect_one()) {
+#pragma unroll 1
+                for (int sj = 0; sj < nsub; ++sj) {
+                  const uint32_t d_tmem = d_tmem0 + (uint32_t)(((c * p.TD + dd) * p.ks + sj) * p.cout);
+                  const uint32_t a_sj = a_lo0 + (uint32_t)sj * a_sub;
+                  uint32_t acc = accf;
+#pragma unroll 1
+                  for (int kh = 0; kh < p.nkh; ++kh)
+#pragma unroll 1
+                    for (int kw = 0; kw < p.nkw; ++kw) {
+                      const int tp = p.ctapw[c][kdi * 9 + kh * 3 + kw];
+                      if (tp < 0) continue;
+                      const uint32_t a_lo = a_sj + (uint32_t)kh * a_kh + (uint32_t)kw * a_kw;
+                      const uint32_t b_lo = b_base + (uint32_t)tp * w_tap16;
+                      h_umma2(d_tmem, a_lo, a_hi, b_lo, b_hi, p.idesc, acc);
+                      acc = 1u;
+                      if (ksteps > 1) h_umma2(d_tmem, a_lo + 2, a_hi, b_lo + 2, b_hi, p.idesc, 1u);
+                      if (ksteps > 2) {
+                        h_umma2(d_tmem, a_lo + 4, a_hi, b_lo + 4, b_hi, p.idesc, 1u);
+                        h_umma2(d_tmem, a_lo + 6, a_hi, b_lo + 6, b_hi, p.idesc, 1u);
+                      }
+                    }
+                }
+              }
+              __syncwarp();
+            }
+          }
+        } else if (p.concat) {
           // output planes fed by input plane z: z-1-d0 .. z+1-d0 (depth taps kd = 2, 1, 0), clipped to the tile
           const int dlo = max(0, z - 1 - d0), dhi = min(nd_out - 1, z + 1 - d0);
           const int skip = dlo - (z - 1 - d0);
@@ -429,7 +486,7 @@ gconv_halo_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_consta
     const int lh = r >> 3, lw = r & 7;
     TileIter ti; ti.init(p, t_begin);
     Ring ac; ac.init(p.nacc);
-    const uint32_t acc_cols = (uint32_t)(p.TD * p.ks * p.cout);
+    const uint32_t acc_cols = (uint32_t)(p.ncls * p.TD * p.ks * p.cout);
     constexpr bool do_stats = STATS;
     RunStat rs[4];
 #pragma unroll
@@ -443,14 +500,15 @@ gconv_halo_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_consta
       h_mbar_wait_warp(&tfull[ac.idx], ac.phase);
       h_fence_after();
       if (warp == kEpiWarp0 && lane == 0) TL(2, k, 1);
-      for (int dd = 0; dd < p.TD; ++dd) {
+      for (int cd = 0; cd < p.ncls * p.TD; ++cd) {
+        const int cls = cd / p.TD, dd = cd - cls * p.TD;
         const int d = d0 + dd;
         if (d >= dmax) continue;                       // warp-uniform: accumulators never written
-        const long long opix0 = (((long long)ti.nn * p.OD + (d * p.os + p.ood)) * p.OH + (y * p.os + p.ooh)) * p.OW +
-                                (x0 * p.os + p.oow);
-        // accumulator columns: [dd][sj][cout], or [sj][dd][cout] in concat mode
+        const long long opix0 = (((long long)ti.nn * p.OD + (d * p.os + p.coff[cls][0])) * p.OH + (y * p.os + p.coff[cls][1])) * p.OW +
+                                (x0 * p.os + p.coff[cls][2]);
+        // accumulator columns: [class][dd][sj][cout], or [sj][dd][cout] in concat mode
         const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)ac.idx * acc_cols +
-                                (uint32_t)((p.concat ? dd : dd * p.ks) * p.cout);
+                                (uint32_t)((p.concat ? dd : cd * p.ks) * p.cout);
         const uint32_t sj_cols = (uint32_t)((p.concat ? p.TD : 1) * p.cout);
         for (int c0 = 0; c0 < p.cout_store; c0 += 16) {
           // TMEM loads of a group of sub-tiles in flight, one wait, then statistics + stores.  With
@@ -559,13 +617,14 @@ gconv_halo_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_consta
   }
 }
 
-bool halo_plan(const GConv& g, int in_dtype, int out_dtype, int cout_store, HaloParams* pp) {
+bool halo_plan(const GConv& g, int in_dtype, int out_dtype, int cout_store, HaloParams* pp, int ncls = 1) {
   HaloParams& p = *pp;
   memset(&p, 0, sizeof(p));
   if (getenv("URN_NO_HALO")) return false;
   if (in_dtype != URN_BF16 && in_dtype != URN_F16) return false;
   if (out_dtype != URN_F32 && out_dtype != URN_BF16) return false;
   if ((g.is != 1 && g.is != 2) || (g.os != 1 && g.os != 2) || (g.is == 2 && g.os == 2)) return false;
+  if (ncls != 1 && ncls != 4 && ncls != 8) return false;
   if (g.cin != 16 && g.cin != 32 && g.cin != 64) return false;
   if (g.cout % 16 || g.cout > 64) return false;
   if (cout_store <= 0) cout_store = g.cout;
@@ -608,12 +667,14 @@ bool halo_plan(const GConv& g, int in_dtype, int out_dtype, int cout_store, Halo
   if (const char* e = getenv("URN_HALO_KS")) p.ks = std::max(1, std::min(p.ks, atoi(e)));
   while (p.ks > 1 && (p.gw + kTW - 1) / kTW <= p.ks / 2) p.ks /= 2;
   while (p.ks > 1 && p.hr * p.nkw * 8 * p.ks * cpr > kNCH * 256) p.ks /= 2;
-  p.rw = p.nkw * 8 * p.ks;
-  if (p.hr * p.rw * cpr > kNCH * 256) return false;
   const bool has_d = g.gd > 1 || p.nkd > 1;
   p.TD = has_d ? 4 : 1;
-  while (p.TD > 1 && p.TD * p.ks * g.cout * 2 > 512) p.TD /= 2;
-  if (p.TD * p.ks * g.cout * 2 > 512) return false;
+  p.ncls = ncls;
+  while (p.TD > 1 && ncls * p.TD * p.ks * g.cout * 2 > 512) p.TD /= 2;
+  while (p.ks > 1 && ncls * p.TD * p.ks * g.cout * 2 > 512) p.ks /= 2;
+  if (ncls * p.TD * p.ks * g.cout * 2 > 512) return false;
+  p.rw = p.nkw * 8 * p.ks;
+  if (p.hr * p.rw * cpr > kNCH * 256) return false;
   if (p.gd < p.TD) p.TD = std::max(1, p.gd);
   p.ntw = (p.gw + kTW * p.ks - 1) / (kTW * p.ks); p.nth = (p.gh + kTH - 1) / kTH; p.ntd = (p.gd + p.TD - 1) / p.TD;
   p.ntiles = (long long)p.n * p.ntd * p.nth * p.ntw;
@@ -635,7 +696,9 @@ bool halo_plan(const GConv& g, int in_dtype, int out_dtype, int cout_store, Halo
   p.adesc_hi = (layout << 61) | (1ull << 46) | ((((uint64_t)(g.is * p.rw) * pitch) >> 4) << 32) | (1ull << 16);
   p.bdesc_hi = (layout << 61) | (1ull << 46) | (((8 * pitch) >> 4) << 32) | (1ull << 16);
   // concat mode: 3x3x3 stride-1 convs; the zero block is one B tile of N = TD*cout rows
-  p.concat = (p.nkd == 3 && p.nkh == 3 && p.nkw == 3 && g.is == 1 && g.os == 1 && 3 * g.cout <= 256 && p.TD >= 2 &&
+  p.coff[0][0] = g.ood; p.coff[0][1] = g.ooh; p.coff[0][2] = g.oow;
+  for (int i = 0; i < 27; ++i) p.ctapw[0][i] = p.tapw[i];
+  p.concat = (ncls == 1 && p.nkd == 3 && p.nkh == 3 && p.nkw == 3 && g.is == 1 && g.os == 1 && 3 * g.cout <= 256 && p.TD >= 2 &&
               !getenv("URN_HALO_NO_CONCAT")) ? 1 : 0;
   if (p.concat) {
     p.zero_bytes = ((p.TD * g.cout * (int)pitch + 1023) / 1024) * 1024;
@@ -645,9 +708,9 @@ bool halo_plan(const GConv& g, int in_dtype, int out_dtype, int cout_store, Halo
     p.stages = std::min(kHMaxStages, (budget - p.zero_bytes) / p.plane_bytes);
     if (p.stages < 2) { p.concat = 0; p.zero_bytes = 0; p.stages = std::min(kHMaxStages, budget / p.plane_bytes); }
   }
-  p.nacc = std::max(2, std::min(kMaxAcc, 512 / (p.TD * p.ks * g.cout)));
+  p.nacc = std::max(2, std::min(kMaxAcc, 512 / (ncls * p.TD * p.ks * g.cout)));
   if (const char* e = getenv("URN_HALO_NACC")) p.nacc = std::max(2, std::min(p.nacc, atoi(e)));
-  p.tmem_cols = std::max(32, pow2c(p.nacc * p.TD * p.ks * g.cout));
+  p.tmem_cols = std::max(32, pow2c(p.nacc * ncls * p.TD * p.ks * g.cout));
   if (p.tmem_cols > 512) return false;
   if (const char* e = getenv("URN_HALO_DBG")) p.dbg = atoi(e);
   // Cin = 64 with 1-4 taps: the tap-box kernel (128-byte TMA rows, few boxes) is as fast or faster
@@ -656,7 +719,80 @@ bool halo_plan(const GConv& g, int in_dtype, int out_dtype, int cout_store, Halo
   return true;
 }
 
+// All parity classes of a stride-2 scatter in one launch: gs[c] are the per-class gather launches
+// (gconv_scatter_class).  The union of their taps is a 2x2(x2) box of offsets {-1, 0}.
+bool halo_plan_classes(const GConv* gs, int ncls, int in_dtype, int out_dtype, HaloParams* pp) {
+  if (getenv("URN_HALO_NO_CLASSES") || (ncls != 4 && ncls != 8)) return false;
+  const GConv& g0 = gs[0];
+  GConv u = g0;                              // union launch: geometry of class 0, taps = the full box
+  int lo[3] = {1 << 20, 1 << 20, 1 << 20}, hi[3] = {-(1 << 20), -(1 << 20), -(1 << 20)};
+  int maxw = 0;
+  for (int c = 0; c < ncls; ++c) {
+    const GConv& g = gs[c];
+    if (g.is != 1 || g.os != 2 || g.ntaps < 1) return false;
+    if (g.n != g0.n || g.id != g0.id || g.ih != g0.ih || g.iw != g0.iw || g.cin != g0.cin || g.cout != g0.cout ||
+        g.od != g0.od || g.oh != g0.oh || g.ow != g0.ow || g.gd != g0.gd || g.gh != g0.gh || g.gw != g0.gw ||
+        g.ldin != g0.ldin || g.ldout != g0.ldout || g.accumulate != g0.accumulate)
+      return false;
+    for (int t = 0; t < g.ntaps; ++t) {
+      const int o[3] = {g.taps[t].od, g.taps[t].oh, g.taps[t].ow};
+      for (int k = 0; k < 3; ++k) { lo[k] = std::min(lo[k], o[k]); hi[k] = std::max(hi[k], o[k]); }
+      maxw = std::max(maxw, g.taps[t].widx);
+    }
+  }
+  for (int k = 0; k < 3; ++k)
+    if (hi[k] - lo[k] > 1) return false;
+  u.ntaps = 0;
+  for (int a = lo[0]; a <= hi[0]; ++a)
+    for (int b = lo[1]; b <= hi[1]; ++b)
+      for (int c2 = lo[2]; c2 <= hi[2]; ++c2) {
+        GTap& t = u.taps[u.ntaps];
+        t.od = a; t.oh = b; t.ow = c2; t.widx = u.ntaps;
+        ++u.ntaps;
+      }
+  if (!halo_plan(u, in_dtype, out_dtype, 0, pp, ncls)) return false;
+  HaloParams& p = *pp;
+  if (p.concat) return false;
+  p.ntaps_w = maxw + 1;
+  p.w_tap_bytes = g0.cout * g0.cin * 2;
+  // smem budget again with the real number of resident taps
+  {
+    const int w_bytes = ((p.ntaps_w * p.w_tap_bytes + 1023) / 1024) * 1024;
+    p.stages = std::min(kHMaxStages, (224 * 1024 - w_bytes) / p.plane_bytes);
+    if (p.stages < 2) return false;
+  }
+  for (int c = 0; c < ncls; ++c) {
+    const GConv& g = gs[c];
+    p.coff[c][0] = g.ood; p.coff[c][1] = g.ooh; p.coff[c][2] = g.oow;
+    for (int i = 0; i < 27; ++i) p.ctapw[c][i] = -1;
+    bool has0 = false;
+    for (int t = 0; t < g.ntaps; ++t) {
+      const GTap& tp = g.taps[t];
+      p.ctapw[c][(tp.od - lo[0]) * 9 + (tp.oh - lo[1]) * 3 + (tp.ow - lo[2])] = tp.widx;
+      if (tp.od == 0 && tp.oh == 0 && tp.ow == 0) has0 = true;
+    }
+    if (!has0) return false;               // the always-inside tap that guarantees a written accumulator
+  }
+  return true;
+}
+
 }  // namespace
+
+bool gconv_halo_classes_supported(const GConv* gs, int ncls, int in_dtype, int out_dtype) {
+  HaloParams p;
+  return halo_plan_classes(gs, ncls, in_dtype, out_dtype, &p);
+}
+
+static int halo_launch_params(HaloParams& p, int cin, int cout, int in_dtype, int out_dtype, const void* in,
+                              const void* wpack, void* out, cudaStream_t st);
+
+int gconv_halo_classes_launch(const GConv* gs, int ncls, int in_dtype, const void* in, const void* wpack, void* out,
+                              int out_dtype, cudaStream_t st) {
+  HaloParams p;
+  URN_CHECK(halo_plan_classes(gs, ncls, in_dtype, out_dtype, &p), "gconv_halo: unsupported class set");
+  if (p.ntiles == 0) return 0;
+  return halo_launch_params(p, gs[0].cin, gs[0].cout, in_dtype, out_dtype, in, wpack, out, st);
+}
 
 bool gconv_halo_supported(const GConv& g, int in_dtype, int out_dtype) {
   HaloParams p;
@@ -682,15 +818,20 @@ int gconv_halo_launch_stats(const GConv& g, int in_dtype, const void* in, const 
     p.stats_part = stats_part;
     *nparts = grid_ * 4;
   }
+  return halo_launch_params(p, g.cin, g.cout, in_dtype, out_dtype, in, wpack, out, st);
+}
+
+static int halo_launch_params(HaloParams& p, int cin, int cout, int in_dtype, int out_dtype, const void* in,
+                              const void* wpack, void* out, cudaStream_t st) {
   EncodeTiledFnH enc = get_encode_h();
   URN_CHECK(enc, "gconv_halo: cuTensorMapEncodeTiled not available");
   CUtensorMap map_w;
   {
     const CUtensorMapDataType dt = in_dtype == URN_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
-    const CUtensorMapSwizzle sw = g.cin == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (g.cin == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
-    cuuint64_t dims[3] = {(cuuint64_t)g.cin, (cuuint64_t)g.cout, (cuuint64_t)p.ntaps_w};
-    cuuint64_t strides[2] = {(cuuint64_t)g.cin * 2, (cuuint64_t)g.cin * 2 * g.cout};
-    cuuint32_t box[3] = {(cuuint32_t)g.cin, (cuuint32_t)g.cout, 1};
+    const CUtensorMapSwizzle sw = cin == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (cin == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+    cuuint64_t dims[3] = {(cuuint64_t)cin, (cuuint64_t)cout, (cuuint64_t)p.ntaps_w};
+    cuuint64_t strides[2] = {(cuuint64_t)cin * 2, (cuuint64_t)cin * 2 * cout};
+    cuuint32_t box[3] = {(cuuint32_t)cin, (cuuint32_t)cout, 1};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = enc(&map_w, dt, 3, const_cast<void*>(wpack), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

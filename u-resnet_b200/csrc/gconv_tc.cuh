@@ -34,6 +34,16 @@ int gconv_halo_launch_stats(const GConv& g, int in_dtype, const void* in, const 
 // Chan merge of the partials -> stats (mean | rstd), deterministic (bn.cu).
 int bn_stats_merge_launch(const float* parts, int nparts, int c_stride, int c, long long rows, float eps,
                           float* stats, cudaStream_t st);
+// All parity classes of a stride-2 scatter (conv input gradient / conv-transpose forward) in ONE
+// launch: the small side is staged once, every class has its own TMEM accumulators and the
+// interleaved outputs of a tile are written by the same CTA.
+bool gconv_halo_classes_supported(const GConv* gs, int ncls, int in_dtype, int out_dtype);
+int gconv_halo_classes_launch(const GConv* gs, int ncls, int in_dtype, const void* in, const void* wpack, void* out,
+                              int out_dtype, cudaStream_t st);
+// Scatter form of a conv relation: one fused launch if possible, else one launch per parity class.
+// Returns -1 when the tensor-core path does not take the shape at all (caller falls back).
+static inline int gconv_scatter_tc(const urn_conv_desc& d, int64_t ldy, int64_t ldx, int accumulate, int in_dtype,
+                                   const void* in, const void* wpack, void* out, int out_dtype, cudaStream_t st);
 // Picks the best tensor-core kernel for the shape.
 static inline int gconv_tc_auto(const GConv& g, int in_dtype, const void* in, const void* wpack, void* out,
                                 int out_dtype, cudaStream_t st) {
@@ -72,4 +82,17 @@ static inline int64_t wgrad_any_workspace(const urn_conv_desc& d) {
   int64_t a = wgrad_ffma_workspace(d), b = wgrad_tc_workspace(d), c = wgrad_halo_workspace(d), e = stemhead_wgrad_workspace(d);
   a = a > b ? a : b; c = c > e ? c : e;
   return a > c ? a : c;
+}
+
+static inline int gconv_scatter_tc(const urn_conv_desc& d, int64_t ldy, int64_t ldx, int accumulate, int in_dtype,
+                                   const void* in, const void* wpack, void* out, int out_dtype, cudaStream_t st) {
+  GConv gs[8];
+  int n = 0;
+  for (int pd = 0; pd < d.s; ++pd)
+    for (int ph = 0; ph < d.s; ++ph)
+      for (int pw = 0; pw < d.s; ++pw)
+        if (gconv_scatter_class(d, ldy, ldx, pd, ph, pw, accumulate, &gs[n])) ++n;
+  if ((n == 4 || n == 8) && gconv_halo_classes_supported(gs, n, in_dtype, out_dtype))
+    return gconv_halo_classes_launch(gs, n, in_dtype, in, wpack, out, out_dtype, st);
+  return -1;
 }

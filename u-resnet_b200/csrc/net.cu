@@ -650,6 +650,11 @@ int run_conv_fwd(urn_net* h, int li, const float* params, void* ws, cudaStream_t
       if (gconv_halo_launch_stats(g, in.dtype, P(ws, in.off), P(ws, h->wpg_off + L.w_off * 2), raw, URN_F32, 0, parts, &nparts, st)) return 1;
     } else if (run_gconv(h, g, in.dtype, P(ws, in.off), w, P(ws, h->wpg_off + L.w_off * 2), raw, URN_F32, st)) return 1;
   } else {
+    int rc = -1;
+    if (tc_enabled(h) && L.d.s == 2)
+      rc = gconv_scatter_tc(L.d, in.ld, L.cout, 0, in.dtype, P(ws, in.off), P(ws, h->wps_off + L.w_off * 2), raw, URN_F32, st);
+    if (rc > 0) return 1;
+    if (rc < 0)
     for (int pd = 0; pd < L.d.s; ++pd)
       for (int ph = 0; ph < L.d.s; ++ph)
         for (int pw = 0; pw < L.d.s; ++pw) {
@@ -874,6 +879,11 @@ extern "C" int urn_backward(urn_net* h, const float* params, float* grads, int a
       } else if (!L.transpose && h->cfg.impl != URN_IMPL_FFMA && head_supported(L.d, in.ld, L.cout) && in.ld % 4 == 0) {
         if (head_dgrad_launch(L.d, T, draw(L), L.cout, w, gptr(in), in.ld, s.accumulate, st)) return 1;
       } else if (!L.transpose) {
+        int rc = -1;
+        if (tc_enabled(h) && L.d.s == 2 && L.d.kh == 3)
+          rc = gconv_scatter_tc(L.d, L.cout, in.ld, s.accumulate, T, draw(L), P(ws, h->wps_off + L.w_off * 2), gptr(in), T, st);
+        if (rc > 0) return 1;
+        if (rc < 0)
         for (int pd = 0; pd < L.d.s; ++pd)
           for (int ph = 0; ph < L.d.s; ++ph)
             for (int pw = 0; pw < L.d.s; ++pw) {
