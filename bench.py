@@ -303,7 +303,7 @@ def main():
             "config": {"workload": wl["name"], "per_gpu_batch": B, "global_batch": world * B, "kernel_impl": args.kimpl,
                        "l2": "inputs larger than L2 (%.1f GB of activations per step)" % (net.workspace_bytes(B) / 1e9),
                        "parallelism": "dp%d" % world,
-                       "cuda_graphs": ("forward+backward" if net._exchange is None else "forward") if net._use_graphs else "off"},
+                       "cuda_graphs": "forward+backward" if net._use_graphs else "off"},
             "clocks": clocks,
             "e2e": {"value": world * B / t_e2e, "unit": "images/s", "h2d_bytes_per_step": int(data.nbytes + label.nbytes + weight.nbytes),
                     "d2h_bytes_per_step": 32, "steps": e2e_steps},

@@ -812,6 +812,9 @@ extern "C" int urn_backward(urn_net* h, const float* params, float* grads, int a
     return P(ws, h->arena_off + h->gbufs[n.gbuf].off) + (int64_t)n.choff * esize(T);
   };
   auto draw = [&](const Layer& L) -> char* { return P(ws, h->arena_off + h->gbufs[L.draw_gbuf].off); };
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(st, &cap);
+  const bool capturing = cap == cudaStreamCaptureStatusActive;
   for (const BStep& s : h->bwd) {
     const Layer& L = h->layers[s.layer];
     ProfScope ps(h, s.layer, s.kind == B_BN ? PH_BNBWD : (s.kind == B_WGRAD ? PH_WGRAD : PH_DGRAD), st);
@@ -900,7 +903,10 @@ extern "C" int urn_backward(urn_net* h, const float* params, float* grads, int a
     }
     if (s.last_for_layer && ready_events && ready_events[s.layer]) {
       ps.end();
-      URN_CUDA(cudaEventRecord((cudaEvent_t)ready_events[s.layer], st));
+      // inside a stream capture (CUDA-graph replay of the backward sequence) the event must be an
+      // EXTERNAL record node, so that the communication stream can wait on it after every launch
+      URN_CUDA(cudaEventRecordWithFlags((cudaEvent_t)ready_events[s.layer], st,
+                                        capturing ? cudaEventRecordExternal : cudaEventRecordDefault));
     }
   }
   return 0;

@@ -15,6 +15,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 import sys
 from collections import OrderedDict
 
@@ -263,9 +264,10 @@ class ssnet_base(object):
     def _graphed(self, key, launch, dp_safe=False):
         """Run `launch()` (a sequence of library launches on the current stream with fixed
         pointers) -- eagerly the first two times for a key, then captured once into a CUDA graph
-        and replayed: ~300 kernel launches become one cudaGraphLaunch.  The backward sequence stays
-        eager in data-parallel runs (it records the per-layer events the gradient exchange waits
-        on); nothing is captured while the per-layer profiler records."""
+        and replayed: ~300 kernel launches become one cudaGraphLaunch.  In data-parallel runs the
+        per-layer ready events of the backward sequence are captured as external event-record
+        nodes (urn_backward), so the communication stream keeps waiting on them after each replay;
+        nothing is captured while the per-layer profiler records."""
         if not self._use_graphs or (self._exchange is not None and not dp_safe) or self._profiling:
             return launch()
         g = self._graphs.get(key)
@@ -353,7 +355,7 @@ class ssnet_base(object):
                                                ws.data_ptr(), events, self._stream()))
         key = ("bwd", batch, feed["data"].data_ptr(), feed["label"].data_ptr(),
                feed["weight"].data_ptr() if (self._use_weight and "weight" in feed) else 0, ws.data_ptr())
-        self._graphed(key, loss_and_backward)
+        self._graphed(key, loss_and_backward, dp_safe=os.environ.get("URESNET_B200_DP_GRAPH", "1") != "0")
         if self._exchange is not None:
             self._exchange.backward_enqueued()
         if not fetch:
