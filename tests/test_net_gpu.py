@@ -329,3 +329,48 @@ def test_padded_head_matches_cuda_core_head(dims, B, monkeypatch):
     # the tensor-core filter gradient multiplies the bf16 shadow of the activations (2^-9 rounding),
     # the CUDA-core one their fp16 copy
     assert relerr(gb["UResNet/conv2/weights"], ga["UResNet/conv2/weights"]) < 8e-3
+
+
+def test_full_size_properties_3d():
+    """BASELINE configs[3] shape (192^3, F=16, S=5) at batch 1: size-independent properties of the
+    full-size 3D path (27-tap halo kernels with N-concatenated depth taps, 8-class conv-transposes):
+    determinism, linear gradient accumulation, BN output statistics of the head, finite values."""
+    dims, B = [192, 192, 192, 1], 1
+    data, label, weight = S.make_batch(B, dims, seed=1234)
+    weight /= weight.sum(axis=1, keepdims=True)
+    net = make_net(dims, 16, 5, 3, "mix16")
+    net.zero_gradients(None)
+    r1, _ = net.accum_gradients(None, data, label, weight)
+    g1 = net._accum.clone()
+    r2, _ = net.accum_gradients(None, data, label, weight)
+    assert np.isfinite(r1[1]) and r1[1] == r2[1]
+    assert torch.isfinite(g1).all()
+    assert torch.allclose(net._accum, 2 * g1, rtol=1e-5, atol=1e-8)
+    lg = net.logits(B).reshape(-1, 3).double()
+    assert torch.allclose(lg.mean(0), torch.zeros(3, dtype=torch.float64, device=lg.device), atol=1e-3)
+    assert torch.all(lg.var(0, unbiased=False) <= 1.0 + 1e-3)
+    assert 0.0 <= r1[2] <= 1.0
+
+
+def test_cuda_graph_replay_is_bit_identical():
+    """The forward and loss+backward launch sequences are replayed as CUDA graphs from the third
+    call on: accumulators, loss and Adam-updated variables must equal the eager run bit for bit."""
+    dims, B, F, St = [64, 96, 1], 2, 16, 3
+    data, label, weight = S.make_batch(B, dims, seed=5)
+    weight /= weight.sum(axis=1, keepdims=True)
+    P = O.init_params(2, base=F, num_strides=St, seed=2)
+    out = []
+    for graphs in (False, True):
+        net = make_net(dims, F, St, 3, "mix16", lr=1e-3)
+        net._use_graphs = graphs
+        net.set_variables(P)
+        losses = []
+        for _ in range(5):
+            net.zero_gradients(None)
+            res, _ = net.accum_gradients(None, data, label, weight)
+            net.apply_gradients(None)
+            losses.append(float(res[1]))
+        assert (len(net._graphs) == 2) == graphs
+        out.append((losses, net._accum.clone(), net._params.clone()))
+    assert out[0][0] == out[1][0]
+    assert torch.equal(out[0][1], out[1][1]) and torch.equal(out[0][2], out[1][2])
