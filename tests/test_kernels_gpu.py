@@ -146,6 +146,11 @@ TC_CASES = [
     (3, 1, (8, 8, 16), 32, 64, 3, 2),
     (3, 1, (6, 6, 6), 64, 64, 3, 1),     # small grid: tile box larger than the grid
     (3, 1, (8, 8, 8), 32, 64, 1, 2),
+    (2, 1, (17, 23), 16, 32, 3, 2),      # odd sizes, stride 2, Cin=16 (halo kernels: pad_before = 1)
+    (2, 2, (40, 72), 32, 16, 1, 1),      # 1x1 stride 1, several super-tiles
+    (2, 1, (34, 70), 16, 32, 1, 2),      # 1x1 stride 2
+    (3, 1, (10, 12, 16), 16, 32, 3, 2),  # 27 taps, stride 2
+    (3, 1, (7, 9, 11), 16, 16, 3, 2),    # odd 3D sizes, stride 2
 ]
 
 

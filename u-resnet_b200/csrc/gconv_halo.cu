@@ -855,7 +855,7 @@ static int halo_launch_params(HaloParams& p, int cin, int cout, int in_dtype, in
     }                                                                                                         \
     gconv_halo_kernel<F32, MODE, F3, ST><<<grid, kHThreads, smem, st>>>(map_w, p, in, out, tl);               \
   } while (0)
-  URN_CHECK(mode != 2 || full3, "gconv_halo: padded filters only with 3x3 taps");
+  URN_CHECK(mode != 2 || full3, "gconv_halo: padded filters only with 3x3 taps (cout %d store %d taps %dx%dx%d classes %d cin %d)", p.cout, p.cout_store, p.nkd, p.nkh, p.nkw, p.ncls, p.cin);
   URN_CHECK(!stats || (out_dtype == URN_F32 && mode != 1), "gconv_halo: statistics need a freshly written f32 output");
   if (out_dtype == URN_F32) {
     if (mode == 0) {

@@ -363,7 +363,9 @@ static int build_plan(urn_net& N) {
       N.wpg_off = b.alloc(N.param_total * 2);
       N.wps_off = b.alloc(N.param_total * 2);
       for (auto& L : N.layers) {
-        if (L.transpose || L.d.cy >= 16 || L.d.cx % 16 || !c.training || getenv("URN_NO_PADDED_HEAD")) continue;
+        if (L.transpose || L.d.cy >= 16 || L.d.cx % 16 || L.d.kh != 3 || L.d.s != 1 || !c.training ||
+            getenv("URN_NO_PADDED_HEAD"))
+          continue;
         urn_conv_desc dp = L.d;
         dp.cy = 16;
         const Node& in = N.nodes[L.in_node];

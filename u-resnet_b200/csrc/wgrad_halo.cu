@@ -40,7 +40,12 @@ constexpr int kWMaxStages = 8;
 constexpr int kYMaxStages = 8;                         // dY ring: 3 planes live + the producers' look-ahead
 
 struct WHParams {
-  int n, D, H, W;
+  int n, D, H, W;            // Y (small side) grid: the positions the GEMM's K dimension runs over
+  int XD, XH, XW;            // X (big side) dims
+  int s;                     // X sampling stride (1 / 2)
+  int nkh, nkw, ntp;         // in-plane tap box, taps per plane
+  int od0, oh0, ow0;         // first tap offset per dim (= -pad)
+  int hr;                    // staged X halo rows = (kWTH-1)*s + nkh
   int cx, cy;
   long long ldx, ldy;
   int nkd, LA;               // depth taps (1 / 3); dY look-ahead in planes (0 / 1)
@@ -118,16 +123,16 @@ wgrad_halo_kernel(const __grid_constant__ WHParams p, const void* __restrict__ x
     // slot 0; interior tiles skip the border test.
     const int t = threadIdx.x;
     const int pitch = p.cx * 2, cpr = pitch / 16;
-    const int total = (kWTH + 2) * p.rw * cpr;
+    const int total = p.hr * p.rw * cpr;
     const int cpr_log2 = cpr == 8 ? 3 : (cpr == 4 ? 2 : 1);
     const int sw_shift = cpr == 8 ? 0 : (cpr == 4 ? 1 : 2);
     const int sw_mask = cpr == 8 ? 7 : (cpr == 4 ? 3 : 1);
     const int run = 8 * p.ks;
     const char* x_base = reinterpret_cast<const char*>(x);
     const char* y_base = reinterpret_cast<const char*>(dy);
-    const int xpix = (int)(p.ldx * 2), xrow = xpix * p.W;
+    const int xpix = (int)(p.ldx * 2), xrow = xpix * p.XW;
     const int ypix = (int)(p.ldy * 2), yrow = ypix * p.W;
-    const int H = p.H, W = p.W;
+    const int H = p.H, W = p.W, XH = p.XH, XW = p.XW;
     int soff[kWNCH], hyv[kWNCH], dxv[kWNCH];
     uint32_t doff[kWNCH];
 #pragma unroll
@@ -138,7 +143,7 @@ wgrad_halo_kernel(const __grid_constant__ WHParams p, const void* __restrict__ x
       const int hy = row / p.rw;
       const int rem = row - hy * p.rw;
       const int kw = rem / run;
-      const int dx = kw + (rem - kw * run);
+      const int dx = kw + (rem - kw * run) * p.s;              // X column relative to the tile origin
       const int sw = (row >> sw_shift) & sw_mask;
       doff[j] = (uint32_t)(row * (pitch >> 4) + (c ^ sw)) << 4;
       soff[j] = hy * xrow + dx * xpix + c * 16;
@@ -170,25 +175,29 @@ wgrad_halo_kernel(const __grid_constant__ WHParams p, const void* __restrict__ x
     for (int k = 0; k < my_units; ++k, ui.next(p)) {
       const int d0 = ui.dc * p.DC, d1 = min(d0 + p.DC, p.D);
       const int y0 = ui.ht * kWTH, x0 = ui.wt * kWTW * p.ks;
-      const bool interior = y0 >= 1 && y0 + kWTH < H && x0 >= 1 && x0 + run < W;
-      const long long xorg = (long long)(y0 - 1) * xrow + (long long)(x0 - 1) * xpix;
+      const int xyb = y0 * p.s + p.oh0, xxb = x0 * p.s + p.ow0;          // X origin of the staged halo
+      const bool interior = xyb >= 0 && xyb + p.hr <= XH && xxb >= 0 && xxb + (run - 1) * p.s + p.nkw <= XW &&
+                            y0 + kWTH <= H && x0 + run <= W;
+      const long long xorg = (long long)xyb * xrow + (long long)xxb * xpix;
       const long long yorg = (long long)y0 * yrow + (long long)x0 * ypix;
-      for (int z = d0 - p.LA; z <= d1 - 1 + p.LA; ++z) {
-        const bool xvalid = z >= 0 && z < p.D;
-        const int yp = z + p.LA;
-        const bool yvalid = yp < d1;
+      for (int z = d0 * p.s + p.od0; z <= (d1 - 1) * p.s + p.od0 + p.nkd - 1; ++z) {
+        const bool xvalid = z >= 0 && z < p.XD;
+        // the dY plane first needed at this step (depth tap 0 of X plane z)
+        const int tnew = z - p.od0;
+        const int yp = p.s == 2 ? tnew >> 1 : tnew;
+        const bool yvalid = !(p.s == 2 && (tnew & 1)) && yp >= d0 && yp < d1;
         h_mbar_wait_warp(&empty[st.idx], st.phase ^ 1);
         if (yvalid) h_mbar_wait_warp(&yempty[yr.idx], yr.phase ^ 1);
         if (xvalid) {
           const uint32_t dst_base = h_smem_u32(smem_x + (size_t)st.idx * p.xplane_bytes);
-          const char* origin = x_base + ((long long)ui.nn * p.D + z) * H * (long long)xrow + xorg;
+          const char* origin = x_base + ((long long)ui.nn * p.XD + z) * XH * (long long)xrow + xorg;
           if (interior) {
 #pragma unroll
             for (int j = 0; j < kWNCH; ++j) cp_async16_zfill(dst_base + doff[j], origin + soff[j], 16u);
           } else {
 #pragma unroll
             for (int j = 0; j < kWNCH; ++j) {
-              const bool ok = (unsigned)(y0 - 1 + hyv[j]) < (unsigned)H && (unsigned)(x0 - 1 + dxv[j]) < (unsigned)W;
+              const bool ok = (unsigned)(xyb + hyv[j]) < (unsigned)XH && (unsigned)(xxb + dxv[j]) < (unsigned)XW;
               cp_async16_zfill(dst_base + doff[j], ok ? origin + soff[j] : x_base, ok ? 16u : 0u);
             }
           }
@@ -238,7 +247,7 @@ wgrad_halo_kernel(const __grid_constant__ WHParams p, const void* __restrict__ x
     const uint32_t a_lo_base = (uint32_t)p.adesc_hi, b_lo_base = (uint32_t)p.bdesc_hi;
     const uint32_t pitch = (uint32_t)p.cx * 2;
     const uint32_t a_mstep = ((uint32_t)(p.tpm * 8 * p.ks) * pitch) >> 4;   // next M tile: tpm taps further (taps are 8*KS rows apart)
-    const uint32_t a_kstep = ((uint32_t)(2 * p.rw) * pitch) >> 4;           // 16 positions = 2 image rows
+    const uint32_t a_kstep = ((uint32_t)(2 * p.s * p.rw) * pitch) >> 4;     // 16 positions = 2 output rows = 2*s halo rows
     const uint32_t a_sub = (8u * pitch) >> 4;                               // next sub-tile: 8 pixels further in the run
     const uint32_t b_kstep = (16u * (uint32_t)p.cy * 2u) >> 4;
     const uint32_t b_sub = (128u * (uint32_t)p.cy * 2u) >> 4;
@@ -250,8 +259,8 @@ wgrad_halo_kernel(const __grid_constant__ WHParams p, const void* __restrict__ x
     for (int k = 0; k < my_units; ++k, ui.next(p)) {
       const int d0 = ui.dc * p.DC, d1 = min(d0 + p.DC, p.D);
       const int nsub = min(p.ks, (p.W - ui.wt * kWTW * p.ks + kWTW - 1) / kWTW);   // sub-tiles inside the image
-      for (int z = d0 - p.LA; z <= d1 - 1 + p.LA; ++z) {
-        const bool xvalid = z >= 0 && z < p.D;
+      for (int z = d0 * p.s + p.od0; z <= (d1 - 1) * p.s + p.od0 + p.nkd - 1; ++z) {
+        const bool xvalid = z >= 0 && z < p.XD;
         h_mbar_wait(&full[st.idx], st.phase);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // cp.async (generic proxy) -> UMMA (async proxy)
         h_fence_after();
@@ -261,9 +270,45 @@ wgrad_halo_kernel(const __grid_constant__ WHParams p, const void* __restrict__ x
           // chunk; consecutive planes sit in consecutive ring slots, so the whole window is ONE B
           // operand of N = (#planes)*cy (LBO = slot stride) and the three depth taps share one
           // read of the X views.  Accumulator columns of M tile mi: [(mi*3 + g)*cy], g = plane-(z-1).
-          const int pa = max(d0, z - p.LA), pb = min(d1 - 1, z + p.LA);
+          // window of dY planes: (z - od0 - kdi) / s for the depth taps kdi = nkd-1 .. 0
+          int pa, pb, wlo;
+          if (p.s == 1) {
+            wlo = z - p.od0 - (p.nkd - 1);
+            pa = max(d0, wlo); pb = min(d1 - 1, z - p.od0);
+          } else {
+            // stride 2: taps of one parity only; handled one plane at a time (window of length 1 per tap)
+            wlo = 0; pa = 1; pb = 0;
+            for (int kdi = 0; kdi < p.nkd; ++kdi) {
+              const int tt = z - p.od0 - kdi;
+              if (tt < 0 || (tt & 1)) continue;
+              const int pl = tt >> 1;
+              if (pl < d0 || pl >= d1) continue;
+              const uint32_t slot = (yseq0 + (uint32_t)(pl - d0)) & ymask;
+              const uint32_t b_lo0 = b_lo_base | (y_lo0 + slot * y_stage);
+              const int gs = p.nkd - 1 - kdi;
+#pragma unroll 1
+              for (int mi = 0; mi < p.nM; ++mi) {
+                const uint32_t bit1 = 1u << (mi * p.nkd + gs);
+                const uint32_t af = (touched & bit1) ? 1u : 0u;
+                touched |= bit1;
+                const uint32_t d_tmem = tmem_base + (uint32_t)((mi * p.nkd + gs) * p.cy);
+                const uint32_t a_lo = a_lo0 + (uint32_t)mi * a_mstep;
+                const int last = mi == p.nM - 1 ? 1 : 0;
+                if (h_elect_one()) {
+#pragma unroll 1
+                  for (int sj = 0; sj < nsub; ++sj)
+#pragma unroll
+                    for (int kk = 0; kk < 8; ++kk)
+                      h_umma2(d_tmem, a_lo + (uint32_t)sj * a_sub + (uint32_t)kk * a_kstep, a_hi,
+                              b_lo0 + (uint32_t)sj * b_sub + (uint32_t)kk * b_kstep, b_hi, p.idesc_n[last][0],
+                              (sj | kk) == 0 ? af : 1u);
+                }
+                __syncwarp();
+              }
+            }
+          }
           if (pa <= pb) {
-            const int g0 = pa - (z - p.LA);
+            const int g0 = pa - wlo;
             const uint32_t s0 = (yseq0 + (uint32_t)(pa - d0)) & ymask;            // ring slot of plane pa
             int nseg = 1, len0 = pb - pa + 1;
             if (!p.ymirror && (int)s0 + len0 > p.ystages) { len0 = p.ystages - (int)s0; nseg = 2; }
@@ -315,10 +360,13 @@ wgrad_halo_kernel(const __grid_constant__ WHParams p, const void* __restrict__ x
             }
           }
         }
-        const int rel = z - p.LA;                              // last use of dY plane `rel` was this step
+        // last use of a dY plane is its depth tap nkd-1: plane (z - od0 - (nkd-1)) / s
+        const int trel = z - p.od0 - (p.nkd - 1);
+        const int rel = p.s == 2 ? trel >> 1 : trel;
+        const bool relv = trel >= 0 && !(p.s == 2 && (trel & 1)) && rel >= d0 && rel < d1;
         if (h_elect_one()) {
           h_commit(&empty[st.idx]);
-          if (rel >= d0 && rel < d1) h_commit(&yempty[(yseq0 + (uint32_t)(rel - d0)) & ymask]);
+          if (relv) h_commit(&yempty[(yseq0 + (uint32_t)(rel - d0)) & ymask]);
         }
         __syncwarp();
         st.next();
@@ -344,9 +392,9 @@ wgrad_halo_kernel(const __grid_constant__ WHParams p, const void* __restrict__ x
       for (int mi = 0; mi < p.nM; ++mi) {
         const int ai = mi * p.nkd + (p.nkd - 1 - oi);          // column block g = plane - (z-1) = 2 - oi
         const int tap_local = mi * p.tpm + tl;
-        const bool valid = tap_local < 9;
+        const bool valid = tap_local < p.ntp;
         const bool have = (touched >> ai) & 1u;
-        float* dst = partial + (((long long)blockIdx.x * p.ntaps + (oi * 9 + tap_local)) * p.cx + ci) * p.cy;
+        float* dst = partial + (((long long)blockIdx.x * p.ntaps + (oi * p.ntp + tap_local)) * p.cx + ci) * p.cy;
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ai * p.cy);
         for (int c0 = 0; c0 < p.cy; c0 += 16) {
           float v[16];
@@ -395,42 +443,52 @@ bool wh_plan(const urn_conv_desc& d, int x_dtype, int y_dtype, int64_t ldx, int6
   memset(&p, 0, sizeof(p));
   if (getenv("URN_NO_HALO_WGRAD")) return false;
   if ((x_dtype != URN_BF16 && x_dtype != URN_F16) || x_dtype != y_dtype) return false;
-  if (d.s != 1 || d.kh != 3 || d.kw != 3 || (d.kd != 1 && d.kd != 3)) return false;
-  if (d.xd != d.yd || d.xh != d.yh || d.xw != d.yw) return false;
-  if (d.pad_h != 1 || d.pad_w != 1 || d.pad_d != (d.kd == 3 ? 1 : 0)) return false;
+  if (d.s != 1 && d.s != 2) return false;
+  if (!((d.kh == 3 && d.kw == 3) || (d.kh == 1 && d.kw == 1)) || (d.kd != 1 && d.kd != d.kh)) return false;
+  if (getenv("URN_WHALO_ONLY3X3S1") && !(d.s == 1 && d.kh == 3)) return false;
+  if (d.yd != (d.xd + d.s - 1) / d.s || d.yh != (d.xh + d.s - 1) / d.s || d.yw != (d.xw + d.s - 1) / d.s) return false;
   if (d.cx != 16 && d.cx != 32 && d.cx != 64) return false;
   if (d.cy != 16 && d.cy != 32 && d.cy != 64) return false;
   if (ldx % 8 || ldy % 8) return false;
-  p.n = d.n; p.D = d.xd; p.H = d.xh; p.W = d.xw; p.cx = d.cx; p.cy = d.cy; p.ldx = ldx; p.ldy = ldy;
-  if ((long long)p.H * p.W * std::max(ldx, ldy) * 2 >= (1ll << 31)) return false;   // 32-bit in-plane offsets
-  p.nkd = d.kd; p.LA = d.kd == 3 ? 1 : 0;
-  p.ntaps = 9 * p.nkd;
+  p.n = d.n; p.D = d.yd; p.H = d.yh; p.W = d.yw; p.XD = d.xd; p.XH = d.xh; p.XW = d.xw;
+  p.s = d.s; p.cx = d.cx; p.cy = d.cy; p.ldx = ldx; p.ldy = ldy;
+  if ((long long)p.XH * p.XW * ldx * 2 >= (1ll << 31) || (long long)p.H * p.W * ldy * 2 >= (1ll << 31)) return false;
+  p.nkd = d.kd; p.nkh = d.kh; p.nkw = d.kw; p.ntp = d.kh * d.kw;
+  p.od0 = -d.pad_d; p.oh0 = -d.pad_h; p.ow0 = -d.pad_w;
+  p.LA = 0;
+  p.ntaps = p.ntp * p.nkd;
+  p.hr = (kWTH - 1) * d.s + d.kh;
   p.ndc = (p.D + 47) / 48;
   p.DC = (p.D + p.ndc - 1) / p.ndc;
   p.ndc = (p.D + p.DC - 1) / p.DC;
   p.tpm = 128 / p.cx;
-  p.nM = (9 + p.tpm - 1) / p.tpm;
+  p.nM = (p.ntp + p.tpm - 1) / p.tpm;
   const int cols = p.nkd * p.nM * p.cy;
   if (cols > 512) return false;
   p.tmem_cols = std::max(32, pow2c(cols));
-  // super-tile: KS sub-tiles share one staged X plane (~55 KB) and one barrier round trip
-  p.ks = p.cx == 16 ? 4 : (p.cx == 32 ? 2 : 1);
+  // super-tile: KS sub-tiles share one staged X plane (<= 56 KB) and one barrier round trip
+  const int cpr = p.cx * 2 / 16;
+  p.ks = 4;
   if (const char* e = getenv("URN_WHALO_KS")) p.ks = std::max(1, std::min(p.ks, atoi(e)));
   while (p.ks > 1 && (p.W + kWTW - 1) / kWTW <= p.ks / 2) p.ks /= 2;
   while (p.ks > 1 && p.ks * 128 * (p.cy * 2 / 16) > kWYCH * kWProdThreads) p.ks /= 2;
-  p.rw = 24 * p.ks;
+  while (p.ks > 1 && p.hr * p.nkw * 8 * p.ks * cpr > kWNCH * kWProdThreads) p.ks /= 2;
+  p.rw = p.nkw * 8 * p.ks;
   p.ntw = (p.W + kWTW * p.ks - 1) / (kWTW * p.ks); p.nth = (p.H + kWTH - 1) / kWTH;
   p.nunits = (long long)p.n * p.ndc * p.nth * p.ntw;
   if (p.nunits >= (1ll << 31)) return false;
-  p.xplane_bytes = (kWTH + 2) * p.rw * p.cx * 2;
+  p.xplane_bytes = p.hr * p.rw * p.cx * 2;
   p.yplane_bytes = p.ks * 128 * p.cy * 2;
-  if ((kWTH + 2) * p.rw * (p.cx * 2 / 16) > kWNCH * kWProdThreads) return false;
+  if (p.hr * p.rw * cpr > kWNCH * kWProdThreads) return false;
+  // the garbage taps of the last M tile read up to (nM*tpm - ntp) tap strides past the plane: keep
+  // that inside the dY region that follows the X stages
+  if ((p.nM * p.tpm - p.ntp) * 8 * p.ks * p.cx * 2 > 2 * p.yplane_bytes + 8192) return false;
   // Producers run `pf` cp.async groups ahead of the full-barrier arrival; the dY slot of plane z+1
   // frees two steps after its previous tenant's last use, so the dY ring needs >= pf + 3 slots
   // (and the X ring >= pf + 1) or producers and MMA warp would wait on each other.
   const int budget = 222 * 1024;
   p.pf = 0;
-  p.ymirror = p.nkd == 3 ? 2 : 0;
+  p.ymirror = (p.nkd == 3 && p.s == 1) ? 2 : 0;
   for (int pf : {4, 2, 1}) {
     const int ys = pow2c(pf + (p.nkd == 3 ? 3 : 1));
     const int st = std::min(kWMaxStages, (budget - (ys + p.ymirror) * p.yplane_bytes) / p.xplane_bytes);
@@ -443,10 +501,11 @@ bool wh_plan(const urn_conv_desc& d, int x_dtype, int y_dtype, int64_t ldx, int6
   p.idesc = idesc0 | ((uint32_t)(128 >> 4) << 24);
   // cx = 16: the last M tile holds one live tap (accumulator rows 0..15 = TMEM lanes 0..15 in the
   // M = 64 layout too): a half-height MMA reads half the shared memory.
-  p.idesc_last = (p.cx == 16 && !getenv("URN_WHALO_NO_M64")) ? (idesc0 | ((uint32_t)(64 >> 4) << 24)) : p.idesc;
+  const bool m64 = p.cx == 16 && (p.ntp - (p.nM - 1) * p.tpm) == 1 && !getenv("URN_WHALO_NO_M64");
+  p.idesc_last = m64 ? (idesc0 | ((uint32_t)(64 >> 4) << 24)) : p.idesc;
   {
     const uint32_t idm = (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | (1u << 15) | (1u << 16);
-    const uint32_t m_last = (p.cx == 16 && !getenv("URN_WHALO_NO_M64")) ? 64u : 128u;
+    const uint32_t m_last = m64 ? 64u : 128u;
     for (int nb = 0; nb < 3; ++nb) {
       const uint32_t nfield = (uint32_t)(((nb + 1) * p.cy) >> 3) << 17;
       p.idesc_n[0][nb] = idm | nfield | ((128u >> 4) << 24);
@@ -456,7 +515,7 @@ bool wh_plan(const urn_conv_desc& d, int x_dtype, int y_dtype, int64_t ldx, int6
   auto layout_of = [](uint64_t bytes) -> uint64_t { return bytes == 128 ? 2 : (bytes == 64 ? 4 : 6); };
   const uint64_t xp = (uint64_t)p.cx * 2, yp = (uint64_t)p.cy * 2;
   // MN-major: SBO = next 8 positions (K), LBO = next channel group (MN)
-  p.adesc_hi = (layout_of(xp) << 61) | (1ull << 46) | ((((uint64_t)p.rw * xp) >> 4) << 32) | ((((uint64_t)(8 * p.ks) * xp) >> 4) << 16);
+  p.adesc_hi = (layout_of(xp) << 61) | (1ull << 46) | ((((uint64_t)(p.s * p.rw) * xp) >> 4) << 32) | ((((uint64_t)(8 * p.ks) * xp) >> 4) << 16);
   // B: N groups of cy channels = consecutive dY ring slots (LBO = slot stride)
   p.bdesc_hi = (layout_of(yp) << 61) | (1ull << 46) | (((8 * yp) >> 4) << 32) | ((((uint64_t)p.yplane_bytes) >> 4) << 16);
   if (((uint64_t)p.yplane_bytes >> 4) >= (1u << 14)) return false;
