@@ -78,6 +78,7 @@ struct UnitIter {
   }
 };
 
+template <bool S2>    // S2: X sampled with stride 2 (compile-time, so that the stride-1 kernel keeps its tight loops)
 __global__ void __launch_bounds__(kWThreads, 1)
 wgrad_halo_kernel(const __grid_constant__ WHParams p, const void* __restrict__ x, const void* __restrict__ dy,
                   float* __restrict__ partial) {
@@ -94,6 +95,7 @@ wgrad_halo_kernel(const __grid_constant__ WHParams p, const void* __restrict__ x
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull + 1);
   uint32_t* touched_slot = tmem_slot + 1;
 
+  constexpr int PS = S2 ? 2 : 1;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long u_begin = p.nunits * (long long)blockIdx.x / gridDim.x;
   const long long u_end = p.nunits * (long long)(blockIdx.x + 1) / gridDim.x;
@@ -133,7 +135,7 @@ wgrad_halo_kernel(const __grid_constant__ WHParams p, const void* __restrict__ x
     const int xpix = (int)(p.ldx * 2), xrow = xpix * p.XW;
     const int ypix = (int)(p.ldy * 2), yrow = ypix * p.W;
     const int H = p.H, W = p.W, XH = p.XH, XW = p.XW;
-    int soff[kWNCH], hyv[kWNCH], dxv[kWNCH];
+    int soff[kWNCH], hdv[kWNCH];          // hdv = halo row | X column << 8 (border test of edge tiles)
     uint32_t doff[kWNCH];
 #pragma unroll
     for (int j = 0; j < kWNCH; ++j) {
@@ -143,11 +145,11 @@ wgrad_halo_kernel(const __grid_constant__ WHParams p, const void* __restrict__ x
       const int hy = row / p.rw;
       const int rem = row - hy * p.rw;
       const int kw = rem / run;
-      const int dx = kw + (rem - kw * run) * p.s;              // X column relative to the tile origin
+      const int dx = kw + (rem - kw * run) * PS;              // X column relative to the tile origin
       const int sw = (row >> sw_shift) & sw_mask;
       doff[j] = (uint32_t)(row * (pitch >> 4) + (c ^ sw)) << 4;
       soff[j] = hy * xrow + dx * xpix + c * 16;
-      hyv[j] = hy; dxv[j] = dx;
+      hdv[j] = hy | (dx << 8);
     }
     // dY tile: rows ordered (sub-tile, h, w8), cy*2 bytes each
     const int ypitch = p.cy * 2, ycpr = ypitch / 16;
@@ -155,7 +157,7 @@ wgrad_halo_kernel(const __grid_constant__ WHParams p, const void* __restrict__ x
     const int ysw_shift = ycpr == 8 ? 0 : (ycpr == 4 ? 1 : 2);
     const int ysw_mask = ycpr == 8 ? 7 : (ycpr == 4 ? 3 : 1);
     const int ytotal = p.ks * 128 * ycpr;
-    int ysoff[kWYCH], yhv[kWYCH], yxv[kWYCH];
+    int ysoff[kWYCH], yhx[kWYCH];
     uint32_t ydoff[kWYCH];
 #pragma unroll
     for (int j = 0; j < kWYCH; ++j) {
@@ -165,7 +167,7 @@ wgrad_halo_kernel(const __grid_constant__ WHParams p, const void* __restrict__ x
       const int sj = row >> 7, h = (row >> 3) & 15, w = row & 7;
       const int sw = (row >> ysw_shift) & ysw_mask;
       ydoff[j] = (uint32_t)(row * ycpr + (c ^ sw)) << 4;
-      yhv[j] = h; yxv[j] = sj * 8 + w;
+      yhx[j] = h | ((sj * 8 + w) << 8);
       ysoff[j] = h * yrow + (sj * 8 + w) * ypix + c * 16;
     }
     UnitIter ui; ui.init(p, u_begin);
@@ -175,17 +177,17 @@ wgrad_halo_kernel(const __grid_constant__ WHParams p, const void* __restrict__ x
     for (int k = 0; k < my_units; ++k, ui.next(p)) {
       const int d0 = ui.dc * p.DC, d1 = min(d0 + p.DC, p.D);
       const int y0 = ui.ht * kWTH, x0 = ui.wt * kWTW * p.ks;
-      const int xyb = y0 * p.s + p.oh0, xxb = x0 * p.s + p.ow0;          // X origin of the staged halo
-      const bool interior = xyb >= 0 && xyb + p.hr <= XH && xxb >= 0 && xxb + (run - 1) * p.s + p.nkw <= XW &&
+      const int xyb = y0 * PS + p.oh0, xxb = x0 * PS + p.ow0;          // X origin of the staged halo
+      const bool interior = xyb >= 0 && xyb + p.hr <= XH && xxb >= 0 && xxb + (run - 1) * PS + p.nkw <= XW &&
                             y0 + kWTH <= H && x0 + run <= W;
       const long long xorg = (long long)xyb * xrow + (long long)xxb * xpix;
       const long long yorg = (long long)y0 * yrow + (long long)x0 * ypix;
-      for (int z = d0 * p.s + p.od0; z <= (d1 - 1) * p.s + p.od0 + p.nkd - 1; ++z) {
+      for (int z = d0 * PS + p.od0; z <= (d1 - 1) * PS + p.od0 + p.nkd - 1; ++z) {
         const bool xvalid = z >= 0 && z < p.XD;
         // the dY plane first needed at this step (depth tap 0 of X plane z)
         const int tnew = z - p.od0;
-        const int yp = p.s == 2 ? tnew >> 1 : tnew;
-        const bool yvalid = !(p.s == 2 && (tnew & 1)) && yp >= d0 && yp < d1;
+        const int yp = S2 ? tnew >> 1 : tnew;
+        const bool yvalid = !(S2 && (tnew & 1)) && yp >= d0 && yp < d1;
         h_mbar_wait_warp(&empty[st.idx], st.phase ^ 1);
         if (yvalid) h_mbar_wait_warp(&yempty[yr.idx], yr.phase ^ 1);
         if (xvalid) {
@@ -197,7 +199,7 @@ wgrad_halo_kernel(const __grid_constant__ WHParams p, const void* __restrict__ x
           } else {
 #pragma unroll
             for (int j = 0; j < kWNCH; ++j) {
-              const bool ok = (unsigned)(xyb + hyv[j]) < (unsigned)XH && (unsigned)(xxb + dxv[j]) < (unsigned)XW;
+              const bool ok = (unsigned)(xyb + (hdv[j] & 255)) < (unsigned)XH && (unsigned)(xxb + (hdv[j] >> 8)) < (unsigned)XW;
               cp_async16_zfill(dst_base + doff[j], ok ? origin + soff[j] : x_base, ok ? 16u : 0u);
             }
           }
@@ -216,7 +218,7 @@ wgrad_halo_kernel(const __grid_constant__ WHParams p, const void* __restrict__ x
             } else {
 #pragma unroll
               for (int j = 0; j < kWYCH; ++j) {
-                const bool ok = y0 + yhv[j] < H && x0 + yxv[j] < W;
+                const bool ok = y0 + (yhx[j] & 255) < H && x0 + (yhx[j] >> 8) < W;
                 cp_async16_zfill(dstb + ydoff[j], ok ? origin + ysoff[j] : y_base, ok ? 16u : 0u);
               }
             }
@@ -247,7 +249,7 @@ wgrad_halo_kernel(const __grid_constant__ WHParams p, const void* __restrict__ x
     const uint32_t a_lo_base = (uint32_t)p.adesc_hi, b_lo_base = (uint32_t)p.bdesc_hi;
     const uint32_t pitch = (uint32_t)p.cx * 2;
     const uint32_t a_mstep = ((uint32_t)(p.tpm * 8 * p.ks) * pitch) >> 4;   // next M tile: tpm taps further (taps are 8*KS rows apart)
-    const uint32_t a_kstep = ((uint32_t)(2 * p.s * p.rw) * pitch) >> 4;     // 16 positions = 2 output rows = 2*s halo rows
+    const uint32_t a_kstep = ((uint32_t)(2 * PS * p.rw) * pitch) >> 4;     // 16 positions = 2 output rows = 2*s halo rows
     const uint32_t a_sub = (8u * pitch) >> 4;                               // next sub-tile: 8 pixels further in the run
     const uint32_t b_kstep = (16u * (uint32_t)p.cy * 2u) >> 4;
     const uint32_t b_sub = (128u * (uint32_t)p.cy * 2u) >> 4;
@@ -259,7 +261,7 @@ wgrad_halo_kernel(const __grid_constant__ WHParams p, const void* __restrict__ x
     for (int k = 0; k < my_units; ++k, ui.next(p)) {
       const int d0 = ui.dc * p.DC, d1 = min(d0 + p.DC, p.D);
       const int nsub = min(p.ks, (p.W - ui.wt * kWTW * p.ks + kWTW - 1) / kWTW);   // sub-tiles inside the image
-      for (int z = d0 * p.s + p.od0; z <= (d1 - 1) * p.s + p.od0 + p.nkd - 1; ++z) {
+      for (int z = d0 * PS + p.od0; z <= (d1 - 1) * PS + p.od0 + p.nkd - 1; ++z) {
         const bool xvalid = z >= 0 && z < p.XD;
         h_mbar_wait(&full[st.idx], st.phase);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // cp.async (generic proxy) -> UMMA (async proxy)
@@ -272,7 +274,7 @@ wgrad_halo_kernel(const __grid_constant__ WHParams p, const void* __restrict__ x
           // read of the X views.  Accumulator columns of M tile mi: [(mi*3 + g)*cy], g = plane-(z-1).
           // window of dY planes: (z - od0 - kdi) / s for the depth taps kdi = nkd-1 .. 0
           int pa, pb, wlo;
-          if (p.s == 1) {
+          if (!S2) {
             wlo = z - p.od0 - (p.nkd - 1);
             pa = max(d0, wlo); pb = min(d1 - 1, z - p.od0);
           } else {
@@ -362,8 +364,8 @@ wgrad_halo_kernel(const __grid_constant__ WHParams p, const void* __restrict__ x
         }
         // last use of a dY plane is its depth tap nkd-1: plane (z - od0 - (nkd-1)) / s
         const int trel = z - p.od0 - (p.nkd - 1);
-        const int rel = p.s == 2 ? trel >> 1 : trel;
-        const bool relv = trel >= 0 && !(p.s == 2 && (trel & 1)) && rel >= d0 && rel < d1;
+        const int rel = S2 ? trel >> 1 : trel;
+        const bool relv = trel >= 0 && !(S2 && (trel & 1)) && rel >= d0 && rel < d1;
         if (h_elect_one()) {
           h_commit(&empty[st.idx]);
           if (relv) h_commit(&yempty[(yseq0 + (uint32_t)(rel - d0)) & ymask]);
@@ -446,6 +448,7 @@ bool wh_plan(const urn_conv_desc& d, int x_dtype, int y_dtype, int64_t ldx, int6
   if (d.s != 1 && d.s != 2) return false;
   if (!((d.kh == 3 && d.kw == 3) || (d.kh == 1 && d.kw == 1)) || (d.kd != 1 && d.kd != d.kh)) return false;
   if (getenv("URN_WHALO_ONLY3X3S1") && !(d.s == 1 && d.kh == 3)) return false;
+  if (d.kh == 1 && d.s == 2) return false;      // only every other staged row would be used: the tap-box kernel is faster
   if (d.yd != (d.xd + d.s - 1) / d.s || d.yh != (d.xh + d.s - 1) / d.s || d.yw != (d.xw + d.s - 1) / d.s) return false;
   if (d.cx != 16 && d.cx != 32 && d.cx != 64) return false;
   if (d.cy != 16 && d.cy != 32 && d.cy != 64) return false;
@@ -543,12 +546,14 @@ int wgrad_halo_launch(const urn_conv_desc& d, int x_dtype, const void* x, int64_
   const size_t smem = 1024 + (size_t)x_bytes + (size_t)(p.ystages + p.ymirror) * p.yplane_bytes + 1024;
   static bool attr_set = false;
   if (!attr_set) {
-    URN_CUDA(cudaFuncSetAttribute(wgrad_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    URN_CUDA(cudaFuncSetAttribute(wgrad_halo_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    URN_CUDA(cudaFuncSetAttribute(wgrad_halo_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
   const int grid = (int)std::min<long long>(p.nunits, num_sms());
   float* partial = (float*)ws;
-  wgrad_halo_kernel<<<grid, kWThreads, smem, st>>>(p, x, y, partial);
+  if (p.s == 2) wgrad_halo_kernel<true><<<grid, kWThreads, smem, st>>>(p, x, y, partial);
+  else wgrad_halo_kernel<false><<<grid, kWThreads, smem, st>>>(p, x, y, partial);
   URN_LAUNCH_CHECK();
   const int nw = p.ntaps * d.cx * d.cy;
   wgrad_halo_reduce_kernel<<<(nw + 127) / 128, 128, 0, st>>>(partial, nw, grid, dw, accumulate);
