@@ -787,10 +787,17 @@ static int halo_launch_params(HaloParams& p, int cin, int cout, int in_dtype, in
                               const void* wpack, void* out, cudaStream_t st);
 
 int gconv_halo_classes_launch(const GConv* gs, int ncls, int in_dtype, const void* in, const void* wpack, void* out,
-                              int out_dtype, cudaStream_t st) {
+                              int out_dtype, float* stats_part, int* nparts, cudaStream_t st) {
   HaloParams p;
   URN_CHECK(halo_plan_classes(gs, ncls, in_dtype, out_dtype, &p), "gconv_halo: unsupported class set");
+  if (nparts) *nparts = 0;
   if (p.ntiles == 0) return 0;
+  // the classes together write every output element exactly once: statistics can be fused
+  if (stats_part && nparts && out_dtype == URN_F32 && !gs[0].accumulate && !getenv("URN_NO_FUSED_STATS") &&
+      (long long)gs[0].gd * 2 == gs[0].od + (gs[0].od == 1) && gs[0].gh * 2 == gs[0].oh && gs[0].gw * 2 == gs[0].ow) {
+    p.stats_part = stats_part;
+    *nparts = (int)std::min<long long>(p.ntiles, num_sms()) * 4;
+  }
   return halo_launch_params(p, gs[0].cin, gs[0].cout, in_dtype, out_dtype, in, wpack, out, st);
 }
 

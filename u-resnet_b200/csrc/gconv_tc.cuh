@@ -39,11 +39,12 @@ int bn_stats_merge_launch(const float* parts, int nparts, int c_stride, int c, l
 // interleaved outputs of a tile are written by the same CTA.
 bool gconv_halo_classes_supported(const GConv* gs, int ncls, int in_dtype, int out_dtype);
 int gconv_halo_classes_launch(const GConv* gs, int ncls, int in_dtype, const void* in, const void* wpack, void* out,
-                              int out_dtype, cudaStream_t st);
+                              int out_dtype, float* stats_part, int* nparts, cudaStream_t st);
 // Scatter form of a conv relation: one fused launch if possible, else one launch per parity class.
 // Returns -1 when the tensor-core path does not take the shape at all (caller falls back).
 static inline int gconv_scatter_tc(const urn_conv_desc& d, int64_t ldy, int64_t ldx, int accumulate, int in_dtype,
-                                   const void* in, const void* wpack, void* out, int out_dtype, cudaStream_t st);
+                                   const void* in, const void* wpack, void* out, int out_dtype, cudaStream_t st,
+                                   float* stats_part = nullptr, int* nparts = nullptr);
 // Picks the best tensor-core kernel for the shape.
 static inline int gconv_tc_auto(const GConv& g, int in_dtype, const void* in, const void* wpack, void* out,
                                 int out_dtype, cudaStream_t st) {
@@ -85,7 +86,8 @@ static inline int64_t wgrad_any_workspace(const urn_conv_desc& d) {
 }
 
 static inline int gconv_scatter_tc(const urn_conv_desc& d, int64_t ldy, int64_t ldx, int accumulate, int in_dtype,
-                                   const void* in, const void* wpack, void* out, int out_dtype, cudaStream_t st) {
+                                   const void* in, const void* wpack, void* out, int out_dtype, cudaStream_t st,
+                                   float* stats_part, int* nparts) {
   GConv gs[8];
   int n = 0;
   for (int pd = 0; pd < d.s; ++pd)
@@ -93,6 +95,6 @@ static inline int gconv_scatter_tc(const urn_conv_desc& d, int64_t ldy, int64_t 
       for (int pw = 0; pw < d.s; ++pw)
         if (gconv_scatter_class(d, ldy, ldx, pd, ph, pw, accumulate, &gs[n])) ++n;
   if ((n == 4 || n == 8) && gconv_halo_classes_supported(gs, n, in_dtype, out_dtype))
-    return gconv_halo_classes_launch(gs, n, in_dtype, in, wpack, out, out_dtype, st);
+    return gconv_halo_classes_launch(gs, n, in_dtype, in, wpack, out, out_dtype, stats_part, nparts, st);
   return -1;
 }

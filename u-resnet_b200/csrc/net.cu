@@ -654,7 +654,8 @@ int run_conv_fwd(urn_net* h, int li, const float* params, void* ws, cudaStream_t
   } else {
     int rc = -1;
     if (tc_enabled(h) && L.d.s == 2)
-      rc = gconv_scatter_tc(L.d, in.ld, L.cout, 0, in.dtype, P(ws, in.off), P(ws, h->wps_off + L.w_off * 2), raw, URN_F32, st);
+      rc = gconv_scatter_tc(L.d, in.ld, L.cout, 0, in.dtype, P(ws, in.off), P(ws, h->wps_off + L.w_off * 2), raw, URN_F32, st,
+                            parts, &nparts);
     if (rc > 0) return 1;
     if (rc < 0)
     for (int pd = 0; pd < L.d.s; ++pd)
