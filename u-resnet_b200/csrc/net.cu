@@ -568,36 +568,40 @@ __global__ void round_params_kernel(const float* __restrict__ src, long long n, 
     if (dst_g != dst_a) dst_g[i] = dt_g == URN_F16 ? vh : vb;
   }
 }
-// One launch per layer: 16-bit copies of the filter in both contraction orders.
+// 16-bit copies of every filter in both contraction orders:
 //   gather form  Wg[t][cy][cx]  (conv forward / deconv input-gradient)
 //   scatter form Ws[t][cx][cy]  (conv input-gradient / deconv forward) == TF layout
-template <typename TGa, typename TSc>
-__global__ void pack_filter_kernel(const float* __restrict__ w, int taps, int cx, int cy,
-                                   TGa* __restrict__ wg, TSc* __restrict__ wsc) {
-  const long long n = (long long)taps * cx * cy;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int y = (int)(i % cy);
-    const int x = (int)((i / cy) % cx);
-    const long long t = i / ((long long)cx * cy);
-    const float v = w[i];
-    st1(wsc + i, v);
-    st1(wg + (t * cy + y) * cx + x, v);
-  }
+// All layers in ONE launch (blockIdx.y = table entry): the per-layer packing kernels were 60+
+// launch-bound launches per step.  The table travels as a kernel parameter.
+struct PackEntry {
+  long long w_off;        // element offset of the f32 filter in the flat parameter buffer
+  long long wg_off, ws_off;   // byte offsets of the gather / scatter packs in the workspace
+  int taps, cx, cy, cpad;     // cpad > 0: zero-pad cy to cpad output channels
+  int dt_g, dt_s;             // storage dtypes of the two packs
+};
+struct PackTable {
+  int n;
+  PackEntry e[64];
+};
+__device__ __forceinline__ void st_dt(void* base, long long idx, int dt, float v) {
+  if (dt == URN_F16) reinterpret_cast<f16*>(base)[idx] = __float2half_rn(v);
+  else reinterpret_cast<bf16*>(base)[idx] = __float2bfloat16_rn(v);
 }
-// Zero-padded variant for the head: cy -> cpad output channels.
-template <typename TGa, typename TSc>
-__global__ void pack_filter_padded_kernel(const float* __restrict__ w, int taps, int cx, int cy, int cpad,
-                                          TGa* __restrict__ wg, TSc* __restrict__ wsc) {
-  const long long n = (long long)taps * cx * cpad;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int y = (int)(i % cpad);
-    const int x = (int)((i / cpad) % cx);
-    const long long t = i / ((long long)cx * cpad);
-    const float v = y < cy ? w[(t * cx + x) * cy + y] : 0.f;
-    st1(wsc + i, v);
-    st1(wg + (t * cpad + y) * cx + x, v);
+__global__ void pack_all_kernel(const __grid_constant__ PackTable tb, const float* __restrict__ params,
+                                char* __restrict__ ws) {
+  const PackEntry& e = tb.e[blockIdx.y];
+  const int cyp = e.cpad > 0 ? e.cpad : e.cy;
+  const long long n = (long long)e.taps * e.cx * cyp;
+  const float* w = params + e.w_off;
+  void* wg = ws + e.wg_off;
+  void* wsc = ws + e.ws_off;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int y = (int)(i % cyp);
+    const int x = (int)((i / cyp) % e.cx);
+    const long long t = i / ((long long)e.cx * cyp);
+    const float v = y < e.cy ? w[(t * e.cx + x) * e.cy + y] : 0.f;
+    st_dt(wsc, i, e.dt_s, v);
+    st_dt(wg, (t * cyp + y) * e.cx + x, e.dt_g, v);
   }
 }
 // grads[t][cx][cy] (+)= dw_pad[t][cx][cpad]
@@ -701,45 +705,28 @@ extern "C" int urn_forward(urn_net* h, const float* params, const float* data, v
       URN_LAUNCH_CHECK();
     }
     if (tc_enabled(h)) {
-      for (const Layer& L : h->layers) {
-        if (L.cpad) {
-          const int taps = L.d.kd * L.d.kh * L.d.kw;
-          const long long n = (long long)taps * L.d.cx * L.cpad;
-          const unsigned nbp = (unsigned)std::min<long long>((n + 255) / 256, 148 * 4);
-          // gather form multiplies activations (TA), scatter form multiplies gradients (TG)
-          if (dispatch_dtype(h->TA, [&](auto pg) {
-                using TGa = URN_T(pg);
-                return dispatch_dtype(h->TG, [&](auto psc) {
-                  using TSc = URN_T(psc);
-                  pack_filter_padded_kernel<TGa, TSc><<<nbp, 256, 0, st>>>(params + L.w_off, taps, L.d.cx, L.d.cy, L.cpad,
-                                                                        (TGa*)P(ws, L.wpg_pad_off), (TSc*)P(ws, L.wps_pad_off));
-                  return 0;
-                });
-              }))
-            return 1;
-          URN_LAUNCH_CHECK();
-          continue;
-        }
-        if (L.d.cx % 16 || L.d.cy % 16) continue;       // stem / head stay on the CUDA cores
-        const int taps = L.d.kd * L.d.kh * L.d.kw;
-        const long long n = (long long)taps * L.d.cx * L.d.cy;
-        const unsigned nb3 = (unsigned)std::min<long long>((n + 255) / 256, 148 * 4);
-        const float* w = params + L.w_off;
-        void* wg = P(ws, h->wpg_off + L.w_off * 2);
-        void* wsc = P(ws, h->wps_off + L.w_off * 2);
-        // conv: gather multiplies activations (TA), scatter multiplies gradients (TG); deconv: swapped
-        const int dt_g = L.transpose ? h->TG : h->TA, dt_s = L.transpose ? h->TA : h->TG;
-        if (dispatch_dtype(dt_g, [&](auto pg) {
-              using TGa = URN_T(pg);
-              return dispatch_dtype(dt_s, [&](auto psc) {
-                using TSc = URN_T(psc);
-                pack_filter_kernel<TGa, TSc><<<nb3, 256, 0, st>>>(w, taps, L.d.cx, L.d.cy, (TGa*)wg, (TSc*)wsc);
-                return 0;
-              });
-            }))
-          return 1;
+      PackTable tb;
+      tb.n = 0;
+      auto flush = [&]() -> int {
+        if (tb.n == 0) return 0;
+        pack_all_kernel<<<dim3(32, (unsigned)tb.n), 256, 0, st>>>(tb, params, (char*)ws);
         URN_LAUNCH_CHECK();
+        tb.n = 0;
+        return 0;
+      };
+      for (const Layer& L : h->layers) {
+        if (!L.cpad && (L.d.cx % 16 || L.d.cy % 16)) continue;       // stem / unpadded head stay on the CUDA cores
+        PackEntry& e = tb.e[tb.n++];
+        e.w_off = L.w_off;
+        e.taps = L.d.kd * L.d.kh * L.d.kw; e.cx = L.d.cx; e.cy = L.d.cy; e.cpad = L.cpad;
+        // conv: gather multiplies activations (TA), scatter multiplies gradients (TG); deconv: swapped
+        e.dt_g = L.transpose ? h->TG : h->TA;
+        e.dt_s = L.transpose ? h->TA : h->TG;
+        e.wg_off = L.cpad ? L.wpg_pad_off : h->wpg_off + L.w_off * 2;
+        e.ws_off = L.cpad ? L.wps_pad_off : h->wps_off + L.w_off * 2;
+        if (tb.n == 64 && flush()) return 1;
       }
+      if (flush()) return 1;
     }
   }
   for (const FStep& s : h->fwd) {
