@@ -497,6 +497,26 @@ gconv_halo_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_consta
       const int nsub = min(p.ks, (p.gw - ti.wt * kTW * p.ks + kTW - 1) / kTW);
       const int dmax = min(d0 + p.TD, p.gd);
       if (warp == kEpiWarp0 && lane == 0) TL(2, k, 0);
+      // accumulate mode (bf16 gradients): the old values of a group of sub-tiles are fetched BEFORE
+      // the accumulators are waited for, so the read-modify-write does not serialise behind the MMAs
+      uint4 oldv[4][2];
+      bool old_ready = false;
+      auto fetch_old = [&](long long opix0_, int c0_) {
+#pragma unroll
+        for (int sj = 0; sj < 4; ++sj) {
+          if (sj < nsub && y < p.gh && x0 + sj * kTW < p.gw) {
+            const bf16* o = reinterpret_cast<const bf16*>(out) + (opix0_ + sj * kTW * p.os) * p.ldout + c0_;
+            oldv[sj][0] = *reinterpret_cast<const uint4*>(o);
+            oldv[sj][1] = *reinterpret_cast<const uint4*>(o + 8);
+          }
+        }
+      };
+      if (!OUT_F32 && MODE == 1) {
+        const long long opix_first = (((long long)ti.nn * p.OD + (d0 * p.os + p.coff[0][0])) * p.OH + (y * p.os + p.coff[0][1])) * p.OW +
+                                     (x0 * p.os + p.coff[0][2]);
+        fetch_old(opix_first, 0);
+        old_ready = true;
+      }
       h_mbar_wait_warp(&tfull[ac.idx], ac.phase);
       h_fence_after();
       if (warp == kEpiWarp0 && lane == 0) TL(2, k, 1);
@@ -527,6 +547,10 @@ gconv_halo_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_consta
 #pragma unroll
             for (int g = 0; g < G; ++g)
               if (s0 + g < nsub) h_tmem_ld16_nowait(taddr0 + (uint32_t)(s0 + g) * sj_cols + (uint32_t)c0, v[g]);
+            if (!OUT_F32 && MODE == 1) {
+              if (!old_ready) fetch_old(opix0, c0);
+              old_ready = false;
+            }
             h_tmem_wait_ld();
 #pragma unroll
             for (int g = 0; g < G; ++g) {
@@ -569,10 +593,13 @@ gconv_halo_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_consta
               } else {
                 bf16* o = reinterpret_cast<bf16*>(out) + opix * p.ldout + c0;
                 if (MODE == 1) {
-                  float old[16];
-                  load8(o, old); load8(o + 8, old + 8);
+                  const uint32_t w[8] = {oldv[sj][0].x, oldv[sj][0].y, oldv[sj][0].z, oldv[sj][0].w,
+                                         oldv[sj][1].x, oldv[sj][1].y, oldv[sj][1].z, oldv[sj][1].w};
 #pragma unroll
-                  for (int j = 0; j < 16; ++j) v[g][j] += old[j];
+                  for (int j = 0; j < 8; ++j) {
+                    v[g][2 * j] += __uint_as_float(w[j] << 16);
+                    v[g][2 * j + 1] += __uint_as_float(w[j] & 0xffff0000u);
+                  }
                 }
                 store8(o, v[g]); store8(o + 8, v[g] + 8);
               }
