@@ -545,7 +545,17 @@ namespace {
 template <typename TT>
 __global__ void convert_in_kernel(const float* __restrict__ src, long long n, TT* __restrict__ dst,
                                   bf16* __restrict__ dst2) {
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+  // 8 elements per thread (two 16-byte loads, one 16-byte store per copy); scalar tail
+  const long long n8 = ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst) |
+                         reinterpret_cast<uintptr_t>(dst2)) & 15) == 0 ? n / 8 : 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8;
+       i += (long long)gridDim.x * blockDim.x) {
+    float v[8];
+    load8(src + i * 8, v);
+    store8(dst + i * 8, v);
+    if (dst2) store8(dst2 + i * 8, v);
+  }
+  for (long long i = n8 * 8 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x) {
     st1(dst + i, src[i]);
     if (dst2) st1(dst2 + i, src[i]);
@@ -709,7 +719,7 @@ extern "C" int urn_forward(urn_net* h, const float* params, const float* data, v
       tb.n = 0;
       auto flush = [&]() -> int {
         if (tb.n == 0) return 0;
-        pack_all_kernel<<<dim3(32, (unsigned)tb.n), 256, 0, st>>>(tb, params, (char*)ws);
+        pack_all_kernel<<<dim3(148, (unsigned)tb.n), 256, 0, st>>>(tb, params, (char*)ws);
         URN_LAUNCH_CHECK();
         tb.n = 0;
         return 0;
