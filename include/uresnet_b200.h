@@ -87,7 +87,8 @@ int urn_conv_dgrad_tc(const urn_conv_desc* d, int dtype, const void* dy, int64_t
 /* urn_conv_fwd_tc (f32 output) with the slim.batch_norm statistics of y fused into the conv
  * epilogue (K5 without a separate pass over the raw tensor): stats = float[2*cy] (mean | rstd) as
  * urn_bn_stats would produce them.  ws: urn_bn_workspace(cy).  Fails (non-zero) when the layer
- * shape is not one the halo-tile kernel takes. */
+ * shape is not one whose kernel fuses the statistics (halo-tile kernel: Cin <= 64; tap-box kernel:
+ * Cout <= 256). */
 int urn_conv_fwd_tc_stats(const urn_conv_desc* d, int dtype, const void* x, int64_t ldx, const float* w,
                           void* wpack, float* y, int64_t ldy, float eps, float* stats, void* ws,
                           void* stream);

@@ -253,7 +253,9 @@ def test_conv_halo_wgrad(lib, xdt, nd, n, sp, cin, cout, ldf):
 @pytest.mark.parametrize("nd,n,sp,cin,cout,k,s", [
     (2, 3, (40, 72), 16, 16, 3, 1), (2, 2, (33, 19), 16, 32, 3, 1), (2, 1, (64, 64), 32, 64, 3, 1),
     (2, 2, (32, 48), 16, 32, 3, 2), (2, 2, (16, 40), 32, 16, 1, 1), (3, 1, (9, 20, 12), 16, 16, 3, 1),
-    (3, 1, (8, 16, 16), 16, 32, 3, 2)])
+    (3, 1, (8, 16, 16), 16, 32, 3, 2),
+    (2, 2, (16, 24), 128, 128, 3, 1), (2, 1, (12, 20), 128, 256, 3, 2), (2, 3, (8, 8), 256, 128, 1, 1),
+    (3, 1, (4, 8, 8), 128, 64, 3, 1)])                 # tap-box kernel (Cin >= 128)
 def test_conv_fused_bn_statistics(lib, nd, n, sp, cin, cout, k, s):
     """BN statistics fused into the conv epilogue (per-warp butterfly + Chan merges) against
     float64 mean / biased variance of the kernel's own fp32 output."""

@@ -212,10 +212,13 @@ extern "C" int urn_conv_fwd_tc_stats(const urn_conv_desc* d, int dtype, const vo
   cudaStream_t st = (cudaStream_t)stream;
   GConv g;
   gconv_gather(*d, ldx, ldy, &g);
-  URN_CHECK(gconv_halo_supported(g, dtype, URN_F32), "urn_conv_fwd_tc_stats: shape/dtype not taken by the halo-tile kernel");
+  const bool halo = gconv_halo_supported(g, dtype, URN_F32);
+  URN_CHECK(halo || gconv_tc_supported(g, dtype, URN_F32), "urn_conv_fwd_tc_stats: shape/dtype not taken by the tensor-core kernels");
   if (pack_filter(*d, dtype, w, wpack, true, st)) return 1;
   int nparts = 0;
-  if (gconv_halo_launch_stats(g, dtype, x, wpack, y, URN_F32, 0, (float*)ws, &nparts, st)) return 1;
+  if (halo) {
+    if (gconv_halo_launch_stats(g, dtype, x, wpack, y, URN_F32, 0, (float*)ws, &nparts, st)) return 1;
+  } else if (gconv_tc_launch_stats(g, dtype, x, wpack, y, URN_F32, (float*)ws, &nparts, st)) return 1;
   URN_CHECK(nparts > 0, "urn_conv_fwd_tc_stats: statistics were not fused for this launch");
   const long long rows = (long long)d->n * d->yd * d->yh * d->yw;
   return bn_stats_merge_launch((const float*)ws, nparts, d->cy, d->cy, rows, eps, stats, st);

@@ -22,6 +22,7 @@
 
 #include "common.cuh"
 #include "gconv_tc.cuh"
+#include "bn_stat_fuse.cuh"
 
 namespace {
 
@@ -47,6 +48,7 @@ struct TcParams {
   uint32_t idesc;               // tcgen05 instruction descriptor
   uint64_t desc_hi;             // smem descriptor without the start address (layout, SBO, LBO)
   int tmem_cols;                // allocated TMEM columns (2 accumulators)
+  float* stats_part;            // fused BN statistics partials [(cta*4 + warp)][cout][3], or NULL
 };
 
 // ------------------------------ PTX wrappers ------------------------------
@@ -166,6 +168,8 @@ struct Ring {
 // loop costs ~4x more cycles per pipeline stage (measured: 3370 -> 830 cycles per 9 MMAs).
 
 // ------------------------------ the kernel ------------------------------
+// STATS: BN statistics of the fp32 output fused into the epilogue (one N tile per layer only).
+template <bool STATS>
 __global__ void __launch_bounds__(kThreads, 1)
 gconv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                 const __grid_constant__ TcParams p, void* __restrict__ out) {
@@ -260,6 +264,11 @@ gconv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     const int r = q * 32 + lane;              // accumulator row = position inside the tile box
     const int lw = r % p.tw, lh = (r / p.tw) % p.th, ld_ = r / (p.tw * p.th);
     uint32_t wi = 0;
+    RunStat rs[STATS ? 16 : 1];
+    if (STATS) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) { rs[i].n = 0.f; rs[i].mean = 0.f; rs[i].m2 = 0.f; }
+    }
     for (long long w = blockIdx.x; w < nwork; w += gridDim.x, ++wi) {
       const uint32_t acc = wi & 1;
       const int nt = (int)(w % p.n_tiles);
@@ -286,6 +295,15 @@ gconv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
           if (lane == 0) mbar_arrive(&tempty[acc]);
         }
         const int c = c_base + c0;
+        if (STATS) {
+          float a[16], b[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) { a[j] = valid ? v[j] : 0.f; b[j] = a[j] * a[j]; }
+          const unsigned nv = __popc(__ballot_sync(0xffffffffu, valid));
+#pragma unroll
+          for (int ci = 0; ci < 16; ++ci)
+            if (ci * 16 == c0) stat_merge(rs[ci], a, b, nv, lane);
+        }
         if (!valid || c >= p.cout) continue;
         if (p.out_dtype == URN_F32) {
           float* o = reinterpret_cast<float*>(out) + opix * p.ldout + c;
@@ -310,6 +328,15 @@ gconv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             st4(o + j, x);
           }
         }
+      }
+    }
+    if (STATS && !(lane & 1)) {
+      // lane L owns channel ci*16 + (L >> 1) of every 16-channel chunk; partial[(cta*4 + q)][cout][3]
+      float* dst = p.stats_part + ((long long)(blockIdx.x * 4 + q) * p.cout) * 3;
+#pragma unroll
+      for (int ci = 0; ci < 16; ++ci) {
+        const int ch = ci * 16 + (lane >> 1);
+        if (ch < p.cout) { dst[ch * 3 + 0] = rs[ci].n; dst[ch * 3 + 1] = rs[ci].mean; dst[ch * 3 + 2] = rs[ci].m2; }
       }
     }
   }
@@ -357,6 +384,12 @@ bool gconv_tc_supported(const GConv& g, int in_dtype, int out_dtype) {
 // wpack: 16-bit filter (same dtype as `in`) laid out [tap][cout][cin]
 int gconv_tc_launch(const GConv& g, int in_dtype, const void* in, const void* wpack, void* out,
                     int out_dtype, cudaStream_t st) {
+  return gconv_tc_launch_stats(g, in_dtype, in, wpack, out, out_dtype, nullptr, nullptr, st);
+}
+
+int gconv_tc_launch_stats(const GConv& g, int in_dtype, const void* in, const void* wpack, void* out,
+                          int out_dtype, float* stats_part, int* nparts, cudaStream_t st) {
+  if (nparts) *nparts = 0;
   URN_CHECK(gconv_tc_supported(g, in_dtype, out_dtype), "gconv_tc: unsupported shape/dtype");
   EncodeTiledFn enc = get_encode();
   URN_CHECK(enc, "gconv_tc: cuTensorMapEncodeTiled not available");
@@ -434,13 +467,22 @@ int gconv_tc_launch(const GConv& g, int in_dtype, const void* in, const void* wp
   const size_t smem = 1024 + (size_t)p.stages * stage_bytes + 256;
   static bool attr_set = false;
   if (!attr_set) {
-    URN_CUDA(cudaFuncSetAttribute(gconv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    URN_CUDA(cudaFuncSetAttribute(gconv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    URN_CUDA(cudaFuncSetAttribute(gconv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
   long long nwork = p.ntiles * p.n_tiles;
   URN_CHECK(nwork < (1ll << 31), "gconv_tc: too many tiles");
   int grid = (int)std::min<long long>(nwork, num_sms());
-  gconv_tc_kernel<<<grid, kThreads, smem, st>>>(map_a, map_b, p, out);
+  // fused statistics: a single launch writing the whole fp32 tensor once, one N tile of <= 256 channels
+  const bool stats = stats_part && nparts && out_dtype == URN_F32 && !g.accumulate && g.os == 1 && g.gd == g.od &&
+                     g.gh == g.oh && g.gw == g.ow && p.n_tiles == 1 && p.n_tile <= 256 && !getenv("URN_NO_FUSED_STATS");
+  if (stats) {
+    p.stats_part = stats_part;
+    *nparts = grid * 4;
+    gconv_tc_kernel<true><<<grid, kThreads, smem, st>>>(map_a, map_b, p, out);
+  } else
+  gconv_tc_kernel<false><<<grid, kThreads, smem, st>>>(map_a, map_b, p, out);
   URN_LAUNCH_CHECK();
   return 0;
 }

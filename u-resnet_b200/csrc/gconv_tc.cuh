@@ -14,6 +14,8 @@ int urn_softmax_only(const float* logits, int64_t ld, int64_t total, int c, floa
 bool gconv_tc_supported(const GConv& g, int in_dtype, int out_dtype);
 int gconv_tc_launch(const GConv& g, int in_dtype, const void* in, const void* wpack, void* out,
                     int out_dtype, cudaStream_t st);
+int gconv_tc_launch_stats(const GConv& g, int in_dtype, const void* in, const void* wpack, void* out,
+                          int out_dtype, float* stats_part, int* nparts, cudaStream_t st);
 bool wgrad_tc_supported(const urn_conv_desc& d, int x_dtype, int y_dtype, int64_t ldx, int64_t ldy);
 int64_t wgrad_tc_workspace(const urn_conv_desc& d);
 int wgrad_tc_launch(const urn_conv_desc& d, int x_dtype, const void* x, int64_t ldx, int y_dtype,

@@ -5,6 +5,7 @@
 #include <stdint.h>
 
 #include "common.cuh"
+#include "bn_stat_fuse.cuh"
 
 namespace {
 

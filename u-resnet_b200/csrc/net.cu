@@ -664,6 +664,8 @@ int run_conv_fwd(urn_net* h, int li, const float* params, void* ws, cudaStream_t
     gconv_gather(L.d, in.ld, L.cout, &g);
     if (tc_enabled(h) && gconv_halo_supported(g, in.dtype, URN_F32)) {
       if (gconv_halo_launch_stats(g, in.dtype, P(ws, in.off), P(ws, h->wpg_off + L.w_off * 2), raw, URN_F32, 0, parts, &nparts, st)) return 1;
+    } else if (tc_enabled(h) && gconv_tc_supported(g, in.dtype, URN_F32)) {
+      if (gconv_tc_launch_stats(g, in.dtype, P(ws, in.off), P(ws, h->wpg_off + L.w_off * 2), raw, URN_F32, parts, &nparts, st)) return 1;
     } else if (run_gconv(h, g, in.dtype, P(ws, in.off), w, P(ws, h->wpg_off + L.w_off * 2), raw, URN_F32, st)) return 1;
   } else {
     int rc = -1;
