@@ -1,23 +1,27 @@
-// Halo-tile tcgen05 filter gradient for the narrow stride-1 3x3 / 3x3x3 layers
-// (cx, cy in {16, 32, 64}):   dW[t][cx][cy] = sum_p X[p + t - 1][cx] * dY[p][cy].
+// Halo-tile tcgen05 filter gradient for the narrow layers (cx, cy in {16, 32, 64}): 3x3 / 3x3x3
+// and 1x1 taps, X sampled with stride 1 or 2 (template S2):
+//     dW[t][cx][cy] = sum_p X[p*s + t - pad][cx] * dY[p][cy].
 //
 // Why: the tap-box kernel (wgrad_tc_kernel) issues one TMA box per (tap, channel group) and
 // K block, i.e. it re-reads every activation 9 / 27 times through TMA rows of only 32-64 bytes
 // and is bound by the TMA box-row rate (0.85 ms per 2D C=16 layer, 7-26 ms in 3D).  Here each
-// X plane of a 16x8 tile is staged ONCE (with its halo, 16-byte cp.async, zero fill = TF 'same'
-// padding) into the same (hy, kw, w)-ordered swizzled layout the forward halo kernel uses; the
-// 9 in-plane taps are then descriptor views 8 rows apart, which is exactly the MN-group stride
-// (LBO) of an MN-major UMMA operand: ONE tcgen05.mma with M = 128 covers 128/cx taps.
-//   GEMM view   M = (tap, cx)   N = cy   K = 128 positions of the tile (8 MMAs of K = 16)
-//   A = X views (MN-major, SBO = 24 rows = next image row, LBO = 8 rows = next tap)
+// X plane of a 16 x (8*KS) super-tile is staged ONCE (with its halo, 16-byte cp.async, zero fill =
+// TF 'same' padding) into the same (halo row, kw, w)-ordered swizzled layout the forward halo
+// kernel uses; the in-plane taps are then descriptor views 8*KS rows apart, which is exactly the
+// MN-group stride (LBO) of an MN-major UMMA operand: ONE tcgen05.mma with M = 128 covers 128/cx
+// taps (the last M tile of a cx = 16 layer holds one live tap and is issued with M = 64).
+//   GEMM view   M = (tap, cx)   N = cy   K = 128 positions of a sub-tile (8 MMAs of K = 16)
+//   A = X views (MN-major, SBO = s*RW rows = next output row, LBO = 8*KS rows = next tap)
 //   B = dY tile (MN-major, rows = positions)
-// In 3D a CTA walks a column of planes: X plane z meets dY planes z+1, z, z-1 (depth taps
-// -1, 0, +1), each pair accumulating into its own TMEM accumulator, so X and dY are read once
-// per depth chunk.  Accumulators stay in TMEM for the CTA's whole range of tiles; at the end
-// every CTA writes one fp32 partial [tap][cx][cy] and a fixed-order second stage sums the
+// In 3D a CTA walks a column of planes: X plane z meets the dY planes of its depth taps.  With
+// stride 1 those are z+1, z, z-1: they sit in consecutive slots of the dY ring (slots 0, 1 are
+// mirrored behind the ring so that the window never wraps) and are issued as ONE MMA with
+// N = 3*cy whose N groups are the ring slots (LBO = slot stride), so the X views are read once
+// for all three depth taps.  Accumulators stay in TMEM for the CTA's whole range of tiles; at the
+// end every CTA writes one fp32 partial [tap][cx][cy] and a fixed-order second stage sums the
 // <= 148 partials (deterministic).
-//   warps 0-7 : cp.async producers (X plane + dY tile per step)   warp 8 : TMEM alloc, MMA issue
-//   warps 9-12: final epilogue (tcgen05.ld -> fp32 partial)
+//   warps 0-7 : cp.async producers (X plane + dY tile per step, register-resident offset tables)
+//   warp 8    : TMEM alloc, MMA issue        warps 9-12: final epilogue (tcgen05.ld -> fp32 partial)
 #include <cuda.h>
 #include <stdlib.h>
 #include <string.h>
