@@ -161,6 +161,15 @@ int urn_ce_fwd_bwd(const float* logits, int64_t ld, const float* label, const fl
                    int64_t lddl, int dl_dtype, float* softmax, double* result, void* ws,
                    void* stream);
 
+/* Shower/track decision of the analysis step (lib/ssnet_trainval.py:269-287, the numpy
+ * expression applied per entry before the larcv write):
+ *   decision[p] = (1*(p1 > p2) + 2*(p2 >= p1)) * (data[p*data_ld] > threshold),
+ * p = softmax(logits[p*ld .. +num_class)) evaluated exactly as urn_ce_fwd_bwd's softmax output,
+ * so the result equals the host expression on that softmax value for value.  num_class >= 3. */
+int urn_ssnet_decision(const float* logits, int64_t ld, int64_t total, int num_class,
+                       const float* data, int64_t data_ld, float threshold, float* decision,
+                       void* stream);
+
 /* TF-1.x AdamOptimizer apply (lib/ssnet.py:72-79), epsilon outside the bias
  * correction, on flat f32 buffers; t is the 1-based step. */
 int urn_adam_step(float* param, const float* grad, float* m, float* v, int64_t count, float lr,
@@ -205,6 +214,11 @@ int urn_forward(urn_net* h, const float* params, const float* data, void* ws, vo
 /* Loss/metrics on the logits left by urn_forward; if want_grad, seeds backward. */
 int urn_loss_metrics(urn_net* h, const float* label, const float* weight, const float* data,
                      float* softmax, double* result, int want_grad, void* ws, void* stream);
+
+/* urn_ssnet_decision on the logits left by urn_forward; data as given to urn_forward (channel 0
+ * is thresholded); decision f32 [batch*pixels]. */
+int urn_decision(urn_net* h, const float* data, float threshold, float* decision, void* ws,
+                 void* stream);
 
 /* tf.gradients of the loss w.r.t. all parameters, accumulated (+=) into grads when
  * accumulate != 0 (lib/ssnet.py:76-78).  If ready_events != NULL it is a host array

@@ -358,6 +358,17 @@ def run(P_np, data, label, weight=None, base=16, num_strides=5, dtype=torch.floa
 # --------------------------------------------------------------------------
 # TF AdamOptimizer                                   ssnet.py:72-79, SURVEY 3.4
 # --------------------------------------------------------------------------
+def ssnet_decision(softmax, data, threshold=1.0):
+    """lib/ssnet_trainval.py:269-287: shower (class 1) vs track (class 2) map of the analysis
+    step, zeroed where data <= threshold.  softmax [..., num_class] numpy, data [...] numpy."""
+    shower_score = softmax[..., 1]
+    track_score = softmax[..., 2]
+    ssnet_result = (shower_score > track_score).astype(np.float32) + \
+                   (track_score >= shower_score).astype(np.float32) * 2.0
+    nonzero_map = (data > threshold).astype(np.int32)
+    return (ssnet_result * nonzero_map).astype(np.float32)
+
+
 def adam_tf(var, grad, m, v, t, lr=1e-3, b1=0.9, b2=0.999, eps=1e-8):
     """One TF-1.x ``ApplyAdam`` step in float32, in place; t is the 1-based step count.
 

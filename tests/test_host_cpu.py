@@ -102,3 +102,22 @@ def test_bucket_plan_covers_everything_in_backward_order():
     for (lo, hi, ls), nxt in zip(buckets, buckets[1:]):
         assert nxt[1] == lo                                        # contiguous, no gaps
     assert all(hi - lo >= 4000 for lo, hi, _ in buckets[:-1])
+
+
+def test_summary_log_writes_reference_tags(tmp_path):
+    """tf.summary stand-in (ssnet.py:81-89): scalars accuracy_all / accuracy_nonzero / loss, image
+    data_example (first 10 of the minibatch), one record per summary step."""
+    import json
+    from uresnet_b200.ssnet_trainval import _summary_log
+    w = _summary_log(str(tmp_path / "train"))
+    w.add_summary({"loss": 1.0, "accuracy_all": 0.5, "accuracy_nonzero": 0.25}, 0, np.random.rand(12, 16, 16, 1))
+    w.add_summary({"loss": 0.5, "accuracy_all": 0.75, "accuracy_nonzero": 0.5}, 20, None)
+    w.close()
+    recs = [json.loads(l) for l in (tmp_path / "train" / "scalars.jsonl").read_text().splitlines()]
+    assert [r["step"] for r in recs] == [0, 20] and recs[1]["loss"] == 0.5
+    ea = pytest.importorskip("tensorboard.backend.event_processing.event_accumulator")
+    acc = ea.EventAccumulator(str(tmp_path / "train"))
+    acc.Reload()
+    assert set(acc.Tags()["scalars"]) == {"accuracy_all", "accuracy_nonzero", "loss"}
+    assert [e.step for e in acc.Scalars("accuracy_all")] == [0, 20]
+    assert acc.Tags()["images"] == ["data_example"]

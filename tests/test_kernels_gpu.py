@@ -462,6 +462,41 @@ def test_ce_metrics(lib, B, P, c, use_w):
     assert np.isnan(res.cpu().numpy()[0])
 
 
+@pytest.mark.parametrize("total,c,ld,dld", [(5000, 3, 3, 1), (777, 5, 8, 2), (0, 3, 3, 1)])
+def test_ssnet_decision(lib, total, c, ld, dld):
+    """lib/ssnet_trainval.py:269-287 on the device: equal, value for value, to the host expression
+    applied to the softmax this library returns (ties -> track) and to the oracle's softmax away
+    from ties."""
+    rng = np.random.default_rng(total + c)
+    logits = np.zeros((max(total, 1), ld), np.float32)
+    logits[:, :c] = (rng.standard_normal((max(total, 1), c)) * 2).astype(np.float32)
+    logits[:50, 2] = logits[:50, 1]                             # exact shower/track ties
+    data = np.zeros((max(total, 1), dld), np.float32)
+    data[:, 0] = rng.choice([0.0, 0.5, 1.0, 1.5, 30.0], size=max(total, 1)).astype(np.float32)
+    lgd, dad = dev(logits), dev(data)
+    dec = torch.full((max(total, 1),), -1.0, dtype=torch.float32, device=DEV)
+    _capi.check(lib.urn_ssnet_decision(lgd.data_ptr(), ld, total, c, dad.data_ptr(), dld, 1.0, dec.data_ptr(), st()))
+    if total == 0:
+        assert float(dec[0]) == -1.0
+        return
+    # the library's own softmax of the same logits
+    ws = torch.zeros(int(lib.urn_loss_workspace(total)), dtype=torch.uint8, device=DEV)
+    res = torch.zeros(4, dtype=torch.float64, device=DEV)
+    sm = torch.empty((total, c), dtype=torch.float32, device=DEV)
+    lab = torch.zeros(total, dtype=torch.float32, device=DEV)
+    _capi.check(lib.urn_ce_fwd_bwd(lgd.data_ptr(), ld, lab.data_ptr(), None, dad.data_ptr(), 1, total, c, None, c, F32,
+                                   sm.data_ptr(), res.data_ptr(), ws.data_ptr(), st()))
+    smh = host(sm)
+    want = O.ssnet_decision(smh, data[:, 0])
+    got = host(dec)
+    assert np.array_equal(got, want)
+    assert np.all(got[:50][data[:50, 0] > 1.0] == 2.0)
+    ref_sm = torch.softmax(torch.tensor(logits[:, :c], dtype=torch.float64), -1).numpy()
+    clear = np.abs(ref_sm[:, 1] - ref_sm[:, 2]) > 1e-6
+    assert np.array_equal(got[clear], O.ssnet_decision(ref_sm, data[:, 0])[clear])
+    assert lib.urn_ssnet_decision(lgd.data_ptr(), ld, total, 2, dad.data_ptr(), dld, 1.0, dec.data_ptr(), st()) != 0
+
+
 def test_adam_matches_tf_formula(lib):
     rng = np.random.default_rng(0)
     n = 1003

@@ -204,6 +204,14 @@ def test_inference_and_run_test_api():
     assert relerr(out[0], ref["softmax"]) < 1e-3
     sm, acc_all, acc_nz = net.inference(None, data, label)
     assert abs(acc_all - ref["acc_all"]) < 2e-3
+    # shower/track map of the analysis step (ssnet_trainval.py:269-287), computed on the device
+    sm2, a2, nz2, dec = net.inference(None, data, label, with_decision=True)
+    want = O.ssnet_decision(sm2, data.reshape(shp))
+    assert dec.shape == tuple(shp) and dec.dtype == np.float32 and np.array_equal(dec, want)
+    assert set(np.unique(dec)) <= {0.0, 1.0, 2.0} and np.all(dec[data.reshape(shp) <= 1.0] == 0)
+    dec2, a3, nz3 = net.decision(None, data, label)
+    assert np.array_equal(dec2, dec) and a3 == a2 and (nz3 == nz2 or (np.isnan(nz3) and np.isnan(nz2)))
+    assert np.array_equal(net.decision(None, data)[0], dec)
     (loss, a, nz), doc = net.run_test(None, data, label)
     assert doc == ['loss', 'acc. all', 'acc. nonzero'] and abs(loss - ref["loss"]) < 1e-3 * ref["loss"]
     # weighted net refuses to run without weights (ssnet.py:143-146)
@@ -273,6 +281,11 @@ def test_trainval_driver_train_checkpoint_and_ana(tmp_path, capsys):
     z = np.load(ck[-1])
     assert z["UResNet/conv0/weights"].shape == (3, 3, 1, 4) and "UResNet/conv0/BatchNorm/moving_variance" in z
     assert (tmp_path / "log" / "train" / "scalars.jsonl").read_text().count("\n") == 2
+    ea = pytest.importorskip("tensorboard.backend.event_processing.event_accumulator")
+    acc = ea.EventAccumulator(str(tmp_path / "log" / "train"))
+    acc.Reload()
+    assert set(acc.Tags()["scalars"]) == {"accuracy_all", "accuracy_nonzero", "loss"}      # ssnet.py:84-86
+    assert [e.step for e in acc.Scalars("loss")] == [0, 2] and "data_example" in acc.Tags()["images"]
     saved = t._net.get_variables()
     t.reset()
     # inference from the checkpoint
@@ -293,6 +306,20 @@ def test_trainval_driver_train_checkpoint_and_ana(tmp_path, capsys):
     assert res["softmax"].shape == (2, 64, 64, 3) and res["input"].shape == (2, 64, 64, 1)
     assert 0.0 <= res["acc_all"] <= 1.0 and set(res) == {"entries", "input", "label", "softmax", "acc_all", "acc_nonzero"}
     a.reset()
+    # analysis with an output: per-batch npz with the shower/track map (larcv output stand-in)
+    cfg3 = tmp_path / "ana_out.cfg"
+    cfg3.write_text(cfg2.read_text() + "\nANA_OUTPUT_CONFIG '%s'" % (tmp_path / "ana_result.cfg"))
+    b = ssnet_trainval()
+    b.override_config(str(cfg3))
+    b.initialize()
+    r1 = b.ana_step()                                        # interactive: softmax + map
+    z1 = np.load(tmp_path / "ana_result_out" / ("ssnet_%06d.npz" % b.current_iteration()))
+    assert np.array_equal(z1["ssnet"], O.ssnet_decision(r1["softmax"], r1["input"][..., 0]))
+    b.ana_step(batch_mode=True)                              # batch mode: map only, no softmax download
+    z2 = np.load(tmp_path / "ana_result_out" / ("ssnet_%06d.npz" % b.current_iteration()))
+    assert z2["ssnet"].shape == (2, 64, 64) and set(np.unique(z2["ssnet"])) <= {0.0, 1.0, 2.0}
+    assert len(z2["entries"]) == 2
+    b.reset()
 
 
 @pytest.mark.parametrize("dims,B", [([32, 64, 1], 2), ([8, 16, 16, 1], 1)])

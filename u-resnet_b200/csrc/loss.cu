@@ -105,6 +105,28 @@ __global__ void softmax_only_kernel(const float* __restrict__ logits, long long 
   }
 }
 
+// Shower/track decision of the analysis step (lib/ssnet_trainval.py:269-287):
+//   decision = (1*(p1 > p2) + 2*(p2 >= p1)) * (data > threshold),  p = softmax(logits)
+// computed from the same softmax arithmetic as softmax_only_kernel, so that it equals the host
+// expression applied to the softmax this library returns, value for value (ties included).
+__global__ void decision_kernel(const float* __restrict__ logits, long long ld, long long total, int c,
+                                const float* __restrict__ data, long long data_ld, float threshold,
+                                float* __restrict__ decision) {
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < total;
+       p += (long long)gridDim.x * blockDim.x) {
+    float z[CE_MAX_CLASSES];
+    const float* lp = logits + p * ld;
+    float mx = -INFINITY;
+    for (int k = 0; k < c; ++k) { z[k] = lp[k]; mx = fmaxf(mx, z[k]); }
+    float se = 0.f;
+    for (int k = 0; k < c; ++k) { z[k] = expf(z[k] - mx); se += z[k]; }
+    const float inv = 1.0f / se;
+    const float shower = z[1] * inv, track = z[2] * inv;
+    const float r = (shower > track ? 1.f : 0.f) + (track >= shower ? 2.f : 0.f);
+    decision[p] = data[p * data_ld] > threshold ? r : 0.f;
+  }
+}
+
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, long long n, float lr_t, float b1, float b2,
                             float eps) {
@@ -169,6 +191,22 @@ int urn_softmax_only(const float* logits, int64_t ld, int64_t total, int c, floa
   int nb = (int)((total + 255) / 256);
   if (nb > CE_MAX_BLOCKS) nb = CE_MAX_BLOCKS;
   softmax_only_kernel<float><<<nb, 256, 0, st>>>(logits, ld, total, c, softmax);
+  URN_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int urn_ssnet_decision(const float* logits, int64_t ld, int64_t total, int num_class,
+                                  const float* data, int64_t data_ld, float threshold,
+                                  float* decision, void* stream) {
+  URN_CHECK(logits && data && decision, "urn_ssnet_decision: null argument");
+  URN_CHECK(num_class >= 3 && num_class <= CE_MAX_CLASSES,
+            "urn_ssnet_decision: needs shower (1) and track (2) classes, num_class=%d", num_class);
+  URN_CHECK(ld >= num_class && data_ld >= 1 && total >= 0, "urn_ssnet_decision: bad strides");
+  if (total == 0) return 0;
+  int nb = (int)((total + 255) / 256);
+  if (nb > CE_MAX_BLOCKS) nb = CE_MAX_BLOCKS;
+  decision_kernel<<<nb, 256, 0, (cudaStream_t)stream>>>(logits, ld, total, num_class, data, data_ld,
+                                                         threshold, decision);
   URN_LAUNCH_CHECK();
   return 0;
 }

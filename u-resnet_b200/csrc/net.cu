@@ -799,6 +799,15 @@ extern "C" int urn_loss_metrics(urn_net* h, const float* label, const float* wei
                         P(ws, h->loss_ws_off), st);
 }
 
+extern "C" int urn_decision(urn_net* h, const float* data, float threshold, float* decision, void* ws,
+                            void* stream) {
+  URN_CHECK(h && data && decision && ws, "urn_decision: null argument");
+  const Node& lg = h->nodes[h->logits_node];
+  ProfScope ps(h, (int)h->layers.size() - 1, PH_MISC, (cudaStream_t)stream);
+  return urn_ssnet_decision((const float*)P(ws, lg.off), lg.ld, lg.rows, lg.c, data,
+                            h->cfg.in_channels, threshold, decision, stream);
+}
+
 extern "C" int urn_check_labels(urn_net* h, void* stream) {
   (void)h; (void)stream;
   return 0;

@@ -381,15 +381,41 @@ class ssnet_base(object):
         loss, acc_all, acc_nz = self._metrics(batch)
         return [loss, acc_all, acc_nz], ['loss', 'acc. all', 'acc. nonzero']
 
-    def inference(self, sess, input_data, input_label=None):
+    def inference(self, sess, input_data, input_label=None, with_decision=False, threshold=1.0):
         """ssnet.py:130-139: [softmax] or [softmax, acc_all, acc_nonzero]; softmax is a host
-        numpy array [B,H,W,(D,)num_class]."""
+        numpy array [B,H,W,(D,)num_class].  ``with_decision`` appends the shower/track map
+        of ssnet_trainval.py:269-287 ([B,H,W,(D)] f32: 0 where data <= threshold, 1 shower,
+        2 track), computed on the device from the same forward pass."""
         # like the reference, this raises TypeError when constructed with use_weight=True
         # (ssnet.py:132 feeds no weights; ana configs set USE_WEIGHTS False)
         feed = self.feed_dict(input_data=input_data, input_label=input_label)
         h, ws, batch = self._forward(feed)
         sm = self._loss_metrics(h, ws, feed, want_grad=False, want_softmax=True)
+        dec = self._decision(h, ws, feed, threshold) if with_decision else None
         out = [sm.cpu().numpy()]
+        if input_label is not None:
+            _, acc_all, acc_nz = self._metrics(batch)
+            out += [acc_all, acc_nz]
+        if dec is not None:
+            out.append(dec.cpu().numpy())
+        return out
+
+    def _decision(self, h, ws, feed, threshold=1.0):
+        batch = feed["data"].shape[0]
+        dec = torch.empty((batch,) + tuple(int(d) for d in self._dims[:-1]), dtype=torch.float32,
+                          device=self._device)
+        _capi.check(self._lib.urn_decision(h, feed["data"].data_ptr(), float(threshold), dec.data_ptr(),
+                                           ws.data_ptr(), self._stream()))
+        return dec
+
+    def decision(self, sess, input_data, input_label=None, threshold=1.0):
+        """Analysis fast path: [decision] or [decision, acc_all, acc_nonzero] without the
+        device->host read of the softmax (1 instead of num_class floats per pixel come back)."""
+        feed = self.feed_dict(input_data=input_data, input_label=input_label)
+        h, ws, batch = self._forward(feed)
+        if input_label is not None:
+            self._loss_metrics(h, ws, feed, want_grad=False, want_softmax=False)
+        out = [self._decision(h, ws, feed, threshold).cpu().numpy()]
         if input_label is not None:
             _, acc_all, acc_nz = self._metrics(batch)
             out += [acc_all, acc_nz]

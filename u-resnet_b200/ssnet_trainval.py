@@ -9,7 +9,10 @@ replaced because it cannot exist here:
   * tf.train.Saver      -> ``.npz`` files keyed by the TF variable names
                             (``<SAVE_FILE>-<iteration>.npz``; ``LOAD_FILE`` / ``AVOID_LOAD_PARAMS``
                             / iteration-from-suffix behave like ssnet_trainval.py:139-151)
-  * tf.summary          -> JSON-lines scalar logs under ``LOGDIR/{train,test}/scalars.jsonl``
+  * tf.summary          -> ``LOGDIR/{train,test}``: TensorBoard event files with the reference's tags
+                            (scalars ``accuracy_all`` / ``accuracy_nonzero`` / ``loss``, image
+                            ``data_example`` for 2D, ssnet.py:81-89) when ``tensorboard`` is
+                            importable, plus a ``scalars.jsonl`` copy of the scalars
   * larcv output        -> ``.npz`` per analysed batch next to ``ANA_OUTPUT_CONFIG``
 Under ``torch.distributed`` (one process per GPU) the minibatch is sharded by rank and the
 gradient accumulators are all-reduced (``dp.GradientExchange``) before Adam.
@@ -28,6 +31,39 @@ import numpy as np
 from .config import ssnet_config
 from .synthetic_io import synthetic_threadio
 from .uresnet import uresnet
+
+
+class _summary_log(object):
+    """tf.summary.FileWriter stand-in (ssnet_trainval.py:120-127, ssnet.py:81-89)."""
+
+    def __init__(self, logdir):
+        os.makedirs(logdir, exist_ok=True)
+        self._jsonl = open(os.path.join(logdir, 'scalars.jsonl'), 'a')
+        try:
+            from torch.utils.tensorboard import SummaryWriter
+            self._tb = SummaryWriter(logdir)
+        except Exception:                 # tensorboard not installed: JSON lines only
+            self._tb = None
+
+    def add_summary(self, scalars, step, images=None):
+        rec = dict(scalars)
+        rec['step'] = int(step)
+        self._jsonl.write(json.dumps(rec) + '\n')
+        self._jsonl.flush()
+        if self._tb is not None:
+            for tag, value in scalars.items():
+                self._tb.add_scalar(tag, value, step)
+            if images is not None:        # tf.summary.image('data_example', grayscale_to_rgb(data), 10)
+                img = np.asarray(images[:10], dtype=np.float32)
+                lo, hi = float(img.min()), float(img.max())
+                img = (img - lo) / (hi - lo) if hi > lo else np.zeros_like(img)
+                self._tb.add_images('data_example', np.repeat(img, 3, axis=-1), step, dataformats='NHWC')
+            self._tb.flush()
+
+    def close(self):
+        self._jsonl.close()
+        if self._tb is not None:
+            self._tb.close()
 
 
 class ssnet_trainval(object):
@@ -131,13 +167,9 @@ class ssnet_trainval(object):
         self._writer_train = None
         self._writer_test = None
         if cfg.LOGDIR and self._rank == 0:
-            logdir = os.path.join(cfg.LOGDIR, 'train')
-            os.makedirs(logdir, exist_ok=True)
-            self._writer_train = open(os.path.join(logdir, 'scalars.jsonl'), 'a')
+            self._writer_train = _summary_log(os.path.join(cfg.LOGDIR, 'train'))
             if self._input_test:
-                logdir = os.path.join(cfg.LOGDIR, 'test')
-                os.makedirs(logdir, exist_ok=True)
-                self._writer_test = open(os.path.join(logdir, 'scalars.jsonl'), 'a')
+                self._writer_test = _summary_log(os.path.join(cfg.LOGDIR, 'test'))
         if cfg.SAVE_FILE:
             save_dir = cfg.SAVE_FILE[0:cfg.SAVE_FILE.rfind('/')] if '/' in cfg.SAVE_FILE else ''
             if save_dir and not os.path.isdir(save_dir):
@@ -220,17 +252,17 @@ class ssnet_trainval(object):
                 self._report(res, doc)
 
         if summary_step:
+            is2d = len(self._net._dims) == 3 and self._net._dims[-1] == 1      # ssnet.py:81-82
+
+            def example(data):
+                return np.asarray(data[:10]).reshape([-1] + list(self._net._dims)) if is2d else None
             s = self._net.make_summary(self._sess, minibatch_data, minibatch_label, minibatch_weight)
             if self._writer_train:
-                s['step'] = self._iteration
-                self._writer_train.write(json.dumps(s) + '\n')
-                self._writer_train.flush()
+                self._writer_train.add_summary(s, self._iteration, example(minibatch_data))
             if self._input_test:
                 s = self._net.make_summary(self._sess, test_data, test_label, test_weight)
                 if self._writer_test:
-                    s['step'] = self._iteration
-                    self._writer_test.write(json.dumps(s) + '\n')
-                    self._writer_test.flush()
+                    self._writer_test.add_summary(s, self._iteration, example(test_data))
 
         if checkpt_step and self._cfg.SAVE_FILE and self._rank == 0:
             print('saved @', self._save())
@@ -244,7 +276,16 @@ class ssnet_trainval(object):
         self._iteration += 1
         batch_data = self._input_main.fetch_data(cfg.KEYWORD_DATA).data()
         batch_label = self._input_main.fetch_data(cfg.KEYWORD_LABEL).data()
-        softmax, acc_all, acc_nonzero = self.ana(input_data=batch_data, input_label=batch_label)
+        decision = None
+        if batch_mode and self._output:
+            # nothing but the shower/track map is kept: skip the softmax download altogether
+            softmax = None
+            decision, acc_all, acc_nonzero = self._net.decision(self._sess, batch_data, batch_label)
+        elif self._output:
+            softmax, acc_all, acc_nonzero, decision = self._net.inference(
+                sess=self._sess, input_data=batch_data, input_label=batch_label, with_decision=True)
+        else:
+            softmax, acc_all, acc_nonzero = self.ana(input_data=batch_data, input_label=batch_label)
 
         copy_data, copy_label, copy_entries = (None, None, None)
         if not batch_mode:
@@ -256,19 +297,12 @@ class ssnet_trainval(object):
 
         if self._output:
             entries = self._input_main.fetch_entries()
-            results = []
-            for entry in range(len(softmax)):
+            # ssnet_trainval.py:269-287: (shower > track) + 2 (track >= shower), masked by data > 1,
+            # evaluated on the device (urn_decision)
+            for entry in range(len(decision)):
                 print('Entry', entries[entry], 'Acc', acc_nonzero)
-                data = np.array(batch_data[entry]).reshape(softmax.shape[1:-1])
-                shower_score = softmax[entry, ..., 1]
-                track_score = softmax[entry, ..., 2]
-                # ssnet_trainval.py:285-287
-                ssnet_result = (shower_score > track_score).astype(np.float32) + \
-                               (track_score >= shower_score).astype(np.float32) * 2.0
-                nonzero_map = (data > 1.0).astype(np.int32)
-                results.append((ssnet_result * nonzero_map).astype(np.float32))
             np.savez_compressed(os.path.join(self._output, 'ssnet_%06d.npz' % self._iteration),
-                                entries=np.asarray(entries), ssnet=np.stack(results))
+                                entries=np.asarray(entries), ssnet=decision)
 
         self._input_main.next(store_entries=(not cfg.TRAIN), store_event_ids=(not cfg.TRAIN))
         if not batch_mode:
