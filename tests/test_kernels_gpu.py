@@ -209,6 +209,69 @@ def test_conv_tcgen05_wgrad(lib, xdt, ydt, nd, n, sp, cin, cout, k, s):
     assert relerr(host(dw), 2 * dwo.numpy()) < 4e-5
 
 
+GUARD_CASES = [c for c in TC_CASES if c[3] <= 64] + [(2, 1, (16, 16), 128, 128, 3, 1)]
+
+
+@pytest.mark.parametrize("nd,n,sp,cin,cout,k,s", GUARD_CASES)
+def test_conv_kernels_stay_inside_their_buffers(lib, nd, n, sp, cin, cout, k, s):
+    """No sanitizer on the GPU pool, so: operands sit in the middle of NaN-filled arenas and results
+    in the middle of sentinel-filled ones.  Any read outside the operand that reaches the arithmetic
+    turns the result NaN / changes bits against the run on tight buffers; any write outside the
+    result damages the sentinels.  Covers forward, input gradient (store + accumulate, fp32 + bf16)
+    and filter gradient of the halo-tile (cp.async address arithmetic by hand) and tap-box kernels."""
+    G = 8192                                                   # guard elements on each side
+    rng = np.random.default_rng(hash((nd, n, sp, cin, cout, k, s, 9)) % 2**32)
+    d = _capi.conv_desc_same(nd, n, sp, cin, cout, k, s)
+    osp = (d.yd, d.yh, d.yw)[3 - nd:]
+    xs, ys = (n,) + sp + (cin,), (n,) + osp + (cout,)
+    w = dev((rng.standard_normal((k,) * nd + (cin, cout)) / np.sqrt(k**nd * cin)).astype(np.float32))
+    wpack = torch.empty(2 * w.numel() + 64, dtype=torch.uint8, device=DEV)
+
+    def arena(shape, tdt, fill, value=None):
+        a = torch.full((int(np.prod(shape)) + 2 * G,), fill, dtype=tdt, device=DEV)
+        mid = a[G:G + int(np.prod(shape))].view(shape)
+        if value is not None:
+            mid.copy_(value)
+        return a, mid
+
+    def intact(a, fill):
+        g = torch.cat([a[:G], a[-G:]]).float()
+        return bool(torch.isnan(g).all()) if fill != fill else bool((g == fill).all())
+
+    nan = float("nan")
+    for dt in (F16, BF16):
+        tdt = TORCH_DT[dt]
+        x = dev(rng.standard_normal(xs).astype(np.float32), dt)
+        g = dev(rng.standard_normal(ys).astype(np.float32), BF16)
+        gx = dev(rng.standard_normal(ys).astype(np.float32), dt)    # filter gradient: one format for both
+        xa, xm = arena(xs, tdt, nan, x)
+        ga, gm = arena(ys, torch.bfloat16, nan, g)
+        gxa, gxm = arena(ys, tdt, nan, gx)
+        # forward
+        y0 = torch.zeros(ys, dtype=torch.float32, device=DEV)
+        _capi.check(lib.urn_conv_fwd_tc(C.byref(d), dt, x.data_ptr(), cin, w.data_ptr(), wpack.data_ptr(), y0.data_ptr(), cout, F32, 0, st()))
+        ya, ym = arena(ys, torch.float32, 7.25)
+        _capi.check(lib.urn_conv_fwd_tc(C.byref(d), dt, xm.data_ptr(), cin, w.data_ptr(), wpack.data_ptr(), ym.data_ptr(), cout, F32, 0, st()))
+        assert torch.equal(ym, y0) and not torch.isnan(ym).any() and intact(ya, 7.25)
+        # input gradient, fp32 store then accumulate, bf16 store
+        for odt, acc in ((F32, 0), (F32, 1), (BF16, 0), (BF16, 1)):
+            todt = TORCH_DT[odt]
+            d0 = torch.ones(xs, dtype=todt, device=DEV)
+            _capi.check(lib.urn_conv_dgrad_tc(C.byref(d), BF16, g.data_ptr(), cout, w.data_ptr(), wpack.data_ptr(), d0.data_ptr(), cin, odt, acc, st()))
+            da, dm = arena(xs, todt, 7.25, torch.ones(xs, dtype=todt, device=DEV))
+            _capi.check(lib.urn_conv_dgrad_tc(C.byref(d), BF16, gm.data_ptr(), cout, w.data_ptr(), wpack.data_ptr(), dm.data_ptr(), cin, odt, acc, st()))
+            assert torch.equal(dm, d0) and not torch.isnan(dm.float()).any() and intact(da, 7.25), (dt, odt, acc)
+        # filter gradient
+        ws = torch.empty(max(int(lib.urn_conv_wgrad_workspace(C.byref(d))), 16), dtype=torch.uint8, device=DEV)
+        w0 = torch.zeros(tuple(w.shape), dtype=torch.float32, device=DEV)
+        _capi.check(lib.urn_conv_wgrad(C.byref(d), dt, 2, x.data_ptr(), cin, gx.data_ptr(), cout, dt, w0.data_ptr(), 0, ws.data_ptr(), st()))
+        wa, wm = arena(tuple(w.shape), torch.float32, 7.25)
+        _capi.check(lib.urn_conv_wgrad(C.byref(d), dt, 2, xm.data_ptr(), cin, gxm.data_ptr(), cout, dt, wm.data_ptr(), 0, ws.data_ptr(), st()))
+        assert torch.equal(wm, w0) and not torch.isnan(wm).any() and intact(wa, 7.25)
+        assert intact(xa, nan) and intact(ga, nan) and intact(gxa, nan)
+    torch.cuda.synchronize()
+
+
 HALO_WGRAD_CASES = [
     # nd, n, spatial, cin, cout, ldx factor  (stride-1 3x3(x3): the halo-tile filter-gradient kernel)
     (2, 3, (40, 24), 16, 16, 1),         # several tiles per image, ragged in h
@@ -426,6 +489,77 @@ def test_bn_backward(lib, dt, c, rows, relu, mode):
         assert relerr(host(dbeta2), grads[1].numpy()) < 1e-4
     if mode == "identity":
         assert relerr(host(dres), 1 + grads[2].numpy()) < tol   # accumulated onto the ones
+
+
+@pytest.mark.parametrize("c,rows,relu,mode", [(16, 70001, 1, "plain"), (32, 5003, 0, "plain"), (64, 129, 1, "identity"),
+                                              (128, 300, 1, "conv_sc"), (512, 33, 0, "plain"), (8, 999, 1, "identity"),
+                                              (16, 4096, 1, "conv_sc"), (3, 500, 0, "plain")])
+def test_bn_kernels_stay_inside_their_buffers(lib, c, rows, relu, mode):
+    """Same guard-arena check as the conv kernels for the batch-norm family (statistics, apply with
+    bf16 shadow, backward with and without beta): the fast kernels keep several packed 16-byte
+    loads of consecutive rows in flight, so the last rows are where a stray access would happen."""
+    G = 8192
+    rng = np.random.default_rng(rows * 7 + c)
+    nan = float("nan")
+
+    def arena(tdt, fill, value=None, shape=(rows, c)):
+        a = torch.full((int(np.prod(shape)) + 2 * G,), fill, dtype=tdt, device=DEV)
+        mid = a[G:G + int(np.prod(shape))].view(shape)
+        if value is not None:
+            mid.copy_(value)
+        return a, mid
+
+    def intact(a, fill):
+        g = torch.cat([a[:G], a[-G:]]).float()
+        return bool(torch.isnan(g).all()) if fill != fill else bool((g == fill).all())
+
+    ws = torch.empty(int(lib.urn_bn_workspace(c)), dtype=torch.uint8, device=DEV)
+    raw, raw2 = (dev(rng.standard_normal((rows, c)).astype(np.float32) * 2 + 0.5) for _ in range(2))
+    res = dev(rng.standard_normal((rows, c)).astype(np.float32), F16)
+    beta = dev(rng.standard_normal(c).astype(np.float32) * 0.3)
+    dout = dev(rng.standard_normal((rows, c)).astype(np.float32), BF16)
+    ra, rm = arena(torch.float32, nan, raw)
+    r2a, r2m = arena(torch.float32, nan, raw2)
+    rsa, rsm = arena(torch.float16, nan, res)
+    doa, dom = arena(torch.bfloat16, nan, dout)
+
+    def run(raw, raw2, res, dout, mk):
+        """mk(tdt) -> (arena or None, tensor) for every result."""
+        s1 = torch.empty(2 * c, dtype=torch.float32, device=DEV)
+        s2 = torch.empty(2 * c, dtype=torch.float32, device=DEV)
+        _capi.check(lib.urn_bn_stats(raw.data_ptr(), c, rows, c, 1e-3, s1.data_ptr(), ws.data_ptr(), st()))
+        _capi.check(lib.urn_bn_stats(raw2.data_ptr(), c, rows, c, 1e-3, s2.data_ptr(), ws.data_ptr(), st()))
+        out, shadow = mk(torch.float16), mk(torch.bfloat16)
+        _capi.check(lib.urn_bn_apply(
+            raw.data_ptr(), c, rows, c, s1.data_ptr(), beta.data_ptr(),
+            res.data_ptr() if mode == "identity" else None, c, F16,
+            raw2.data_ptr() if mode == "conv_sc" else None, c, s2.data_ptr() if mode == "conv_sc" else None,
+            beta.data_ptr() if mode == "conv_sc" else None, relu, out[1].data_ptr(), c, F16, shadow[1].data_ptr(), st()))
+        results = [out, shadow]
+        for with_beta in (0, 1):
+            draw, draw2, dres = mk(torch.bfloat16), mk(torch.bfloat16), mk(torch.bfloat16)
+            dres[1].fill_(1.0)
+            dbeta = torch.zeros(2 * c, dtype=torch.float32, device=DEV)
+            fn = lib.urn_bn_bwd_beta if with_beta else lib.urn_bn_bwd
+            extra = (beta.data_ptr(),) if with_beta else ()
+            _capi.check(fn(
+                dout.data_ptr(), c, out[1].data_ptr(), c, BF16, F16, relu, rows, c, raw.data_ptr(), c, s1.data_ptr(), *extra,
+                dbeta.data_ptr(), draw[1].data_ptr(), c,
+                raw2.data_ptr() if mode == "conv_sc" else None, c, s2.data_ptr() if mode == "conv_sc" else None,
+                dbeta[c:].data_ptr() if mode == "conv_sc" else None, draw2[1].data_ptr() if mode == "conv_sc" else None, c,
+                dres[1].data_ptr() if mode == "identity" else None, c, 1, 0, ws.data_ptr(), st()))
+            results += [draw] + ([draw2] if mode == "conv_sc" else []) + ([dres] if mode == "identity" else []) + [(None, dbeta)]
+        return [s1, s2], results
+
+    tight = run(raw, raw2, res, dout, lambda tdt: (None, torch.full((rows, c), 7.25, dtype=tdt, device=DEV)))
+    guarded = run(rm, r2m, rsm, dom, lambda tdt: arena(tdt, 7.25))
+    for a, b in zip(tight[0], guarded[0]):
+        assert torch.equal(a, b) and not torch.isnan(a).any()
+    for (_, a), (ar, b) in zip(tight[1], guarded[1]):
+        assert torch.equal(a, b) and not torch.isnan(b.float()).any()
+        assert ar is None or intact(ar, 7.25)
+    assert all(intact(a, nan) for a in (ra, r2a, rsa, doa))
+    torch.cuda.synchronize()
 
 
 @pytest.mark.parametrize("B,P,c,use_w", [(2, 1000, 3, True), (3, 257, 3, False), (1, 64, 5, True)])
