@@ -35,6 +35,10 @@ class _optimizer_state(object):
         self._t = 0
 
 
+# bytes per host->device chunk of the pinned staging pipeline
+_H2D_CHUNK_BYTES = int(float(os.environ.get("URESNET_B200_H2D_CHUNK_MB", "4")) * (1 << 20))
+
+
 class ssnet_base(object):
 
     def __init__(self, dims, num_class):
@@ -214,21 +218,26 @@ class ssnet_base(object):
                 self._staging[key] = st
             if st[2] is not None:
                 st[2].synchronize()                 # previous H2D out of this pinned buffer is done
-            st[0].copy_(torch.from_numpy(np.ascontiguousarray(a)))     # multi-threaded host copy
+            src = torch.from_numpy(np.ascontiguousarray(a)).view(-1)
+            pin, dst = st[0].view(-1), st[1].view(-1)
+            # chunked: the DMA of chunk k runs while the host copies chunk k+1 into pinned memory
+            step = max(1, _H2D_CHUNK_BYTES // 4)
             if side:
                 if self._copy_stream is None:
                     self._copy_stream = torch.cuda.Stream(device=self._device)
-                with torch.cuda.stream(self._copy_stream):
-                    if self._step_start is not None:
-                        self._copy_stream.wait_event(self._step_start)   # earlier consumers of st[1] are done
-                    st[1].copy_(st[0], non_blocking=True)
-                    st[2] = torch.cuda.Event()
-                    st[2].record(self._copy_stream)
-                self._side_pending.append(st[2])
+                stream = self._copy_stream
+                if self._step_start is not None:
+                    stream.wait_event(self._step_start)   # earlier consumers of st[1] are done
             else:
-                st[1].copy_(st[0], non_blocking=True)
+                stream = torch.cuda.current_stream(self._device)
+            with torch.cuda.stream(stream):
+                for i in range(0, max(src.numel(), 1), step):
+                    pin[i:i + step].copy_(src[i:i + step])                  # multi-threaded host copy
+                    dst[i:i + step].copy_(pin[i:i + step], non_blocking=True)
                 st[2] = torch.cuda.Event()
-                st[2].record(torch.cuda.current_stream(self._device))
+                st[2].record(stream)
+            if side:
+                self._side_pending.append(st[2])
             t = st[1]
         if batch is not None and t.shape[0] != batch:
             raise ValueError("batch mismatch between data and %s" % key)
