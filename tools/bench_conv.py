@@ -44,8 +44,8 @@ def run(nd, n, sp, cin, cout, k, s, what="fwd"):
         byts = x.numel() * 2 + y.numel() * 4
     else:
         g = torch.randn((n,) + tuple(osp) + (cout,), device="cuda").bfloat16()
-        dx = torch.empty((n,) + tuple(sp) + (cin,), dtype=torch.bfloat16, device="cuda")
-        fn = lambda: _capi.check(lib.urn_conv_dgrad_tc(C.byref(d), BF16, g.data_ptr(), cout, w.data_ptr(), wpack.data_ptr(), dx.data_ptr(), cin, BF16, 0, st()))
+        dx = torch.zeros((n,) + tuple(sp) + (cin,), dtype=torch.bfloat16, device="cuda")
+        fn = lambda: _capi.check(lib.urn_conv_dgrad_tc(C.byref(d), BF16, g.data_ptr(), cout, w.data_ptr(), wpack.data_ptr(), dx.data_ptr(), cin, BF16, int(os.environ.get('ACC', '0')), st()))
         byts = g.numel() * 2 + dx.numel() * 2
     ms = time_it(fn)
     print("%s nd=%d n=%d sp=%s %d->%d k%d s%d : %.3f ms  %.1f TFLOP/s  %.0f GB/s (algorithmic)" % (
@@ -57,6 +57,8 @@ if __name__ == "__main__":
              (2, 32, (64, 64), 128, 128, 3, 1), (2, 32, (32, 32), 256, 256, 3, 1), (2, 32, (16, 16), 512, 512, 3, 1),
              (3, 2, (192, 192, 192), 16, 16, 3, 1), (3, 4, (96, 96, 96), 32, 32, 3, 1), (3, 4, (48, 48, 48), 64, 64, 3, 1),
              (3, 4, (24, 24, 24), 128, 128, 3, 1)]
+    if os.environ.get("CASE"):        # e.g. CASE="2,32,(512,512),16,32,3,2"
+        cases = [eval("(" + os.environ["CASE"] + ")")]
     sel = os.environ.get("CASES")
     if sel:
         cases = [cases[int(i)] for i in sel.split(",")]

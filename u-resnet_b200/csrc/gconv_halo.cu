@@ -220,8 +220,8 @@ gconv_halo_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_consta
         }
         // One barrier arrival per WARP (256 per-thread arrivals on one mbarrier word serialise
         // for ~2 us per stage): each thread waits until its copies of the stage issued kPF stages
-        // ago have landed, the warp converges, lane 0 arrives.  The consumer issues the
-        // generic->async proxy fence after its barrier wait.
+        // ago have landed and fences them towards the async proxy, the warp converges,
+        // lane 0 arrives.
         if (!(p.dbg & 4096)) asm volatile("cp.async.commit_group;" ::: "memory");
         if (t == 0) TL(0, k, 1);
         if (issued >= (uint32_t)pf) {
@@ -230,6 +230,8 @@ gconv_halo_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_consta
           else if (pf == 3) asm volatile("cp.async.wait_group 3;" ::: "memory");
           else if (pf == 2) asm volatile("cp.async.wait_group 2;" ::: "memory");
           else asm volatile("cp.async.wait_group 1;" ::: "memory");
+          // writer-side generic->async proxy fence: the copies that just landed are read by UMMA
+          if (!(p.dbg & 16384)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           __syncwarp();
           if (lane == 0) h_mbar_arrive(&full[ar.idx]);
           ar.next();
@@ -240,6 +242,7 @@ gconv_halo_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_consta
       }
     }
     asm volatile("cp.async.wait_all;" ::: "memory");
+    if (!(p.dbg & 16384)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncwarp();
     if (lane == 0)
       for (uint32_t j = (issued > (uint32_t)pf ? issued - pf : 0); j < issued; ++j) { h_mbar_arrive(&full[ar.idx]); ar.next(); }
@@ -310,7 +313,9 @@ gconv_halo_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_consta
         if (!plane_used(p, z, d0, nd_out)) continue;
         h_mbar_wait_warp(&full[st.idx], st.phase);
         if (lane == 0) TL(1, k, 2);
-        if (!(p.dbg & 2048)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // cp.async (generic proxy) -> UMMA (async proxy)
+        // (the cp.async -> UMMA proxy fence is issued by the producers before they arrive; a
+        // consumer-side fence here stalls the issue warp for up to ~900 cycles per tile)
+        if (p.dbg & 2048) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         h_fence_after();
         if (lane == 0) TL(1, k, 3);
         const uint32_t a_lo0 = a_lo_base | (h_smem_u32(smem_a + (size_t)st.idx * p.plane_bytes) >> 4);

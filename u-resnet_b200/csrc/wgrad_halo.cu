@@ -235,6 +235,7 @@ wgrad_halo_kernel(const __grid_constant__ WHParams p, const void* __restrict__ x
           else if (pf == 3) asm volatile("cp.async.wait_group 3;" ::: "memory");
           else if (pf == 2) asm volatile("cp.async.wait_group 2;" ::: "memory");
           else asm volatile("cp.async.wait_group 1;" ::: "memory");
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // cp.async (generic proxy) -> UMMA (async proxy)
           __syncwarp();
           if (lane == 0) h_mbar_arrive(&full[ar.idx]);
           ar.next();
@@ -244,6 +245,7 @@ wgrad_halo_kernel(const __grid_constant__ WHParams p, const void* __restrict__ x
       }
     }
     asm volatile("cp.async.wait_all;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncwarp();
     if (lane == 0)
       for (uint32_t j = (issued > (uint32_t)pf ? issued - pf : 0); j < issued; ++j) { h_mbar_arrive(&full[ar.idx]); ar.next(); }
@@ -268,8 +270,7 @@ wgrad_halo_kernel(const __grid_constant__ WHParams p, const void* __restrict__ x
       for (int z = d0 * PS + p.od0; z <= (d1 - 1) * PS + p.od0 + p.nkd - 1; ++z) {
         const bool xvalid = z >= 0 && z < p.XD;
         h_mbar_wait(&full[st.idx], st.phase);
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // cp.async (generic proxy) -> UMMA (async proxy)
-        h_fence_after();
+        h_fence_after();                   // (proxy fence: issued by the producers before they arrive)
         if (xvalid) {
           const uint32_t a_lo0 = a_lo_base | (h_smem_u32(smem_x + (size_t)st.idx * p.xplane_bytes) >> 4);
           // dY planes paired with this X plane: z-1 .. z+1 (depth taps kd = 2, 1, 0), clipped to the
