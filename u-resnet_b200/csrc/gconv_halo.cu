@@ -255,6 +255,7 @@ gconv_halo_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_consta
     // (kh,kw) are placed next to each other in DESCENDING kd order: they form one [3*cout][cin]
     // B tile whose N blocks line up with the ascending output planes z-1, z, z+1 of input plane z.
     for (int i = lane * 16; i < p.zero_bytes; i += 32 * 16) *reinterpret_cast<uint4*>(smem_zero + i) = make_uint4(0, 0, 0, 0);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy zeros -> read by UMMA (async proxy)
     if (p.ncls > 1) {
       if (h_elect_one()) {
         h_mbar_expect_tx(wfull, (uint32_t)(p.ntaps_w * p.w_tap_bytes));
