@@ -190,7 +190,7 @@ def test_conv_tcgen05_fwd_dgrad(lib, dt, nd, n, sp, cin, cout, k, s):
 
 @pytest.mark.parametrize("xdt,ydt", [(BF16, BF16), (F16, F16)])   # kind::f16 needs one format for both operands
 @pytest.mark.parametrize("nd,n,sp,cin,cout,k,s", TC_CASES)
-def test_conv_tcgen05_wgrad(lib, xdt, ydt, nd, n, sp, cin, cout, k, s):
+def test_conv_tcgen05_wgrad(lib, xdt, ydt, nd, n, sp, cin, cout, k, s, tol=2e-5):
     """Filter gradient on tcgen05 (MN-major operands, split-K, deterministic reduce)."""
     rng = np.random.default_rng(hash((nd, n, sp, cin, cout, k, s, 2)) % 2**32)
     x = host(dev(rng.standard_normal((n,) + sp + (cin,)).astype(np.float32), xdt))
@@ -204,9 +204,9 @@ def test_conv_tcgen05_wgrad(lib, xdt, ydt, nd, n, sp, cin, cout, k, s):
     ws = torch.empty(max(int(lib.urn_conv_wgrad_workspace(C.byref(d))), 16), dtype=torch.uint8, device=DEV)
     dw = torch.full(tuple(wt.shape), 2.0, dtype=torch.float32, device=DEV)
     _capi.check(lib.urn_conv_wgrad(C.byref(d), xdt, 2, xd.data_ptr(), cin, gd.data_ptr(), cout, ydt, dw.data_ptr(), 0, ws.data_ptr(), st()))
-    assert relerr(host(dw), dwo.numpy()) < 2e-5
+    assert relerr(host(dw), dwo.numpy()) < tol
     _capi.check(lib.urn_conv_wgrad(C.byref(d), xdt, 2, xd.data_ptr(), cin, gd.data_ptr(), cout, ydt, dw.data_ptr(), 1, ws.data_ptr(), st()))
-    assert relerr(host(dw), 2 * dwo.numpy()) < 4e-5
+    assert relerr(host(dw), 2 * dwo.numpy()) < 2 * tol
 
 
 GUARD_CASES = [c for c in TC_CASES if c[3] <= 64] + [(2, 1, (16, 16), 128, 128, 3, 1)]
@@ -270,6 +270,23 @@ def test_conv_kernels_stay_inside_their_buffers(lib, nd, n, sp, cin, cout, k, s)
         assert torch.equal(wm, w0) and not torch.isnan(wm).any() and intact(wa, 7.25)
         assert intact(xa, nan) and intact(ga, nan) and intact(gxa, nan)
     torch.cuda.synchronize()
+
+
+MANY_TILE_CASES = [TC_CASES[i] for i in (0, 1, 2, 3, 5, 6, 7, 9, 10, 14, 16)] + [(2, 3, (64, 96), 16, 16, 3, 1), (2, 2, (48, 160), 32, 32, 3, 1)]
+
+
+@pytest.mark.parametrize("ctas", [1, 3])
+@pytest.mark.parametrize("nd,n,sp,cin,cout,k,s", MANY_TILE_CASES)
+def test_conv_many_tiles_per_cta(lib, monkeypatch, ctas, nd, n, sp, cin, cout, k, s):
+    """The persistent kernels capped to 1 / 3 CTAs (URN_MAX_CTAS): every CTA walks many tiles, so the
+    ring wrap-arounds, accumulator recycling, look-ahead barrier waits and partial merges that the
+    full-size network relies on are checked against the oracle on small shapes too."""
+    monkeypatch.setenv("URN_MAX_CTAS", str(ctas))
+    test_conv_tcgen05_fwd_dgrad(lib, F16, nd, n, sp, cin, cout, k, s)
+    # one CTA sums every position in a single fp32 chain instead of <= 148 partials: slightly more rounding
+    test_conv_tcgen05_wgrad(lib, BF16, BF16, nd, n, sp, cin, cout, k, s, tol=6e-5)
+    if k == 3 and s == 1 or (nd, cin, cout, k, s) == (2, 32, 16, 1, 1):
+        test_conv_fused_bn_statistics(lib, nd, n, sp, cin, cout, k, s)
 
 
 HALO_WGRAD_CASES = [

@@ -1,5 +1,6 @@
 // Shared helpers for the uresnet_b200 kernels (sm_100a only).
 #pragma once
+#include <cstdlib>
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
@@ -47,6 +48,16 @@ static inline int num_sms() {
     if (n <= 0) n = 148;
   }
   return n;
+}
+
+// CTAs of a persistent kernel: one per SM.  URN_MAX_CTAS (tests) caps it so that small shapes
+// exercise the many-tiles-per-CTA paths (ring wrap-around, look-ahead waits, partial merges).
+static inline int persistent_ctas() {
+  if (const char* e = getenv("URN_MAX_CTAS")) {
+    const int v = atoi(e);
+    if (v > 0) return v < num_sms() ? v : num_sms();
+  }
+  return num_sms();
 }
 
 // ---- typed element access: storage T in {float, bf16}, math in fp32 ----

@@ -784,7 +784,7 @@ int gconv_halo_classes_launch(const GConv* gs, int ncls, int in_dtype, const voi
   if (stats_part && nparts && out_dtype == URN_F32 && !gs[0].accumulate && !getenv("URN_NO_FUSED_STATS") &&
       (long long)gs[0].gd * 2 == gs[0].od + (gs[0].od == 1) && gs[0].gh * 2 == gs[0].oh && gs[0].gw * 2 == gs[0].ow) {
     p.stats_part = stats_part;
-    *nparts = (int)std::min<long long>(p.ntiles, num_sms()) * 4;
+    *nparts = (int)std::min<long long>(p.ntiles, persistent_ctas()) * 4;
   }
   return halo_launch_params(p, gs[0].cin, gs[0].cout, in_dtype, out_dtype, in, wpack, out, st);
 }
@@ -806,7 +806,7 @@ int gconv_halo_launch_stats(const GConv& g, int in_dtype, const void* in, const 
   URN_CHECK(halo_plan(g, in_dtype, out_dtype, cout_store, &p), "gconv_halo: unsupported shape/dtype");
   if (nparts) *nparts = 0;
   if (p.ntiles == 0) return 0;
-  const int grid_ = (int)std::min<long long>(p.ntiles, num_sms());
+  const int grid_ = (int)std::min<long long>(p.ntiles, persistent_ctas());
   // statistics only when this single launch produces the whole raw tensor, freshly written
   if (stats_part && nparts && out_dtype == URN_F32 && !g.accumulate && g.os == 1 && g.gd == g.od && g.gh == g.oh &&
       g.gw == g.ow && !getenv("URN_NO_FUSED_STATS")) {
@@ -834,7 +834,7 @@ static int halo_launch_params(HaloParams& p, int cin, int cout, int in_dtype, in
   }
   const int w_bytes = ((p.ntaps_w * p.w_tap_bytes + 1023) / 1024) * 1024;
   const size_t smem = 1024 + (size_t)w_bytes + (size_t)p.zero_bytes + (size_t)p.stages * p.plane_bytes + 1024;
-  const int grid = (int)std::min<long long>(p.ntiles, num_sms());
+  const int grid = (int)std::min<long long>(p.ntiles, persistent_ctas());
   long long* tl = nullptr;
   if (const char* e = getenv("URN_HALO_TIMELINE")) tl = (long long*)strtoull(e, nullptr, 0);
   const int mode = (p.cout_store & 15) ? 2 : (p.accumulate ? 1 : 0);

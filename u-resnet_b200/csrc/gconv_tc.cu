@@ -473,7 +473,7 @@ int gconv_tc_launch_stats(const GConv& g, int in_dtype, const void* in, const vo
   }
   long long nwork = p.ntiles * p.n_tiles;
   URN_CHECK(nwork < (1ll << 31), "gconv_tc: too many tiles");
-  int grid = (int)std::min<long long>(nwork, num_sms());
+  int grid = (int)std::min<long long>(nwork, persistent_ctas());
   // fused statistics: a single launch writing the whole fp32 tensor once, one N tile of <= 256 channels
   const bool stats = stats_part && nparts && out_dtype == URN_F32 && !g.accumulate && g.os == 1 && g.gd == g.od &&
                      g.gh == g.oh && g.gw == g.ow && p.n_tiles == 1 && p.n_tile <= 256 && !getenv("URN_NO_FUSED_STATS");
@@ -804,7 +804,7 @@ int wgrad_tc_launch(const urn_conv_desc& d, int x_dtype, const void* x, int64_t 
     attr_set = true;
   }
   const long long nwork = (long long)p.m_tiles * p.n_tiles * p.ksplit;
-  const int grid = (int)std::min<long long>(nwork, num_sms());
+  const int grid = (int)std::min<long long>(nwork, persistent_ctas());
   wgrad_tc_kernel<<<grid, kThreads, smem, st>>>(map_x, map_y, p, (float*)ws);
   URN_LAUNCH_CHECK();
   const long long nw = (long long)d.kd * d.kh * d.kw * d.cx * d.cy;

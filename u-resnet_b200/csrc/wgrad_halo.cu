@@ -555,7 +555,7 @@ int wgrad_halo_launch(const urn_conv_desc& d, int x_dtype, const void* x, int64_
     URN_CUDA(cudaFuncSetAttribute(wgrad_halo_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  const int grid = (int)std::min<long long>(p.nunits, num_sms());
+  const int grid = (int)std::min<long long>(p.nunits, persistent_ctas());
   float* partial = (float*)ws;
   if (p.s == 2) wgrad_halo_kernel<true><<<grid, kWThreads, smem, st>>>(p, x, y, partial);
   else wgrad_halo_kernel<false><<<grid, kWThreads, smem, st>>>(p, x, y, partial);
