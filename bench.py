@@ -18,6 +18,11 @@ configs[2] / configs[4]):  2d = U-ResNet F=16 S=5, 512x512, batch 32 per GPU;
            the timed region).
 `roofline`: the dominant kernel family (conv forward/dgrad/wgrad launches), algorithmic FLOPs
            of those launches / their CUDA-event time, against MEASURED_PEAKS.json.
+           `roofline.top_launch`: the single slowest conv launch group of the step (layer, phase)
+           against the roofline that bounds it (HBM or tensor by its arithmetic intensity), from
+           the same live CUDA-event profile; `traffic` = DRAM bytes of the committed ncu capture
+           when that instance was captured (profiles/), else null.
+           `roofline_hbm`: algorithmic bytes of the WHOLE step / step time against the HBM peak.
 `cpu_baseline`: the CPU oracle (torch-CPU fp32 restatement of the reference graph -- the
            reference's own TF-1.x path cannot run here) on a bounded sample, rank 0 only.
 """
@@ -93,6 +98,43 @@ def conv_flops(layer_table):
         if scope != "conv0":
             f["dgrad"] += fl
     return f
+
+
+# dram__bytes_read.sum + dram__bytes_write.sum of committed `ncu --set full` captures, per launch
+# (profiles/raw_*_r01e_*.summary.txt); keyed by (workload, scope suffix, phase)
+NCU_TRAFFIC = {("2d", "16->16 k3 s1 @512", "conv_fwd"): 289.1e6 + 485.8e6}
+
+
+def top_launch(layer_table, prof_ms, prof_steps, pk, workload=""):
+    """The single conv launch group (layer, phase) with the largest measured time per step, with
+    the roofline that bounds it: algorithmic FLOPs 2*|Y|*taps*cx*cy and bytes (16-bit operands in,
+    fp32 raw / bf16 gradient out) over its CUDA-event time; HBM-bound when its arithmetic
+    intensity is under the ridge of the measured peaks, tensor-bound otherwise."""
+    phases = {0: "conv_fwd", 4: "wgrad", 5: "dgrad"}
+    best = None
+    for i, (scope, d, tr) in enumerate(layer_table):
+        for col, name in phases.items():
+            ms = float(prof_ms[i, col]) / prof_steps
+            if best is None or ms > best[0]:
+                best = (ms, i, name)
+    ms, i, name = best
+    scope, d, tr = layer_table[i]
+    big = float(d.n) * d.xd * d.xh * d.xw * d.cx
+    small = float(d.n) * d.yd * d.yh * d.yw * d.cy
+    ein, eout = (small, big) if tr else (big, small)
+    flops = 2.0 * d.n * d.yd * d.yh * d.yw * d.kd * d.kh * d.kw * d.cx * d.cy
+    byts = {"conv_fwd": ein * 2 + eout * 4, "dgrad": eout * 2 + ein * 2, "wgrad": ein * 2 + eout * 2}[name]
+    ridge = pk["tf_sus"] * 1e12 / (pk["hbm"] * 1e9)
+    hbm_bound = flops / byts < ridge
+    sec = max(ms, 1e-9) * 1e-3
+    achieved = byts / sec / 1e9 if hbm_bound else flops / sec / 1e12
+    peak = pk["hbm"] if hbm_bound else pk["tf_sus"]
+    side = max(d.xh, d.xw)
+    shape = "%d->%d k%d s%d @%d" % (((d.cy, d.cx) if tr else (d.cx, d.cy)) + (d.kh, d.s, side))
+    return {"kernel": "%s %s (%s%s)" % (scope, name, shape, ", transposed" if tr else ""), "bound": "hbm" if hbm_bound else "tensor",
+            "achieved": achieved, "peak": peak, "unit": "GB/s" if hbm_bound else "TFLOP/s", "frac": achieved / peak,
+            "ms": ms, "algorithmic_bytes": byts, "algorithmic_flops": flops,
+            "traffic": NCU_TRAFFIC.get((workload, shape, name))}
 
 
 def hbm_bytes(layer_table, elt_act=2, elt_grad=2):
@@ -311,7 +353,8 @@ def main():
             "roofline": {"bound": "tensor", "kernel": "conv fwd + dgrad + wgrad launches (%d launch groups/step)" % n_conv_launch_groups,
                          "achieved": achieved, "peak": pk["tf_sus"], "unit": "TFLOP/s", "frac": achieved / pk["tf_sus"],
                          "peak_source": pk["src"] + " (sustained bf16)", "traffic": None,
-                         "share_of_step": conv_ms / ms if ms > 0 else None, "profiled_steps": prof_steps},
+                         "share_of_step": conv_ms / ms if ms > 0 else None, "profiled_steps": prof_steps,
+                         "top_launch": top_launch(net.layer_table(B), prof_ms, prof_steps, pk, args.workload)},
             "roofline_hbm": {"bound": "hbm", "kernel": "whole step (all kernels), algorithmic bytes lower bound",
                              "achieved": hbm_bytes(net.layer_table(B)) / (ms * 1e-3) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
                              "frac": hbm_bytes(net.layer_table(B)) / (ms * 1e-3) / 1e9 / pk["hbm"], "peak_source": pk["src"]},

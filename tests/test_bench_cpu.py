@@ -42,3 +42,28 @@ def test_hbm_byte_model():
     want = (e * 2 + e * 4) + e * 4 + (e * 4 + e * 4) + (2 * (e * 2 + e * 4) + e * 2) + (e * 2 + e * 2) + (e * 2 + e * 2)
     assert bench.hbm_bytes([("some/layer", D, False)]) == want
     assert bench.hbm_bytes([("conv0", D, False)]) == want - (e * 2 + e * 2)      # no input gradient for the stem
+
+
+def test_top_launch_picks_the_slowest_conv_group_and_its_bound():
+    sys.path.insert(0, ROOT)
+    import numpy as np
+    import bench
+
+    class D16:    # 3x3 16 -> 16 on 32 x 512 x 512: HBM-bound (intensity 48 FLOP/B << ridge)
+        n, xd, xh, xw, cx, yd, yh, yw, cy, kd, kh, kw, s = 32, 1, 512, 512, 16, 1, 512, 512, 16, 1, 3, 3, 1
+
+    class D512:   # 3x3 512 -> 512 on 32 x 16 x 16: tensor-bound
+        n, xd, xh, xw, cx, yd, yh, yw, cy, kd, kh, kw, s = 32, 1, 16, 16, 512, 1, 16, 16, 512, 1, 3, 3, 1
+    table = [("a/b", D16, False), ("c/d", D512, False)]
+    pk = dict(hbm=6540.8, tf_sus=1373.9, tf_burst=1667.1, src="measured")
+    ms = np.zeros((2, 8))
+    ms[0, 0], ms[1, 4] = 0.6, 0.1                   # two profiled steps: 0.3 ms fwd of layer 0
+    t = bench.top_launch(table, ms, 2, pk, "2d")
+    e = 32 * 512 * 512 * 16
+    assert t["bound"] == "hbm" and t["unit"] == "GB/s" and t["kernel"].startswith("a/b conv_fwd (16->16 k3 s1 @512")
+    assert abs(t["achieved"] - (e * 2 + e * 4) / 0.3e-3 / 1e9) < 1e-6 and abs(t["frac"] - t["achieved"] / 6540.8) < 1e-12
+    assert t["traffic"] == bench.NCU_TRAFFIC[("2d", "16->16 k3 s1 @512", "conv_fwd")]
+    ms[1, 4] = 5.0
+    t = bench.top_launch(table, ms, 2, pk, "2d")
+    assert t["bound"] == "tensor" and t["unit"] == "TFLOP/s" and t["traffic"] is None
+    assert abs(t["achieved"] - 2.0 * 32 * 16 * 16 * 9 * 512 * 512 / 2.5e-3 / 1e12) < 1e-9
