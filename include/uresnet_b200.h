@@ -228,8 +228,10 @@ int urn_decision(urn_net* h, const float* data, float threshold, float* decision
 int urn_backward(urn_net* h, const float* params, float* grads, int accumulate, void* ws,
                  void* const* ready_events, void* stream);
 
-/* Returns (host) the sticky device-side label error flag and clears it. Synchronises. */
-int urn_check_labels(urn_net* h, void* stream);
+/* Host-side check of the device flag the last urn_loss_metrics call raised for a label outside
+ * [0, num_class) (the same call makes the loss NaN): returns nonzero and sets urn_last_error()
+ * if it is set.  Reads 4 bytes from the workspace and synchronises the stream. */
+int urn_check_labels(urn_net* h, void* ws, void* stream);
 
 /* Per-layer timing/debug access: pointer + geometry of a layer's tensors in ws. */
 int urn_layer_info(const urn_net* h, int layer, const char** scope, urn_conv_desc* d,

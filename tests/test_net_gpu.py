@@ -222,6 +222,12 @@ def test_inference_and_run_test_api():
     bad[0, 0] = 7
     with pytest.raises(ValueError):
         net.run_test(None, data, bad)
+    # the C ABI reports the same condition through urn_check_labels (device flag of the last loss call)
+    h, ws = net._handle(B)
+    assert net._lib.urn_check_labels(h, ws.data_ptr(), net._stream()) != 0
+    assert b"label out of range" in net._lib.urn_last_error()
+    net.run_test(None, data, label)
+    assert net._lib.urn_check_labels(h, ws.data_ptr(), net._stream()) == 0
 
 
 def test_dims_validation():

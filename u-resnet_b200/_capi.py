@@ -72,7 +72,7 @@ SIGNATURES = {
     "urn_forward": (_i, [_vp, _vp, _vp, _vp, _vp]),
     "urn_loss_metrics": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp]),
     "urn_backward": (_i, [_vp, _vp, _vp, _i, _vp, C.POINTER(_vp), _vp]),
-    "urn_check_labels": (_i, [_vp, _vp]),
+    "urn_check_labels": (_i, [_vp, _vp, _vp]),
     "urn_decision": (_i, [_vp, _vp, C.c_float, _vp, _vp, _vp]),
     "urn_ssnet_decision": (_i, [_vp, _i64, _i64, _i, _vp, _i64, C.c_float, _vp, _vp]),
     "urn_launch_count": (_i64, []),

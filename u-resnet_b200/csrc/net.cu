@@ -808,8 +808,13 @@ extern "C" int urn_decision(urn_net* h, const float* data, float threshold, floa
                             h->cfg.in_channels, threshold, decision, stream);
 }
 
-extern "C" int urn_check_labels(urn_net* h, void* stream) {
-  (void)h; (void)stream;
+extern "C" int urn_check_labels(urn_net* h, void* ws, void* stream) {
+  URN_CHECK(h && ws, "urn_check_labels: null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  int flag = 0;      // first word of the loss workspace: set by ce_kernel, cleared by every urn_loss_metrics
+  URN_CUDA(cudaMemcpyAsync(&flag, P(ws, h->loss_ws_off), sizeof(int), cudaMemcpyDeviceToHost, st));
+  URN_CUDA(cudaStreamSynchronize(st));
+  URN_CHECK(flag == 0, "label out of range [0, %d) in the last urn_loss_metrics call", h->cfg.num_class);
   return 0;
 }
 
