@@ -289,6 +289,19 @@ def test_conv_many_tiles_per_cta(lib, monkeypatch, ctas, nd, n, sp, cin, cout, k
         test_conv_fused_bn_statistics(lib, nd, n, sp, cin, cout, k, s)
 
 
+@pytest.mark.parametrize("nd,n,sp,cin,cout,k,s", [(2, 2, (32, 48), 16, 16, 3, 1), (2, 18, (24, 40), 32, 32, 3, 1), (2, 3, (40, 72), 16, 32, 3, 1),
+                                                  (2, 33, (20, 24), 32, 16, 3, 1)])
+def test_conv_images_as_rows_plan(lib, monkeypatch, nd, n, sp, cin, cout, k, s):
+    """URN_HALO_ROWS=1 (experimental, off by default): 2D stride-1 3x3 layers through the 3D concat
+    path with relabelled axes (halo_plan_rows).  Same oracle checks as the default plan, with batches
+    below, at and above one 16-image tile row group."""
+    monkeypatch.setenv("URN_HALO_ROWS", "1")
+    test_conv_tcgen05_fwd_dgrad(lib, F16, nd, n, sp, cin, cout, k, s)
+    test_conv_tcgen05_fwd_dgrad(lib, BF16, nd, n, sp, cin, cout, k, s)
+    test_conv_fused_bn_statistics(lib, nd, n, sp, cin, cout, k, s)
+    test_conv_kernels_stay_inside_their_buffers(lib, nd, n, sp, cin, cout, k, s)
+
+
 HALO_WGRAD_CASES = [
     # nd, n, spatial, cin, cout, ldx factor  (stride-1 3x3(x3): the halo-tile filter-gradient kernel)
     (2, 3, (40, 24), 16, 16, 1),         # several tiles per image, ragged in h

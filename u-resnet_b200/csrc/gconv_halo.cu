@@ -69,6 +69,9 @@ struct HaloParams {
   int zero_bytes;            // shared-memory zero block (accumulator clearing MMAs), 0 if !concat
   uint32_t idesc_n[3];       // instruction descriptors for N = 1,2,3 x cout
   uint32_t idesc_zero;       // N = TD*cout
+  int in_row_b;              // input strides in bytes: next row (y), next plane (z), next image (n)
+  long long in_plane_b, in_img_b;
+  long long o_row, o_plane, o_img;   // output strides in pixels
   float* stats_part;         // fused BN statistics: per (CTA, epilogue warp, channel) (n, mean, M2) partials, or NULL
   int dbg;                   // URN_HALO_DBG bitmask (perf experiments): 1 no stores, 2 no loads, 4 no MMA
 };
@@ -170,7 +173,7 @@ gconv_halo_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_consta
     const int run = 8 * p.ks;                                  // pixels per (hy, kw) run
     const char* src_base = reinterpret_cast<const char*>(in);
     const int pix_bytes = (int)(p.ldin * 2);        // one plane is < 2 GB: 32-bit offsets inside it
-    const int row_bytes = pix_bytes * p.W;
+    const int row_bytes = p.in_row_b;
     const int H = p.H, W = p.W;
     int soff[kNCH], hyv[kNCH], dxv[kNCH];
     uint32_t doff[kNCH];
@@ -206,7 +209,7 @@ gconv_halo_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_consta
         h_mbar_wait_warp(&empty[st.idx], st.phase ^ 1);
         if (t == 0) TL(0, k, 0);
         const uint32_t dst_base = h_smem_u32(smem_a + (size_t)st.idx * p.plane_bytes);
-        const char* origin = src_base + ((long long)ti.nn * p.D + z) * H * (long long)row_bytes + org_off;
+        const char* origin = src_base + (long long)ti.nn * p.in_img_b + (long long)z * p.in_plane_b + org_off;
         if (no_load) {
         } else if (interior) {
 #pragma unroll
@@ -377,7 +380,8 @@ gconv_halo_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_consta
                         p.idesc_zero, 0u);
               const uint32_t d_tmem = d_tmem0 + (uint32_t)((sj * p.TD + dlo) * p.cout);
 #pragma unroll
-              for (int kh = 0; kh < 3; ++kh)
+              for (int kh = 0; kh < 3; ++kh) {
+                if (!FULL3 && kh >= p.nkh) break;      // images-as-rows plan of a 2D layer: nkh = 1
 #pragma unroll
                 for (int kw = 0; kw < 3; ++kw) {
                   const uint32_t a_lo = a_sj + (uint32_t)kh * a_kh + (uint32_t)kw * a_kw;
@@ -389,6 +393,7 @@ gconv_halo_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_consta
                     h_umma2(d_tmem, a_lo + 6, a_hi, b_lo + 6, b_hi, idn, 1u);
                   }
                 }
+              }
             }
           }
           __syncwarp();
@@ -473,8 +478,8 @@ gconv_halo_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_consta
         }
       };
       if (!OUT_F32 && MODE == 1) {
-        const long long opix_first = (((long long)ti.nn * p.OD + (d0 * p.os + p.coff[0][0])) * p.OH + (y * p.os + p.coff[0][1])) * p.OW +
-                                     (x0 * p.os + p.coff[0][2]);
+        const long long opix_first = (long long)ti.nn * p.o_img + (long long)(d0 * p.os + p.coff[0][0]) * p.o_plane +
+                                     (long long)(y * p.os + p.coff[0][1]) * p.o_row + (x0 * p.os + p.coff[0][2]);
         fetch_old(opix_first, 0);
         old_ready = true;
       }
@@ -485,8 +490,8 @@ gconv_halo_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_consta
         const int cls = cd / p.TD, dd = cd - cls * p.TD;
         const int d = d0 + dd;
         if (d >= dmax) continue;                       // warp-uniform: accumulators never written
-        const long long opix0 = (((long long)ti.nn * p.OD + (d * p.os + p.coff[cls][0])) * p.OH + (y * p.os + p.coff[cls][1])) * p.OW +
-                                (x0 * p.os + p.coff[cls][2]);
+        const long long opix0 = (long long)ti.nn * p.o_img + (long long)(d * p.os + p.coff[cls][0]) * p.o_plane +
+                                (long long)(y * p.os + p.coff[cls][1]) * p.o_row + (x0 * p.os + p.coff[cls][2]);
         // accumulator columns: [class][dd][sj][cout], or [sj][dd][cout] in concat mode
         const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)ac.idx * acc_cols +
                                 (uint32_t)((p.concat ? dd : cd * p.ks) * p.cout);
@@ -648,6 +653,10 @@ bool halo_plan(const GConv& g, int in_dtype, int out_dtype, int cout_store, Halo
     if (lo[k] > 0 || hi[k] < 0 || (gs[k] - 1) * g.is > ins[k] - 1) return false;
   p.cin = g.cin; p.cout = g.cout; p.cout_store = cout_store; p.ldin = g.ldin; p.ldout = g.ldout;
   if ((long long)p.H * p.W * g.ldin * 2 >= (1ll << 31)) return false;     // 32-bit offsets inside a plane
+  p.in_row_b = (int)(g.ldin * 2 * p.W);
+  p.in_plane_b = (long long)p.in_row_b * p.H;
+  p.in_img_b = p.in_plane_b * p.D;
+  p.o_row = p.OW; p.o_plane = (long long)p.OH * p.OW; p.o_img = p.o_plane * p.OD;
   p.hr = (kTH - 1) * g.is + p.nkh;
   const int cpr = g.cin * 2 / 16;
   // super-tile width: the widest whose staged plane fits kNCH chunks per producer thread
@@ -686,7 +695,7 @@ bool halo_plan(const GConv& g, int in_dtype, int out_dtype, int cout_store, Halo
   // concat mode: 3x3x3 stride-1 convs; the zero block is one B tile of N = TD*cout rows
   p.coff[0][0] = g.ood; p.coff[0][1] = g.ooh; p.coff[0][2] = g.oow;
   for (int i = 0; i < 27; ++i) p.ctapw[0][i] = p.tapw[i];
-  p.concat = (ncls == 1 && p.nkd == 3 && p.nkh == 3 && p.nkw == 3 && g.is == 1 && g.os == 1 && 3 * g.cout <= 256 && p.TD >= 2 &&
+  p.concat = (ncls == 1 && p.nkd == 3 && (p.nkh == 3 || p.nkh == 1) && p.nkw == 3 && g.is == 1 && g.os == 1 && 3 * g.cout <= 256 && p.TD >= 2 &&
               !getenv("URN_HALO_NO_CONCAT")) ? 1 : 0;
   if (p.concat) {
     p.zero_bytes = ((p.TD * g.cout * (int)pitch + 1023) / 1024) * 1024;
@@ -704,6 +713,39 @@ bool halo_plan(const GConv& g, int in_dtype, int out_dtype, int cout_store, Halo
   // Cin = 64 with 1-4 taps: the tap-box kernel (128-byte TMA rows, few boxes) is as fast or faster
   if (g.cin == 64 && !(p.nkh == 3 && p.nkw == 3) && !getenv("URN_HALO_ALL")) return false;
   if (getenv("URN_HALO_ONLY3X3") && !(g.is == 1 && g.os == 1 && p.nkh == 3 && p.nkw == 3)) return false;
+  return true;
+}
+
+// EXPERIMENTAL (URN_HALO_ROWS=1, off by default): a 2D stride-1 3x3 layer run through the 3D concat
+// path by relabelling the axes -- planes := image rows, tile rows := the IMAGES of the batch, columns
+// := image columns.  The kh taps become the depth taps, which the concat mode fuses along N: per
+// 128 outputs 3 MMAs of N = 3*cout instead of 9 of N = cout (the 2D layers are bound by the tensor
+// pipe's instruction rate at N = 16).  Only the strides differ from a real volume:
+// the next "row" is the next image, the next "plane" the next image row.
+bool halo_plan_rows(const GConv& g, int in_dtype, int out_dtype, int cout_store, HaloParams* pp) {
+  if (!getenv("URN_HALO_ROWS")) return false;
+  if (g.id != 1 || g.od != 1 || g.gd != 1 || g.is != 1 || g.os != 1 || g.ntaps != 9) return false;
+  if (g.ood || g.ooh || g.oow || g.gh != g.oh || g.gw != g.ow || g.ih != g.oh || g.iw != g.ow) return false;
+  if (cout_store > 0 && cout_store != g.cout) return false;
+  if (g.ih < 4 || (long long)g.n * g.ih * g.iw * g.ldin * 2 >= (1ll << 31)) return false;   // 32-bit offsets across the images of a plane
+  GConv v = g;
+  v.n = 1;
+  v.id = g.ih; v.ih = g.n; v.iw = g.iw;
+  v.od = g.oh; v.oh = g.n; v.ow = g.ow;
+  v.gd = g.gh; v.gh = g.n; v.gw = g.gw;
+  for (int t = 0; t < g.ntaps; ++t) {
+    if (g.taps[t].od != 0) return false;
+    v.taps[t].od = g.taps[t].oh; v.taps[t].oh = 0; v.taps[t].ow = g.taps[t].ow;
+  }
+  if (!halo_plan(v, in_dtype, out_dtype, cout_store, pp, 1)) return false;
+  HaloParams& p = *pp;
+  if (!p.concat) return false;
+  p.in_plane_b = (long long)g.ldin * 2 * g.iw;              // next image row
+  const long long img_b = p.in_plane_b * g.ih;              // next image
+  if (img_b * 17 >= (1ll << 31)) return false;
+  p.in_row_b = (int)img_b;
+  p.in_img_b = 0;
+  p.o_plane = g.ow; p.o_row = (long long)g.oh * g.ow; p.o_img = 0;
   return true;
 }
 
@@ -803,7 +845,8 @@ bool gconv_halo_supported_padded(const GConv& g, int in_dtype, int out_dtype, in
 int gconv_halo_launch_stats(const GConv& g, int in_dtype, const void* in, const void* wpack, void* out,
                             int out_dtype, int cout_store, float* stats_part, int* nparts, cudaStream_t st) {
   HaloParams p;
-  URN_CHECK(halo_plan(g, in_dtype, out_dtype, cout_store, &p), "gconv_halo: unsupported shape/dtype");
+  if (!halo_plan_rows(g, in_dtype, out_dtype, cout_store, &p))
+    URN_CHECK(halo_plan(g, in_dtype, out_dtype, cout_store, &p), "gconv_halo: unsupported shape/dtype");
   if (nparts) *nparts = 0;
   if (p.ntiles == 0) return 0;
   const int grid_ = (int)std::min<long long>(p.ntiles, persistent_ctas());
