@@ -10,6 +10,7 @@ from uresnet_b200.config import ssnet_config
 from uresnet_b200.uresnet import uresnet
 
 REF_CFG = "/root/reference/config"
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def write(tmp_path, text, name="a.cfg"):
@@ -121,3 +122,37 @@ def test_summary_log_writes_reference_tags(tmp_path):
     assert set(acc.Tags()["scalars"]) == {"accuracy_all", "accuracy_nonzero", "loss"}
     assert [e.step for e in acc.Scalars("accuracy_all")] == [0, 20]
     assert acc.Tags()["images"] == ["data_example"]
+
+
+def test_run_ssnet_usage_without_cfg(capsys):
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("run_ssnet_entry", os.path.join(ROOT, "run_ssnet.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    assert mod.main(["not_a_config.txt"]) == 2
+    assert "run_ssnet.py" in capsys.readouterr().err
+
+
+def test_iteration_from_checkpoint_name():
+    """lib/ssnet_trainval.py:41-42: the iteration is the integer after the last '-' of the file name."""
+    from uresnet_b200.ssnet_trainval import ssnet_trainval
+    t = ssnet_trainval()
+    assert t.iteration_from_file_name("weights/uresnet-1200") == 1200
+    assert t.iteration_from_file_name("weights/uresnet-37.npz") == 37
+
+
+def test_oracle_decision_map_matches_per_pixel_loops():
+    """lib/ssnet_trainval.py:269-287 restated per pixel: 1 = shower, 2 = track (ties go to track),
+    0 where the input is not above the threshold."""
+    from oracle import uresnet_oracle as O
+    rng = np.random.default_rng(5)
+    sm = rng.random((2, 6, 7, 3)).astype(np.float32)
+    sm[0, 0, :3, 2] = sm[0, 0, :3, 1]                     # ties
+    data = rng.choice([0.0, 1.0, 1.5, 40.0], size=(2, 6, 7)).astype(np.float32)
+    got = O.ssnet_decision(sm, data)
+    for idx in np.ndindex(2, 6, 7):
+        want = 0.0
+        if data[idx] > 1.0:
+            want = 1.0 if sm[idx + (1,)] > sm[idx + (2,)] else 2.0
+        assert got[idx] == want
+    assert got.dtype == np.float32
