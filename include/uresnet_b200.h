@@ -238,6 +238,61 @@ int urn_layer_info(const urn_net* h, int layer, const char** scope, urn_conv_des
                    int* is_transpose, int64_t* raw_off_bytes, int64_t* out_off_bytes,
                    int64_t* out_ld, int64_t* stats_off_bytes);
 
+/* ---------------- plan introspection + partial execution (parity hooks) ----------------
+ * The reference exposes every intermediate of its graph by name (any tf.Tensor can be fetched or
+ * fed through sess.run's feed_dict, lib/ssnet.py:91-139).  These entry points give the same
+ * access to the static launch schedule: where each graph node / layer tensor lives in the
+ * workspace, what each schedule step reads and writes, and execution of a sub-range of steps, so
+ * that a test can feed one step the reference's (oracle's) tensors and fetch what it produces
+ * (tests/test_parity_gpu.py: teacher-forced per-layer parity).  Not used by the product path. */
+typedef struct urn_tensor_ref {
+  int64_t off_bytes;   /* byte offset of element (row 0, channel 0) in the workspace; -1 = absent */
+  int64_t ld;          /* element pitch between consecutive rows (pixels)                         */
+  int64_t rows;        /* batch * spatial positions                                              */
+  int32_t c;           /* channels                                                               */
+  int32_t dtype;       /* URN_F32 | URN_BF16 | URN_F16                                           */
+} urn_tensor_ref;
+
+/* One step of the forward / backward schedule.
+ * forward:  kind 0 = conv (+BN statistics): reads node_a, writes raw/stats of `layer`;
+ *           kind 1 = BN apply (+ReLU): reads raw/stats of `layer`, writes node_a;
+ *           kind 2 = residual merge relu(BN(layer) + shortcut): shortcut = BN(layer2) if
+ *                    layer2 >= 0 else node_b (identity); writes node_a.
+ * backward: kind 0 = BN(+ReLU) backward of `layer`: reads the gradient of node_a, writes
+ *                    d(raw) + d(beta) of `layer` (and of the conv shortcut `layer2` if >= 0) and,
+ *                    if node_b >= 0, the masked gradient into the gradient of node_b (identity
+ *                    shortcut; added when `accumulate`);
+ *           kind 1 = filter gradient of `layer` (reads its input node node_a and d(raw));
+ *           kind 2 = input gradient of `layer`: d(raw) -> gradient of node_a (added when
+ *                    `accumulate`). */
+typedef struct urn_step_info {
+  int32_t kind, layer, layer2, node_a, node_b, relu, accumulate;
+} urn_step_info;
+
+int urn_plan_counts(const urn_net* h, int* n_nodes, int* n_fwd_steps, int* n_bwd_steps);
+/* Graph node `node`: name = producing scope under UResNet/ ("conv0", "resnet_module3/module1"
+ * [the module output], "resnet_module3/module1/resnet_conv1" [BN output inside the module],
+ * "deconv2", "concat2", "data"); value = stored activation; shadow = its bf16 copy (mix16) or
+ * absent; grad = its gradient buffer in the backward arena (valid only while live). */
+int urn_node_info(const urn_net* h, int node, const char** name, urn_tensor_ref* value,
+                  urn_tensor_ref* shadow, urn_tensor_ref* grad);
+/* Layer tensors: raw fp32 conv output, d(raw) (pitch = padded width for the tensor-core head),
+ * byte offset of the statistics (float[2*c]: mean | rstd), element offsets of the filter / beta
+ * in the flat parameter + gradient buffers, input node, node written by its own BN apply (-1 if
+ * it is merged into a module output). */
+int urn_layer_tensors(const urn_net* h, int layer, urn_tensor_ref* raw, urn_tensor_ref* draw,
+                      int64_t* stats_off_bytes, int64_t* w_off, int64_t* b_off, int* in_node,
+                      int* out_node);
+int urn_fwd_step_info(const urn_net* h, int step, urn_step_info* info);
+int urn_bwd_step_info(const urn_net* h, int step, urn_step_info* info);
+/* Steps [first, last) of urn_forward / urn_backward.  urn_forward_range runs the input
+ * conversion and the per-step filter packing first when data != NULL (pass NULL to keep what a
+ * previous urn_forward left). */
+int urn_forward_range(urn_net* h, const float* params, const float* data, void* ws, int first,
+                      int last, void* stream);
+int urn_backward_range(urn_net* h, const float* params, float* grads, int accumulate, void* ws,
+                       int first, int last, void* stream);
+
 /* ---------------- measurement hooks ---------------- */
 /* Number of kernels this library has launched in this process (host-side counter). */
 int64_t urn_launch_count(void);

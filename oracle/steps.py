@@ -1,0 +1,252 @@
+"""Step-by-step form of the CPU oracle (TEST INFRASTRUCTURE ONLY; parity unpinned, see
+``oracle/__init__.py``).
+
+``uresnet_oracle.forward`` states the graph of /root/reference/lib/uresnet.py:22-123 and
+lib/resnet_module.py:10-87 as one autograd expression.  ``StepOracle`` states the SAME graph one
+slim layer at a time, with the SAME primitives (``conv_same``, ``conv_transpose_same``,
+``batch_norm``), keeps every intermediate by name, and derives the backward pass one schedule
+step at a time with *local* autograd on those primitives:
+
+  forward, per layer ``<scope>``        raw = conv(x, W);  (mean, rstd) of raw;  BN(+ReLU) output
+  forward, per residual module          relu(shortcut + BN(raw of resnet_conv2))   (resnet_module.py:68)
+  backward ``("bn", scope)``            d(raw), d(beta) [+ the shortcut's, + the masked gradient that
+                                        flows to an identity shortcut] from the gradient of the node
+  backward ``("wgrad", scope)``         d(W) from (input node, d(raw))
+  backward ``("dgrad", scope)``         contribution of the layer to the gradient of its input node
+
+Node names are the TF scopes under ``UResNet/`` that produce them: ``conv0``, ``deconv<k>``,
+``conv1``, ``conv2`` (simple layers), ``resnet_module<i>/module<j>`` (module outputs),
+``resnet_module<i>/module<j>/resnet_conv1`` (the BN output between the two 3x3 convs),
+``concat<k>`` (uresnet.py:91-93, deconv channels first) and ``data``.  The CUDA library names its
+plan nodes the same way (``urn_node_info``), which is what lets tests/test_parity_gpu.py feed
+each of its schedule steps the oracle's tensors ("teacher forcing") and compare what the step
+produces with what is recorded here.
+
+``tests/test_oracle.py`` checks that the gradients assembled from these per-step records equal the
+whole-graph autograd gradients of ``uresnet_oracle.run`` to fp64 round-off, so the two statements
+of the graph cannot drift apart.
+"""
+from __future__ import annotations
+
+from collections import OrderedDict
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from . import uresnet_oracle as O
+
+
+def _cl(t):
+    """channel-first torch tensor -> channel-last numpy [rows, C]"""
+    nd = t.dim() - 2
+    return t.detach().permute(0, *range(2, nd + 2), 1).reshape(-1, t.shape[1]).numpy()
+
+
+class StepOracle(object):
+
+    def __init__(self, P_np, data, label, weight=None, base=16, num_strides=5, dtype=torch.float64):
+        """data [B,...,Cin], label / weight [B,...] numpy (as for ``uresnet_oracle.run``)."""
+        self.dt = dtype
+        self.P = OrderedDict((k, torch.tensor(v, dtype=dtype)) for k, v in P_np.items())
+        d = torch.tensor(data, dtype=dtype)
+        self.nd = d.dim() - 2
+        self.data_cl = d
+        self.label = torch.tensor(label, dtype=dtype)
+        self.weight = None if weight is None else torch.tensor(weight, dtype=dtype)
+        self.base, self.S = base, num_strides
+        self.nodes = OrderedDict()          # name -> channel-first tensor
+        self.layers = OrderedDict()         # scope -> dict(x, raw, mean, rstd, stride, transpose, relu, out)
+        self.recs = []                      # forward records: ("layer", scope) / ("module", scope, sc|None) / ("concat", k)
+        self._forward()
+
+    # ------------------------------------------------------------------ forward
+    def _w(self, scope):
+        return self.P["UResNet/%s/weights" % scope], self.P["UResNet/%s/BatchNorm/beta" % scope]
+
+    def _conv(self, scope, x):
+        L = self.layers[scope]
+        w, _ = self._w(scope)
+        return O.conv_transpose_same(x, w, L["stride"]) if L["transpose"] else O.conv_same(x, w, L["stride"])
+
+    def _layer(self, scope, x_name, stride, relu, transpose=False, out=None):
+        self.layers[scope] = L = dict(x=x_name, stride=stride, relu=relu, transpose=transpose, out=out)
+        raw = self._conv(scope, self.nodes[x_name])
+        axes = [0] + list(range(2, raw.dim()))
+        mu = raw.mean(dim=axes)
+        var = ((raw - mu.view([1, -1] + [1] * self.nd)) ** 2).mean(dim=axes)     # biased
+        L.update(raw=raw, mean=mu, rstd=torch.rsqrt(var + O.BN_EPS))
+        if out is not None:
+            y = O.batch_norm(raw, self._w(scope)[1])
+            self.nodes[out] = F.relu(y) if relu else y
+            self.recs.append(("layer", scope))
+
+    def _module(self, scope, x_name, cout, stride):                    # resnet_module.py:10-68
+        x = self.nodes[x_name]
+        sc = None
+        if not (x.shape[1] == cout and stride == 1):
+            sc = scope + "/shortcut"
+            self._layer(sc, x_name, stride, False)
+        c1, c2 = scope + "/resnet_conv1", scope + "/resnet_conv2"
+        self._layer(c1, x_name, stride, False, out=c1)
+        self.recs.pop()                                                # recorded as part of the module
+        self._layer(c2, c1, 1, False)
+        self.nodes[scope] = self._merge(scope, sc, self.layers[c2]["raw"],
+                                        self.layers[sc]["raw"] if sc else None, x if sc is None else None)
+        self.recs.append(("module", scope, sc, x_name))
+        return scope
+
+    def _merge(self, scope, sc, raw2, raw_sc, x_res):
+        r = O.batch_norm(raw2, self._w(scope + "/resnet_conv2")[1])
+        s = O.batch_norm(raw_sc, self._w(sc)[1]) if sc else x_res
+        return F.relu(s + r)                                            # resnet_module.py:68
+
+    def _double(self, idx, x_name, cout, stride):                       # resnet_module.py:70-87
+        m1 = self._module("resnet_module%d/module1" % idx, x_name, cout, stride)
+        return self._module("resnet_module%d/module2" % idx, m1, cout, 1)
+
+    def _forward(self):
+        nd = self.nd
+        self.nodes["data"] = self.data_cl.permute(0, nd + 1, *range(1, nd + 1))
+        self._layer("conv0", "data", 1, True, out="conv0")
+        net = "conv0"
+        skips = {self.nodes[net].shape[1]: net}                         # keyed by channel count (uresnet.py:47,64)
+        for step in range(self.S):
+            net = self._double(step, net, self.nodes[net].shape[1] * 2, 2)
+            skips[self.nodes[net].shape[1]] = net
+        for step in range(self.S):
+            cout = self.nodes[net].shape[1] // 2
+            dn = "deconv%d" % step
+            self._layer(dn, net, 2, True, transpose=True, out=dn)
+            cat = "concat%d" % step
+            self.nodes[cat] = torch.cat([self.nodes[dn], self.nodes[skips[cout]]], dim=1)
+            self.recs.append(("concat", cat, dn, skips[cout]))
+            net = self._double(step + 5, cat, cout, 1)                   # scope step+5 (uresnet.py:100)
+        self._layer("conv1", net, 1, True, out="conv1")
+        self._layer("conv2", "conv1", 1, False, out="conv2")
+        self.logits = self.nodes["conv2"].permute(0, *range(2, nd + 2), 1).contiguous()
+
+    # ------------------------------------------------------------------ loss
+    def loss(self):
+        lg = self.logits.detach().requires_grad_(True)
+        res = O.loss_and_metrics(lg, self.data_cl, self.label, self.weight)
+        (dl,) = torch.autograd.grad(res["loss"], [lg])
+        self.result = dict(loss=float(res["loss"].detach()), acc_all=res["acc_all"], acc_nonzero=res["acc_nonzero"],
+                           n_correct_all=res["n_correct_all"], n_correct_nz=res["n_correct_nz"], n_nz=res["n_nz"])
+        nd = self.nd
+        return dl.permute(0, nd + 1, *range(1, nd + 1))                 # channel first
+
+    # ------------------------------------------------------------------ backward
+    def _bn_bwd(self, scope, dout, relu):
+        """Local autograd through y = [relu](BN(raw, beta)).  Returns (draw, dbeta)."""
+        L = self.layers[scope]
+        raw = L["raw"].detach().requires_grad_(True)
+        beta = self._w(scope)[1].detach().requires_grad_(True)
+        y = O.batch_norm(raw, beta)
+        if relu:
+            y = F.relu(y)
+        return torch.autograd.grad(y, [raw, beta], dout)
+
+    def _conv_bwd(self, scope, draw):
+        """Local autograd through raw = conv(x, W).  Returns (dx or None for the stem, dW)."""
+        L = self.layers[scope]
+        x = self.nodes[L["x"]].detach().requires_grad_(L["x"] != "data")
+        w = self._w(scope)[0].detach().requires_grad_(True)
+        y = O.conv_transpose_same(x, w, L["stride"]) if L["transpose"] else O.conv_same(x, w, L["stride"])
+        if L["x"] == "data":
+            (dw,) = torch.autograd.grad(y, [w], draw)
+            return None, dw
+        dx, dw = torch.autograd.grad(y, [x, w], draw)
+        return dx, dw
+
+    def backward(self):
+        """Fills ``node_grad`` (total gradient of every node), ``bn[scope]`` = dict(dout, draw,
+        dbeta[, g]), ``dw[scope]``, ``dx[scope]`` (channel-first torch tensors) and ``grads``
+        (numpy, keyed like the parameter dict)."""
+        G = {}
+        self.bn, self.dw, self.dx = {}, {}, {}
+
+        def add(name, g):
+            G[name] = g if name not in G else G[name] + g
+
+        def conv_part(scope):
+            dx, dw = self._conv_bwd(scope, self.bn[scope]["draw"])
+            self.dw[scope] = dw
+            if dx is not None:
+                self.dx[scope] = dx
+                add(self.layers[scope]["x"], dx)
+
+        G["conv2"] = self.loss()
+        for rec in reversed(self.recs):
+            if rec[0] == "layer":
+                scope = rec[1]
+                L = self.layers[scope]
+                dout = G[L["out"]]
+                draw, dbeta = self._bn_bwd(scope, dout, L["relu"])
+                self.bn[scope] = dict(dout=dout, draw=draw, dbeta=dbeta)
+                conv_part(scope)
+            elif rec[0] == "concat":
+                _, cat, dn, skip = rec
+                c = self.nodes[dn].shape[1]
+                add(dn, G[cat][:, :c])
+                add(skip, G[cat][:, c:])
+            else:
+                _, scope, sc, x_name = rec
+                c1, c2 = scope + "/resnet_conv1", scope + "/resnet_conv2"
+                dout = G[scope]
+                raw2 = self.layers[c2]["raw"].detach().requires_grad_(True)
+                b2 = self._w(c2)[1].detach().requires_grad_(True)
+                if sc:
+                    raws = self.layers[sc]["raw"].detach().requires_grad_(True)
+                    bs = self._w(sc)[1].detach().requires_grad_(True)
+                    y = self._merge_local(raw2, b2, O.batch_norm(raws, bs))
+                    d2, db2, ds, dbs = torch.autograd.grad(y, [raw2, b2, raws, bs], dout)
+                    self.bn[c2] = dict(dout=dout, draw=d2, dbeta=db2)
+                    self.bn[sc] = dict(dout=dout, draw=ds, dbeta=dbs)
+                else:
+                    xr = self.nodes[x_name].detach().requires_grad_(True)
+                    y = self._merge_local(raw2, b2, xr)
+                    d2, db2, g = torch.autograd.grad(y, [raw2, b2, xr], dout)
+                    self.bn[c2] = dict(dout=dout, draw=d2, dbeta=db2, g=g)
+                    add(x_name, g)
+                conv_part(c2)
+                draw1, db1 = self._bn_bwd(c1, G[c1], False)
+                self.bn[c1] = dict(dout=G[c1], draw=draw1, dbeta=db1)
+                conv_part(c1)
+                if sc:
+                    conv_part(sc)
+        self.node_grad = G
+        self.grads = OrderedDict()
+        for scope in self.layers:
+            self.grads["UResNet/%s/weights" % scope] = self.dw[scope].numpy()
+            self.grads["UResNet/%s/BatchNorm/beta" % scope] = self.bn[scope]["dbeta"].numpy()
+        return self.grads
+
+    @staticmethod
+    def _merge_local(raw2, b2, s):
+        return F.relu(s + O.batch_norm(raw2, b2))
+
+    # ------------------------------------------------------------------ views for the tests
+    def node(self, name):
+        """[rows, C] float64 numpy, channel-last (the layout of the CUDA workspace)."""
+        return _cl(self.nodes[name])
+
+    def node_gradient(self, name):
+        return _cl(self.node_grad[name])
+
+    def raw(self, scope):
+        return _cl(self.layers[scope]["raw"])
+
+    def stats(self, scope):
+        L = self.layers[scope]
+        return np.concatenate([L["mean"].numpy(), L["rstd"].numpy()])    # mean | rstd, as urn_bn_stats stores them
+
+    def draw(self, scope):
+        return _cl(self.bn[scope]["draw"])
+
+    def masked_gradient(self, scope):
+        """gradient handed to the identity shortcut by the merge of module ``scope``"""
+        return _cl(self.bn[scope + "/resnet_conv2"]["g"])
+
+    def input_gradient(self, scope):
+        return _cl(self.dx[scope])

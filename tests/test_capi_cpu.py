@@ -89,6 +89,86 @@ def test_create_rejects_bad_configs(lib):
         assert len(lib.urn_last_error()) > 0
 
 
+def test_create_rejects_more_than_five_strides(lib):
+    """uresnet.py:100 hard-codes the decoder scope as step+5: with num_strides > 5 encoder and
+    decoder modules would share variable names (TF raises); the plan must refuse, not overwrite."""
+    h = C.c_void_p()
+    bad = _cfg(2, (64, 64), 1, F=4, S=6)
+    assert lib.urn_create(C.byref(bad), C.byref(h)) != 0
+    assert b"num_strides" in lib.urn_last_error()
+    from uresnet_b200.uresnet import uresnet
+    with pytest.raises(ValueError):
+        uresnet(dims=[64, 64, 1], num_class=3, num_strides=6, base_num_outputs=4)._build()
+
+
+@pytest.mark.parametrize("nd,sp,B,F,S,dt", [(2, (64, 64), 2, 16, 5, 2), (3, (16, 16, 16), 1, 16, 3, 2), (2, (32, 32), 1, 4, 2, 0)])
+def test_plan_introspection_matches_step_oracle(lib, nd, sp, B, F, S, dt):
+    """The parity hooks (urn_plan_counts / urn_node_info / urn_layer_tensors / urn_*_step_info) describe
+    the same graph as oracle/steps.py: same node names and shapes, every forward tensor inside the
+    workspace, every schedule step well formed.  (Host-only: nothing is launched.)"""
+    from oracle.steps import StepOracle
+    h = C.c_void_p()
+    cfg = _cfg(nd, sp, B, F, S, dt=dt)
+    _capi.check(lib.urn_create(C.byref(cfg), C.byref(h)))
+    rng = np.random.default_rng(0)
+    shp = [B] + list(sp)
+    so = StepOracle(O.init_params(nd, base=F, num_strides=S, seed=1), rng.random(shp + [1]),
+                    rng.integers(0, 3, shp).astype(np.float64), None, base=F, num_strides=S)
+    n, nf, nb = C.c_int(), C.c_int(), C.c_int()
+    _capi.check(lib.urn_plan_counts(h, C.byref(n), C.byref(nf), C.byref(nb)))
+    ws_bytes = lib.urn_workspace_bytes(h)
+    names = []
+    for i in range(n.value):
+        name = C.c_char_p()
+        v, sh, g = _capi.urn_tensor_ref(), _capi.urn_tensor_ref(), _capi.urn_tensor_ref()
+        _capi.check(lib.urn_node_info(h, i, C.byref(name), C.byref(v), C.byref(sh), C.byref(g)))
+        nm = name.value.decode()
+        names.append(nm)
+        assert nm in so.nodes, nm
+        assert (v.rows, v.c) == so.node(nm).shape
+        es = 4 if v.dtype == 0 else 2
+        assert 0 <= v.off_bytes and v.off_bytes + ((v.rows - 1) * v.ld + v.c) * es <= ws_bytes
+        assert (sh.off_bytes >= 0) == (dt == 2 and nm != "conv2")           # bf16 shadow of fp16 activations
+        if nm != "data":
+            assert g.off_bytes >= 0 and g.dtype == (1 if dt == 2 else dt) and (g.rows, g.c, g.ld) == (v.rows, v.c, v.ld)
+    assert set(names) == set(so.nodes)
+    nl = lib.urn_layer_count(h)
+    scopes = []
+    for li in range(nl):
+        raw, draw = _capi.urn_tensor_ref(), _capi.urn_tensor_ref()
+        so_, wo, bo, inn, outn = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int(), C.c_int()
+        _capi.check(lib.urn_layer_tensors(h, li, C.byref(raw), C.byref(draw), C.byref(so_), C.byref(wo), C.byref(bo),
+                                          C.byref(inn), C.byref(outn)))
+        scope = C.c_char_p()
+        _capi.check(lib.urn_layer_info(h, li, C.byref(scope), None, None, None, None, None, None))
+        sc = scope.value.decode()
+        scopes.append(sc)
+        assert (raw.rows, raw.c) == so.raw(sc).shape and raw.dtype == 0
+        assert names[inn.value] == so.layers[sc]["x"]
+        assert (names[outn.value] if outn.value >= 0 else None) == so.layers[sc]["out"]
+        assert draw.c == raw.c and draw.ld >= draw.c
+    assert scopes == list(so.layers)
+    kinds = []
+    for i in range(nf.value):
+        st = _capi.urn_step_info()
+        _capi.check(lib.urn_fwd_step_info(h, i, C.byref(st)))
+        kinds.append(st.kind)
+        if st.kind == 2:                       # merge: conv shortcut xor identity residual
+            assert (st.layer2 >= 0) != (st.node_b >= 0)
+            assert names[st.node_a] == scopes[st.layer][:-len("/resnet_conv2")]
+    assert kinds.count(0) == nl and kinds.count(2) == 4 * S and kinds.count(1) == nl - 4 * S - (sum(1 for s_ in scopes if s_.endswith("shortcut")))
+    nw = nd_ = 0
+    for j in range(nb.value):
+        st = _capi.urn_step_info()
+        _capi.check(lib.urn_bwd_step_info(h, j, C.byref(st)))
+        nw += st.kind == 1
+        nd_ += st.kind == 2
+        if st.kind == 0 and st.node_b >= 0:
+            assert names[st.node_b] == so.layers[scopes[st.layer][:-1] + "1"]["x"]   # identity shortcut = module input
+    assert nw == nl and nd_ == nl - 1          # every layer has a filter gradient; conv0 has no input gradient
+    lib.urn_destroy(h)
+
+
 def test_same_padding_formula(lib):
     for n in range(1, 40):
         for k, s in ((3, 1), (3, 2), (1, 2), (1, 1)):

@@ -156,3 +156,26 @@ def test_oracle_decision_map_matches_per_pixel_loops():
             want = 1.0 if sm[idx + (1,)] > sm[idx + (2,)] else 2.0
         assert got[idx] == want
     assert got.dtype == np.float32
+
+
+def test_synthetic_streams_do_not_overlap():
+    """Batch seeds are SeedSequence([seed, rank, step]): rank r never replays rank r+1's batches and the
+    test stream (seed + 500000) never collides with the train stream."""
+    from uresnet_b200.synthetic_io import synthetic_threadio
+    seen = {}
+    for seed in (1234, 1234 + 500000):
+        for rank in (0, 1, 2):
+            io = synthetic_threadio()
+            io.configure({"dims": [16, 16, 1], "seed": seed, "rank": rank})
+            io.start_manager(1)
+            for step in range(4):
+                io.next()
+                key = io.fetch_data("data").data().tobytes()
+                assert key not in seen, (seed, rank, step, seen.get(key))
+                seen[key] = (seed, rank, step)
+    a, b = synthetic_threadio(), synthetic_threadio()
+    for io in (a, b):
+        io.configure({"dims": [16, 16, 1], "seed": 7, "rank": 3})
+        io.start_manager(2)
+        io.next()
+    assert np.array_equal(a.fetch_data("data").data(), b.fetch_data("data").data())     # still deterministic

@@ -1,0 +1,427 @@
+"""Parity of the composed launch schedule in the BENCHMARKED mode (mix16) and in f32 (GPU).
+
+What is asserted, and where the tolerances come from (BASELINE.json north_star: 1e-3 relative in
+fp32, 2e-2 in 16-bit storage, argmax agreement >= 99.9 % of nonzero pixels; metric per tensor
+max|a-b| / max|b|):
+
+1. teacher-forced per-step parity (``test_teacher_forced_*``): every step of the library's forward
+   and backward schedule (conv + statistics, BN apply, residual merge, loss, BN backward, filter
+   gradient, input gradient -- the composed plan with its concat slices, accumulate flags, padded
+   head and arena) is fed the ORACLE's tensors (rounded to the storage dtype) through the plan
+   introspection hooks of the C ABI and must reproduce the oracle's output of that step within
+   2e-2 (mix16) / 1e-3 (f32).  This is the form of north_star's gradient bound that a reduced
+   precision evaluation can meet -- see 2.
+2. conditioning-derived end-to-end gradient bound (``test_end_to_end_gradients_*``): the fp64
+   oracle's OWN gradients move by 5-16 % (median per tensor) when its parameters are perturbed by
+   2^-11 relative (oracle/conditioning.py, tests/test_oracle.py::test_gradient_conditioning), so the
+   end-to-end mix16 bound per tensor is that measured sensitivity (max over draws) times SLACK,
+   computed inside the test for the very inputs it runs -- not a constant from prose.
+3. BASELINE-size comparisons (``test_baseline_size_*``): 2D 512x512 F=16 S=5 B=2 and 3D 64^3 F=16 S=5
+   B=1 against the fp64 oracle: f32 logits / loss / all 116 gradients within 1e-3; mix16 logits and
+   loss within 2e-2, argmax agreement >= 99.9 % of nonzero pixels.
+4. training trajectory (``test_training_trajectory``): 30 Adam steps, f32 vs mix16 vs the oracle
+   (fp64 autograd + TF-Adam): loss curves within 2 %.
+5. data-parallel overlap machinery on one GPU (``test_dp_graph_replay_records_events``): with
+   NUM_MINIBATCHES > 1 the graph captured for a non-final minibatch must not be replayed for the
+   final one (the per-layer ready events would never be re-recorded).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import uresnet_oracle as O
+from oracle.conditioning import gradient_sensitivity, relerr
+from oracle.steps import StepOracle
+from uresnet_b200 import _capi
+from uresnet_b200 import synthetic_io as S
+from uresnet_b200.uresnet import uresnet
+
+pytestmark = pytest.mark.gpu
+TOL = {"f32": 1e-3, "mix16": 2e-2}
+TDT = {_capi.URN_F32: torch.float32, _capi.URN_BF16: torch.bfloat16, _capi.URN_F16: torch.float16}
+
+
+def make_case(dims, B, F, St, seed_d, seed_p):
+    nd = len(dims) - 1
+    data, label, weight = S.make_batch(B, dims, seed=seed_d)
+    weight /= weight.sum(axis=1, keepdims=True)
+    P = O.init_params(nd, base=F, num_strides=St, seed=seed_p)
+    shp = [B] + list(dims[:-1])
+    return P, data, label, weight, (data.reshape(shp + [1]), label.reshape(shp), weight.reshape(shp))
+
+
+def make_net(dims, F, St, dtype, lr=None, use_weight=True, trainable=True):
+    net = uresnet(dims=dims, num_class=3, num_strides=St, base_num_outputs=F)
+    net.construct(trainable=trainable, use_weight=use_weight, learning_rate=lr, dtype=dtype)
+    return net
+
+
+# --------------------------------------------------------------------------------------------
+# workspace access through the plan introspection hooks
+# --------------------------------------------------------------------------------------------
+class Plan(object):
+
+    def __init__(self, net, batch):
+        self.net, self.lib = net, net._lib
+        self.h, self.ws = net._handle(batch)
+        n, nf, nb = C.c_int(), C.c_int(), C.c_int()
+        _capi.check(self.lib.urn_plan_counts(self.h, C.byref(n), C.byref(nf), C.byref(nb)))
+        self.nodes = []
+        for i in range(n.value):
+            name = C.c_char_p()
+            v, s, g = _capi.urn_tensor_ref(), _capi.urn_tensor_ref(), _capi.urn_tensor_ref()
+            _capi.check(self.lib.urn_node_info(self.h, i, C.byref(name), C.byref(v), C.byref(s), C.byref(g)))
+            self.nodes.append(dict(name=name.value.decode(), value=v, shadow=s, grad=g))
+        self.layers = []
+        for i in range(net._num_layers):
+            scope, d, tr = C.c_char_p(), _capi.urn_conv_desc(), C.c_int()
+            _capi.check(self.lib.urn_layer_info(self.h, i, C.byref(scope), C.byref(d), C.byref(tr), None, None, None, None))
+            raw, draw = _capi.urn_tensor_ref(), _capi.urn_tensor_ref()
+            so, wo, bo, inn, outn = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int(), C.c_int()
+            _capi.check(self.lib.urn_layer_tensors(self.h, i, C.byref(raw), C.byref(draw), C.byref(so), C.byref(wo),
+                                                   C.byref(bo), C.byref(inn), C.byref(outn)))
+            self.layers.append(dict(scope=scope.value.decode(), raw=raw, draw=draw, stats_off=so.value, w_off=wo.value,
+                                    b_off=bo.value, in_node=inn.value, out_node=outn.value, cout=raw.c))
+        self.fwd = [self._step(self.lib.urn_fwd_step_info, i) for i in range(nf.value)]
+        self.bwd = [self._step(self.lib.urn_bwd_step_info, i) for i in range(nb.value)]
+
+    def _step(self, fn, i):
+        s = _capi.urn_step_info()
+        _capi.check(fn(self.h, i, C.byref(s)))
+        return s
+
+    def view(self, ref, full_pitch=False):
+        """torch view [rows, c] (or [rows, ld]) of a workspace tensor"""
+        assert ref.off_bytes >= 0
+        tdt = TDT[ref.dtype]
+        es = 4 if ref.dtype == _capi.URN_F32 else 2
+        c = ref.ld if full_pitch else ref.c
+        n = (ref.rows - 1) * ref.ld + c
+        flat = self.ws[ref.off_bytes:ref.off_bytes + n * es].view(tdt)
+        return flat.as_strided((ref.rows, c), (ref.ld, 1))
+
+    def put(self, ref, arr):
+        self.view(ref).copy_(torch.from_numpy(np.ascontiguousarray(arr)).to(self.ws.device))
+
+    def get(self, ref):
+        return self.view(ref).to(torch.float64).cpu().numpy()
+
+    def stats_view(self, layer):
+        L = self.layers[layer]
+        return self.ws[L["stats_off"]:L["stats_off"] + 8 * L["cout"]].view(torch.float32)
+
+    def put_node(self, i, arr):
+        n = self.nodes[i]
+        self.put(n["value"], arr)
+        if n["shadow"].off_bytes >= 0:
+            self.put(n["shadow"], arr)
+
+    def put_layer_forward(self, li, so):
+        L = self.layers[li]
+        self.put(L["raw"], so.raw(L["scope"]))
+        self.stats_view(li).copy_(torch.from_numpy(so.stats(L["scope"])).to(self.ws.device))
+
+    def stream(self):
+        return self.net._stream()
+
+
+def run_teacher_forced(dims, B, F, St, dtype, seed_d=31, seed_p=17):
+    P, data, label, weight, shaped = make_case(dims, B, F, St, seed_d, seed_p)
+    so = StepOracle(P, *shaped, base=F, num_strides=St)
+    so.backward()
+    net = make_net(dims, F, St, dtype)
+    net.set_variables(P)
+    net.zero_gradients(None)
+    net._use_graphs = False
+    pl = Plan(net, B)
+    lib, h, ws = pl.lib, pl.h, pl.ws
+    params, grads = net._params.data_ptr(), net._accum.data_ptr()
+    feed = net.feed_dict(data, label, weight)
+    tol = TOL[dtype]
+    worst = {}
+
+    def check(kind, what, got, want):
+        e = relerr(got, want)
+        worst[kind] = max(worst.get(kind, 0.0), e)
+        assert e < tol, (kind, what, e)
+
+    # prologue only: input conversion + filter packing
+    _capi.check(lib.urn_forward_range(h, params, feed["data"].data_ptr(), ws.data_ptr(), 0, 0, pl.stream()))
+    name_of = [n["name"] for n in pl.nodes]
+    assert name_of[0] == "data"
+    # ---------------- forward, one schedule step at a time ----------------
+    for i, s in enumerate(pl.fwd):
+        L = pl.layers[s.layer]
+        scope = L["scope"]
+        if s.kind == 0:                                   # conv + statistics
+            pl.put_node(s.node_a, so.node(name_of[s.node_a]))
+        else:                                             # BN apply / merge
+            pl.put_layer_forward(s.layer, so)
+            if s.layer2 >= 0:
+                pl.put_layer_forward(s.layer2, so)
+            if s.node_b >= 0:
+                pl.put_node(s.node_b, so.node(name_of[s.node_b]))
+        _capi.check(lib.urn_forward_range(h, params, None, ws.data_ptr(), i, i + 1, pl.stream()))
+        if s.kind == 0:
+            check("conv_fwd", scope, pl.get(L["raw"]), so.raw(scope))
+            st = pl.stats_view(s.layer).to(torch.float64).cpu().numpy()
+            want = so.stats(scope)
+            c = L["cout"]
+            # the mean is compared on the scale of the channel's spread (a mean of ~0 has no scale of its own)
+            e_mu = float((np.abs(st[:c] - want[:c]) * want[c:]).max())
+            worst["bn_mean"] = max(worst.get("bn_mean", 0.0), e_mu)
+            assert e_mu < tol, ("bn_mean", scope, e_mu)
+            check("bn_rstd", scope, st[c:], want[c:])
+        else:
+            check("bn_apply" if s.kind == 1 else "merge", scope, pl.get(pl.nodes[s.node_a]["value"]),
+                  so.node(name_of[s.node_a]))
+            sh = pl.nodes[s.node_a]["shadow"]
+            if sh.off_bytes >= 0:
+                check("shadow", scope, pl.get(sh), so.node(name_of[s.node_a]))
+    # the workspace now holds the library's own outputs of the last steps: replace the whole forward
+    # state by the oracle's (teacher forcing for the backward pass)
+    for i, n in enumerate(pl.nodes):
+        if n["name"] in so.nodes and not n["name"].startswith("concat"):
+            pl.put_node(i, so.node(n["name"]))
+    for li in range(len(pl.layers)):
+        pl.put_layer_forward(li, so)
+    # ---------------- loss ----------------
+    _capi.check(lib.urn_loss_metrics(h, feed["label"].data_ptr(), feed["weight"].data_ptr(), feed["data"].data_ptr(),
+                                     None, net._result.data_ptr(), 1, ws.data_ptr(), pl.stream()))
+    loss, ca, cnz, nnz = net._fetch_metrics()
+    assert abs(loss - so.result["loss"]) < tol * abs(so.result["loss"])
+    assert (int(ca), int(cnz), int(nnz)) == (so.result["n_correct_all"], so.result["n_correct_nz"], so.result["n_nz"])
+    lnode = name_of.index("conv2")
+    check("dlogits", "conv2", pl.get(pl.nodes[lnode]["grad"]), so.node_gradient("conv2"))
+    # ---------------- backward, one schedule step at a time ----------------
+    acc = net._accum
+
+    def put_draw(li):
+        L = pl.layers[li]
+        pl.view(L["draw"], full_pitch=True).zero_()       # pad channels of the tensor-core head stay zero
+        pl.put(L["draw"], so.draw(L["scope"]))
+
+    for j, s in enumerate(pl.bwd):
+        L = pl.layers[s.layer]
+        scope = L["scope"]
+        if s.kind == 0:                                   # BN (+ReLU, +merge) backward
+            pl.put(pl.nodes[s.node_a]["grad"], so.node_gradient(name_of[s.node_a]))
+            if s.node_b >= 0:
+                pl.view(pl.nodes[s.node_b]["grad"]).zero_()
+        elif s.kind == 1:                                 # filter gradient
+            put_draw(s.layer)
+        else:                                             # input gradient
+            put_draw(s.layer)
+            pl.view(pl.nodes[s.node_a]["grad"]).zero_()
+        _capi.check(lib.urn_backward_range(h, params, grads, 0, ws.data_ptr(), j, j + 1, pl.stream()))
+        torch.cuda.synchronize()
+        if s.kind == 0:
+            check("bn_bwd_draw", scope, pl.get(L["draw"]), so.draw(scope))
+            check("dbeta", scope, acc[L["b_off"]:L["b_off"] + L["cout"]].double().cpu().numpy(), so.bn[scope]["dbeta"].numpy())
+            if s.layer2 >= 0:
+                L2 = pl.layers[s.layer2]
+                check("bn_bwd_draw", L2["scope"], pl.get(L2["draw"]), so.draw(L2["scope"]))
+                check("dbeta", L2["scope"], acc[L2["b_off"]:L2["b_off"] + L2["cout"]].double().cpu().numpy(),
+                      so.bn[L2["scope"]]["dbeta"].numpy())
+            if s.node_b >= 0:
+                check("identity_shortcut_grad", scope, pl.get(pl.nodes[s.node_b]["grad"]),
+                      so.masked_gradient(scope[:-len("/resnet_conv2")]))
+        elif s.kind == 1:
+            want = so.dw[scope].numpy()
+            got = acc[L["w_off"]:L["w_off"] + want.size].double().cpu().numpy().reshape(want.shape)
+            check("wgrad", scope, got, want)
+        else:
+            check("dgrad", scope, pl.get(pl.nodes[s.node_a]["grad"]), so.input_gradient(scope))
+    print("\nteacher-forced %s %s B=%d F=%d S=%d: worst per-step deviation from the fp64 oracle (tolerance %.0e)"
+          % (dtype, "x".join(map(str, dims[:-1])), B, F, St, tol))
+    for k in sorted(worst):
+        print("   %-24s %.2e" % (k, worst[k]))
+    assert {"conv_fwd", "bn_apply", "merge", "bn_bwd_draw", "dbeta", "wgrad", "dgrad", "identity_shortcut_grad", "dlogits"} <= set(worst)
+    return worst
+
+
+@pytest.mark.parametrize("dtype", ["mix16", "f32"])
+def test_teacher_forced_2d(dtype):
+    run_teacher_forced([128, 128, 1], 2, 16, 5, dtype)
+
+
+@pytest.mark.parametrize("dtype", ["mix16", "f32"])
+def test_teacher_forced_3d(dtype):
+    run_teacher_forced([32, 32, 32, 1], 1, 16, 5, dtype)
+
+
+# --------------------------------------------------------------------------------------------
+# end-to-end gradients: tolerance derived from the oracle's own sensitivity
+# --------------------------------------------------------------------------------------------
+SLACK = 3.0      # mix16 rounds activations (fp16), filters (fp16 / bf16) AND gradients (bf16, 2^-9) in
+                 # every layer; the sensitivity run perturbs the parameters alone by 2^-11
+
+
+@pytest.mark.parametrize("dims,B,F,St", [([64, 64, 1], 2, 16, 4), ([32, 32, 32, 1], 1, 8, 3)])
+def test_end_to_end_gradients_mix16_within_oracle_sensitivity(dims, B, F, St):
+    P, data, label, weight, shaped = make_case(dims, B, F, St, 99, 5)
+    ref = O.run(P, *shaped, base=F, num_strides=St)
+    sens = gradient_sensitivity(P, *shaped, base=F, num_strides=St, eps=2.0 ** -11, draws=3, ref=ref)
+    net = make_net(dims, F, St, "mix16")
+    net.set_variables(P)
+    net.zero_gradients(None)
+    res, _ = net.accum_gradients(None, data, label, weight)
+    lg = net.logits(B).cpu().numpy()
+    assert relerr(lg, ref["logits"]) < 2e-2 and abs(res[1] - ref["loss"]) < 2e-2 * abs(ref["loss"])
+    g = net.get_variables("grads")
+    e = {k: relerr(g[k], ref["grads"][k]) for k in g}
+    med = float(np.median(list(e.values())))
+    print("\nmix16 end-to-end gradient deviation: median %.2e worst %.2e | oracle sensitivity at 2^-11: median %.2e worst %.2e"
+          % (med, max(e.values()), sens["median"], sens["worst"]))
+    assert med < SLACK * sens["median"]
+    for k in g:
+        assert e[k] < SLACK * max(sens["grads"][k], sens["median"]), (k, e[k], sens["grads"][k])
+
+
+# --------------------------------------------------------------------------------------------
+# BASELINE sizes against the fp64 oracle
+# --------------------------------------------------------------------------------------------
+_ORACLE_CACHE = {}
+
+
+def baseline_size_check(dims, B, dtype):
+    F, St = 16, 5
+    P, data, label, weight, shaped = make_case(dims, B, F, St, 1234, 4321)
+    key = (tuple(dims), B)
+    if key not in _ORACLE_CACHE:
+        _ORACLE_CACHE.clear()
+        _ORACLE_CACHE[key] = O.run(P, *shaped, base=F, num_strides=St)
+    ref = _ORACLE_CACHE[key]
+    net = make_net(dims, F, St, dtype)
+    net.set_variables(P)
+    net.zero_gradients(None)
+    res, _ = net.accum_gradients(None, data, label, weight)
+    tol = TOL[dtype]
+    lg = net.logits(B).cpu().numpy()
+    e_lg = relerr(lg, ref["logits"])
+    nz = data.reshape(B, -1) > 0
+    pa = lg.reshape(B, -1, 3).argmax(-1)[nz]
+    pb = ref["logits"].reshape(B, -1, 3).argmax(-1)[nz]
+    agree = float((pa == pb).mean())
+    g = net.get_variables("grads")
+    e = {k: relerr(g[k], ref["grads"][k]) for k in g}
+    print("\nBASELINE-size %s %s B=%d: logits %.2e loss %.6f (oracle %.6f) argmax agreement on nonzero pixels %.5f; "
+          "gradients median %.2e worst %.2e" % (dtype, "x".join(map(str, dims[:-1])), B, e_lg, res[1], ref["loss"], agree,
+                                                float(np.median(list(e.values()))), max(e.values())))
+    assert len(g) == 116
+    assert e_lg < tol and abs(res[1] - ref["loss"]) < tol * abs(ref["loss"])
+    assert agree >= 0.999
+    assert abs(res[3] - ref["acc_nonzero"]) < 2e-3 and abs(res[2] - ref["acc_all"]) < 2e-3
+    if dtype == "f32":
+        for k in g:
+            assert e[k] < tol, (k, e[k])
+    return ref, e
+
+
+@pytest.mark.parametrize("dtype", ["f32", "mix16"])
+def test_baseline_size_2d_512(dtype):
+    """BASELINE configs[0]/[1] geometry: 512x512, F=16, S=5, weighted CE, batch 2."""
+    baseline_size_check([512, 512, 1], 2, dtype)
+
+
+@pytest.mark.parametrize("dtype", ["f32", "mix16"])
+def test_baseline_size_3d_64(dtype):
+    """The 3D default topology (F=16, S=5: 27-tap halo kernels with N = 3C depth concatenation, 8-class
+    conv-transposes) end to end against the oracle at 64^3 (192^3 autograd does not fit the host)."""
+    baseline_size_check([64, 64, 64, 1], 1, dtype)
+
+
+# --------------------------------------------------------------------------------------------
+# training trajectory
+# --------------------------------------------------------------------------------------------
+def test_training_trajectory():
+    """30 steps of zero / accumulate / Adam (lib/ssnet_trainval.py:164-191 with NUM_MINIBATCHES = 1)
+    on a fixed batch: the f32 and mix16 loss curves stay within 2 % of the oracle's (fp64 forward +
+    autograd, TF-Adam in fp32 like TF) at every step, and the loss goes down."""
+    dims, B, F, St, steps, lr = [64, 64, 1], 2, 8, 3, 30, 1e-3
+    P0, data, label, weight, shaped = make_case(dims, B, F, St, 77, 13)
+    # oracle trajectory
+    P = {k: v.copy() for k, v in P0.items()}
+    m = {k: np.zeros_like(v) for k, v in P.items()}
+    v = {k: np.zeros_like(vv) for k, vv in P.items()}
+    want = []
+    for t in range(1, steps + 1):
+        r = O.run(P, *shaped, base=F, num_strides=St)
+        want.append(r["loss"])
+        for k in P:
+            O.adam_tf(P[k], r["grads"][k].astype(np.float32), m[k], v[k], t, lr=lr)
+    curves = {}
+    for dtype in ("f32", "mix16"):
+        net = make_net(dims, F, St, dtype, lr=lr)
+        net.set_variables(P0)
+        got = []
+        for _ in range(steps):
+            net.zero_gradients(None)
+            res, _ = net.accum_gradients(None, data, label, weight)
+            net.apply_gradients(None)
+            got.append(float(res[1]))
+        curves[dtype] = got
+    want = np.array(want)
+    for dtype, got in curves.items():
+        dev = np.abs(np.array(got) - want) / want
+        print("\ntrajectory %s: loss %.5f -> %.5f (oracle %.5f -> %.5f), max deviation %.2e" %
+              (dtype, got[0], got[-1], want[0], want[-1], dev.max()))
+        assert dev.max() < 2e-2, (dtype, dev.max())
+        assert dev[0] < TOL[dtype]
+    assert want[-1] < want[0] and curves["mix16"][-1] < curves["mix16"][0]
+
+
+# --------------------------------------------------------------------------------------------
+# data-parallel overlap machinery on one GPU
+# --------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("nmb", [2, 5])
+def test_dp_graph_replay_records_events(nmb, monkeypatch):
+    """With NUM_MINIBATCHES > 1 only the LAST minibatch of a step passes the per-layer ready events
+    to urn_backward (dp.GradientExchange.events_array).  The CUDA graph of the loss+backward sequence
+    is captured on the third call for a key; before the fix that call could be a non-final minibatch,
+    whose capture holds no event-record nodes, and its replay for the final minibatch left the events
+    un-recorded: the bucket all-reduces then started while backward was still accumulating.  Checked
+    on one GPU with a forced one-rank exchange: (a) the communication stream cannot finish before the
+    backward pass of the final minibatch has produced conv0's gradients, in eager and in replayed
+    steps alike; (b) graphs on / off give bit-identical parameters."""
+    import torch.distributed as dist
+    from uresnet_b200 import dp
+    if not dist.is_initialized():
+        monkeypatch.setenv("MASTER_ADDR", "127.0.0.1")
+        monkeypatch.setenv("MASTER_PORT", str(29500 + os.getpid() % 2000))
+        dist.init_process_group("nccl", rank=0, world_size=1, device_id=torch.device("cuda", 0))
+    dims, B, F, St = [128, 128, 1], 4, 16, 3
+    P, data, label, weight, _ = make_case(dims, B, F, St, 3, 4)
+    d_dev, l_dev, w_dev = (torch.from_numpy(a).cuda() for a in (data, label, weight))
+    out = {}
+    for graphs in ("1", "0"):
+        monkeypatch.setenv("URESNET_B200_DP_GRAPH", graphs)
+        net = make_net(dims, F, St, "mix16", lr=1e-3)
+        net.set_variables(P)
+        ex = dp.attach(net, force=True)
+        ex.expected_minibatches = nmb
+        assert ex.active
+        ratios = []
+        for step in range(6):
+            net.zero_gradients(None)
+            for j in range(nmb):
+                last = j == nmb - 1
+                if last:
+                    t0, t_bwd, t_comm = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+                    t0.record()
+                net.accum_gradients(None, d_dev, l_dev, w_dev, fetch=False)
+                if last:
+                    t_bwd.record()
+                    t_comm.record(ex.comm_stream)        # behind the bucket all-reduces
+            net.apply_gradients(None)
+            torch.cuda.synchronize()
+            ratios.append(t0.elapsed_time(t_comm) / t0.elapsed_time(t_bwd))
+        if graphs == "1":
+            assert any(k[0] == "bwd" and k[-1] for k in net._graphs) and any(k[0] == "bwd" and not k[-1] for k in net._graphs)
+        # the last bucket waits for conv0's filter gradient, the final kernel of the backward pass
+        assert min(ratios) > 0.9, ratios
+        out[graphs] = net._params.clone()
+    assert torch.equal(out["0"], out["1"])

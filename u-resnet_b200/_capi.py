@@ -33,7 +33,17 @@ class urn_net_cfg(C.Structure):
                 ("training", C.c_int32)]
 
 
+class urn_tensor_ref(C.Structure):
+    _fields_ = [("off_bytes", C.c_int64), ("ld", C.c_int64), ("rows", C.c_int64), ("c", C.c_int32),
+                ("dtype", C.c_int32)]
+
+
+class urn_step_info(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("kind", "layer", "layer2", "node_a", "node_b", "relu", "accumulate")]
+
+
 _vp, _i, _i64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float
+_tref = C.POINTER(urn_tensor_ref)
 _descp = C.POINTER(urn_conv_desc)
 
 # name -> (restype, argtypes); must list every symbol declared in include/uresnet_b200.h
@@ -75,6 +85,14 @@ SIGNATURES = {
     "urn_check_labels": (_i, [_vp, _vp, _vp]),
     "urn_decision": (_i, [_vp, _vp, C.c_float, _vp, _vp, _vp]),
     "urn_ssnet_decision": (_i, [_vp, _i64, _i64, _i, _vp, _i64, C.c_float, _vp, _vp]),
+    "urn_plan_counts": (_i, [_vp, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),
+    "urn_node_info": (_i, [_vp, _i, C.POINTER(C.c_char_p), _tref, _tref, _tref]),
+    "urn_layer_tensors": (_i, [_vp, _i, _tref, _tref, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64),
+                               C.POINTER(_i), C.POINTER(_i)]),
+    "urn_fwd_step_info": (_i, [_vp, _i, C.POINTER(urn_step_info)]),
+    "urn_bwd_step_info": (_i, [_vp, _i, C.POINTER(urn_step_info)]),
+    "urn_forward_range": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp]),
+    "urn_backward_range": (_i, [_vp, _vp, _vp, _i, _vp, _i, _i, _vp]),
     "urn_launch_count": (_i64, []),
     "urn_profile_enable": (_i, [_vp, _i]),
     "urn_profile_collect": (_i, [_vp, C.POINTER(C.c_double), C.POINTER(_i64)]),

@@ -25,6 +25,7 @@ inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
 inline int esize(int dtype) { return dtype == URN_F32 ? 4 : 2; }
 
 struct Node {
+  std::string name;  // producing scope (layer scope, module scope, "data", "concat<k>")
   int c = 0;
   int64_t rows = 0;
   int dtype = URN_F32;
@@ -155,16 +156,18 @@ struct Builder {
     return o;
   }
   bool shadow = false;
-  int new_node(int c, int64_t rows, int dtype) {
+  int new_node(const std::string& name, int c, int64_t rows, int dtype) {
     Node n;
+    n.name = name;
     n.c = c; n.rows = rows; n.dtype = dtype; n.ld = c;
     n.off = alloc(rows * c * esize(dtype));
     if (shadow && dtype == URN_F16) n.off2 = alloc(rows * c * 2);
     N.nodes.push_back(n);
     return (int)N.nodes.size() - 1;
   }
-  int new_view(int parent, int choff, int c) {
+  int new_view(const std::string& name, int parent, int choff, int c) {
     Node n = N.nodes[parent];
+    n.name = name;
     n.parent = parent; n.choff = choff; n.c = c;
     n.off = N.nodes[parent].off + (int64_t)choff * esize(n.dtype);
     if (n.off2 >= 0) n.off2 = N.nodes[parent].off2 + (int64_t)choff * 2;
@@ -227,6 +230,11 @@ static int build_plan(urn_net& N) {
   N.TA = c.dtype;                                   // activations (and filter operands)
   N.TG = c.dtype == URN_F16 ? URN_BF16 : c.dtype;   // gradients keep the fp32 exponent range
   URN_CHECK((int64_t)c.base_filters << c.num_strides <= 1024, "urn_create: widest layer > 1024 channels");
+  // the decoder scope is hard-coded resnet_module(step+5) (uresnet.py:100): with more than 5
+  // strides encoder and decoder modules would share variable names (TF raises a duplicate-variable
+  // error when the reference builds such a graph)
+  URN_CHECK(c.num_strides <= 5, "urn_create: num_strides > 5 makes encoder and decoder share the variable scope "
+            "resnet_module%d (decoder scopes are step+5, uresnet.py:100)", 5);
   N.nd = c.nd;
   if (c.nd == 2) { N.sp[0] = 1; N.sp[1] = c.spatial[0]; N.sp[2] = c.spatial[1]; }
   else { N.sp[0] = c.spatial[0]; N.sp[1] = c.spatial[1]; N.sp[2] = c.spatial[2]; }
@@ -238,7 +246,7 @@ static int build_plan(urn_net& N) {
   struct Cur { int node; int sp[3]; int ch; };
   int sp0[3] = {N.sp[0], N.sp[1], N.sp[2]};
   const int64_t rows0 = (int64_t)B * sp0[0] * sp0[1] * sp0[2];
-  N.data_node = b.new_node(c.in_channels, rows0, T);
+  N.data_node = b.new_node("data", c.in_channels, rows0, T);
 
   // Spatial dims per encoder level (level 0 = full resolution) so that the concat
   // buffers of the decoder can be allocated before their two producers run.
@@ -255,12 +263,13 @@ static int build_plan(urn_net& N) {
   std::vector<int> znode(S, -1);
   for (int lv = 0; lv < S; ++lv) {
     int64_t rows = (int64_t)B * lvl_sp[lv][0] * lvl_sp[lv][1] * lvl_sp[lv][2];
-    znode[lv] = b.new_node(2 * (F << lv), rows, T);
+    znode[lv] = b.new_node("concat" + std::to_string(S - 1 - lv), 2 * (F << lv), rows, T);   // 'after concat%d' (uresnet.py:94)
   }
   // where the output of encoder level lv lives: slice [C,2C) of z[lv]; bottom is plain
   auto enc_out_node = [&](int lv, int64_t rows) -> int {
-    if (lv < S) return b.new_view(znode[lv], F << lv, F << lv);
-    return b.new_node(F << lv, rows, T);
+    const std::string name = lv == 0 ? std::string("conv0") : "resnet_module" + std::to_string(lv - 1) + "/module2";
+    if (lv < S) return b.new_view(name, znode[lv], F << lv, F << lv);
+    return b.new_node(name, F << lv, rows, T);
   };
 
   auto conv_bn = [&](const std::string& scope, bool tr, int in_node, const int isp[3], int cin,
@@ -290,10 +299,10 @@ static int build_plan(urn_net& N) {
       m.sc = conv_bn(scope + "/shortcut", false, in_node, isp, cin, cout, 1, stride, tmp);
     m.c1 = conv_bn(scope + "/resnet_conv1", false, in_node, isp, cin, cout, 3, stride, osp);
     int64_t rows = N.layers[m.c1].rows_out;
-    m.mid_node = b.new_node(cout, rows, T);
+    m.mid_node = b.new_node(scope + "/resnet_conv1", cout, rows, T);
     apply(m.c1, m.mid_node, 0);                                   // BN only (no ReLU) :43-51
     m.c2 = conv_bn(scope + "/resnet_conv2", false, m.mid_node, osp, cout, cout, 3, 1, tmp);
-    m.out_node = out_node_or_neg >= 0 ? out_node_or_neg : b.new_node(cout, rows, T);
+    m.out_node = out_node_or_neg >= 0 ? out_node_or_neg : b.new_node(scope, cout, rows, T);
     N.fwd.push_back({F_MERGE, m.c2, m.sc, m.sc < 0 ? in_node : -1, m.out_node, 1});  // :68
     mods.push_back(m);
     recs.push_back({1, (int)mods.size() - 1});
@@ -332,7 +341,7 @@ static int build_plan(urn_net& N) {
     char sc[32];
     snprintf(sc, sizeof sc, "deconv%d", s);
     int ld = conv_bn(sc, true, net, cur_sp, ch, ch / 2, 3, 2, osp);
-    int u = b.new_view(znode[lv], 0, ch / 2);      // deconv channels first
+    int u = b.new_view(sc, znode[lv], 0, ch / 2);      // deconv channels first
     apply(ld, u, 1);
     recs.push_back({0, ld});
     cur_sp[0] = osp[0]; cur_sp[1] = osp[1]; cur_sp[2] = osp[2];
@@ -341,11 +350,11 @@ static int build_plan(urn_net& N) {
   }
   // ---- heads (uresnet.py:103-121) ----
   int l1 = conv_bn("conv1", false, net, cur_sp, ch, F, 3, 1, osp);
-  int a1 = b.new_node(F, rows0, T);
+  int a1 = b.new_node("conv1", F, rows0, T);
   apply(l1, a1, 1);
   recs.push_back({0, l1});
   int l2 = conv_bn("conv2", false, a1, cur_sp, F, c.num_class, 3, 1, osp);
-  N.logits_node = b.new_node(c.num_class, rows0, URN_F32);
+  N.logits_node = b.new_node("conv2", c.num_class, rows0, URN_F32);
   apply(l2, N.logits_node, 0);
   recs.push_back({0, l2});
 
@@ -693,10 +702,9 @@ int run_conv_fwd(urn_net* h, int li, const float* params, void* ws, cudaStream_t
 
 }  // namespace
 
-extern "C" int urn_forward(urn_net* h, const float* params, const float* data, void* ws,
-                           void* stream) {
-  URN_CHECK(h && params && data && ws, "urn_forward: null argument");
-  cudaStream_t st = (cudaStream_t)stream;
+// input conversion + per-step filter rounding / packing (everything urn_forward does before the
+// first layer)
+static int forward_prologue(urn_net* h, const float* params, const float* data, void* ws, cudaStream_t st) {
   {
     ProfScope ps(h, 0, PH_MISC, st);
     const Node& dn = h->nodes[h->data_node];
@@ -741,7 +749,12 @@ extern "C" int urn_forward(urn_net* h, const float* params, const float* data, v
       if (flush()) return 1;
     }
   }
-  for (const FStep& s : h->fwd) {
+  return 0;
+}
+
+static int forward_steps(urn_net* h, const float* params, void* ws, int first, int last, cudaStream_t st) {
+  for (int si = first; si < last; ++si) {
+    const FStep& s = h->fwd[si];
     const Layer& L = h->layers[s.layer];
     if (s.kind == F_CONV) {
       if (run_conv_fwd(h, s.layer, params, ws, st)) return 1;
@@ -774,6 +787,23 @@ extern "C" int urn_forward(urn_net* h, const float* params, const float* data, v
     }
   }
   return 0;
+}
+
+extern "C" int urn_forward(urn_net* h, const float* params, const float* data, void* ws,
+                           void* stream) {
+  URN_CHECK(h && params && data && ws, "urn_forward: null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (forward_prologue(h, params, data, ws, st)) return 1;
+  return forward_steps(h, params, ws, 0, (int)h->fwd.size(), st);
+}
+
+extern "C" int urn_forward_range(urn_net* h, const float* params, const float* data, void* ws,
+                                 int first, int last, void* stream) {
+  URN_CHECK(h && params && ws, "urn_forward_range: null argument");
+  URN_CHECK(first >= 0 && first <= last && last <= (int)h->fwd.size(), "urn_forward_range: bad step range [%d,%d)", first, last);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (data && forward_prologue(h, params, data, ws, st)) return 1;
+  return forward_steps(h, params, ws, first, last, st);
 }
 
 extern "C" int urn_loss_metrics(urn_net* h, const float* label, const float* weight,
@@ -818,10 +848,8 @@ extern "C" int urn_check_labels(urn_net* h, void* ws, void* stream) {
   return 0;
 }
 
-extern "C" int urn_backward(urn_net* h, const float* params, float* grads, int accumulate, void* ws,
-                            void* const* ready_events, void* stream) {
-  URN_CHECK(h && params && grads && ws, "urn_backward: null argument");
-  URN_CHECK(h->cfg.training, "urn_backward: handle was created with training=0");
+static int backward_steps(urn_net* h, const float* params, float* grads, int accumulate, void* ws,
+                          void* const* ready_events, int first, int last, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   const int T = h->TG;   // all gradient tensors (node gradients, d(raw)) use the gradient dtype
   auto gptr = [&](const Node& n) -> char* {
@@ -831,7 +859,8 @@ extern "C" int urn_backward(urn_net* h, const float* params, float* grads, int a
   cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
   cudaStreamIsCapturing(st, &cap);
   const bool capturing = cap == cudaStreamCaptureStatusActive;
-  for (const BStep& s : h->bwd) {
+  for (int si = first; si < last; ++si) {
+    const BStep& s = h->bwd[si];
     const Layer& L = h->layers[s.layer];
     ProfScope ps(h, s.layer, s.kind == B_BN ? PH_BNBWD : (s.kind == B_WGRAD ? PH_WGRAD : PH_DGRAD), st);
     if (s.kind == B_BN) {
@@ -925,6 +954,82 @@ extern "C" int urn_backward(urn_net* h, const float* params, float* grads, int a
                                         capturing ? cudaEventRecordExternal : cudaEventRecordDefault));
     }
   }
+  return 0;
+}
+
+extern "C" int urn_backward(urn_net* h, const float* params, float* grads, int accumulate, void* ws,
+                            void* const* ready_events, void* stream) {
+  URN_CHECK(h && params && grads && ws, "urn_backward: null argument");
+  URN_CHECK(h->cfg.training, "urn_backward: handle was created with training=0");
+  return backward_steps(h, params, grads, accumulate, ws, ready_events, 0, (int)h->bwd.size(), stream);
+}
+
+extern "C" int urn_backward_range(urn_net* h, const float* params, float* grads, int accumulate, void* ws,
+                                  int first, int last, void* stream) {
+  URN_CHECK(h && params && grads && ws, "urn_backward_range: null argument");
+  URN_CHECK(h->cfg.training, "urn_backward_range: handle was created with training=0");
+  URN_CHECK(first >= 0 && first <= last && last <= (int)h->bwd.size(), "urn_backward_range: bad step range [%d,%d)", first, last);
+  return backward_steps(h, params, grads, accumulate, ws, nullptr, first, last, stream);
+}
+
+// ---------------- plan introspection (parity hooks) ----------------
+extern "C" int urn_plan_counts(const urn_net* h, int* n_nodes, int* n_fwd_steps, int* n_bwd_steps) {
+  URN_CHECK(h, "urn_plan_counts: null handle");
+  if (n_nodes) *n_nodes = (int)h->nodes.size();
+  if (n_fwd_steps) *n_fwd_steps = (int)h->fwd.size();
+  if (n_bwd_steps) *n_bwd_steps = (int)h->bwd.size();
+  return 0;
+}
+static void no_tensor(urn_tensor_ref* t) { if (t) { t->off_bytes = -1; t->ld = 0; t->rows = 0; t->c = 0; t->dtype = URN_F32; } }
+extern "C" int urn_node_info(const urn_net* h, int node, const char** name, urn_tensor_ref* value,
+                             urn_tensor_ref* shadow, urn_tensor_ref* grad) {
+  URN_CHECK(h && node >= 0 && node < (int)h->nodes.size(), "urn_node_info: bad index");
+  const Node& n = h->nodes[node];
+  if (name) *name = n.name.c_str();
+  if (value) { value->off_bytes = n.off; value->ld = n.ld; value->rows = n.rows; value->c = n.c; value->dtype = n.dtype; }
+  no_tensor(shadow);
+  if (shadow && n.off2 >= 0) { shadow->off_bytes = n.off2; shadow->ld = n.ld; shadow->rows = n.rows; shadow->c = n.c; shadow->dtype = URN_BF16; }
+  no_tensor(grad);
+  if (grad && n.gbuf >= 0 && h->cfg.training) {
+    grad->off_bytes = h->arena_off + h->gbufs[n.gbuf].off + (int64_t)n.choff * esize(h->TG);
+    grad->ld = n.ld; grad->rows = n.rows; grad->c = n.c; grad->dtype = h->TG;
+  }
+  return 0;
+}
+extern "C" int urn_layer_tensors(const urn_net* h, int layer, urn_tensor_ref* raw, urn_tensor_ref* draw,
+                                 int64_t* stats_off_bytes, int64_t* w_off, int64_t* b_off, int* in_node,
+                                 int* out_node) {
+  URN_CHECK(h && layer >= 0 && layer < (int)h->layers.size(), "urn_layer_tensors: bad index");
+  const Layer& L = h->layers[layer];
+  if (raw) { raw->off_bytes = L.raw_off; raw->ld = L.cout; raw->rows = L.rows_out; raw->c = L.cout; raw->dtype = URN_F32; }
+  no_tensor(draw);
+  if (draw && L.draw_gbuf >= 0) {
+    draw->off_bytes = h->arena_off + h->gbufs[L.draw_gbuf].off;
+    draw->ld = L.cpad ? L.cpad : L.cout; draw->rows = L.rows_out; draw->c = L.cout; draw->dtype = h->TG;
+  }
+  if (stats_off_bytes) *stats_off_bytes = L.stats_off;
+  if (w_off) *w_off = L.w_off;
+  if (b_off) *b_off = L.b_off;
+  if (in_node) *in_node = L.in_node;
+  if (out_node) *out_node = L.out_node;
+  return 0;
+}
+extern "C" int urn_fwd_step_info(const urn_net* h, int step, urn_step_info* info) {
+  URN_CHECK(h && info && step >= 0 && step < (int)h->fwd.size(), "urn_fwd_step_info: bad index");
+  const FStep& s = h->fwd[step];
+  info->kind = (int)s.kind; info->layer = s.layer; info->layer2 = s.kind == F_MERGE ? s.layer_sc : -1;
+  info->node_a = s.kind == F_CONV ? h->layers[s.layer].in_node : s.out_node;
+  info->node_b = s.kind == F_MERGE ? s.res_node : -1;
+  info->relu = s.relu; info->accumulate = 0;
+  return 0;
+}
+extern "C" int urn_bwd_step_info(const urn_net* h, int step, urn_step_info* info) {
+  URN_CHECK(h && info && step >= 0 && step < (int)h->bwd.size(), "urn_bwd_step_info: bad index");
+  const BStep& s = h->bwd[step];
+  info->kind = (int)s.kind; info->layer = s.layer; info->layer2 = s.kind == B_BN ? s.layer2 : -1;
+  info->node_a = s.kind == B_BN ? s.dout_node : h->layers[s.layer].in_node;
+  info->node_b = s.kind == B_BN ? s.dres_node : -1;
+  info->relu = s.relu; info->accumulate = s.accumulate;
   return 0;
 }
 

@@ -43,12 +43,18 @@ def plan_buckets(layer_ranges, bucket_elems):
 
 class GradientExchange(object):
 
-    def __init__(self, param_table, num_layers, flat, group=None, bucket_mb=16.0, average=False):
+    def __init__(self, param_table, num_layers, flat, group=None, bucket_mb=16.0, average=False,
+                 force=False):
         """param_table: OrderedDict name -> (shape, offset, count) in creation order (two
-        entries per layer: weights, beta); flat: the flat gradient accumulator tensor."""
+        entries per layer: weights, beta); flat: the flat gradient accumulator tensor.
+        ``force``: run the event / side-stream protocol even in a group of one rank (tests of the
+        overlap machinery on a single GPU; the all-reduce of a one-rank group is the identity)."""
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.active = self.world > 1 or (bool(force) and dist.is_initialized())
         self.average = bool(average)
+        self.time_finish = False          # record CUDA events around finish(): exposed all-reduce time
+        self._finish_events = []
         self.flat = flat
         items = list(param_table.values())
         assert len(items) == 2 * num_layers
@@ -80,7 +86,7 @@ class GradientExchange(object):
     def events_array(self):
         """Event array for urn_backward, or None when this backward is not the last
         minibatch of the step (gradients are still being accumulated locally)."""
-        if self.world == 1 or not self.cuda:
+        if not self.active or not self.cuda:
             return None
         return self._ev_array if self._seen + 1 >= self.expected_minibatches else None
 
@@ -88,7 +94,7 @@ class GradientExchange(object):
         """Called right after urn_backward returned (work is only enqueued): launch every
         bucket's all-reduce on the communication stream behind that bucket's events."""
         self._seen += 1
-        if self.world == 1 or not self.cuda or self._seen < self.expected_minibatches:
+        if not self.active or not self.cuda or self._seen < self.expected_minibatches:
             return
         for lo, hi, layers in self.buckets:
             for l in layers:
@@ -101,8 +107,12 @@ class GradientExchange(object):
     def finish(self, flat=None):
         """Before the optimizer: make the compute stream wait for the exchange (or run it
         now if it was not overlapped)."""
-        if self.world == 1:
+        if not self.active:
             return
+        timed = self.time_finish and self.cuda
+        if timed:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()                   # compute stream: backward has been enqueued up to here
         if not self._launched:
             for lo, hi, _ in self.buckets:
                 self._works.append(dist.all_reduce(self.flat[lo:hi], op=dist.ReduceOp.SUM,
@@ -113,6 +123,19 @@ class GradientExchange(object):
         self._launched = False
         if self.average:
             self.flat.mul_(1.0 / self.world)
+        if timed:
+            e1.record()                   # compute stream resumes here: e1 - e0 = exposed exchange time
+            self._finish_events.append((e0, e1))
+
+    def exposed_ms(self):
+        """Mean milliseconds the compute stream waited for the exchange per step since the last
+        call (needs ``time_finish``; synchronises)."""
+        if not self._finish_events:
+            return None
+        torch.cuda.synchronize()
+        ms = [a.elapsed_time(b) for a, b in self._finish_events]
+        self._finish_events = []
+        return sum(ms) / len(ms)
 
     def allreduce_scalars(self, values):
         """Sum a small list of python floats over ranks (loss / accuracy counters)."""
@@ -123,10 +146,10 @@ class GradientExchange(object):
         return [float(v) for v in t.cpu()]
 
 
-def attach(net, group=None, bucket_mb=16.0, average=False):
+def attach(net, group=None, bucket_mb=16.0, average=False, force=False):
     """Give a constructed, trainable ``uresnet`` a gradient exchange over ``group``."""
     ex = GradientExchange(net._param_table, net._num_layers, net._accum, group=group,
-                          bucket_mb=bucket_mb, average=average)
+                          bucket_mb=bucket_mb, average=average, force=force)
     net._exchange = ex
     return ex
 

@@ -108,6 +108,7 @@ class ssnet_base(object):
         self._side_pending = []
         self._step_start = None
         self._exchange = None              # set by dp.attach(): gradient allreduce hook
+        self._last_handle = None           # (handle, workspace) of the last loss call
         self._constructed = True
 
     # --------------------------------------------------------------- variables
@@ -315,6 +316,7 @@ class ssnet_base(object):
                              dtype=torch.float32, device=self._device)
         lab = feed.get("label")
         wgt = feed.get("weight") if self._use_weight else None
+        self._last_handle = (h, ws)
         _capi.check(self._lib.urn_loss_metrics(
             h, lab.data_ptr() if lab is not None else None,
             wgt.data_ptr() if wgt is not None else None, feed["data"].data_ptr(),
@@ -328,7 +330,14 @@ class ssnet_base(object):
         torch.cuda.current_stream(self._device).synchronize()
         loss, ca, cnz, nnz = (float(v) for v in self._result_host)
         if math.isnan(loss):
-            raise ValueError("label out of range [0, %d) (or non-finite logits)" % self._num_class)
+            # two causes: a label outside [0, num_class) (the loss kernel raises a device flag and
+            # poisons the loss; TF-CPU raises, TF-GPU yields NaN) or a genuinely diverged run
+            # (non-finite logits / weights), which TF reports as a NaN loss and so does this
+            if self._last_handle is not None:
+                h, ws = self._last_handle
+                if self._lib.urn_check_labels(h, ws.data_ptr(), self._stream()) != 0:
+                    raise ValueError("label out of range [0, %d)" % self._num_class)
+            # diverged run: like TF, hand the NaN back to the caller
         return loss, ca, cnz, nnz
 
     def _metrics(self, batch):
@@ -362,8 +371,12 @@ class ssnet_base(object):
             self._loss_metrics(h, ws, feed, want_grad=True, want_softmax=False)
             _capi.check(self._lib.urn_backward(h, self._params.data_ptr(), self._accum.data_ptr(), 1,
                                                ws.data_ptr(), events, self._stream()))
+        # `events is not None` is part of the key: the capture of the last minibatch of a
+        # data-parallel step holds the external per-layer event-record nodes, the capture of the
+        # other minibatches (NUM_MINIBATCHES > 1) must not be replayed in its place
         key = ("bwd", batch, feed["data"].data_ptr(), feed["label"].data_ptr(),
-               feed["weight"].data_ptr() if (self._use_weight and "weight" in feed) else 0, ws.data_ptr())
+               feed["weight"].data_ptr() if (self._use_weight and "weight" in feed) else 0, ws.data_ptr(),
+               events is not None)
         self._graphed(key, loss_and_backward, dp_safe=os.environ.get("URESNET_B200_DP_GRAPH", "1") != "0")
         if self._exchange is not None:
             self._exchange.backward_enqueued()

@@ -14,8 +14,10 @@ replaced because it cannot exist here:
                             ``data_example`` for 2D, ssnet.py:81-89) when ``tensorboard`` is
                             importable, plus a ``scalars.jsonl`` copy of the scalars
   * larcv output        -> ``.npz`` per analysed batch next to ``ANA_OUTPUT_CONFIG``
-Under ``torch.distributed`` (one process per GPU) the minibatch is sharded by rank and the
-gradient accumulators are all-reduced (``dp.GradientExchange``) before Adam.
+Under ``torch.distributed`` (one process per GPU) every rank draws its own ``MINIBATCH_SIZE``
+batch per minibatch (global batch = world x MINIBATCH_SIZE x NUM_MINIBATCHES) and the gradient
+accumulators are all-reduced (SUM, ``dp.GradientExchange``) before Adam: the reference's
+``NUM_MINIBATCHES`` accumulation spread over ranks (ssnet.py:76-79).
 """
 from __future__ import annotations
 

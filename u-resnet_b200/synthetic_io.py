@@ -60,7 +60,9 @@ def make_batch(batch, dims, seed, num_class=3):
     spatial = tuple(int(d) for d in dims[:-1])
     if int(dims[-1]) != 1:
         raise NotImplementedError("synthetic source produces single-channel events")
-    rng = np.random.Generator(np.random.PCG64(int(seed)))
+    # seed: an int, or a sequence (seed, rank, step) hashed by SeedSequence into non-overlapping
+    # streams (consecutive ints as PCG64 seeds would make rank r replay rank r+1's batches)
+    rng = np.random.Generator(np.random.PCG64(np.random.SeedSequence(seed) if not np.isscalar(seed) else int(seed)))
     P = int(np.prod(spatial))
     data = np.empty((batch, P), np.float32)
     label = np.empty((batch, P), np.float32)
@@ -94,7 +96,9 @@ class synthetic_threadio(object):
     ``configure`` accepts the reference's ``{'filler_name','verbosity','filler_cfg'}``
     dict plus the synthetic-only keys ``dims`` (e.g. ``[512,512,1]``), ``seed``,
     ``rank`` and the three stream keywords.  Batch ``i`` of rank ``r`` is drawn from
-    ``PCG64(seed + 1000*r + i)``.
+    ``PCG64(SeedSequence([seed, r, i]))``: streams of different ranks / steps / seeds never
+    overlap.  Every rank draws a full ``MINIBATCH_SIZE`` batch (the global batch is
+    ``world * MINIBATCH_SIZE``, the reference's ``NUM_MINIBATCHES = world`` accumulation).
     """
 
     def __init__(self):
@@ -106,7 +110,8 @@ class synthetic_threadio(object):
     def configure(self, cfg):
         self._cfg = dict(cfg)
         self._dims = [int(v) for v in self._cfg.get("dims", [512, 512, 1])]
-        self._seed = int(self._cfg.get("seed", 1234)) + 1000 * int(self._cfg.get("rank", 0))
+        self._seed = int(self._cfg.get("seed", 1234))
+        self._rank = int(self._cfg.get("rank", 0))
         self._names = {"data": self._cfg.get("keyword_data", "data"),
                        "label": self._cfg.get("keyword_label", "label"),
                        "weight": self._cfg.get("keyword_weight", "weight")}
@@ -116,7 +121,7 @@ class synthetic_threadio(object):
 
     def next(self, store_entries=False, store_event_ids=False):
         self._step += 1
-        d, l, w = make_batch(self._batch, self._dims, self._seed + self._step)
+        d, l, w = make_batch(self._batch, self._dims, (self._seed, self._rank, self._step))
         self._cur = {self._names["data"]: (d, [self._batch] + self._dims),
                      self._names["label"]: (l, [self._batch] + self._dims[:-1] + [1]),
                      self._names["weight"]: (w, [self._batch] + self._dims[:-1] + [1])}

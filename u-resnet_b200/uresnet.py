@@ -24,6 +24,11 @@ class uresnet(ssnet_base):
         spatial, cin = dims[:-1], dims[-1]
         nd = len(spatial)
         F, S = self._base_num_outputs, self._num_strides
+        if S > 5:
+            # decoder scopes are hard-coded resnet_module(step+5) (uresnet.py:100): TF raises a
+            # duplicate-variable error for num_strides > 5
+            raise ValueError("Variable UResNet/resnet_module5/module1/shortcut/weights already exists "
+                             "(num_strides=%d > 5: decoder scopes are step+5, uresnet.py:100)" % S)
         for d in spatial:
             if d % (1 << S):
                 raise ValueError("spatial size %d is not divisible by 2^%d: the concat at "
