@@ -22,6 +22,15 @@ plan nodes the same way (``urn_node_info``), which is what lets tests/test_parit
 each of its schedule steps the oracle's tensors ("teacher forcing") and compare what the step
 produces with what is recorded here.
 
+``storage`` ("mix16" / "f32") adds, next to every chain value, the value the SAME step yields when
+its inputs are first rounded to the dtype the CUDA library stores them in (activations fp16, their
+bf16 shadow for the filter gradient, gradients bf16, raw conv outputs / statistics fp32): the
+``expected=True`` accessors.  The chain itself is never rounded -- every step is taught the fp64
+trajectory -- so a deviation between the library and ``expected`` is the arithmetic of that one
+step on identical inputs, which is what north_star's per-tensor tolerance can be asked of (sums
+that cancel, e.g. the beta gradient behind a zero-mean d(raw), amplify INPUT rounding without
+bound; see oracle/conditioning.py).
+
 ``tests/test_oracle.py`` checks that the gradients assembled from these per-step records equal the
 whole-graph autograd gradients of ``uresnet_oracle.run`` to fp64 round-off, so the two statements
 of the graph cannot drift apart.
@@ -37,6 +46,19 @@ import torch.nn.functional as F
 from . import uresnet_oracle as O
 
 
+def _rounder(tdt):
+    return lambda t: t.to(torch.float32).to(tdt).to(t.dtype)
+
+
+STORAGE = {
+    None: None,
+    "f32": dict(act=_rounder(torch.float32), shadow=_rounder(torch.float32), grad=_rounder(torch.float32)),
+    "mix16": dict(act=_rounder(torch.float16), shadow=_rounder(torch.bfloat16), grad=_rounder(torch.bfloat16)),
+    "bf16": dict(act=_rounder(torch.bfloat16), shadow=_rounder(torch.bfloat16), grad=_rounder(torch.bfloat16)),
+}
+_r32 = _rounder(torch.float32)
+
+
 def _cl(t):
     """channel-first torch tensor -> channel-last numpy [rows, C]"""
     nd = t.dim() - 2
@@ -45,9 +67,12 @@ def _cl(t):
 
 class StepOracle(object):
 
-    def __init__(self, P_np, data, label, weight=None, base=16, num_strides=5, dtype=torch.float64):
+    def __init__(self, P_np, data, label, weight=None, base=16, num_strides=5, dtype=torch.float64,
+                 storage=None):
         """data [B,...,Cin], label / weight [B,...] numpy (as for ``uresnet_oracle.run``)."""
         self.dt = dtype
+        self.q = STORAGE[storage]
+        self.nodes_e = OrderedDict()        # name -> the producing step's output on storage-rounded inputs
         self.P = OrderedDict((k, torch.tensor(v, dtype=dtype)) for k, v in P_np.items())
         d = torch.tensor(data, dtype=dtype)
         self.nd = d.dim() - 2
@@ -76,10 +101,24 @@ class StepOracle(object):
         mu = raw.mean(dim=axes)
         var = ((raw - mu.view([1, -1] + [1] * self.nd)) ** 2).mean(dim=axes)     # biased
         L.update(raw=raw, mean=mu, rstd=torch.rsqrt(var + O.BN_EPS))
+        if self.q:                                                     # the same conv on the stored input
+            raw_e = self._conv(scope, self.q["act"](self.nodes[x_name]))
+            mu_e = raw_e.mean(dim=axes)
+            var_e = ((raw_e - mu_e.view([1, -1] + [1] * self.nd)) ** 2).mean(dim=axes)
+            L.update(raw_e=raw_e, mean_e=mu_e, rstd_e=torch.rsqrt(var_e + O.BN_EPS))
         if out is not None:
             y = O.batch_norm(raw, self._w(scope)[1])
             self.nodes[out] = F.relu(y) if relu else y
+            if self.q:
+                y = self._bn_stored(scope)
+                self.nodes_e[out] = F.relu(y) if relu else y
             self.recs.append(("layer", scope))
+
+    def _bn_stored(self, scope):
+        """BN output from the STORED raw tensor and statistics (fp32), as the apply kernels see them."""
+        L = self.layers[scope]
+        shp = [1, -1] + [1] * self.nd
+        return (_r32(L["raw"]) - _r32(L["mean"]).view(shp)) * _r32(L["rstd"]).view(shp) + self._w(scope)[1].view(shp)
 
     def _module(self, scope, x_name, cout, stride):                    # resnet_module.py:10-68
         x = self.nodes[x_name]
@@ -93,6 +132,9 @@ class StepOracle(object):
         self._layer(c2, c1, 1, False)
         self.nodes[scope] = self._merge(scope, sc, self.layers[c2]["raw"],
                                         self.layers[sc]["raw"] if sc else None, x if sc is None else None)
+        if self.q:
+            s_e = self._bn_stored(sc) if sc else self.q["act"](x)
+            self.nodes_e[scope] = F.relu(s_e + self._bn_stored(c2))
         self.recs.append(("module", scope, sc, x_name))
         return scope
 
@@ -128,7 +170,7 @@ class StepOracle(object):
 
     # ------------------------------------------------------------------ loss
     def loss(self):
-        lg = self.logits.detach().requires_grad_(True)
+        lg = (_r32(self.logits) if self.q else self.logits).detach().requires_grad_(True)
         res = O.loss_and_metrics(lg, self.data_cl, self.label, self.weight)
         (dl,) = torch.autograd.grad(res["loss"], [lg])
         self.result = dict(loss=float(res["loss"].detach()), acc_all=res["acc_all"], acc_nonzero=res["acc_nonzero"],
@@ -137,20 +179,26 @@ class StepOracle(object):
         return dl.permute(0, nd + 1, *range(1, nd + 1))                 # channel first
 
     # ------------------------------------------------------------------ backward
-    def _bn_bwd(self, scope, dout, relu):
+    def _bn_bwd(self, scope, dout, relu, stored=False):
         """Local autograd through y = [relu](BN(raw, beta)).  Returns (draw, dbeta)."""
         L = self.layers[scope]
-        raw = L["raw"].detach().requires_grad_(True)
+        raw = (_r32(L["raw"]) if stored else L["raw"]).detach().requires_grad_(True)
+        if stored:
+            dout = self.q["grad"](dout)
         beta = self._w(scope)[1].detach().requires_grad_(True)
         y = O.batch_norm(raw, beta)
         if relu:
             y = F.relu(y)
         return torch.autograd.grad(y, [raw, beta], dout)
 
-    def _conv_bwd(self, scope, draw):
+    def _conv_bwd(self, scope, draw, stored=False):
         """Local autograd through raw = conv(x, W).  Returns (dx or None for the stem, dW)."""
         L = self.layers[scope]
-        x = self.nodes[L["x"]].detach().requires_grad_(L["x"] != "data")
+        x = self.nodes[L["x"]]
+        if stored:       # filter gradient reads the bf16 shadow of the activation (the fp16 data node for the stem)
+            x = self.q["act" if L["x"] == "data" else "shadow"](x)
+            draw = self.q["grad"](draw)
+        x = x.detach().requires_grad_(L["x"] != "data")
         w = self._w(scope)[0].detach().requires_grad_(True)
         y = O.conv_transpose_same(x, w, L["stride"]) if L["transpose"] else O.conv_same(x, w, L["stride"])
         if L["x"] == "data":
@@ -165,6 +213,8 @@ class StepOracle(object):
         (numpy, keyed like the parameter dict)."""
         G = {}
         self.bn, self.dw, self.dx = {}, {}, {}
+        self.bn_e, self.dw_e, self.dx_e = {}, {}, {}      # the same steps on storage-rounded inputs
+        q = self.q
 
         def add(name, g):
             G[name] = g if name not in G else G[name] + g
@@ -175,6 +225,8 @@ class StepOracle(object):
             if dx is not None:
                 self.dx[scope] = dx
                 add(self.layers[scope]["x"], dx)
+            if q:
+                self.dx_e[scope], self.dw_e[scope] = self._conv_bwd(scope, self.bn[scope]["draw"], stored=True)
 
         G["conv2"] = self.loss()
         for rec in reversed(self.recs):
@@ -184,6 +236,9 @@ class StepOracle(object):
                 dout = G[L["out"]]
                 draw, dbeta = self._bn_bwd(scope, dout, L["relu"])
                 self.bn[scope] = dict(dout=dout, draw=draw, dbeta=dbeta)
+                if q:
+                    d_e, db_e = self._bn_bwd(scope, dout, L["relu"], stored=True)
+                    self.bn_e[scope] = dict(draw=d_e, dbeta=db_e)
                 conv_part(scope)
             elif rec[0] == "concat":
                 _, cat, dn, skip = rec
@@ -194,24 +249,35 @@ class StepOracle(object):
                 _, scope, sc, x_name = rec
                 c1, c2 = scope + "/resnet_conv1", scope + "/resnet_conv2"
                 dout = G[scope]
-                raw2 = self.layers[c2]["raw"].detach().requires_grad_(True)
-                b2 = self._w(c2)[1].detach().requires_grad_(True)
-                if sc:
-                    raws = self.layers[sc]["raw"].detach().requires_grad_(True)
-                    bs = self._w(sc)[1].detach().requires_grad_(True)
-                    y = self._merge_local(raw2, b2, O.batch_norm(raws, bs))
-                    d2, db2, ds, dbs = torch.autograd.grad(y, [raw2, b2, raws, bs], dout)
-                    self.bn[c2] = dict(dout=dout, draw=d2, dbeta=db2)
-                    self.bn[sc] = dict(dout=dout, draw=ds, dbeta=dbs)
-                else:
-                    xr = self.nodes[x_name].detach().requires_grad_(True)
-                    y = self._merge_local(raw2, b2, xr)
-                    d2, db2, g = torch.autograd.grad(y, [raw2, b2, xr], dout)
-                    self.bn[c2] = dict(dout=dout, draw=d2, dbeta=db2, g=g)
-                    add(x_name, g)
+                for stored in ((False, True) if q else (False,)):
+                    rnd = _r32 if stored else (lambda t: t)
+                    bn = self.bn_e if stored else self.bn
+                    do = q["grad"](dout) if stored else dout
+                    raw2 = rnd(self.layers[c2]["raw"]).detach().requires_grad_(True)
+                    b2 = self._w(c2)[1].detach().requires_grad_(True)
+                    if stored:
+                        # the kernels take the ReLU mask of a merge from the STORED module output
+                        do = do * (q["act"](self.nodes[scope]) > 0).to(do.dtype)
+                    if sc:
+                        raws = rnd(self.layers[sc]["raw"]).detach().requires_grad_(True)
+                        bs = self._w(sc)[1].detach().requires_grad_(True)
+                        y = self._merge_local(raw2, b2, O.batch_norm(raws, bs), relu=not stored)
+                        d2, db2, ds, dbs = torch.autograd.grad(y, [raw2, b2, raws, bs], do)
+                        bn[c2] = dict(dout=dout, draw=d2, dbeta=db2)
+                        bn[sc] = dict(dout=dout, draw=ds, dbeta=dbs)
+                    else:
+                        xr = (q["act"](self.nodes[x_name]) if stored else self.nodes[x_name]).detach().requires_grad_(True)
+                        y = self._merge_local(raw2, b2, xr, relu=not stored)
+                        d2, db2, g = torch.autograd.grad(y, [raw2, b2, xr], do)
+                        bn[c2] = dict(dout=dout, draw=d2, dbeta=db2, g=g)
+                        if not stored:
+                            add(x_name, g)
                 conv_part(c2)
                 draw1, db1 = self._bn_bwd(c1, G[c1], False)
                 self.bn[c1] = dict(dout=G[c1], draw=draw1, dbeta=db1)
+                if q:
+                    d_e, db_e = self._bn_bwd(c1, G[c1], False, stored=True)
+                    self.bn_e[c1] = dict(draw=d_e, dbeta=db_e)
                 conv_part(c1)
                 if sc:
                     conv_part(sc)
@@ -223,30 +289,39 @@ class StepOracle(object):
         return self.grads
 
     @staticmethod
-    def _merge_local(raw2, b2, s):
-        return F.relu(s + O.batch_norm(raw2, b2))
+    def _merge_local(raw2, b2, s, relu=True):
+        y = s + O.batch_norm(raw2, b2)
+        return F.relu(y) if relu else y
 
     # ------------------------------------------------------------------ views for the tests
-    def node(self, name):
+    # ``expected=True``: the producing step's output on storage-rounded inputs (needs ``storage``)
+    def node(self, name, expected=False):
         """[rows, C] float64 numpy, channel-last (the layout of the CUDA workspace)."""
-        return _cl(self.nodes[name])
+        return _cl((self.nodes_e if expected else self.nodes)[name])
 
     def node_gradient(self, name):
         return _cl(self.node_grad[name])
 
-    def raw(self, scope):
-        return _cl(self.layers[scope]["raw"])
+    def raw(self, scope, expected=False):
+        return _cl(self.layers[scope]["raw_e" if expected else "raw"])
 
-    def stats(self, scope):
+    def stats(self, scope, expected=False):
         L = self.layers[scope]
-        return np.concatenate([L["mean"].numpy(), L["rstd"].numpy()])    # mean | rstd, as urn_bn_stats stores them
+        e = "_e" if expected else ""
+        return np.concatenate([L["mean" + e].numpy(), L["rstd" + e].numpy()])    # mean | rstd, as urn_bn_stats stores them
 
-    def draw(self, scope):
-        return _cl(self.bn[scope]["draw"])
+    def draw(self, scope, expected=False):
+        return _cl((self.bn_e if expected else self.bn)[scope]["draw"])
 
-    def masked_gradient(self, scope):
+    def dbeta(self, scope, expected=False):
+        return (self.bn_e if expected else self.bn)[scope]["dbeta"].numpy()
+
+    def filter_gradient(self, scope, expected=False):
+        return (self.dw_e if expected else self.dw)[scope].numpy()
+
+    def masked_gradient(self, scope, expected=False):
         """gradient handed to the identity shortcut by the merge of module ``scope``"""
-        return _cl(self.bn[scope + "/resnet_conv2"]["g"])
+        return _cl((self.bn_e if expected else self.bn)[scope + "/resnet_conv2"]["g"])
 
-    def input_gradient(self, scope):
-        return _cl(self.dx[scope])
+    def input_gradient(self, scope, expected=False):
+        return _cl((self.dx_e if expected else self.dx)[scope])

@@ -32,6 +32,7 @@ def test_reference_arm_non_zero_rank_is_silent():
 
 
 def test_hbm_byte_model():
+    """SURVEY 8d byte model: no bf16 shadow, no separate statistics pass (fused into the conv epilogue)."""
     sys.path.insert(0, ROOT)
     import bench
 
@@ -39,12 +40,13 @@ def test_hbm_byte_model():
         n, xd, xh, xw, cx = 2, 1, 8, 8, 16
         yd, yh, yw, cy = 1, 8, 8, 16
     e = 2 * 8 * 8 * 16
-    want = (e * 2 + e * 4) + e * 4 + (e * 4 + e * 4) + (2 * (e * 2 + e * 4) + e * 2) + (e * 2 + e * 2) + (e * 2 + e * 2)
+    want = (e * 2 + e * 4) + (e * 4 + e * 2) + e * (2 + 4) + e * (2 + 4 + 2) + (e * 2 + e * 2) + (e * 2 + e * 2)
     assert bench.hbm_bytes([("some/layer", D, False)]) == want
     assert bench.hbm_bytes([("conv0", D, False)]) == want - (e * 2 + e * 2)      # no input gradient for the stem
+    assert bench.hbm_bytes([("some/layer", D, False)], 4, 4) == (e * 4 + e * 4) + (e * 4 + e * 4) + e * 8 + e * 12 + e * 8 + e * 8
 
 
-def test_top_launch_picks_the_slowest_conv_group_and_its_bound():
+def test_launch_groups_pool_equal_shapes_and_pick_the_bound():
     sys.path.insert(0, ROOT)
     import numpy as np
     import bench
@@ -54,16 +56,19 @@ def test_top_launch_picks_the_slowest_conv_group_and_its_bound():
 
     class D512:   # 3x3 512 -> 512 on 32 x 16 x 16: tensor-bound
         n, xd, xh, xw, cx, yd, yh, yw, cy, kd, kh, kw, s = 32, 1, 16, 16, 512, 1, 16, 16, 512, 1, 3, 3, 1
-    table = [("a/b", D16, False), ("c/d", D512, False)]
+    table = [("a/b", D16, False), ("c/d", D512, False), ("e/f", D16, False)]
     pk = dict(hbm=6540.8, tf_sus=1373.9, tf_burst=1667.1, src="measured")
-    ms = np.zeros((2, 8))
-    ms[0, 0], ms[1, 4] = 0.6, 0.1                   # two profiled steps: 0.3 ms fwd of layer 0
-    t = bench.top_launch(table, ms, 2, pk, "2d")
+    ms = np.zeros((3, 8))
+    ms[0, 0], ms[2, 0], ms[1, 4] = 0.6, 0.4, 0.1    # two profiled steps: 0.3 + 0.2 ms fwd of the two 16->16 layers
+    groups = bench.launch_groups(table, ms, 2, pk, "2d")
+    assert len(groups) == 2
+    g = max(groups, key=lambda x: x["ms_per_step"])
     e = 32 * 512 * 512 * 16
-    assert t["bound"] == "hbm" and t["unit"] == "GB/s" and t["kernel"].startswith("a/b conv_fwd (16->16 k3 s1 @512")
-    assert abs(t["achieved"] - (e * 2 + e * 4) / 0.3e-3 / 1e9) < 1e-6 and abs(t["frac"] - t["achieved"] / 6540.8) < 1e-12
-    assert t["traffic"] == bench.NCU_TRAFFIC[("2d", "16->16 k3 s1 @512", "conv_fwd")]
-    ms[1, 4] = 5.0
-    t = bench.top_launch(table, ms, 2, pk, "2d")
+    assert g["bound"] == "hbm" and g["unit"] == "GB/s" and g["kernel"] == "conv_fwd 16->16 k3 s1 @512"
+    assert g["launches_per_step"] == 2 and g["layers"] == ["a/b", "e/f"] and abs(g["ms_per_launch"] - 0.25) < 1e-12
+    assert abs(g["achieved"] - 2 * (e * 2 + e * 4) / 0.5e-3 / 1e9) < 1e-6 and abs(g["frac"] - g["achieved"] / 6540.8) < 1e-12
+    assert g["algorithmic_bytes_per_launch"] == e * 6
+    assert g["traffic"] == bench.NCU_TRAFFIC[("2d", "16->16 k3 s1 @512", "conv_fwd")]
+    t = [x for x in groups if x is not g][0]
     assert t["bound"] == "tensor" and t["unit"] == "TFLOP/s" and t["traffic"] is None
-    assert abs(t["achieved"] - 2.0 * 32 * 16 * 16 * 9 * 512 * 512 / 2.5e-3 / 1e12) < 1e-9
+    assert abs(t["achieved"] - 2.0 * 32 * 16 * 16 * 9 * 512 * 512 / 0.05e-3 / 1e12) < 1e-9

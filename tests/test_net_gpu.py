@@ -19,19 +19,19 @@ from uresnet_b200.uresnet import uresnet
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 TOL = {"f32": 1e-3, "bf16": 2e-2, "mix16": 2e-2}
-# Gradients in bf16 mode.  The loss is an ill-conditioned function of the forward state for this
-# network (58 conv+BN layers, batch statistics, ~99 % constant background): perturbing the fp64
-# oracle's weights by 1e-3 relative moves most of ITS gradients by 15-60 % (DESIGN.md 'Numerics').
-# bf16 storage perturbs every activation by ~2^-9, and two bf16 runs decorrelate to that level
-# within a few layers (rounding turns a difference d into sqrt(d*ulp)), so no bf16 run -- ours or
-# the oracle evaluated with bf16 storage (quant='bf16') -- can track fp64 gradients to 2e-2.
-# What is asserted for bf16: forward (logits, loss, argmax) against the fp64 oracle at 2e-2;
-# every backward KERNEL at bf16 precision on identical inputs (tests/test_kernels_gpu.py); and
-# end-to-end gradients whose median deviation from fp64 is within GRAD_SLACK x the median
-# deviation of the oracle itself evaluated with the same 16-bit storage (no tensor beyond
-# 10 x that), with cosine similarity >= GRAD_COS on every filter gradient.
+# Gradients in the 16-bit modes.  The gradient of this network is an ill-conditioned function of
+# its parameters: perturbing the fp64 oracle's OWN weights by 2^-11 relative (half an ulp of fp16 /
+# TF32 operands) moves most of its gradient tensors by 5-16 % while logits move by 1.5e-3 -- measured,
+# not asserted from prose: oracle/conditioning.py, tests/test_oracle.py::test_gradient_conditioning.
+# No 10-bit-operand evaluation can therefore track fp64 gradients END TO END at 2e-2.  What is
+# asserted for mix16:  forward (logits, loss, argmax) against the fp64 oracle at 2e-2;  every step of
+# the composed schedule at 2e-2 on identical inputs (teacher forcing, tests/test_parity_gpu.py);  and
+# end-to-end gradients within GRAD_SLACK x the oracle's measured sensitivity for the very inputs of
+# the test (per tensor: max over draws of max|g(p(1+2^-11 u)) - g(p)| / max|g(p)|; median likewise).
+# GRAD_SLACK: the sensitivity run perturbs the parameters alone by 2^-11, mix16 also stores every
+# gradient tensor in bf16 (2^-9: a factor 2 by the measured ~sqrt(eps) response) and the per-tensor
+# maximum over 3 draws is itself a noisy estimate (x1.5).
 GRAD_SLACK = 3.0
-GRAD_COS = 0.90
 
 
 def oracle(P, data, label, weight, dims, B, F, St, quant=None):
@@ -56,8 +56,16 @@ def make_net(dims, F, St, C, dtype, use_weight=True, trainable=True, impl=None, 
     return net
 
 
-def check_against(net, P, data, label, weight, ref, dtype, B, dims, refq=None):
-    """ref: fp64 oracle result; refq: the oracle with bf16 storage (needed for dtype='bf16')."""
+def sensitivity(P, data, label, weight, dims, B, F, St, ref):
+    from oracle.conditioning import gradient_sensitivity
+    shp = [B] + list(dims[:-1])
+    return gradient_sensitivity(P, data.reshape(shp + [1]), label.reshape(shp),
+                                None if weight is None else weight.reshape(shp), base=F, num_strides=St,
+                                eps=2.0 ** -11, draws=3, ref=ref)
+
+
+def check_against(net, P, data, label, weight, ref, dtype, B, dims, sens=None):
+    """ref: fp64 oracle result; sens: the oracle's gradient sensitivity (needed for the 16-bit modes)."""
     net.set_variables(P)
     net.zero_gradients(None)
     res, doc = net.accum_gradients(None, data, label, weight)
@@ -77,15 +85,11 @@ def check_against(net, P, data, label, weight, ref, dtype, B, dims, refq=None):
         for k, gr in ref["grads"].items():
             assert relerr(g[k], gr) < tol, (k, relerr(g[k], gr))
     else:
-        # two reduced-precision realisations are compared through robust statistics
         e = {k: relerr(g[k], gr) for k, gr in ref["grads"].items()}
-        eq = {k: relerr(refq["grads"][k], gr) for k, gr in ref["grads"].items()}
-        med, medq = np.median(list(e.values())), np.median(list(eq.values()))
-        assert med < max(tol, GRAD_SLACK * medq), (med, medq)
-        for k, gr in ref["grads"].items():
-            assert e[k] < max(tol, 10 * GRAD_SLACK * medq), (k, e[k], medq)
-            if k.endswith("/weights"):
-                assert cosine(g[k], gr) > GRAD_COS, (k, cosine(g[k], gr))
+        med = np.median(list(e.values()))
+        assert med < max(tol, GRAD_SLACK * sens["median"]), (med, sens["median"])
+        for k in ref["grads"]:
+            assert e[k] < max(tol, GRAD_SLACK * max(sens["grads"][k], sens["median"])), (k, e[k], sens["grads"][k])
 
 
 @pytest.mark.parametrize("dtype", ["f32", "mix16"])
@@ -101,10 +105,12 @@ def test_golden_small(path, dtype):
     net = make_net(dims, F, St, C, dtype, use_weight=bool(z["use_weight"]))
     assert [n for n, _ in net.trainable_variables()] == names
     label = z["label"].astype(np.float32)
-    refq = None
+    sens = None
     if dtype != "f32":
-        refq = oracle(P, z["data"], label, z["weight"] if bool(z["use_weight"]) else None, dims, B, F, St, dtype)
-    check_against(net, P, z["data"], label, z["weight"], ref, dtype, B, dims, refq)
+        w = z["weight"] if bool(z["use_weight"]) else None
+        full = oracle(P, z["data"], label, w, dims, B, F, St)
+        sens = sensitivity(P, z["data"], label, w, dims, B, F, St, full)
+    check_against(net, P, z["data"], label, z["weight"], ref, dtype, B, dims, sens)
 
 
 @pytest.mark.parametrize("dtype", ["f32", "mix16"])
@@ -127,8 +133,13 @@ def test_golden_default_topology(dtype):
     l2 = np.array([np.sqrt((g[k].astype(np.float64) ** 2).sum()) for k in names])
     if dtype == "f32":
         np.testing.assert_allclose(l2, z["grad_l2"], rtol=5 * tol, atol=1e-6 * z["grad_l2"].max())
-    else:   # gradient norms within the conditioning-limited band (see GRAD_SLACK note above)
-        np.testing.assert_allclose(l2, z["grad_l2"], rtol=0.5, atol=1e-3 * z["grad_l2"].max())
+    else:   # gradient norms within the measured sensitivity of the oracle's own gradients (GRAD_SLACK note above)
+        shp = [B] + dims[:-1]
+        lab = z["label"].astype(np.float32)
+        full = O.run(P, z["data"].reshape(shp + [1]), lab.reshape(shp), None)
+        sens = sensitivity(P, z["data"], lab, None, dims, B, 16, 5, full)
+        band = GRAD_SLACK * max(sens["worst"], 2e-2)
+        np.testing.assert_allclose(l2, z["grad_l2"], rtol=band, atol=1e-3 * z["grad_l2"].max())
 
 
 @pytest.mark.parametrize("dtype", ["f32", "mix16"])
@@ -139,9 +150,9 @@ def test_live_oracle(dims, B, F, St, dtype):
     weight /= weight.sum(axis=1, keepdims=True)
     P = O.init_params(nd, base=F, num_strides=St, seed=5)
     ref = oracle(P, data, label, weight, dims, B, F, St)
-    refq = oracle(P, data, label, weight, dims, B, F, St, dtype) if dtype != "f32" else None
+    sens = sensitivity(P, data, label, weight, dims, B, F, St, ref) if dtype != "f32" else None
     net = make_net(dims, F, St, 3, dtype)
-    check_against(net, P, data, label, weight, ref, dtype, B, dims, refq)
+    check_against(net, P, data, label, weight, ref, dtype, B, dims, sens)
 
 
 def test_all_bf16_mode_forward():

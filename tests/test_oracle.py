@@ -221,3 +221,26 @@ def test_gradient_conditioning():
     assert s11["median"] > 2e-2 and s11["worst"] > 5e-2                  # gradients are not
     assert s11["median"] / s11["eps"] > 10 * (s24["median"] / s24["eps"])   # non-linear amplification
     assert s10["median"] < 1.8 * s11["median"]                           # sub-linear beyond (sqrt-like)
+
+
+def test_step_oracle_storage_rounded_expectations():
+    """storage='mix16': the chain (teacher) values are unchanged; the per-step expectations on
+    storage-rounded inputs stay within the rounding they model (fp16 activations 2^-11, bf16
+    gradients 2^-9) of the chain for well-conditioned steps."""
+    from oracle.steps import StepOracle
+    P, data, label, weight = _case([32, 32, 1], 2, 4, 3)
+    a = StepOracle(P, data, label, weight, base=4, num_strides=3)
+    b = StepOracle(P, data, label, weight, base=4, num_strides=3, storage="mix16")
+    ga, gb = a.backward(), b.backward()
+    for k in ga:                                       # chain not rounded (only the logits -> fp32 before the loss)
+        assert np.abs(ga[k] - gb[k]).max() <= 1e-5 * max(np.abs(ga[k]).max(), 1e-300), k
+
+    def rel(x, y):
+        return np.abs(x - y).max() / np.abs(y).max()
+    for scope in b.layers:
+        assert rel(b.raw(scope, True), b.raw(scope)) < 4e-3, scope
+        assert rel(b.draw(scope, True), b.draw(scope)) < 3e-2, scope
+        assert rel(b.filter_gradient(scope, True), b.filter_gradient(scope)) < 3e-2, scope
+    assert rel(b.node("conv1", True), b.node("conv1")) < 1e-5          # fp32 raw + statistics in, fp64 math
+    m = "resnet_module7/module2"
+    assert rel(b.masked_gradient(m, True), b.masked_gradient(m)) < 2e-2

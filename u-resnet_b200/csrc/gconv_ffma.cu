@@ -52,11 +52,16 @@ gconv_ffma_kernel(const GConv g, const TI* __restrict__ in, const float* __restr
     }
   }
 
+  // two-level accumulation: fp32 FMAs inside a KC-wide channel chunk, the chunk sums added in
+  // double.  A single fp32 accumulator over K = taps*cin (up to 13824 terms) carries ~sqrt(K) ulp of
+  // rounding noise, which this network's backward pass amplifies by orders of magnitude
+  // (oracle/conditioning.py); this keeps the exact mode within ~1 ulp of the fp64 result.
   float acc[RM][4];
+  double tot[RM][4];
 #pragma unroll
   for (int i = 0; i < RM; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < 4; ++j) { acc[i][j] = 0.f; tot[i][j] = 0.0; }
 
   const bool vec_in = (g.cin % 4 == 0) && (g.ldin % 4 == 0);
 
@@ -122,10 +127,18 @@ gconv_ffma_kernel(const GConv g, const TI* __restrict__ in, const float* __restr
           acc[i][3] = fmaf(a[i], b.w, acc[i][3]);
         }
       }
+#pragma unroll
+      for (int i = 0; i < RM; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { tot[i][j] += (double)acc[i][j]; acc[i][j] = 0.f; }
       __syncthreads();
     }
   }
   if (g.ntaps == 0) __syncthreads();
+#pragma unroll
+  for (int i = 0; i < RM; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = (float)tot[i][j];
 
   // ---- epilogue ----
   const int co = n0 + tx * 4;
@@ -194,10 +207,11 @@ wgrad_ffma_kernel(const urn_conv_desc d, const T* __restrict__ x, long long ldx,
   const bool vy = (d.cy % 4 == 0) && (ldy % 4 == 0);
 
   float acc[RX][RY];
+  double tot[RX][RY];            // two-level accumulation (see gconv_ffma_kernel): PK positions in fp32, then double
 #pragma unroll
   for (int i = 0; i < RX; ++i)
 #pragma unroll
-    for (int j = 0; j < RY; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < RY; ++j) { acc[i][j] = 0.f; tot[i][j] = 0.0; }
 
   for (long long o0 = o_begin; o0 < o_end; o0 += PK) {
     __syncthreads();
@@ -267,7 +281,15 @@ wgrad_ffma_kernel(const urn_conv_desc d, const T* __restrict__ x, long long ldx,
 #pragma unroll
         for (int j = 0; j < RY; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
     }
+#pragma unroll
+    for (int i = 0; i < RX; ++i)
+#pragma unroll
+      for (int j = 0; j < RY; ++j) { tot[i][j] += (double)acc[i][j]; acc[i][j] = 0.f; }
   }
+#pragma unroll
+  for (int i = 0; i < RX; ++i)
+#pragma unroll
+    for (int j = 0; j < RY; ++j) acc[i][j] = (float)tot[i][j];
   const long long nw = (long long)d.kd * d.kh * d.kw * d.cx * d.cy;
   float* dst = partial + (long long)blockIdx.y * nw + (long long)tap * d.cx * d.cy;
 #pragma unroll
@@ -286,9 +308,9 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, long long
                                     float* __restrict__ dw, int accumulate) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nw) return;
-  float s = 0.f;
-  for (int k = 0; k < nsplit; ++k) s += partial[(long long)k * nw + i];
-  dw[i] = accumulate ? dw[i] + s : s;
+  double s = 0.0;
+  for (int k = 0; k < nsplit; ++k) s += (double)partial[(long long)k * nw + i];
+  dw[i] = accumulate ? dw[i] + (float)s : (float)s;
 }
 
 struct WgradPlan {

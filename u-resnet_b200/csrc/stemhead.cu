@@ -215,9 +215,9 @@ __global__ void sh_partial_reduce_kernel(const float* __restrict__ partial, int 
                                          float* __restrict__ dw, int accumulate) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nw) return;
-  float s = 0.f;
-  for (int b = 0; b < nblocks; ++b) s += partial[(long long)b * nw + i];
-  dw[i] = accumulate ? dw[i] + s : s;
+  double s = 0.0;
+  for (int b = 0; b < nblocks; ++b) s += (double)partial[(long long)b * nw + i];
+  dw[i] = accumulate ? dw[i] + (float)s : (float)s;
 }
 
 // ------------------------------------------------------------------------------------

@@ -100,6 +100,7 @@ class ssnet_base(object):
         self._result = torch.zeros(4, dtype=torch.float64, device=dev)
         self._result_host = torch.zeros(4, dtype=torch.float64).pin_memory()
         self._staging = {}
+        self._pinned_arrays = []
         self._graphs = {}                 # CUDA graphs of the forward / loss+backward launch sequences
         self._graph_calls = {}
         self._use_graphs = os.environ.get("URESNET_B200_GRAPHS", "1") != "0"
@@ -203,46 +204,115 @@ class ssnet_base(object):
             feed["weight"] = self._to_device("weight", input_weight, self._label_size, batch)
         return feed
 
-    def _to_device(self, key, arr, row, batch=None, side=False):
-        """Host array -> pinned staging buffer -> device (async).  With ``side=True`` the copy is
-        enqueued on the copy stream so that it (and the host-side memcpy into pinned memory that
-        precedes it) overlaps the forward pass already running on the compute stream; the
-        compute stream is made to wait for it by ``_join_side_copies``."""
-        if isinstance(arr, torch.Tensor) and arr.is_cuda:
-            t = arr.to(torch.float32).reshape(-1, row)
-        else:
-            a = np.asarray(arr, dtype=np.float32).reshape(-1, row)
-            st = self._staging.get(key)
-            if st is None or st[0].shape != a.shape:
-                st = [torch.empty(a.shape, dtype=torch.float32).pin_memory(),
-                      torch.empty(a.shape, dtype=torch.float32, device=self._device), None]
-                self._staging[key] = st
-            if st[2] is not None:
-                st[2].synchronize()                 # previous H2D out of this pinned buffer is done
-            src = torch.from_numpy(np.ascontiguousarray(a)).view(-1)
-            pin, dst = st[0].view(-1), st[1].view(-1)
-            # chunked: the DMA of chunk k runs while the host copies chunk k+1 into pinned memory
-            step = max(1, _H2D_CHUNK_BYTES // 4)
-            if side:
-                if self._copy_stream is None:
-                    self._copy_stream = torch.cuda.Stream(device=self._device)
-                stream = self._copy_stream
-                if self._step_start is not None:
-                    stream.wait_event(self._step_start)   # earlier consumers of st[1] are done
+    # Staging: every stream (data / label / weight) owns a ring of two slots, each a pinned host
+    # buffer + a device buffer, used alternately so that the transfer of minibatch k+1 can run while
+    # the kernels of minibatch k still read the other slot.
+    def _slot(self, key, shape, index=None):
+        ring = self._staging.get(key)
+        if ring is None or ring["shape"] != tuple(shape):
+            ring = self._staging[key] = {"shape": tuple(shape), "slots": [None, None], "next": 0}
+        i = ring["next"] if index is None else index
+        ring["next"] = 1 - i
+        if ring["slots"][i] is None:
+            ring["slots"][i] = {"pin": None, "dev": torch.empty(shape, dtype=torch.float32, device=self._device),
+                                "event": None, "sig": None}
+        return ring["slots"][i]
+
+    @staticmethod
+    def _signature(a):
+        return (a.ctypes.data, a.shape, a.strides)
+
+    def _copy_in(self, slot, a, stream):
+        """host array -> slot's device buffer on `stream` (async).  A pinned source is DMA'd directly;
+        a pageable one goes through the slot's pinned buffer in chunks, so that the DMA of chunk k runs
+        while the host copies chunk k+1 into pinned memory."""
+        if slot["event"] is not None:
+            slot["event"].synchronize()             # previous transfer out of this slot's pinned buffer is done
+        src = torch.from_numpy(a).view(-1)
+        dst = slot["dev"].view(-1)
+        with torch.cuda.stream(stream):
+            if src.is_pinned():
+                dst.copy_(src, non_blocking=True)
             else:
-                stream = torch.cuda.current_stream(self._device)
-            with torch.cuda.stream(stream):
+                if slot["pin"] is None:
+                    slot["pin"] = torch.empty(a.shape, dtype=torch.float32).pin_memory()
+                pin = slot["pin"].view(-1)
+                step = max(1, _H2D_CHUNK_BYTES // 4)
                 for i in range(0, max(src.numel(), 1), step):
                     pin[i:i + step].copy_(src[i:i + step])                  # multi-threaded host copy
                     dst[i:i + step].copy_(pin[i:i + step], non_blocking=True)
-                st[2] = torch.cuda.Event()
-                st[2].record(stream)
-            if side:
-                self._side_pending.append(st[2])
-            t = st[1]
+            slot["event"] = torch.cuda.Event()
+            slot["event"].record(stream)
+
+    def _copy_stream_ready(self):
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=self._device)
+        if self._step_start is not None:
+            # every kernel enqueued before the current step started has finished: the slot that is
+            # about to be overwritten (last read one step earlier) is free
+            self._copy_stream.wait_event(self._step_start)
+        return self._copy_stream
+
+    def _to_device(self, key, arr, row, batch=None, side=False):
+        """Host array -> device (async).  If the array was announced with ``stage_next`` its transfer is
+        already in flight (or done) and only an event wait is enqueued.  With ``side=True`` the copy
+        is enqueued on the copy stream so that it (and the host-side memcpy into pinned memory that
+        precedes it) overlaps the forward pass already running on the compute stream; the compute
+        stream is made to wait for it by ``_join_side_copies``."""
+        if isinstance(arr, torch.Tensor) and arr.is_cuda:
+            t = arr.to(torch.float32).reshape(-1, row)
+        else:
+            a = np.ascontiguousarray(np.asarray(arr, dtype=np.float32).reshape(-1, row))
+            ring = self._staging.get(key)
+            slot = None
+            if ring is not None and ring["shape"] == a.shape:
+                for i, sl in enumerate(ring["slots"]):
+                    if sl is not None and sl["sig"] is not None and sl["sig"] == self._signature(a):
+                        slot, sl["sig"] = sl, None                # prefetched by stage_next: consume once
+                        ring["next"] = 1 - i
+            if slot is not None:
+                self._side_pending.append(slot["event"])
+                if not side:
+                    self._join_side_copies()
+            else:
+                if ring is not None:
+                    for sl in ring["slots"]:                      # a staged minibatch that was skipped expires
+                        if sl is not None:
+                            sl["sig"] = None
+                slot = self._slot(key, a.shape)
+                stream = self._copy_stream_ready() if side else torch.cuda.current_stream(self._device)
+                self._copy_in(slot, a, stream)
+                if side:
+                    self._side_pending.append(slot["event"])
+            t = slot["dev"]
         if batch is not None and t.shape[0] != batch:
             raise ValueError("batch mismatch between data and %s" % key)
         return t
+
+    def stage_next(self, input_data, input_label=None, input_weight=None):
+        """Announce the NEXT minibatch: its host->device transfer starts now on the copy stream, under
+        the kernels of the minibatch that was just enqueued (``accum_gradients(..., fetch=False)``).
+        The ``accum_gradients`` / ``run_test`` / ``inference`` call that later receives the same arrays
+        (recognised by address and shape) only waits for the transfer.  The arrays must not be
+        modified in between.  Pinned arrays (``pinned_empty``) are DMA'd without a host-side copy."""
+        stream = self._copy_stream_ready()
+        for key, arr, row in (("data", input_data, self._data_size), ("label", input_label, self._label_size),
+                              ("weight", input_weight, self._label_size)):
+            if arr is None or (isinstance(arr, torch.Tensor) and arr.is_cuda):
+                continue
+            a = np.asarray(arr, dtype=np.float32).reshape(-1, row)
+            if not a.flags["C_CONTIGUOUS"]:
+                continue                                   # would be copied again anyway
+            slot = self._slot(key, a.shape)
+            self._copy_in(slot, a, stream)
+            slot["sig"] = self._signature(a)
+
+    def pinned_empty(self, shape):
+        """float32 numpy array in page-locked host memory (kept alive by this object): inputs built in
+        such arrays reach the device without the pageable -> pinned staging copy."""
+        t = torch.empty(tuple(int(v) for v in shape), dtype=torch.float32).pin_memory()
+        self._pinned_arrays.append(t)
+        return t.numpy()
 
     def _join_side_copies(self):
         cur = torch.cuda.current_stream(self._device)
@@ -345,6 +415,12 @@ class ssnet_base(object):
         acc_all = ca / float(batch * self._label_size)
         acc_nz = (cnz / nnz) if nnz > 0 else float("nan")   # tf.reduce_mean of empty -> NaN
         return np.float32(loss), np.float32(acc_all), np.float32(acc_nz)
+
+    def fetch_metrics(self, batch):
+        """Metrics of the last ``accum_gradients(..., fetch=False)`` call, in its return format
+        (synchronises the compute stream)."""
+        loss, acc_all, acc_nz = self._metrics(batch)
+        return [None, loss, acc_all, acc_nz], ['', 'loss', 'acc. all', 'acc. nonzero']
 
     # ------------------------------------------------------- reference methods
     def make_summary(self, sess, input_data, input_label, input_weight=None):

@@ -119,6 +119,7 @@ class ssnet_trainval(object):
                 is3d = 'Tensor3D' in open(cfg_file).read()
             dims = [192, 192, 192, 1] if is3d else [512, 512, 1]
         io = synthetic_threadio()
+        self._io_list = getattr(self, '_io_list', []) + [io]
         io.configure({'filler_name': name, 'verbosity': 0, 'filler_cfg': cfg_file, 'dims': dims,
                       'seed': self._cfg.SYNTHETIC_SEED + seed_offset, 'rank': self._rank,
                       'keyword_data': keywords[0], 'keyword_label': keywords[1],
@@ -160,6 +161,8 @@ class ssnet_trainval(object):
         else:
             self._net.construct(trainable=cfg.TRAIN, use_weight=cfg.USE_WEIGHTS, dtype=cfg.DTYPE,
                                 impl=cfg.KERNEL_IMPL, seed=cfg.TF_RANDOM_SEED)
+        for io in getattr(self, '_io_list', []):          # later batches land in page-locked buffers
+            io._alloc = self._net.pinned_empty
         if self._world > 1 and cfg.TRAIN:
             from . import dp
             dp.broadcast_variables(self._net)
@@ -206,6 +209,21 @@ class ssnet_trainval(object):
             os.remove(f)
         return path
 
+    def _train_batch(self):
+        """Current batch of the main stream; weights normalised per event ONCE per batch
+        (ssnet_trainval.py:173)."""
+        cfg = self._cfg
+        io = self._input_main
+        data = io.fetch_data(cfg.KEYWORD_DATA).data()
+        label = io.fetch_data(cfg.KEYWORD_LABEL).data()
+        weight = None
+        if cfg.USE_WEIGHTS:
+            weight = io.fetch_data(cfg.KEYWORD_WEIGHT or 'weight').data()
+            if getattr(self, '_normalised_step', None) != (id(io), io._step):
+                weight /= (np.sum(weight, axis=1).reshape([weight.shape[0], 1]))
+                self._normalised_step = (id(io), io._step)
+        return data, label, weight
+
     def train_step(self):
         cfg = self._cfg
         self._iteration += 1
@@ -215,20 +233,20 @@ class ssnet_trainval(object):
 
         self._net.zero_gradients(self._sess)
         for j in range(cfg.NUM_MINIBATCHES):
-            minibatch_data = self._input_main.fetch_data(cfg.KEYWORD_DATA).data()
-            minibatch_label = self._input_main.fetch_data(cfg.KEYWORD_LABEL).data()
-            minibatch_weight = None
-            if cfg.USE_WEIGHTS:
-                minibatch_weight = self._input_main.fetch_data(cfg.KEYWORD_WEIGHT or 'weight').data()
-                # per-event normalization (ssnet_trainval.py:173)
-                minibatch_weight /= (np.sum(minibatch_weight, axis=1).reshape([minibatch_weight.shape[0], 1]))
-            res, doc = self._net.accum_gradients(sess=self._sess, input_data=minibatch_data,
-                                                 input_label=minibatch_label, input_weight=minibatch_weight)
+            minibatch_data, minibatch_label, minibatch_weight = self._train_batch()
+            # the reference's sess.run blocks until the step is done and larcv's filler threads prepare
+            # the next batch meanwhile (ssnet_trainval.py:176,187).  Same pipeline here, explicitly: the
+            # kernels of minibatch j are only ENQUEUED, then the host produces minibatch j+1 and starts
+            # its host->device transfer under them, and only then are the metrics of j fetched.
+            self._net.accum_gradients(sess=self._sess, input_data=minibatch_data, input_label=minibatch_label,
+                                      input_weight=minibatch_weight, fetch=False)
+            self._input_main.next(store_entries=(not cfg.TRAIN), store_event_ids=(not cfg.TRAIN))
+            self._net.stage_next(*self._train_batch())
+            res, doc = self._net.fetch_metrics(minibatch_data.shape[0])
             if self._batch_metrics is None:
                 self._batch_metrics = np.zeros((cfg.NUM_MINIBATCHES, len(res) - 1), dtype=np.float32)
                 self._descr_metrics = doc[1:]
             self._batch_metrics[j, :] = res[1:]
-            self._input_main.next(store_entries=(not cfg.TRAIN), store_event_ids=(not cfg.TRAIN))
 
         self._net.apply_gradients(self._sess)
 

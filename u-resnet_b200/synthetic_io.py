@@ -51,11 +51,12 @@ def _draw_event(rng, spatial):
     return data, label
 
 
-def make_batch(batch, dims, seed, num_class=3):
+def make_batch(batch, dims, seed, num_class=3, out=None):
     """Return (data [B,prod(dims)], label [B,P], weight [B,P]) float32.
 
     weight = per-event inverse class frequency at each pixel (NOT yet divided
     by the per-event sum -- the driver does that, ``ssnet_trainval.py:173``).
+    ``out``: optional (data, label, weight) arrays to fill (e.g. page-locked buffers).
     """
     spatial = tuple(int(d) for d in dims[:-1])
     if int(dims[-1]) != 1:
@@ -64,9 +65,13 @@ def make_batch(batch, dims, seed, num_class=3):
     # streams (consecutive ints as PCG64 seeds would make rank r replay rank r+1's batches)
     rng = np.random.Generator(np.random.PCG64(np.random.SeedSequence(seed) if not np.isscalar(seed) else int(seed)))
     P = int(np.prod(spatial))
-    data = np.empty((batch, P), np.float32)
-    label = np.empty((batch, P), np.float32)
-    weight = np.empty((batch, P), np.float32)
+    if out is not None:
+        data, label, weight = out
+        assert data.shape == label.shape == weight.shape == (batch, P) and data.dtype == np.float32
+    else:
+        data = np.empty((batch, P), np.float32)
+        label = np.empty((batch, P), np.float32)
+        weight = np.empty((batch, P), np.float32)
     for b in range(batch):
         d, l = _draw_event(rng, spatial)
         data[b] = d.reshape(-1)
@@ -112,6 +117,11 @@ class synthetic_threadio(object):
         self._dims = [int(v) for v in self._cfg.get("dims", [512, 512, 1])]
         self._seed = int(self._cfg.get("seed", 1234))
         self._rank = int(self._cfg.get("rank", 0))
+        # optional allocator(shape) -> float32 array (``ssnet_base.pinned_empty``): batches are then
+        # produced in a ring of three page-locked buffer sets and reach the device without a
+        # pageable -> pinned staging copy (larcv's filler threads hand over buffers the same way)
+        self._alloc = self._cfg.get("allocator")
+        self._ring = None
         self._names = {"data": self._cfg.get("keyword_data", "data"),
                        "label": self._cfg.get("keyword_label", "label"),
                        "weight": self._cfg.get("keyword_weight", "weight")}
@@ -121,7 +131,13 @@ class synthetic_threadio(object):
 
     def next(self, store_entries=False, store_event_ids=False):
         self._step += 1
-        d, l, w = make_batch(self._batch, self._dims, (self._seed, self._rank, self._step))
+        out = None
+        if self._alloc is not None:
+            if self._ring is None:
+                P = int(np.prod(self._dims[:-1]))
+                self._ring = [tuple(self._alloc((self._batch, P)) for _ in range(3)) for _ in range(3)]
+            out = self._ring[self._step % 3]
+        d, l, w = make_batch(self._batch, self._dims, (self._seed, self._rank, self._step), out=out)
         self._cur = {self._names["data"]: (d, [self._batch] + self._dims),
                      self._names["label"]: (l, [self._batch] + self._dims[:-1] + [1]),
                      self._names["weight"]: (w, [self._batch] + self._dims[:-1] + [1])}
