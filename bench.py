@@ -108,11 +108,11 @@ NCU_TRAFFIC = {
 }
 
 
-def launch_groups(layer_table, prof_ms, prof_steps, pk, workload, elt_act=2, elt_grad=2):
+def launch_groups(layer_table, prof_ms, prof_steps, pk, workload, elt_act=2, elt_grad=2, elt_raw=4):
     """Conv launch groups of one step keyed by (phase, geometry): the per-launch CUDA-event times of all
     layers with the same shape are pooled.  Every group is rated against the roofline its arithmetic
     intensity selects: algorithmic bytes = each operand tensor once (activations `elt_act` B, gradients
-    `elt_grad` B, fp32 raw conv output 4 B), algorithmic FLOPs = 2*|Y|*taps*cx*cy."""
+    `elt_grad` B, raw conv output `elt_raw` B as stored), algorithmic FLOPs = 2*|Y|*taps*cx*cy."""
     phases = {0: "conv_fwd", 4: "wgrad", 5: "dgrad"}
     ridge = pk["tf_sus"] * 1e12 / (pk["hbm"] * 1e9)
     groups = {}
@@ -127,7 +127,8 @@ def launch_groups(layer_table, prof_ms, prof_steps, pk, workload, elt_act=2, elt
             ms = float(prof_ms[i, col]) / prof_steps
             if ms <= 0.0:
                 continue
-            byts = {"conv_fwd": ein * elt_act + eout * 4, "dgrad": eout * elt_grad + ein * elt_grad,
+            er = elt_raw if (d.cy % 16 == 0 or tr) and scope not in ("conv0", "conv2") else 4
+            byts = {"conv_fwd": ein * elt_act + eout * er, "dgrad": eout * elt_grad + ein * elt_grad,
                     "wgrad": ein * elt_act + eout * elt_grad}[name]
             g = groups.setdefault((name, shape, tr), dict(ms=0.0, bytes=0.0, flops=0.0, launches=0, layers=[]))
             g["ms"] += ms
@@ -152,9 +153,10 @@ def launch_groups(layer_table, prof_ms, prof_steps, pk, workload, elt_act=2, elt
     return out
 
 
-def hbm_bytes(layer_table, elt_act=2, elt_grad=2):
+def hbm_bytes(layer_table, elt_act=2, elt_grad=2, elt_raw=4):
     """Algorithmic HBM bytes of one training step by SURVEY 8d's definition (every logical tensor once
-    per kernel that must touch it; `e` = stored element size): conv forward (input + fp32 raw output),
+    per kernel that must touch it; `e` = stored element size): conv forward (input + raw output, `elt_raw`
+    bytes as stored: 4, or 2 in mix16 except stem and head),
     BN statistics 0 (fused into the conv epilogue), BN apply (raw in, activation out: 2 tensors), BN
     backward reductions (dout + raw: 2 tensors) and apply (dout + raw in, d(raw) out: 3 tensors), input
     gradient (d(raw) in, dX out), filter gradient (X + d(raw) in).  Residual / shortcut / concat extras,
@@ -165,10 +167,11 @@ def hbm_bytes(layer_table, elt_act=2, elt_grad=2):
         big = float(d.n) * d.xd * d.xh * d.xw * d.cx      # X side elements
         small = float(d.n) * d.yd * d.yh * d.yw * d.cy    # Y side elements
         ein, eout = (small, big) if tr else (big, small)
-        tot += ein * elt_act + eout * 4                    # conv forward
-        tot += eout * 4 + eout * elt_act                   # BN apply
-        tot += eout * (elt_grad + 4)                       # BN backward reductions
-        tot += eout * (elt_grad + 4 + elt_grad)            # BN backward apply
+        er = elt_raw if scope not in ("conv0", "conv2") else 4
+        tot += ein * elt_act + eout * er                   # conv forward
+        tot += eout * er + eout * elt_act                  # BN apply
+        tot += eout * (elt_grad + er)                      # BN backward reductions
+        tot += eout * (elt_grad + er + elt_grad)           # BN backward apply
         if scope != "conv0":
             tot += eout * elt_grad + ein * elt_grad        # input gradient
         tot += ein * elt_act + eout * elt_grad             # filter gradient
@@ -369,16 +372,17 @@ def run_leg(cx, workload, dtype, B, steps, warmup, want_e2e=True, want_profile=T
         pk = cx.pk
         tab = net.layer_table(B)
         ea = 4 if dtype == "f32" else 2
+        er = 2 if (dtype == "mix16" and not os.environ.get("URN_RAW_F32")) else 4
         flops = conv_flops(tab)
         ph = {n: float(prof_ms[:, i].sum()) / prof_steps for i, n in enumerate(net.PHASES)}      # ms per step
         conv_ms = ph["conv_fwd"] + ph["dgrad"] + ph["wgrad"]
         conv_fl = (flops["conv_fwd"] + flops["dgrad"] + flops["wgrad"]) * nmb
-        groups = launch_groups(tab, prof_ms, prof_steps * nmb, pk, workload, ea, ea)
+        groups = launch_groups(tab, prof_ms, prof_steps * nmb, pk, workload, ea, ea, er)
         dom = max(groups, key=lambda g: g["ms_per_step"])                 # largest share of the step
         top = max(groups, key=lambda g: g["ms_per_launch"])               # slowest single launch
         for g in (dom, top):
             g["share_of_step"] = g["ms_per_step"] * nmb / ms
-        byts = hbm_bytes(tab, ea, ea) * nmb
+        byts = hbm_bytes(tab, ea, ea, er) * nmb
         out["gpu_launches_per_step"] = int(launches_per_step)
         out["roofline"] = dict(dom, peak_source=pk["src"], profiled_steps=prof_steps,
                                note="dominant conv launch group of the step (largest summed CUDA-event time); "

@@ -79,7 +79,8 @@ int urn_conv_dgrad(const urn_conv_desc* d, int dtype, int impl, const void* dy, 
 /* The same two operations on the tcgen05 tensor-core path (16-bit operands, fp32 accumulate;
  * needs cx % 16 == 0 and cy % 16 == 0).  The f32 TF-layout filter is first packed to the
  * operand dtype into `wpack` (caller scratch, >= 2*taps*cx*cy bytes); inside a network handle
- * the packing happens once per step instead.  y_dtype/x_dtype: URN_F32 or URN_BF16. */
+ * the packing happens once per step instead.  y_dtype/x_dtype: URN_F32 or URN_BF16; y_dtype may
+ * also be URN_F16 (the mix16 raw output; not with accumulate). */
 int urn_conv_fwd_tc(const urn_conv_desc* d, int dtype, const void* x, int64_t ldx, const float* w,
                     void* wpack, void* y, int64_t ldy, int y_dtype, int accumulate, void* stream);
 int urn_conv_dgrad_tc(const urn_conv_desc* d, int dtype, const void* dy, int64_t ldy, const float* w,
@@ -88,10 +89,14 @@ int urn_conv_dgrad_tc(const urn_conv_desc* d, int dtype, const void* dy, int64_t
  * epilogue (K5 without a separate pass over the raw tensor): stats = float[2*cy] (mean | rstd) as
  * urn_bn_stats would produce them.  ws: urn_bn_workspace(cy).  Fails (non-zero) when the layer
  * shape is not one whose kernel fuses the statistics (halo-tile kernel: Cin <= 64; tap-box kernel:
- * Cout <= 256). */
+ * Cout <= 256).  urn_conv_fwd_tc_stats_t: y stored as y_dtype (URN_F32 or URN_F16); the statistics
+ * are those of the fp32 accumulators either way. */
 int urn_conv_fwd_tc_stats(const urn_conv_desc* d, int dtype, const void* x, int64_t ldx, const float* w,
                           void* wpack, float* y, int64_t ldy, float eps, float* stats, void* ws,
                           void* stream);
+int urn_conv_fwd_tc_stats_t(const urn_conv_desc* d, int dtype, const void* x, int64_t ldx, const float* w,
+                            void* wpack, void* y, int y_dtype, int64_t ldy, float eps, float* stats, void* ws,
+                            void* stream);
 
 /* Conv*BackpropFilter: dw[t][cx][cy] (+)= sum_o x[o*s+t-pad][cx] * y[o][cy].
  * ws must hold urn_conv_wgrad_workspace(d) bytes. */
@@ -147,6 +152,29 @@ int urn_bn_bwd_beta(const void* dout, int64_t lddout, const void* out, int64_t l
                     void* draw2, int64_t lddraw2,
                     void* dres, int64_t lddres, int dres_accumulate, int acc_beta,
                     void* ws, void* stream);
+
+/* The three batch-norm entry points with an explicit storage type of the raw conv output(s):
+ * raw_dtype = URN_F32 (the functions above) or URN_F16.  In the mix16 network mode the conv
+ * epilogues store raw as fp16 next to the fp16 activations (statistics are still taken from the
+ * fp32 accumulators): 2 instead of 4 bytes per element in the conv write, the apply read and
+ * both backward reads.  URN_F16 needs power-of-two channel counts >= 8, pitches that are multiples
+ * of 8 elements, fp16 activations and bf16 gradients.  urn_bn_bwd_t takes beta like
+ * urn_bn_bwd_beta (may be NULL); raw2 / res_raw share raw_dtype. */
+int urn_bn_stats_t(const void* raw, int raw_dtype, int64_t ld, int64_t rows, int c, float eps,
+                   float* stats, void* ws, void* stream);
+int urn_bn_apply_t(const void* raw, int raw_dtype, int64_t ld, int64_t rows, int c, const float* stats,
+                   const float* beta, const void* res, int64_t ldres, int res_dtype,
+                   const void* res_raw, int64_t ldres_raw, const float* res_stats,
+                   const float* res_beta, int relu, void* out, int64_t ldout, int out_dtype,
+                   void* out2, void* stream);
+int urn_bn_bwd_t(const void* dout, int64_t lddout, const void* out, int64_t ldo, int dtype,
+                 int out_dtype, int relu, int64_t rows, int c,
+                 const void* raw, int raw_dtype, int64_t ldraw, const float* stats, const float* beta,
+                 float* dbeta, void* draw, int64_t lddraw,
+                 const void* raw2, int64_t ldraw2, const float* stats2, float* dbeta2,
+                 void* draw2, int64_t lddraw2,
+                 void* dres, int64_t lddres, int dres_accumulate, int acc_beta,
+                 void* ws, void* stream);
 
 /* K9/K10/K11  tf.nn.sparse_softmax_cross_entropy_with_logits + weight + per-image
  * sum + batch mean, argmax accuracies, softmax (lib/ssnet.py:57-71).

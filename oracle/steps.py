@@ -57,6 +57,7 @@ STORAGE = {
     "bf16": dict(act=_rounder(torch.bfloat16), shadow=_rounder(torch.bfloat16), grad=_rounder(torch.bfloat16)),
 }
 _r32 = _rounder(torch.float32)
+_r16 = _rounder(torch.float16)
 
 
 def _cl(t):
@@ -68,10 +69,13 @@ def _cl(t):
 class StepOracle(object):
 
     def __init__(self, P_np, data, label, weight=None, base=16, num_strides=5, dtype=torch.float64,
-                 storage=None):
-        """data [B,...,Cin], label / weight [B,...] numpy (as for ``uresnet_oracle.run``)."""
+                 storage=None, raw16=()):
+        """data [B,...,Cin], label / weight [B,...] numpy (as for ``uresnet_oracle.run``).
+        ``raw16``: scopes whose raw conv output the library stores as fp16 (``urn_layer_tensors``);
+        all others are stored as fp32."""
         self.dt = dtype
         self.q = STORAGE[storage]
+        self.raw16 = set(raw16)
         self.nodes_e = OrderedDict()        # name -> the producing step's output on storage-rounded inputs
         self.P = OrderedDict((k, torch.tensor(v, dtype=dtype)) for k, v in P_np.items())
         d = torch.tensor(data, dtype=dtype)
@@ -114,11 +118,15 @@ class StepOracle(object):
                 self.nodes_e[out] = F.relu(y) if relu else y
             self.recs.append(("layer", scope))
 
+    def _raw_stored(self, scope):
+        """the raw conv output as the library stores it (fp32, or fp16 for the ``raw16`` scopes)"""
+        return (_r16 if scope in self.raw16 else _r32)(self.layers[scope]["raw"])
+
     def _bn_stored(self, scope):
         """BN output from the STORED raw tensor and statistics (fp32), as the apply kernels see them."""
         L = self.layers[scope]
         shp = [1, -1] + [1] * self.nd
-        return (_r32(L["raw"]) - _r32(L["mean"]).view(shp)) * _r32(L["rstd"]).view(shp) + self._w(scope)[1].view(shp)
+        return (self._raw_stored(scope) - _r32(L["mean"]).view(shp)) * _r32(L["rstd"]).view(shp) + self._w(scope)[1].view(shp)
 
     def _module(self, scope, x_name, cout, stride):                    # resnet_module.py:10-68
         x = self.nodes[x_name]
@@ -182,14 +190,34 @@ class StepOracle(object):
     def _bn_bwd(self, scope, dout, relu, stored=False):
         """Local autograd through y = [relu](BN(raw, beta)).  Returns (draw, dbeta)."""
         L = self.layers[scope]
-        raw = (_r32(L["raw"]) if stored else L["raw"]).detach().requires_grad_(True)
         if stored:
-            dout = self.q["grad"](dout)
+            return self._bn_bwd_stored(scope, self.q["grad"](dout), relu=relu)[:2]
+        raw = L["raw"].detach().requires_grad_(True)
         beta = self._w(scope)[1].detach().requires_grad_(True)
         y = O.batch_norm(raw, beta)
         if relu:
             y = F.relu(y)
         return torch.autograd.grad(y, [raw, beta], dout)
+
+    def _bn_bwd_stored(self, scope, g, relu=False, mask=None):
+        """slim.batch_norm backward in closed form on the STORED tensors, as the kernels evaluate it:
+        xhat from the stored raw output and the stored statistics (which were taken from the fp32
+        accumulators -- with an fp16 raw copy they are NOT the statistics of the stored values, so
+        differentiating batch_norm(stored raw) would be a different function):
+            g' = g * mask;  dbeta = sum g';  d(raw) = rstd * (g' - mean(g') - xhat * mean(g' * xhat)).
+        Returns (d(raw), dbeta, g')."""
+        L = self.layers[scope]
+        shp = [1, -1] + [1] * self.nd
+        axes = [0] + list(range(2, g.dim()))
+        mu, rstd = _r32(L["mean"]).view(shp), _r32(L["rstd"]).view(shp)
+        xhat = (self._raw_stored(scope) - mu) * rstd
+        if relu:
+            mask = (xhat + self._w(scope)[1].view(shp)) > 0
+        if mask is not None:
+            g = g * mask.to(g.dtype)
+        mg = g.mean(dim=axes, keepdim=True)
+        mgx = (g * xhat).mean(dim=axes, keepdim=True)
+        return rstd * (g - mg - xhat * mgx), g.sum(dim=axes), g
 
     def _conv_bwd(self, scope, draw, stored=False):
         """Local autograd through raw = conv(x, W).  Returns (dx or None for the stem, dW)."""
@@ -249,29 +277,30 @@ class StepOracle(object):
                 _, scope, sc, x_name = rec
                 c1, c2 = scope + "/resnet_conv1", scope + "/resnet_conv2"
                 dout = G[scope]
-                for stored in ((False, True) if q else (False,)):
-                    rnd = _r32 if stored else (lambda t: t)
-                    bn = self.bn_e if stored else self.bn
-                    do = q["grad"](dout) if stored else dout
-                    raw2 = rnd(self.layers[c2]["raw"]).detach().requires_grad_(True)
-                    b2 = self._w(c2)[1].detach().requires_grad_(True)
-                    if stored:
-                        # the kernels take the ReLU mask of a merge from the STORED module output
-                        do = do * (q["act"](self.nodes[scope]) > 0).to(do.dtype)
+                raw2 = self.layers[c2]["raw"].detach().requires_grad_(True)
+                b2 = self._w(c2)[1].detach().requires_grad_(True)
+                if sc:
+                    raws = self.layers[sc]["raw"].detach().requires_grad_(True)
+                    bs = self._w(sc)[1].detach().requires_grad_(True)
+                    y = self._merge_local(raw2, b2, O.batch_norm(raws, bs))
+                    d2, db2, ds, dbs = torch.autograd.grad(y, [raw2, b2, raws, bs], dout)
+                    self.bn[c2] = dict(dout=dout, draw=d2, dbeta=db2)
+                    self.bn[sc] = dict(dout=dout, draw=ds, dbeta=dbs)
+                else:
+                    xr = self.nodes[x_name].detach().requires_grad_(True)
+                    y = self._merge_local(raw2, b2, xr)
+                    d2, db2, g = torch.autograd.grad(y, [raw2, b2, xr], dout)
+                    self.bn[c2] = dict(dout=dout, draw=d2, dbeta=db2, g=g)
+                    add(x_name, g)
+                if q:
+                    # the kernels take the ReLU mask of a merge from the STORED module output; the same masked
+                    # gradient flows through both batch-norms (and, unchanged, to an identity shortcut)
+                    mask = q["act"](self.nodes[scope]) > 0
+                    d2, db2, g = self._bn_bwd_stored(c2, q["grad"](dout), mask=mask)
+                    self.bn_e[c2] = dict(draw=d2, dbeta=db2, g=g)
                     if sc:
-                        raws = rnd(self.layers[sc]["raw"]).detach().requires_grad_(True)
-                        bs = self._w(sc)[1].detach().requires_grad_(True)
-                        y = self._merge_local(raw2, b2, O.batch_norm(raws, bs), relu=not stored)
-                        d2, db2, ds, dbs = torch.autograd.grad(y, [raw2, b2, raws, bs], do)
-                        bn[c2] = dict(dout=dout, draw=d2, dbeta=db2)
-                        bn[sc] = dict(dout=dout, draw=ds, dbeta=dbs)
-                    else:
-                        xr = (q["act"](self.nodes[x_name]) if stored else self.nodes[x_name]).detach().requires_grad_(True)
-                        y = self._merge_local(raw2, b2, xr, relu=not stored)
-                        d2, db2, g = torch.autograd.grad(y, [raw2, b2, xr], do)
-                        bn[c2] = dict(dout=dout, draw=d2, dbeta=db2, g=g)
-                        if not stored:
-                            add(x_name, g)
+                        ds, dbs, _ = self._bn_bwd_stored(sc, q["grad"](dout), mask=mask)
+                        self.bn_e[sc] = dict(draw=ds, dbeta=dbs)
                 conv_part(c2)
                 draw1, db1 = self._bn_bwd(c1, G[c1], False)
                 self.bn[c1] = dict(dout=G[c1], draw=draw1, dbeta=db1)

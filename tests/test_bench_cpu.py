@@ -44,6 +44,9 @@ def test_hbm_byte_model():
     assert bench.hbm_bytes([("some/layer", D, False)]) == want
     assert bench.hbm_bytes([("conv0", D, False)]) == want - (e * 2 + e * 2)      # no input gradient for the stem
     assert bench.hbm_bytes([("some/layer", D, False)], 4, 4) == (e * 4 + e * 4) + (e * 4 + e * 4) + e * 8 + e * 12 + e * 8 + e * 8
+    # mix16 with fp16 raw conv outputs: 2 bytes wherever raw is touched (not for the stem / head)
+    assert bench.hbm_bytes([("some/layer", D, False)], 2, 2, 2) == want - 4 * e * 2
+    assert bench.hbm_bytes([("conv2", D, False)], 2, 2, 2) == want
 
 
 def test_launch_groups_pool_equal_shapes_and_pick_the_bound():

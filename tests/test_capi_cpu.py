@@ -143,7 +143,10 @@ def test_plan_introspection_matches_step_oracle(lib, nd, sp, B, F, S, dt):
         _capi.check(lib.urn_layer_info(h, li, C.byref(scope), None, None, None, None, None, None))
         sc = scope.value.decode()
         scopes.append(sc)
-        assert (raw.rows, raw.c) == so.raw(sc).shape and raw.dtype == 0
+        assert (raw.rows, raw.c) == so.raw(sc).shape
+        # mix16: raw conv outputs stored as fp16 except the stem, the head and non-power-of-two / narrow widths
+        want16 = dt == 2 and sc not in ("conv0", "conv2") and raw.c % 16 == 0 and (raw.c & (raw.c - 1)) == 0
+        assert raw.dtype == (2 if want16 else 0), (sc, raw.dtype)
         assert names[inn.value] == so.layers[sc]["x"]
         assert (names[outn.value] if outn.value >= 0 else None) == so.layers[sc]["out"]
         assert draw.c == raw.c and draw.ld >= draw.c

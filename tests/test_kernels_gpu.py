@@ -521,6 +521,108 @@ def test_bn_backward(lib, dt, c, rows, relu, mode):
         assert relerr(host(dres), 1 + grads[2].numpy()) < tol   # accumulated onto the ones
 
 
+@pytest.mark.parametrize("c,rows,relu,mode", [(16, 70001, 1, "plain"), (32, 4099, 0, "plain"), (16, 3000, 1, "conv_sc"),
+                                              (64, 129, 1, "identity"), (512, 33, 1, "conv_sc"), (8, 999, 1, "identity")])
+def test_bn_fp16_raw(lib, c, rows, relu, mode):
+    """mix16 stores the raw conv output as fp16 (urn_bn_*_t with raw_dtype = URN_F16): statistics, apply
+    (plain / identity residual / second BN) and backward against float64 on the same fp16 values."""
+    rng = np.random.default_rng(rows * 7 + c)
+    x = host(dev(rng.standard_normal((rows, c)).astype(np.float32) * 2 + 0.5, F16))
+    x2 = host(dev(rng.standard_normal((rows, c)).astype(np.float32), F16))
+    res = host(dev(rng.standard_normal((rows, c)).astype(np.float32), F16))
+    beta = rng.standard_normal(c).astype(np.float32) * 0.3
+    dout = host(dev(rng.standard_normal((rows, c)).astype(np.float32), BF16))
+    xt, x2t, rt = (torch.tensor(v, dtype=torch.float64, requires_grad=True) for v in (x, x2, res))
+    bt = torch.tensor(beta, dtype=torch.float64, requires_grad=True)
+
+    def bn(v, b):
+        mu = v.mean(0)
+        var = ((v - mu) ** 2).mean(0)
+        return (v - mu) * torch.rsqrt(var + 1e-3) + b
+    y = bn(xt, bt)
+    if mode == "conv_sc":
+        y = y + bn(x2t, bt * 0)
+    elif mode == "identity":
+        y = y + rt
+    out = torch.relu(y) if relu else y
+    ins = [xt, bt] + ([x2t] if mode == "conv_sc" else []) + ([rt] if mode == "identity" else [])
+    grads = torch.autograd.grad(out, ins, torch.tensor(dout, dtype=torch.float64))
+    ws = torch.empty(int(lib.urn_bn_workspace(c)), dtype=torch.uint8, device=DEV)
+
+    def stats_of(v):
+        vd = dev(v, F16)
+        s = torch.empty(2 * c, dtype=torch.float32, device=DEV)
+        _capi.check(lib.urn_bn_stats_t(vd.data_ptr(), F16, c, rows, c, 1e-3, s.data_ptr(), ws.data_ptr(), st()))
+        return vd, s
+    xd, s1 = stats_of(x)
+    x2d, s2 = stats_of(x2)
+    mu, var = x.astype(np.float64).mean(0), x.astype(np.float64).var(0)
+    np.testing.assert_allclose(host(s1)[:c], mu, atol=1e-5)
+    np.testing.assert_allclose(host(s1)[c:], 1 / np.sqrt(var + 1e-3), rtol=2e-5)
+    bd, zd, rd = dev(beta), dev(0 * beta), dev(res, F16)
+    outd = torch.empty((rows, c), dtype=torch.float16, device=DEV)
+    sh = torch.empty((rows, c), dtype=torch.bfloat16, device=DEV)
+    _capi.check(lib.urn_bn_apply_t(
+        xd.data_ptr(), F16, c, rows, c, s1.data_ptr(), bd.data_ptr(), rd.data_ptr() if mode == "identity" else None, c, F16,
+        x2d.data_ptr() if mode == "conv_sc" else None, c, s2.data_ptr() if mode == "conv_sc" else None,
+        zd.data_ptr() if mode == "conv_sc" else None, relu, outd.data_ptr(), c, F16, sh.data_ptr(), st()))
+    assert relerr(host(outd), out.detach().numpy()) < 1e-3 and relerr(host(sh), out.detach().numpy()) < 8e-3
+    draw = torch.empty((rows, c), dtype=torch.bfloat16, device=DEV)
+    draw2 = torch.empty((rows, c), dtype=torch.bfloat16, device=DEV)
+    dres = torch.ones((rows, c), dtype=torch.bfloat16, device=DEV)
+    dbeta = torch.zeros(c, dtype=torch.float32, device=DEV)
+    dbeta2 = torch.zeros(c, dtype=torch.float32, device=DEV)
+    doutd = dev(dout, BF16)
+    for with_beta in ((False, True) if mode == "plain" else (False,)):
+        _capi.check(lib.urn_bn_bwd_t(
+            doutd.data_ptr(), c, outd.data_ptr(), c, BF16, F16, relu, rows, c, xd.data_ptr(), F16, c, s1.data_ptr(),
+            bd.data_ptr() if with_beta else None, dbeta.data_ptr(), draw.data_ptr(), c,
+            x2d.data_ptr() if mode == "conv_sc" else None, c, s2.data_ptr() if mode == "conv_sc" else None,
+            dbeta2.data_ptr() if mode == "conv_sc" else None, draw2.data_ptr() if mode == "conv_sc" else None, c,
+            dres.data_ptr() if mode == "identity" else None, c, 1, 0, ws.data_ptr(), st()))
+        assert relerr(host(draw), grads[0].numpy()) < TOL[BF16], with_beta
+        assert relerr(host(dbeta), grads[1].numpy()) < 1e-4
+    if mode == "conv_sc":
+        assert relerr(host(draw2), grads[2].numpy()) < TOL[BF16]
+        assert relerr(host(dbeta2), grads[1].numpy()) < 1e-4
+    if mode == "identity":
+        assert relerr(host(dres), 1 + grads[2].numpy()) < TOL[BF16]
+    # a shape outside the fast path must be refused, not mis-read
+    bad = torch.zeros((8, 3), dtype=torch.float16, device=DEV)
+    sb = torch.empty(6, dtype=torch.float32, device=DEV)
+    assert lib.urn_bn_stats_t(bad.data_ptr(), F16, 3, 8, 3, 1e-3, sb.data_ptr(), ws.data_ptr(), st()) != 0
+
+
+@pytest.mark.parametrize("nd,n,sp,cin,cout,k,s", [
+    (2, 3, (40, 72), 16, 16, 3, 1), (2, 2, (32, 48), 16, 32, 3, 2), (2, 2, (16, 40), 32, 16, 1, 1),
+    (3, 1, (9, 20, 12), 16, 16, 3, 1), (2, 2, (16, 24), 128, 128, 3, 1), (2, 3, (8, 8), 256, 128, 1, 1)])
+def test_conv_fp16_raw_output(lib, nd, n, sp, cin, cout, k, s):
+    """mix16 conv epilogues store the raw output as fp16 while the fused BN statistics are still those of
+    the fp32 accumulators: identical statistics as the fp32-output launch, output = its rounding."""
+    rng = np.random.default_rng(hash((nd, n, sp, cin, cout, k, s, 5)) % 2**32)
+    x = host(dev(rng.standard_normal((n,) + sp + (cin,)).astype(np.float32) + 0.3, F16))
+    w = (rng.standard_normal((k,) * nd + (cin, cout)) / np.sqrt(k**nd * cin)).astype(np.float32)
+    d = _capi.conv_desc_same(nd, n, sp, cin, cout, k, s)
+    osp = (d.yd, d.yh, d.yw)[3 - nd:]
+    xd, wd = dev(x, F16), dev(w)
+    wpack = torch.empty(2 * w.size + 64, dtype=torch.uint8, device=DEV)
+    ws = torch.empty(int(lib.urn_bn_workspace(cout)), dtype=torch.uint8, device=DEV)
+    res = {}
+    for ydt in (F32, F16):
+        y = torch.full((n,) + osp + (cout,), 7.0, dtype=TORCH_DT[ydt], device=DEV)
+        stats = torch.empty(2 * cout, dtype=torch.float32, device=DEV)
+        _capi.check(lib.urn_conv_fwd_tc_stats_t(C.byref(d), F16, xd.data_ptr(), cin, wd.data_ptr(), wpack.data_ptr(),
+                                                y.data_ptr(), ydt, cout, 1e-3, stats.data_ptr(), ws.data_ptr(), st()))
+        res[ydt] = (y, host(stats))
+    assert np.array_equal(res[F32][1], res[F16][1])
+    assert torch.equal(res[F32][0].to(torch.float16), res[F16][0])
+    # and without statistics (plain forward entry point)
+    y2 = torch.empty_like(res[F16][0])
+    _capi.check(lib.urn_conv_fwd_tc(C.byref(d), F16, xd.data_ptr(), cin, wd.data_ptr(), wpack.data_ptr(), y2.data_ptr(), cout,
+                                    F16, 0, st()))
+    assert torch.equal(y2, res[F16][0])
+
+
 @pytest.mark.parametrize("c,rows,relu,mode", [(16, 70001, 1, "plain"), (32, 5003, 0, "plain"), (64, 129, 1, "identity"),
                                               (128, 300, 1, "conv_sc"), (512, 33, 0, "plain"), (8, 999, 1, "identity"),
                                               (16, 4096, 1, "conv_sc"), (3, 500, 0, "plain")])

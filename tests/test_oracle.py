@@ -244,3 +244,14 @@ def test_step_oracle_storage_rounded_expectations():
     assert rel(b.node("conv1", True), b.node("conv1")) < 1e-5          # fp32 raw + statistics in, fp64 math
     m = "resnet_module7/module2"
     assert rel(b.masked_gradient(m, True), b.masked_gradient(m)) < 2e-2
+    # fp32 storage: the closed-form BN backward on stored tensors IS the autograd backward of batch_norm
+    c = StepOracle(P, data, label, weight, base=4, num_strides=3, storage="f32")
+    c.backward()
+    for scope in c.layers:
+        assert rel(c.draw(scope, True), c.draw(scope)) < 1e-5, scope
+        assert rel(c.dbeta(scope, True), c.dbeta(scope)) < 1e-4 or np.abs(c.dbeta(scope)).max() < 1e-12, scope
+        assert rel(c.node(c.layers[scope]["out"], True), c.node(c.layers[scope]["out"])) < 1e-5 if c.layers[scope]["out"] else True
+    # fp16 raw copies: only the named scopes are rounded, by ~2^-11 of the raw scale
+    d = StepOracle(P, data, label, weight, base=4, num_strides=3, storage="mix16", raw16={"conv1"})
+    e1 = rel(d.node("conv1", True), d.node("conv1"))
+    assert 1e-5 < e1 < 5e-3

@@ -130,13 +130,15 @@ class Plan(object):
 
 def run_teacher_forced(dims, B, F, St, dtype, seed_d=31, seed_p=17):
     P, data, label, weight, shaped = make_case(dims, B, F, St, seed_d, seed_p)
-    so = StepOracle(P, *shaped, base=F, num_strides=St, storage=dtype)
-    so.backward()
     net = make_net(dims, F, St, dtype)
     net.set_variables(P)
     net.zero_gradients(None)
     net._use_graphs = False
     pl = Plan(net, B)
+    raw16 = {L["scope"] for L in pl.layers if L["raw"].dtype == _capi.URN_F16}
+    assert (len(raw16) > 40) == (dtype == "mix16" and not os.environ.get("URN_RAW_F32"))
+    so = StepOracle(P, *shaped, base=F, num_strides=St, storage=dtype, raw16=raw16)
+    so.backward()
     lib, h, ws = pl.lib, pl.h, pl.ws
     params, grads = net._params.data_ptr(), net._accum.data_ptr()
     feed = net.feed_dict(data, label, weight)

@@ -66,6 +66,12 @@ SIGNATURES = {
                         _vp, _i64, _vp, _vp, _vp, _i64, _vp, _i64, _i, _i, _vp, _vp]),
     "urn_bn_bwd_beta": (_i, [_vp, _i64, _vp, _i64, _i, _i, _i, _i64, _i, _vp, _i64, _vp, _vp, _vp, _vp, _i64,
                              _vp, _i64, _vp, _vp, _vp, _i64, _vp, _i64, _i, _i, _vp, _vp]),
+    "urn_bn_stats_t": (_i, [_vp, _i, _i64, _i64, _i, _f, _vp, _vp, _vp]),
+    "urn_bn_apply_t": (_i, [_vp, _i, _i64, _i64, _i, _vp, _vp, _vp, _i64, _i, _vp, _i64, _vp, _vp, _i,
+                            _vp, _i64, _i, _vp, _vp]),
+    "urn_bn_bwd_t": (_i, [_vp, _i64, _vp, _i64, _i, _i, _i, _i64, _i, _vp, _i, _i64, _vp, _vp, _vp, _vp, _i64,
+                          _vp, _i64, _vp, _vp, _vp, _i64, _vp, _i64, _i, _i, _vp, _vp]),
+    "urn_conv_fwd_tc_stats_t": (_i, [_descp, _i, _vp, _i64, _vp, _vp, _vp, _i, _i64, _f, _vp, _vp, _vp]),
     "urn_loss_workspace": (_i64, [_i64]),
     "urn_ce_fwd_bwd": (_i, [_vp, _i64, _vp, _vp, _vp, _i64, _i64, _i, _vp, _i64, _i, _vp, _vp, _vp,
                             _vp]),

@@ -105,9 +105,10 @@ __device__ __forceinline__ void channel_partial_sum(const double* __restrict__ p
   for (int k = 0; k < K; ++k) out[k] = sh[k][0];
 }
 
+template <typename TW>
 __global__ void __launch_bounds__(128)
 bn_stats_finalize_kernel(const double* __restrict__ partial, int nblocks, int c, long long rows,
-                         float eps, const float* __restrict__ raw, float* __restrict__ stats) {
+                         float eps, const TW* __restrict__ raw, float* __restrict__ stats) {
   const int ch = blockIdx.x;
   double v[2];
   channel_partial_sum<2>(partial, nblocks, c, ch, v);
@@ -115,7 +116,7 @@ bn_stats_finalize_kernel(const double* __restrict__ partial, int nblocks, int c,
     const double dm = v[0] / (double)rows;                 // mean of (x - K)
     double var = v[1] / (double)rows - dm * dm;
     if (var < 0.0) var = 0.0;
-    stats[ch] = (float)((double)raw[ch] + dm);
+    stats[ch] = (float)((double)ld1(raw + ch) + dm);
     stats[c + ch] = (float)(1.0 / sqrt(var + (double)eps));
   }
 }
@@ -387,18 +388,23 @@ extern "C" int64_t urn_bn_workspace(int c) {
   return b + (int64_t)3 * c * 4 + 256;
 }
 
-extern "C" int urn_bn_stats(const float* raw, int64_t ld, int64_t rows, int c, float eps,
-                            float* stats, void* ws, void* stream) {
+int bn_stats_any(const void* raw_, int raw_dtype, int64_t ld, int64_t rows, int c, float eps, float* stats,
+                 void* ws, cudaStream_t st) {
   URN_CHECK(c >= 1 && c <= 1024, "urn_bn_stats: c=%d out of range", c);
   URN_CHECK(rows > 0, "urn_bn_stats: empty input");
-  cudaStream_t st = (cudaStream_t)stream;
-  if (bn_fast_shape(c, {ld}, {raw})) {
+  URN_CHECK(raw_dtype == URN_F32 || raw_dtype == URN_F16, "urn_bn_stats: raw dtype %d", raw_dtype);
+  if (bn_fast_shape(c, {ld}, {raw_})) {
     int nbf = 0;
-    if (bn_stats_fast_launch(raw, ld, rows, c, (double*)ws, &nbf, st)) return 1;
-    bn_stats_finalize_kernel<<<c, 128, 0, st>>>((const double*)ws, nbf, c, rows, eps, raw, stats);
+    if (bn_stats_fast_launch(raw_, raw_dtype, ld, rows, c, (double*)ws, &nbf, st)) return 1;
+    if (raw_dtype == URN_F16)
+      bn_stats_finalize_kernel<f16><<<c, 128, 0, st>>>((const double*)ws, nbf, c, rows, eps, (const f16*)raw_, stats);
+    else
+      bn_stats_finalize_kernel<float><<<c, 128, 0, st>>>((const double*)ws, nbf, c, rows, eps, (const float*)raw_, stats);
     URN_LAUNCH_CHECK();
     return 0;
   }
+  URN_CHECK(raw_dtype == URN_F32, "urn_bn_stats: f16 raw needs power-of-two channels >= 8 and 8-aligned pitches (c=%d)", c);
+  const float* raw = (const float*)raw_;
   bool al = aligned4(c, {ld}) && ((uintptr_t)raw % 16 == 0);
   ColMap m = col_map(c, al);
   URN_CHECK(m.cg <= BN_THREADS, "urn_bn_stats: c=%d needs 4-aligned pitch", c);
@@ -406,9 +412,18 @@ extern "C" int urn_bn_stats(const float* raw, int64_t ld, int64_t rows, int c, f
   double* partial = (double*)ws;
   bn_stats_kernel<<<nb, BN_THREADS, 0, st>>>(raw, ld, rows, c, al, partial);
   URN_LAUNCH_CHECK();
-  bn_stats_finalize_kernel<<<c, 128, 0, st>>>(partial, nb, c, rows, eps, raw, stats);
+  bn_stats_finalize_kernel<float><<<c, 128, 0, st>>>(partial, nb, c, rows, eps, raw, stats);
   URN_LAUNCH_CHECK();
   return 0;
+}
+
+extern "C" int urn_bn_stats(const float* raw, int64_t ld, int64_t rows, int c, float eps,
+                            float* stats, void* ws, void* stream) {
+  return bn_stats_any(raw, URN_F32, ld, rows, c, eps, stats, ws, (cudaStream_t)stream);
+}
+extern "C" int urn_bn_stats_t(const void* raw, int raw_dtype, int64_t ld, int64_t rows, int c, float eps,
+                              float* stats, void* ws, void* stream) {
+  return bn_stats_any(raw, raw_dtype, ld, rows, c, eps, stats, ws, (cudaStream_t)stream);
 }
 
 template <typename TR, typename TO>
@@ -426,16 +441,18 @@ static int bn_apply_t(const float* raw, int64_t ld, int64_t rows, int c, const f
   return 0;
 }
 
-extern "C" int urn_bn_apply(const float* raw, int64_t ld, int64_t rows, int c, const float* stats,
-                            const float* beta, const void* res, int64_t ldres, int res_dtype,
-                            const float* res_raw, int64_t ldres_raw, const float* res_stats,
-                            const float* res_beta, int relu, void* out, int64_t ldout,
-                            int out_dtype, void* out2, void* stream) {
-  cudaStream_t st = (cudaStream_t)stream;
+int bn_apply_any(const void* raw_, int raw_dtype, int64_t ld, int64_t rows, int c, const float* stats,
+                 const float* beta, const void* res, int64_t ldres, int res_dtype, const void* res_raw_,
+                 int64_t ldres_raw, const float* res_stats, const float* res_beta, int relu, void* out,
+                 int64_t ldout, int out_dtype, void* out2, cudaStream_t st) {
   URN_CHECK(rows > 0 && c >= 1, "urn_bn_apply: empty input");
-  if (bn_fast_shape(c, {ld, ldout, res ? ldres : 0, res_raw ? ldres_raw : 0}, {raw, out, out2, res, res_raw}))
-    return bn_apply_fast_launch(raw, ld, rows, c, stats, beta, res, ldres, res_dtype, res_raw, ldres_raw,
+  URN_CHECK(raw_dtype == URN_F32 || raw_dtype == URN_F16, "urn_bn_apply: raw dtype %d", raw_dtype);
+  if (bn_fast_shape(c, {ld, ldout, res ? ldres : 0, res_raw_ ? ldres_raw : 0}, {raw_, out, out2, res, res_raw_}))
+    return bn_apply_fast_launch(raw_, raw_dtype, ld, rows, c, stats, beta, res, ldres, res_dtype, res_raw_, ldres_raw,
                                 res_stats, res_beta, relu, out, ldout, out_dtype, out2, st);
+  URN_CHECK(raw_dtype == URN_F32, "urn_bn_apply: f16 raw needs power-of-two channels >= 8 and 8-aligned pitches (c=%d)", c);
+  const float* raw = (const float*)raw_;
+  const float* res_raw = (const float*)res_raw_;
   if (!res) res_dtype = out_dtype;
   return dispatch_dtype(res_dtype, [&](auto pr) {
     using TR = URN_T(pr);
@@ -445,6 +462,23 @@ extern "C" int urn_bn_apply(const float* raw, int64_t ld, int64_t rows, int c, c
                                 res_stats, res_beta, relu, out, ldout, out2, st);
     });
   });
+}
+
+extern "C" int urn_bn_apply(const float* raw, int64_t ld, int64_t rows, int c, const float* stats,
+                            const float* beta, const void* res, int64_t ldres, int res_dtype,
+                            const float* res_raw, int64_t ldres_raw, const float* res_stats,
+                            const float* res_beta, int relu, void* out, int64_t ldout,
+                            int out_dtype, void* out2, void* stream) {
+  return bn_apply_any(raw, URN_F32, ld, rows, c, stats, beta, res, ldres, res_dtype, res_raw, ldres_raw, res_stats,
+                      res_beta, relu, out, ldout, out_dtype, out2, (cudaStream_t)stream);
+}
+extern "C" int urn_bn_apply_t(const void* raw, int raw_dtype, int64_t ld, int64_t rows, int c, const float* stats,
+                              const float* beta, const void* res, int64_t ldres, int res_dtype,
+                              const void* res_raw, int64_t ldres_raw, const float* res_stats,
+                              const float* res_beta, int relu, void* out, int64_t ldout,
+                              int out_dtype, void* out2, void* stream) {
+  return bn_apply_any(raw, raw_dtype, ld, rows, c, stats, beta, res, ldres, res_dtype, res_raw, ldres_raw, res_stats,
+                      res_beta, relu, out, ldout, out_dtype, out2, (cudaStream_t)stream);
 }
 
 template <typename T, typename TA>
@@ -483,7 +517,7 @@ extern "C" int urn_bn_bwd(const void* dout, int64_t lddout, const void* out, int
                           int64_t lddraw, const float* raw2, int64_t ldraw2, const float* stats2,
                           float* dbeta2, void* draw2, int64_t lddraw2, void* dres, int64_t lddres,
                           int dres_accumulate, int acc_beta, void* ws, void* stream) {
-  return bn_bwd_full(dout, lddout, out, ldo, dtype, out_dtype, relu, rows, c, raw, ldraw, stats, nullptr, dbeta,
+  return bn_bwd_full(dout, lddout, out, ldo, dtype, out_dtype, relu, rows, c, raw, URN_F32, ldraw, stats, nullptr, dbeta,
                      draw, lddraw, raw2, ldraw2, stats2, dbeta2, draw2, lddraw2, dres, lddres, dres_accumulate,
                      acc_beta, ws, (cudaStream_t)stream);
 }
@@ -495,17 +529,31 @@ extern "C" int urn_bn_bwd_beta(const void* dout, int64_t lddout, const void* out
                                const float* stats2, float* dbeta2, void* draw2, int64_t lddraw2,
                                void* dres, int64_t lddres, int dres_accumulate, int acc_beta, void* ws,
                                void* stream) {
-  return bn_bwd_full(dout, lddout, out, ldo, dtype, out_dtype, relu, rows, c, raw, ldraw, stats, beta, dbeta,
+  return bn_bwd_full(dout, lddout, out, ldo, dtype, out_dtype, relu, rows, c, raw, URN_F32, ldraw, stats, beta, dbeta,
+                     draw, lddraw, raw2, ldraw2, stats2, dbeta2, draw2, lddraw2, dres, lddres, dres_accumulate,
+                     acc_beta, ws, (cudaStream_t)stream);
+}
+extern "C" int urn_bn_bwd_t(const void* dout, int64_t lddout, const void* out, int64_t ldo, int dtype,
+                            int out_dtype, int relu, int64_t rows, int c, const void* raw, int raw_dtype,
+                            int64_t ldraw, const float* stats, const float* beta, float* dbeta,
+                            void* draw, int64_t lddraw, const void* raw2, int64_t ldraw2,
+                            const float* stats2, float* dbeta2, void* draw2, int64_t lddraw2,
+                            void* dres, int64_t lddres, int dres_accumulate, int acc_beta, void* ws,
+                            void* stream) {
+  return bn_bwd_full(dout, lddout, out, ldo, dtype, out_dtype, relu, rows, c, raw, raw_dtype, ldraw, stats, beta, dbeta,
                      draw, lddraw, raw2, ldraw2, stats2, dbeta2, draw2, lddraw2, dres, lddres, dres_accumulate,
                      acc_beta, ws, (cudaStream_t)stream);
 }
 
 int bn_bwd_full(const void* dout, int64_t lddout, const void* out, int64_t ldo, int dtype, int out_dtype,
-                int relu, int64_t rows, int c, const float* raw, int64_t ldraw, const float* stats,
-                const float* beta, float* dbeta, void* draw, int64_t lddraw, const float* raw2,
+                int relu, int64_t rows, int c, const void* raw_, int raw_dtype, int64_t ldraw, const float* stats,
+                const float* beta, float* dbeta, void* draw, int64_t lddraw, const void* raw2_,
                 int64_t ldraw2, const float* stats2, float* dbeta2, void* draw2, int64_t lddraw2, void* dres,
                 int64_t lddres, int dres_accumulate, int acc_beta, void* ws, cudaStream_t st) {
   URN_CHECK(rows > 0 && c >= 1 && c <= 1024, "urn_bn_bwd: bad shape");
+  URN_CHECK(raw_dtype == URN_F32 || raw_dtype == URN_F16, "urn_bn_bwd: raw dtype %d", raw_dtype);
+  const float* raw = (const float*)raw_;      // generic kernels below: fp32 raw only (checked)
+  const float* raw2 = (const float*)raw2_;
   URN_CHECK(!relu || out, "urn_bn_bwd: relu needs the forward output");
   const bool pair_ok = (dtype == URN_F32 && out_dtype == URN_F32) || (dtype == URN_BF16 && out_dtype != URN_F32);
   if (pair_ok && out &&
@@ -515,16 +563,17 @@ int bn_bwd_full(const void* dout, int64_t lddout, const void* out, int64_t ldo, 
     const int64_t pb = ((int64_t)BN_MAX_BLOCKS * 3 * c * 8 + 255) / 256 * 256;
     float* sums = (float*)((char*)ws + pb);
     int nb = 0;
-    if (bn_bwd_fast_launch(0, dout, lddout, out, ldo, dtype, out_dtype, relu, rows, c, raw, ldraw, stats, beta,
-                           draw, lddraw, raw2, ldraw2, stats2, draw2, lddraw2, dres, lddres, dres_accumulate,
+    if (bn_bwd_fast_launch(0, dout, lddout, out, ldo, dtype, out_dtype, relu, rows, c, raw_, raw_dtype, ldraw, stats, beta,
+                           draw, lddraw, raw2_, ldraw2, stats2, draw2, lddraw2, dres, lddres, dres_accumulate,
                            partial, sums, &nb, st))
       return 1;
     bn_bwd_finalize_kernel<<<c, 128, 0, st>>>(partial, nb, c, sums, dbeta, raw2 ? dbeta2 : nullptr, acc_beta);
     URN_LAUNCH_CHECK();
-    return bn_bwd_fast_launch(1, dout, lddout, out, ldo, dtype, out_dtype, relu, rows, c, raw, ldraw, stats, beta,
-                              draw, lddraw, raw2, ldraw2, stats2, draw2, lddraw2, dres, lddres, dres_accumulate,
+    return bn_bwd_fast_launch(1, dout, lddout, out, ldo, dtype, out_dtype, relu, rows, c, raw_, raw_dtype, ldraw, stats, beta,
+                              draw, lddraw, raw2_, ldraw2, stats2, draw2, lddraw2, dres, lddres, dres_accumulate,
                               partial, sums, &nb, st);
   }
+  URN_CHECK(raw_dtype == URN_F32, "urn_bn_bwd: f16 raw needs the fast-path shape (power-of-two channels >= 8, 8-aligned pitches, 16-bit gradients)");
 #define URN_BB(GD, AD, TG, TAA)                                                                   \
   if (dtype == GD && out_dtype == AD)                                                             \
     return bn_bwd_t<TG, TAA>(dout, lddout, out, ldo, relu, rows, c, raw, ldraw, stats, dbeta, draw, \

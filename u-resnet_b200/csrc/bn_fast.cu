@@ -102,8 +102,9 @@ __device__ __forceinline__ void block_group_reduce(float (&acc)[K][8], int cg, i
 // ---------------------------------------------------------------------------------------
 // forward statistics (shifted sums, see bn.cu)
 // ---------------------------------------------------------------------------------------
+template <typename TW>      // TW: storage type of the raw conv output (float, or f16 in the 16-bit network modes)
 __global__ void __launch_bounds__(BF_T)
-bn_stats_fast_kernel(const float* __restrict__ raw, long long ld, long long rows, int c, int lg,
+bn_stats_fast_kernel(const TW* __restrict__ raw, long long ld, long long rows, int c, int lg,
                      double* __restrict__ partial) {
   constexpr int U = 4;
   const int cg = c >> 3;
@@ -111,7 +112,7 @@ bn_stats_fast_kernel(const float* __restrict__ raw, long long ld, long long rows
   const int ch = (int)(tid & (cg - 1)) * 8;
   const long long rstride = ((long long)gridDim.x * BF_T) >> lg;
   float K[8];
-  load_params8(raw + ch, K);
+  load8(raw + ch, K);
   float acc[2][8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) acc[0][j] = acc[1][j] = 0.f;
@@ -141,11 +142,11 @@ bn_stats_fast_kernel(const float* __restrict__ raw, long long ld, long long rows
 // ---------------------------------------------------------------------------------------
 // forward apply: out = act(BN(raw) [+ res | + BN(res_raw)])
 // ---------------------------------------------------------------------------------------
-template <typename TR, typename TO, int RES, bool RELU, bool SHADOW>
+template <typename TW, typename TR, typename TO, int RES, bool RELU, bool SHADOW>
 __global__ void __launch_bounds__(BF_T)
-bn_apply_fast_kernel(const float* __restrict__ raw, long long ld, long long rows, int c, int lg,
+bn_apply_fast_kernel(const TW* __restrict__ raw, long long ld, long long rows, int c, int lg,
                      const float* __restrict__ stats, const float* __restrict__ beta,
-                     const TR* __restrict__ res, long long ldres, const float* __restrict__ res_raw,
+                     const TR* __restrict__ res, long long ldres, const TW* __restrict__ res_raw,
                      long long ldres_raw, const float* __restrict__ res_stats,
                      const float* __restrict__ res_beta, TO* __restrict__ out, long long ldout,
                      bf16* __restrict__ out2) {
@@ -190,12 +191,12 @@ bn_apply_fast_kernel(const float* __restrict__ raw, long long ld, long long rows
 // backward pass 1: per-channel sums of g, g*xhat (and g*xhat2)
 //   XMODE 0: xhat from raw; 1: xhat = out - beta (no ReLU); 2: xhat and the ReLU mask from raw
 // ---------------------------------------------------------------------------------------
-template <typename TG, typename TA, bool RELU, bool DUAL, int XMODE, int U>
+template <typename TW, typename TG, typename TA, bool RELU, bool DUAL, int XMODE, int U>
 __global__ void __launch_bounds__(BF_T, DUAL ? 2 : 3)
 bn_bwd_reduce_fast_kernel(const TG* __restrict__ dout, long long lddout, const TA* __restrict__ outp,
-                          long long ldo, long long rows, int c, int lg, const float* __restrict__ raw,
+                          long long ldo, long long rows, int c, int lg, const TW* __restrict__ raw,
                           long long ldraw, const float* __restrict__ stats, const float* __restrict__ beta,
-                          const float* __restrict__ raw2, long long ldraw2,
+                          const TW* __restrict__ raw2, long long ldraw2,
                           const float* __restrict__ stats2, double* __restrict__ partial) {
   constexpr bool NEED_OUT = (RELU && XMODE != 2) || XMODE == 1;
   constexpr bool NEED_RAW = XMODE != 1;
@@ -213,15 +214,15 @@ bn_bwd_reduce_fast_kernel(const TG* __restrict__ dout, long long lddout, const T
   for (long long r = tid >> lg; r < rows; r += rstride * U) {
     Raw8<TG> gb[U];
     Raw8<TA> ob[NEED_OUT ? U : 1];
-    Raw8<float> xb[NEED_RAW ? U : 1], x2b[DUAL ? U : 1];
+    Raw8<TW> xb[NEED_RAW ? U : 1], x2b[DUAL ? U : 1];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const long long rr = r + u * rstride;
       const bool ok = rr < rows;
       gb[u] = ok ? ldraw8(dout + rr * lddout + ch) : zero8<TG>();
       if (NEED_OUT) ob[u] = ok ? ldraw8(outp + rr * ldo + ch) : zero8<TA>();
-      if (NEED_RAW) xb[u] = ok ? ldraw8(raw + rr * ldraw + ch) : zero8<float>();
-      if (DUAL) x2b[u] = ok ? ldraw8(raw2 + rr * ldraw2 + ch) : zero8<float>();
+      if (NEED_RAW) xb[u] = ok ? ldraw8(raw + rr * ldraw + ch) : zero8<TW>();
+      if (DUAL) x2b[u] = ok ? ldraw8(raw2 + rr * ldraw2 + ch) : zero8<TW>();
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
@@ -252,12 +253,12 @@ bn_bwd_reduce_fast_kernel(const TG* __restrict__ dout, long long lddout, const T
 // backward pass 2: d(raw) = rstd*(g - mean(g) - xhat*mean(g*xhat))  (+ dual BN, + residual fan-out)
 //   DRES 0: none, 1: write g, 2: accumulate g
 // ---------------------------------------------------------------------------------------
-template <typename TG, typename TA, bool RELU, bool DUAL, int DRES, int XMODE>
+template <typename TW, typename TG, typename TA, bool RELU, bool DUAL, int DRES, int XMODE>
 __global__ void __launch_bounds__(BF_T)
 bn_bwd_apply_fast_kernel(const TG* __restrict__ dout, long long lddout, const TA* __restrict__ outp,
-                         long long ldo, long long rows, int c, int lg, const float* __restrict__ raw,
+                         long long ldo, long long rows, int c, int lg, const TW* __restrict__ raw,
                          long long ldraw, const float* __restrict__ stats, const float* __restrict__ beta,
-                         TG* __restrict__ draw, long long lddraw, const float* __restrict__ raw2,
+                         TG* __restrict__ draw, long long lddraw, const TW* __restrict__ raw2,
                          long long ldraw2, const float* __restrict__ stats2, TG* __restrict__ draw2,
                          long long lddraw2, TG* __restrict__ dres, long long lddres,
                          const float* __restrict__ sums) {
@@ -279,7 +280,7 @@ bn_bwd_apply_fast_kernel(const TG* __restrict__ dout, long long lddout, const TA
   for (long long r = tid >> lg; r < rows; r += rstride * U) {
     Raw8<TG> gb[U], drb[DRES == 2 ? U : 1];
     Raw8<TA> ob[NEED_OUT ? U : 1];
-    Raw8<float> xb[NEED_RAW ? U : 1], x2b[DUAL ? U : 1];
+    Raw8<TW> xb[NEED_RAW ? U : 1], x2b[DUAL ? U : 1];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const long long rr = r + u * rstride;
@@ -345,24 +346,25 @@ bool bn_fast_shape(int c, std::initializer_list<long long> lds, std::initializer
   return true;
 }
 
-int bn_stats_fast_launch(const float* raw, long long ld, long long rows, int c, double* partial, int* nblocks,
-                         cudaStream_t st) {
+int bn_stats_fast_launch(const void* raw, int raw_dtype, long long ld, long long rows, int c, double* partial,
+                         int* nblocks, cudaStream_t st) {
   const int nb = std::min(fast_grid(rows, c, 4), 148 * 4);      // partial buffer: BN_MAX_BLOCKS entries
-  bn_stats_fast_kernel<<<nb, BF_T, 0, st>>>(raw, ld, rows, c, ilog2(c >> 3), partial);
+  if (raw_dtype == URN_F16) bn_stats_fast_kernel<f16><<<nb, BF_T, 0, st>>>((const f16*)raw, ld, rows, c, ilog2(c >> 3), partial);
+  else bn_stats_fast_kernel<float><<<nb, BF_T, 0, st>>>((const float*)raw, ld, rows, c, ilog2(c >> 3), partial);
   URN_LAUNCH_CHECK();
   *nblocks = nb;
   return 0;
 }
 
-template <typename TR, typename TO>
-static int bn_apply_fast_t(const float* raw, long long ld, long long rows, int c, const float* stats,
-                           const float* beta, const void* res, long long ldres, const float* res_raw,
+template <typename TW, typename TR, typename TO>
+static int bn_apply_fast_t(const TW* raw, long long ld, long long rows, int c, const float* stats,
+                           const float* beta, const void* res, long long ldres, const TW* res_raw,
                            long long ldres_raw, const float* res_stats, const float* res_beta, int relu,
                            void* out, long long ldout, void* out2, cudaStream_t st) {
   const int nb = fast_grid(rows, c, 8), lg = ilog2(c >> 3);
   const int resk = res_raw ? 2 : (res ? 1 : 0);
 #define BF_APPLY(RESV, RELUV, SHV)                                                                     \
-  bn_apply_fast_kernel<TR, TO, RESV, RELUV, SHV><<<nb, BF_T, 0, st>>>(raw, ld, rows, c, lg, stats, beta, \
+  bn_apply_fast_kernel<TW, TR, TO, RESV, RELUV, SHV><<<nb, BF_T, 0, st>>>(raw, ld, rows, c, lg, stats, beta, \
       (const TR*)res, ldres, res_raw, ldres_raw, res_stats, res_beta, (TO*)out, ldout, (bf16*)out2)
 #define BF_APPLY_SH(RESV, RELUV) do { if (out2) BF_APPLY(RESV, RELUV, true); else BF_APPLY(RESV, RELUV, false); } while (0)
   if (resk == 0) { if (relu) BF_APPLY_SH(0, true); else BF_APPLY_SH(0, false); }
@@ -374,26 +376,31 @@ static int bn_apply_fast_t(const float* raw, long long ld, long long rows, int c
   return 0;
 }
 
-int bn_apply_fast_launch(const float* raw, long long ld, long long rows, int c, const float* stats,
+int bn_apply_fast_launch(const void* raw, int raw_dtype, long long ld, long long rows, int c, const float* stats,
                          const float* beta, const void* res, long long ldres, int res_dtype,
-                         const float* res_raw, long long ldres_raw, const float* res_stats,
+                         const void* res_raw, long long ldres_raw, const float* res_stats,
                          const float* res_beta, int relu, void* out, long long ldout, int out_dtype,
                          void* out2, cudaStream_t st) {
   if (!res) res_dtype = out_dtype;
+  if (raw_dtype == URN_F16) {       // fp16 raw only exists next to fp16 activations
+    URN_CHECK(res_dtype == URN_F16 && out_dtype == URN_F16, "bn_apply: f16 raw needs f16 activations");
+    return bn_apply_fast_t<f16, f16, f16>((const f16*)raw, ld, rows, c, stats, beta, res, ldres, (const f16*)res_raw,
+                                          ldres_raw, res_stats, res_beta, relu, out, ldout, out2, st);
+  }
   return dispatch_dtype(res_dtype, [&](auto pr) {
     using TR = URN_T(pr);
     return dispatch_dtype(out_dtype, [&](auto po) {
       using TO = URN_T(po);
-      return bn_apply_fast_t<TR, TO>(raw, ld, rows, c, stats, beta, res, ldres, res_raw, ldres_raw, res_stats,
-                                     res_beta, relu, out, ldout, out2, st);
+      return bn_apply_fast_t<float, TR, TO>((const float*)raw, ld, rows, c, stats, beta, res, ldres, (const float*)res_raw,
+                                            ldres_raw, res_stats, res_beta, relu, out, ldout, out2, st);
     });
   });
 }
 
-template <typename TG, typename TA>
+template <typename TW, typename TG, typename TA>
 static int bn_bwd_fast_t(const void* dout, long long lddout, const void* out, long long ldo, int relu,
-                         long long rows, int c, const float* raw, long long ldraw, const float* stats,
-                         const float* beta, void* draw, long long lddraw, const float* raw2, long long ldraw2,
+                         long long rows, int c, const TW* raw, long long ldraw, const float* stats,
+                         const float* beta, void* draw, long long lddraw, const TW* raw2, long long ldraw2,
                          const float* stats2, void* draw2, long long lddraw2, void* dres, long long lddres,
                          int dres_acc, double* partial, const float* sums, int phase, int* nblocks,
                          cudaStream_t st) {
@@ -410,11 +417,11 @@ static int bn_bwd_fast_t(const void* dout, long long lddout, const void* out, lo
     static const int uenv = getenv("URN_BN_U") ? atoi(getenv("URN_BN_U")) : 4;
 #define BF_RED(RELUV, DUALV, XM)                                                                        \
   do {                                                                                                  \
-    if (uenv == 8) bn_bwd_reduce_fast_kernel<TG, TA, RELUV, DUALV, XM, 8><<<nb, BF_T, 0, st>>>((const TG*)dout, lddout, \
+    if (uenv == 8) bn_bwd_reduce_fast_kernel<TW, TG, TA, RELUV, DUALV, XM, 8><<<nb, BF_T, 0, st>>>((const TG*)dout, lddout, \
       (const TA*)out, ldo, rows, c, lg, raw, ldraw, stats, beta, raw2, ldraw2, stats2, partial);        \
-    else if (uenv == 2) bn_bwd_reduce_fast_kernel<TG, TA, RELUV, DUALV, XM, 2><<<nb, BF_T, 0, st>>>((const TG*)dout, lddout, \
+    else if (uenv == 2) bn_bwd_reduce_fast_kernel<TW, TG, TA, RELUV, DUALV, XM, 2><<<nb, BF_T, 0, st>>>((const TG*)dout, lddout, \
       (const TA*)out, ldo, rows, c, lg, raw, ldraw, stats, beta, raw2, ldraw2, stats2, partial);        \
-    else bn_bwd_reduce_fast_kernel<TG, TA, RELUV, DUALV, XM, 4><<<nb, BF_T, 0, st>>>((const TG*)dout, lddout, \
+    else bn_bwd_reduce_fast_kernel<TW, TG, TA, RELUV, DUALV, XM, 4><<<nb, BF_T, 0, st>>>((const TG*)dout, lddout, \
       (const TA*)out, ldo, rows, c, lg, raw, ldraw, stats, beta, raw2, ldraw2, stats2, partial);        \
   } while (0)
     if (xmode == 1) BF_RED(false, false, 1);
@@ -428,7 +435,7 @@ static int bn_bwd_fast_t(const void* dout, long long lddout, const void* out, lo
   const int nb = fast_grid(rows, c, 8);
   const int dr = dres ? (dres_acc ? 2 : 1) : 0;
 #define BF_APP(RELUV, DUALV, DRESV, XM)                                                                  \
-  bn_bwd_apply_fast_kernel<TG, TA, RELUV, DUALV, DRESV, XM><<<nb, BF_T, 0, st>>>((const TG*)dout, lddout, \
+  bn_bwd_apply_fast_kernel<TW, TG, TA, RELUV, DUALV, DRESV, XM><<<nb, BF_T, 0, st>>>((const TG*)dout, lddout, \
       (const TA*)out, ldo, rows, c, lg, raw, ldraw, stats, beta, (TG*)draw, lddraw, raw2, ldraw2, stats2,  \
       (TG*)draw2, lddraw2, (TG*)dres, lddres, sums)
 #define BF_APP_DR(RELUV, DUALV)                                         \
@@ -448,20 +455,21 @@ static int bn_bwd_fast_t(const void* dout, long long lddout, const void* out, lo
 }
 
 int bn_bwd_fast_launch(int phase, const void* dout, long long lddout, const void* out, long long ldo, int dtype,
-                       int out_dtype, int relu, long long rows, int c, const float* raw, long long ldraw,
-                       const float* stats, const float* beta, void* draw, long long lddraw, const float* raw2,
+                       int out_dtype, int relu, long long rows, int c, const void* raw, int raw_dtype, long long ldraw,
+                       const float* stats, const float* beta, void* draw, long long lddraw, const void* raw2,
                        long long ldraw2, const float* stats2, void* draw2, long long lddraw2, void* dres,
                        long long lddres, int dres_acc, double* partial, const float* sums, int* nblocks,
                        cudaStream_t st) {
-#define URN_BBF(GD, AD, TGT, TAT)                                                                        \
-  if (dtype == GD && out_dtype == AD)                                                                    \
-    return bn_bwd_fast_t<TGT, TAT>(dout, lddout, out, ldo, relu, rows, c, raw, ldraw, stats, beta, draw,  \
-                                   lddraw, raw2, ldraw2, stats2, draw2, lddraw2, dres, lddres, dres_acc, \
+#define URN_BBF(WD, GD, AD, TWT, TGT, TAT)                                                               \
+  if (raw_dtype == WD && dtype == GD && out_dtype == AD)                                                 \
+    return bn_bwd_fast_t<TWT, TGT, TAT>(dout, lddout, out, ldo, relu, rows, c, (const TWT*)raw, ldraw, stats, beta, draw, \
+                                   lddraw, (const TWT*)raw2, ldraw2, stats2, draw2, lddraw2, dres, lddres, dres_acc, \
                                    partial, sums, phase, nblocks, st);
-  URN_BBF(URN_F32, URN_F32, float, float)
-  URN_BBF(URN_BF16, URN_BF16, bf16, bf16)
-  URN_BBF(URN_BF16, URN_F16, bf16, f16)
+  URN_BBF(URN_F32, URN_F32, URN_F32, float, float, float)
+  URN_BBF(URN_F32, URN_BF16, URN_BF16, float, bf16, bf16)
+  URN_BBF(URN_F32, URN_BF16, URN_F16, float, bf16, f16)
+  URN_BBF(URN_F16, URN_BF16, URN_F16, f16, bf16, f16)
 #undef URN_BBF
-  urn_set_error("bn_bwd_fast: unsupported dtype pair (grad %d, act %d)", dtype, out_dtype);
+  urn_set_error("bn_bwd_fast: unsupported dtypes (raw %d, grad %d, act %d)", raw_dtype, dtype, out_dtype);
   return 1;
 }

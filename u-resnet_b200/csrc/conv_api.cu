@@ -205,23 +205,29 @@ extern "C" int urn_conv_fwd_tc(const urn_conv_desc* d, int dtype, const void* x,
   return gconv_tc_auto(g, dtype, x, wpack, y, y_dtype, st);
 }
 
-extern "C" int urn_conv_fwd_tc_stats(const urn_conv_desc* d, int dtype, const void* x, int64_t ldx,
-                                     const float* w, void* wpack, float* y, int64_t ldy, float eps,
-                                     float* stats, void* ws, void* stream) {
+extern "C" int urn_conv_fwd_tc_stats_t(const urn_conv_desc* d, int dtype, const void* x, int64_t ldx,
+                                       const float* w, void* wpack, void* y, int y_dtype, int64_t ldy, float eps,
+                                       float* stats, void* ws, void* stream) {
   if (check_desc(d)) return 1;
+  URN_CHECK(y_dtype == URN_F32 || y_dtype == URN_F16, "urn_conv_fwd_tc_stats: raw output dtype %d", y_dtype);
   cudaStream_t st = (cudaStream_t)stream;
   GConv g;
   gconv_gather(*d, ldx, ldy, &g);
-  const bool halo = gconv_halo_supported(g, dtype, URN_F32);
-  URN_CHECK(halo || gconv_tc_supported(g, dtype, URN_F32), "urn_conv_fwd_tc_stats: shape/dtype not taken by the tensor-core kernels");
+  const bool halo = gconv_halo_supported(g, dtype, y_dtype);
+  URN_CHECK(halo || gconv_tc_supported(g, dtype, y_dtype), "urn_conv_fwd_tc_stats: shape/dtype not taken by the tensor-core kernels");
   if (pack_filter(*d, dtype, w, wpack, true, st)) return 1;
   int nparts = 0;
   if (halo) {
-    if (gconv_halo_launch_stats(g, dtype, x, wpack, y, URN_F32, 0, (float*)ws, &nparts, st)) return 1;
-  } else if (gconv_tc_launch_stats(g, dtype, x, wpack, y, URN_F32, (float*)ws, &nparts, st)) return 1;
+    if (gconv_halo_launch_stats(g, dtype, x, wpack, y, y_dtype, 0, (float*)ws, &nparts, st)) return 1;
+  } else if (gconv_tc_launch_stats(g, dtype, x, wpack, y, y_dtype, (float*)ws, &nparts, st)) return 1;
   URN_CHECK(nparts > 0, "urn_conv_fwd_tc_stats: statistics were not fused for this launch");
   const long long rows = (long long)d->n * d->yd * d->yh * d->yw;
   return bn_stats_merge_launch((const float*)ws, nparts, d->cy, d->cy, rows, eps, stats, st);
+}
+extern "C" int urn_conv_fwd_tc_stats(const urn_conv_desc* d, int dtype, const void* x, int64_t ldx,
+                                     const float* w, void* wpack, float* y, int64_t ldy, float eps,
+                                     float* stats, void* ws, void* stream) {
+  return urn_conv_fwd_tc_stats_t(d, dtype, x, ldx, w, wpack, y, URN_F32, ldy, eps, stats, ws, stream);
 }
 
 extern "C" int urn_conv_dgrad_tc(const urn_conv_desc* d, int dtype, const void* dy, int64_t ldy,

@@ -107,13 +107,17 @@ __device__ __forceinline__ bool plane_used(const HaloParams& p, int z, int d0, i
   return false;
 }
 
-// OUT_F32: fp32 raw output (else bf16 gradient).  MODE: 0 vector
-// store, 1 vector accumulate, 2 partial scalar store (zero-padded filter).  Template parameters
-// instead of runtime switches keep each instantiation's code small.
-template <bool OUT_F32, int MODE, bool FULL3, bool STATS>   // FULL3: 3x3 in-plane tap box (unrolled issue loop); STATS: fused BN statistics
+// OUTK: 0 fp32 raw output, 1 bf16 gradient, 2 fp16 raw output (mix16: the statistics still come from
+// the fp32 accumulators, only the stored copy is rounded).  MODE: 0 vector store, 1 vector accumulate,
+// 2 partial scalar store (zero-padded filter).  Template parameters instead of runtime switches keep
+// each instantiation's code small.
+template <int OUTK, int MODE, bool FULL3, bool STATS>   // FULL3: 3x3 in-plane tap box (unrolled issue loop); STATS: fused BN statistics
 __global__ void __launch_bounds__(kHThreads, 1)
 gconv_halo_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ HaloParams p,
                   const void* __restrict__ in, void* __restrict__ out, long long* __restrict__ tl) {
+  constexpr bool OUT_F32 = OUTK == 0;
+  using T16 = typename std::conditional<OUTK == 2, f16, bf16>::type;     // 16-bit output element
+  static_assert(!(OUTK == 2 && MODE == 1), "fp16 raw outputs are never accumulated");
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_w = smem;                                             // resident filters
@@ -540,7 +544,7 @@ gconv_halo_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_consta
                   for (int j = 0; j < 16; ++j)
                     if (c0 + j < p.cout_store) o[j] = p.accumulate ? o[j] + v[g][j] : v[g][j];
                 } else {
-                  bf16* o = reinterpret_cast<bf16*>(out) + opix * p.ldout + c0;
+                  T16* o = reinterpret_cast<T16*>(out) + opix * p.ldout + c0;
 #pragma unroll
                   for (int j = 0; j < 16; ++j)
                     if (c0 + j < p.cout_store) st1(o + j, p.accumulate ? ld1(o + j) + v[g][j] : v[g][j]);
@@ -557,7 +561,7 @@ gconv_halo_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_consta
                   *reinterpret_cast<float4*>(o + j) = xx;
                 }
               } else {
-                bf16* o = reinterpret_cast<bf16*>(out) + opix * p.ldout + c0;
+                T16* o = reinterpret_cast<T16*>(out) + opix * p.ldout + c0;
                 if (MODE == 1) {
                   const uint32_t w[8] = {oldv[sj][0].x, oldv[sj][0].y, oldv[sj][0].z, oldv[sj][0].w,
                                          oldv[sj][1].x, oldv[sj][1].y, oldv[sj][1].z, oldv[sj][1].w};
@@ -615,7 +619,8 @@ bool halo_plan(const GConv& g, int in_dtype, int out_dtype, int cout_store, Halo
   memset(&p, 0, sizeof(p));
   if (getenv("URN_NO_HALO")) return false;
   if (in_dtype != URN_BF16 && in_dtype != URN_F16) return false;
-  if (out_dtype != URN_F32 && out_dtype != URN_BF16) return false;
+  if (out_dtype != URN_F32 && out_dtype != URN_BF16 && out_dtype != URN_F16) return false;
+  if (out_dtype == URN_F16 && (g.accumulate || (cout_store > 0 && (cout_store & 15)))) return false;   // fp16 = freshly written raw output
   if ((g.is != 1 && g.is != 2) || (g.os != 1 && g.os != 2) || (g.is == 2 && g.os == 2)) return false;
   if (ncls != 1 && ncls != 4 && ncls != 8) return false;
   if (g.cin != 16 && g.cin != 32 && g.cin != 64) return false;
@@ -823,7 +828,7 @@ int gconv_halo_classes_launch(const GConv* gs, int ncls, int in_dtype, const voi
   if (nparts) *nparts = 0;
   if (p.ntiles == 0) return 0;
   // the classes together write every output element exactly once: statistics can be fused
-  if (stats_part && nparts && out_dtype == URN_F32 && !gs[0].accumulate && !getenv("URN_NO_FUSED_STATS") &&
+  if (stats_part && nparts && out_dtype != URN_BF16 && !gs[0].accumulate && !getenv("URN_NO_FUSED_STATS") &&
       (long long)gs[0].gd * 2 == gs[0].od + (gs[0].od == 1) && gs[0].gh * 2 == gs[0].oh && gs[0].gw * 2 == gs[0].ow) {
     p.stats_part = stats_part;
     *nparts = (int)std::min<long long>(p.ntiles, persistent_ctas()) * 4;
@@ -851,7 +856,7 @@ int gconv_halo_launch_stats(const GConv& g, int in_dtype, const void* in, const 
   if (p.ntiles == 0) return 0;
   const int grid_ = (int)std::min<long long>(p.ntiles, persistent_ctas());
   // statistics only when this single launch produces the whole raw tensor, freshly written
-  if (stats_part && nparts && out_dtype == URN_F32 && !g.accumulate && g.os == 1 && g.gd == g.od && g.gh == g.oh &&
+  if (stats_part && nparts && out_dtype != URN_BF16 && !g.accumulate && g.os == 1 && g.gd == g.od && g.gh == g.oh &&
       g.gw == g.ow && !getenv("URN_NO_FUSED_STATS")) {
     p.stats_part = stats_part;
     *nparts = grid_ * 4;
@@ -883,31 +888,35 @@ static int halo_launch_params(HaloParams& p, int cin, int cout, int in_dtype, in
   const int mode = (p.cout_store & 15) ? 2 : (p.accumulate ? 1 : 0);
   const bool full3 = p.nkh == 3 && p.nkw == 3;
   const bool stats = p.stats_part != nullptr;
-#define HALO_GO(F32, MODE, F3, ST)                                                                            \
+#define HALO_GO(OK, MODE, F3, ST)                                                                             \
   do {                                                                                                        \
     static bool attr_set = false;                                                                             \
     if (!attr_set) {                                                                                          \
-      URN_CUDA(cudaFuncSetAttribute(gconv_halo_kernel<F32, MODE, F3, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+      URN_CUDA(cudaFuncSetAttribute(gconv_halo_kernel<OK, MODE, F3, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                     227 * 1024));                                                             \
       attr_set = true;                                                                                        \
     }                                                                                                         \
-    gconv_halo_kernel<F32, MODE, F3, ST><<<grid, kHThreads, smem, st>>>(map_w, p, in, out, tl);               \
+    gconv_halo_kernel<OK, MODE, F3, ST><<<grid, kHThreads, smem, st>>>(map_w, p, in, out, tl);                \
   } while (0)
   URN_CHECK(mode != 2 || full3, "gconv_halo: padded filters only with 3x3 taps (cout %d store %d taps %dx%dx%d classes %d cin %d)", p.cout, p.cout_store, p.nkd, p.nkh, p.nkw, p.ncls, p.cin);
-  URN_CHECK(!stats || (out_dtype == URN_F32 && mode != 1), "gconv_halo: statistics need a freshly written f32 output");
+  URN_CHECK(!stats || (out_dtype != URN_BF16 && mode != 1), "gconv_halo: statistics need a freshly written raw output");
   if (out_dtype == URN_F32) {
     if (mode == 0) {
-      if (stats) { if (full3) HALO_GO(true, 0, true, true); else HALO_GO(true, 0, false, true); }
-      else { if (full3) HALO_GO(true, 0, true, false); else HALO_GO(true, 0, false, false); }
+      if (stats) { if (full3) HALO_GO(0, 0, true, true); else HALO_GO(0, 0, false, true); }
+      else { if (full3) HALO_GO(0, 0, true, false); else HALO_GO(0, 0, false, false); }
     } else if (mode == 1) {
-      if (full3) HALO_GO(true, 1, true, false); else HALO_GO(true, 1, false, false);
+      if (full3) HALO_GO(0, 1, true, false); else HALO_GO(0, 1, false, false);
     } else {
-      if (stats) HALO_GO(true, 2, true, true); else HALO_GO(true, 2, true, false);
+      if (stats) HALO_GO(0, 2, true, true); else HALO_GO(0, 2, true, false);
     }
+  } else if (out_dtype == URN_F16) {
+    URN_CHECK(mode == 0, "gconv_halo: fp16 outputs are plain stores");
+    if (stats) { if (full3) HALO_GO(2, 0, true, true); else HALO_GO(2, 0, false, true); }
+    else { if (full3) HALO_GO(2, 0, true, false); else HALO_GO(2, 0, false, false); }
   } else {
-    if (mode == 0) { if (full3) HALO_GO(false, 0, true, false); else HALO_GO(false, 0, false, false); }
-    else if (mode == 1) { if (full3) HALO_GO(false, 1, true, false); else HALO_GO(false, 1, false, false); }
-    else HALO_GO(false, 2, true, false);
+    if (mode == 0) { if (full3) HALO_GO(1, 0, true, false); else HALO_GO(1, 0, false, false); }
+    else if (mode == 1) { if (full3) HALO_GO(1, 1, true, false); else HALO_GO(1, 1, false, false); }
+    else HALO_GO(1, 2, true, false);
   }
 #undef HALO_GO
   URN_LAUNCH_CHECK();

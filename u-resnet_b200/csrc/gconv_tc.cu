@@ -316,6 +316,10 @@ gconv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             }
             *reinterpret_cast<float4*>(o + j) = x;
           }
+        } else if (p.out_dtype == URN_F16) {      // fp16 raw output (mix16); the statistics above saw the fp32 values
+          f16* o = reinterpret_cast<f16*>(out) + opix * p.ldout + c;
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) st4(o + j, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
         } else {
           bf16* o = reinterpret_cast<bf16*>(out) + opix * p.ldout + c;
 #pragma unroll
@@ -374,7 +378,8 @@ int pow2_ceil(int v) { int p = 1; while (p < v) p *= 2; return p; }
 
 bool gconv_tc_supported(const GConv& g, int in_dtype, int out_dtype) {
   if (in_dtype != URN_BF16 && in_dtype != URN_F16) return false;
-  if (out_dtype != URN_F32 && out_dtype != URN_BF16) return false;
+  if (out_dtype != URN_F32 && out_dtype != URN_BF16 && out_dtype != URN_F16) return false;
+  if (out_dtype == URN_F16 && g.accumulate) return false;        // fp16 = freshly written raw output
   if (g.cin % 16 || g.cout % 16) return false;
   if (g.ldin % 8 || g.ldout % 4) return false;
   if (g.ntaps < 1) return false;
@@ -475,7 +480,7 @@ int gconv_tc_launch_stats(const GConv& g, int in_dtype, const void* in, const vo
   URN_CHECK(nwork < (1ll << 31), "gconv_tc: too many tiles");
   int grid = (int)std::min<long long>(nwork, persistent_ctas());
   // fused statistics: a single launch writing the whole fp32 tensor once, one N tile of <= 256 channels
-  const bool stats = stats_part && nparts && out_dtype == URN_F32 && !g.accumulate && g.os == 1 && g.gd == g.od &&
+  const bool stats = stats_part && nparts && out_dtype != URN_BF16 && !g.accumulate && g.os == 1 && g.gd == g.od &&
                      g.gh == g.oh && g.gw == g.ow && p.n_tiles == 1 && p.n_tile <= 256 && !getenv("URN_NO_FUSED_STATS");
   if (stats) {
     p.stats_part = stats_part;

@@ -46,6 +46,7 @@ struct Layer {
   int64_t rows_out = 0;
   int in_node = -1;
   int64_t raw_off = 0, stats_off = 0;
+  int raw_dtype = URN_F32;   // storage of the raw conv output: fp16 next to fp16 activations (mix16), else fp32
   int64_t w_off = 0, b_off = 0, w_count = 0;  // elements in the flat parameter buffer
   int draw_gbuf = -1;
   int out_node = -1;     // node produced by this layer's own BN-apply (-1: merged later)
@@ -156,6 +157,7 @@ struct Builder {
     return o;
   }
   bool shadow = false;
+  bool raw16 = false;   // mix16 on the tensor-core path: raw conv outputs of the 16-channel-aligned layers are stored as fp16
   int new_node(const std::string& name, int c, int64_t rows, int dtype) {
     Node n;
     n.name = name;
@@ -188,7 +190,13 @@ struct Builder {
       urn_conv_desc_same(&L.d, nd, n, out_sp[0], out_sp[1], out_sp[2], cout, cin, k, s);
     }
     L.rows_out = (int64_t)n * out_sp[0] * out_sp[1] * out_sp[2];
-    L.raw_off = alloc(L.rows_out * cout * 4);
+    // fp16 raw output: BN statistics still come from the fp32 accumulators in the conv epilogue, only the
+    // stored copy is rounded (|mean|*rstd stays O(1) in this network, so the rounding is ~2^-11 of xhat's
+    // own scale: DESIGN.md section 5).  Not for the stem (Cin = 1: input amplitudes are unbounded) nor the
+    // head (Cout = num_class: its BN output are the fp32 logits); needs the fast BN kernels' shape.
+    if (raw16 && scope != "conv0" && scope != "conv2" && cout % 16 == 0 && cout <= 512 && (cout & (cout - 1)) == 0)
+      L.raw_dtype = URN_F16;
+    L.raw_off = alloc(L.rows_out * cout * esize(L.raw_dtype));
     L.stats_off = alloc((int64_t)2 * cout * 4);
     // parameters: TF creation order = weights then beta
     int kk[3] = {L.d.kd, L.d.kh, L.d.kw};
@@ -242,6 +250,7 @@ static int build_plan(urn_net& N) {
   const int T = N.TA, TG = N.TG, nd = c.nd, B = c.batch, F = c.base_filters, S = c.num_strides;
   Builder b(N);
   b.shadow = (T == URN_F16 && TG == URN_BF16 && c.impl != URN_IMPL_FFMA && c.training);
+  b.raw16 = (T == URN_F16 && c.impl != URN_IMPL_FFMA && !getenv("URN_RAW_F32"));
 
   struct Cur { int node; int sp[3]; int ch; };
   int sp0[3] = {N.sp[0], N.sp[1], N.sp[2]};
@@ -651,7 +660,8 @@ inline const float* conv_weights(const urn_net* h, const Layer& L, const float* 
 int run_conv_fwd(urn_net* h, int li, const float* params, void* ws, cudaStream_t st) {
   const Layer& L = h->layers[li];
   const Node& in = h->nodes[L.in_node];
-  float* raw = (float*)P(ws, L.raw_off);
+  void* raw = P(ws, L.raw_off);
+  const int RT = L.raw_dtype;
   const float* w = conv_weights(h, L, params, ws);
   int nparts = 0;                                   // > 0: BN statistics came out of the conv epilogue
   float* parts = (float*)P(ws, h->bn_ws_off);
@@ -664,22 +674,22 @@ int run_conv_fwd(urn_net* h, int li, const float* params, void* ws, cudaStream_t
     GConv g;
     gconv_gather(dp, in.ld, L.cout, &g);
     if (gconv_halo_launch_stats(g, in.dtype, P(ws, in.off), P(ws, L.wpg_pad_off), raw, URN_F32, L.cout, parts, &nparts, st)) return 1;
-  } else if (!L.transpose && ded && stem_supported(L.d, in.ld, L.cout)) {
-    if (stem_fwd_launch(L.d, in.dtype, P(ws, in.off), in.ld, w, raw, L.cout, st)) return 1;
-  } else if (!L.transpose && ded && head_supported(L.d, in.ld, L.cout)) {
-    if (head_fwd_launch(L.d, in.dtype, P(ws, in.off), in.ld, w, raw, L.cout, st)) return 1;
+  } else if (!L.transpose && ded && RT == URN_F32 && stem_supported(L.d, in.ld, L.cout)) {
+    if (stem_fwd_launch(L.d, in.dtype, P(ws, in.off), in.ld, w, (float*)raw, L.cout, st)) return 1;
+  } else if (!L.transpose && ded && RT == URN_F32 && head_supported(L.d, in.ld, L.cout)) {
+    if (head_fwd_launch(L.d, in.dtype, P(ws, in.off), in.ld, w, (float*)raw, L.cout, st)) return 1;
   } else if (!L.transpose) {
     GConv g;
     gconv_gather(L.d, in.ld, L.cout, &g);
-    if (tc_enabled(h) && gconv_halo_supported(g, in.dtype, URN_F32)) {
-      if (gconv_halo_launch_stats(g, in.dtype, P(ws, in.off), P(ws, h->wpg_off + L.w_off * 2), raw, URN_F32, 0, parts, &nparts, st)) return 1;
-    } else if (tc_enabled(h) && gconv_tc_supported(g, in.dtype, URN_F32)) {
-      if (gconv_tc_launch_stats(g, in.dtype, P(ws, in.off), P(ws, h->wpg_off + L.w_off * 2), raw, URN_F32, parts, &nparts, st)) return 1;
-    } else if (run_gconv(h, g, in.dtype, P(ws, in.off), w, P(ws, h->wpg_off + L.w_off * 2), raw, URN_F32, st)) return 1;
+    if (tc_enabled(h) && gconv_halo_supported(g, in.dtype, RT)) {
+      if (gconv_halo_launch_stats(g, in.dtype, P(ws, in.off), P(ws, h->wpg_off + L.w_off * 2), raw, RT, 0, parts, &nparts, st)) return 1;
+    } else if (tc_enabled(h) && gconv_tc_supported(g, in.dtype, RT)) {
+      if (gconv_tc_launch_stats(g, in.dtype, P(ws, in.off), P(ws, h->wpg_off + L.w_off * 2), raw, RT, parts, &nparts, st)) return 1;
+    } else if (run_gconv(h, g, in.dtype, P(ws, in.off), w, P(ws, h->wpg_off + L.w_off * 2), raw, RT, st)) return 1;
   } else {
     int rc = -1;
     if (tc_enabled(h) && L.d.s == 2)
-      rc = gconv_scatter_tc(L.d, in.ld, L.cout, 0, in.dtype, P(ws, in.off), P(ws, h->wps_off + L.w_off * 2), raw, URN_F32, st,
+      rc = gconv_scatter_tc(L.d, in.ld, L.cout, 0, in.dtype, P(ws, in.off), P(ws, h->wps_off + L.w_off * 2), raw, RT, st,
                             parts, &nparts);
     if (rc > 0) return 1;
     if (rc < 0)
@@ -688,7 +698,7 @@ int run_conv_fwd(urn_net* h, int li, const float* params, void* ws, cudaStream_t
         for (int pw = 0; pw < L.d.s; ++pw) {
           GConv g;
           if (!gconv_scatter_class(L.d, in.ld, L.cout, pd, ph, pw, 0, &g)) continue;
-          if (run_gconv(h, g, in.dtype, P(ws, in.off), w, P(ws, h->wps_off + L.w_off * 2), raw, URN_F32, st)) return 1;
+          if (run_gconv(h, g, in.dtype, P(ws, in.off), w, P(ws, h->wps_off + L.w_off * 2), raw, RT, st)) return 1;
         }
   }
   }
@@ -696,7 +706,7 @@ int run_conv_fwd(urn_net* h, int li, const float* params, void* ws, cudaStream_t
   if (nparts > 0)
     return bn_stats_merge_launch(parts, nparts, L.cpad ? L.cpad : L.cout, L.cout, L.rows_out, kBnEps,
                                  (float*)P(ws, L.stats_off), st);
-  return urn_bn_stats(raw, L.cout, L.rows_out, L.cout, kBnEps, (float*)P(ws, L.stats_off),
+  return bn_stats_any(raw, RT, L.cout, L.rows_out, L.cout, kBnEps, (float*)P(ws, L.stats_off),
                       P(ws, h->bn_ws_off), st);
 }
 
@@ -761,7 +771,7 @@ static int forward_steps(urn_net* h, const float* params, void* ws, int first, i
     } else if (s.kind == F_APPLY) {
       ProfScope ps(h, s.layer, PH_APPLY, st);
       const Node& o = h->nodes[s.out_node];
-      if (urn_bn_apply((const float*)P(ws, L.raw_off), L.cout, L.rows_out, L.cout,
+      if (bn_apply_any(P(ws, L.raw_off), L.raw_dtype, L.cout, L.rows_out, L.cout,
                        (const float*)P(ws, L.stats_off), params + L.b_off, nullptr, 0, 0, nullptr,
                        0, nullptr, nullptr, s.relu, P(ws, o.off), o.ld, o.dtype,
                        o.off2 >= 0 ? P(ws, o.off2) : nullptr, st))
@@ -770,16 +780,18 @@ static int forward_steps(urn_net* h, const float* params, void* ws, int first, i
       ProfScope ps(h, s.layer, PH_APPLY, st);
       const Node& o = h->nodes[s.out_node];
       const void* res = nullptr; int64_t ldres = 0; int rdt = o.dtype;
-      const float *res_raw = nullptr, *res_stats = nullptr, *res_beta = nullptr; int64_t ldrr = 0;
+      const void* res_raw = nullptr;
+      const float *res_stats = nullptr, *res_beta = nullptr; int64_t ldrr = 0;
       if (s.layer_sc >= 0) {
         const Layer& S = h->layers[s.layer_sc];
-        res_raw = (const float*)P(ws, S.raw_off); ldrr = S.cout;
+        URN_CHECK(S.raw_dtype == L.raw_dtype, "urn_forward: shortcut and residual raw dtypes differ (%s)", L.scope.c_str());
+        res_raw = P(ws, S.raw_off); ldrr = S.cout;
         res_stats = (const float*)P(ws, S.stats_off); res_beta = params + S.b_off;
       } else {
         const Node& r = h->nodes[s.res_node];
         res = P(ws, r.off); ldres = r.ld; rdt = r.dtype;
       }
-      if (urn_bn_apply((const float*)P(ws, L.raw_off), L.cout, L.rows_out, L.cout,
+      if (bn_apply_any(P(ws, L.raw_off), L.raw_dtype, L.cout, L.rows_out, L.cout,
                        (const float*)P(ws, L.stats_off), params + L.b_off, res, ldres, rdt, res_raw,
                        ldrr, res_stats, res_beta, 1, P(ws, o.off), o.ld, o.dtype,
                        o.off2 >= 0 ? P(ws, o.off2) : nullptr, st))
@@ -865,11 +877,13 @@ static int backward_steps(urn_net* h, const float* params, float* grads, int acc
     ProfScope ps(h, s.layer, s.kind == B_BN ? PH_BNBWD : (s.kind == B_WGRAD ? PH_WGRAD : PH_DGRAD), st);
     if (s.kind == B_BN) {
       const Node& dn = h->nodes[s.dout_node];
-      const float *raw2 = nullptr, *stats2 = nullptr; float* dbeta2 = nullptr; void* draw2 = nullptr;
+      const void* raw2 = nullptr;
+      const float* stats2 = nullptr; float* dbeta2 = nullptr; void* draw2 = nullptr;
       int64_t ld2 = 0;
       if (s.layer2 >= 0) {
         const Layer& S = h->layers[s.layer2];
-        raw2 = (const float*)P(ws, S.raw_off); stats2 = (const float*)P(ws, S.stats_off);
+        URN_CHECK(S.raw_dtype == L.raw_dtype, "urn_backward: shortcut and residual raw dtypes differ (%s)", L.scope.c_str());
+        raw2 = P(ws, S.raw_off); stats2 = (const float*)P(ws, S.stats_off);
         dbeta2 = grads + S.b_off; draw2 = draw(S); ld2 = S.cout;
       }
       void* dres = nullptr; int64_t lddres = 0;
@@ -877,7 +891,7 @@ static int backward_steps(urn_net* h, const float* params, float* grads, int acc
       const int64_t lddraw = L.cpad ? L.cpad : L.cout;
       if (L.cpad) URN_CUDA(cudaMemsetAsync(draw(L), 0, (size_t)L.rows_out * L.cpad * esize(T), st));   // pad channels = 0
       if (bn_bwd_full(gptr(dn), dn.ld, P(ws, dn.off), dn.ld, T, dn.dtype, s.relu, L.rows_out, L.cout,
-                      (const float*)P(ws, L.raw_off), L.cout, (const float*)P(ws, L.stats_off),
+                      P(ws, L.raw_off), L.raw_dtype, L.cout, (const float*)P(ws, L.stats_off),
                       params + L.b_off, grads + L.b_off, draw(L), lddraw, raw2, ld2, stats2, dbeta2, draw2,
                       ld2, dres, lddres, s.accumulate, accumulate, P(ws, h->bn_ws_off), st))
         return 1;
@@ -1001,7 +1015,7 @@ extern "C" int urn_layer_tensors(const urn_net* h, int layer, urn_tensor_ref* ra
                                  int* out_node) {
   URN_CHECK(h && layer >= 0 && layer < (int)h->layers.size(), "urn_layer_tensors: bad index");
   const Layer& L = h->layers[layer];
-  if (raw) { raw->off_bytes = L.raw_off; raw->ld = L.cout; raw->rows = L.rows_out; raw->c = L.cout; raw->dtype = URN_F32; }
+  if (raw) { raw->off_bytes = L.raw_off; raw->ld = L.cout; raw->rows = L.rows_out; raw->c = L.cout; raw->dtype = L.raw_dtype; }
   no_tensor(draw);
   if (draw && L.draw_gbuf >= 0) {
     draw->off_bytes = h->arena_off + h->gbufs[L.draw_gbuf].off;
