@@ -289,13 +289,15 @@ def test_conv_many_tiles_per_cta(lib, monkeypatch, ctas, nd, n, sp, cin, cout, k
         test_conv_fused_bn_statistics(lib, nd, n, sp, cin, cout, k, s)
 
 
-@pytest.mark.parametrize("nd,n,sp,cin,cout,k,s", [(2, 2, (32, 48), 16, 16, 3, 1), (2, 18, (24, 40), 32, 32, 3, 1), (2, 3, (40, 72), 16, 32, 3, 1),
+@pytest.mark.parametrize("rows", ["1", "0"])
+@pytest.mark.parametrize("nd,n,sp,cin,cout,k,s", [(2, 12, (32, 48), 16, 16, 3, 1), (2, 18, (24, 40), 32, 32, 3, 1), (2, 16, (40, 72), 16, 32, 3, 1),
                                                   (2, 33, (20, 24), 32, 16, 3, 1)])
-def test_conv_images_as_rows_plan(lib, monkeypatch, nd, n, sp, cin, cout, k, s):
-    """URN_HALO_ROWS=1 (experimental, off by default): 2D stride-1 3x3 layers through the 3D concat
-    path with relabelled axes (halo_plan_rows).  Same oracle checks as the default plan, with batches
-    below, at and above one 16-image tile row group."""
-    monkeypatch.setenv("URN_HALO_ROWS", "1")
+def test_conv_images_as_rows_plan(lib, monkeypatch, rows, nd, n, sp, cin, cout, k, s):
+    """2D stride-1 3x3 layers of a batch of >= 12 images run through the 3D concat path with relabelled
+    axes (halo_plan_rows: planes := image rows, tile rows := images; default on, URN_HALO_ROWS=0 keeps
+    the 16x8 tiles).  Same oracle checks for both plans, with batches below, at and above one 16-image
+    tile row group."""
+    monkeypatch.setenv("URN_HALO_ROWS", rows)
     test_conv_tcgen05_fwd_dgrad(lib, F16, nd, n, sp, cin, cout, k, s)
     test_conv_tcgen05_fwd_dgrad(lib, BF16, nd, n, sp, cin, cout, k, s)
     test_conv_fused_bn_statistics(lib, nd, n, sp, cin, cout, k, s)

@@ -721,14 +721,19 @@ bool halo_plan(const GConv& g, int in_dtype, int out_dtype, int cout_store, Halo
   return true;
 }
 
-// EXPERIMENTAL (URN_HALO_ROWS=1, off by default): a 2D stride-1 3x3 layer run through the 3D concat
-// path by relabelling the axes -- planes := image rows, tile rows := the IMAGES of the batch, columns
-// := image columns.  The kh taps become the depth taps, which the concat mode fuses along N: per
-// 128 outputs 3 MMAs of N = 3*cout instead of 9 of N = cout (the 2D layers are bound by the tensor
-// pipe's instruction rate at N = 16).  Only the strides differ from a real volume:
-// the next "row" is the next image, the next "plane" the next image row.
+// Images-as-rows plan (default for 2D stride-1 3x3 layers of a batch of >= 12 images; URN_HALO_ROWS=0
+// disables it): the layer is run through the 3D concat path by relabelling the axes -- planes := image
+// rows, tile rows := the IMAGES of the batch, columns := image columns.  The kh taps become the depth
+// taps, which the concat mode fuses along N: per 128 outputs 3 MMAs of N = 3*cout instead of 9 of
+// N = cout.  Every tcgen05.mma occupies the tensor pipe >= ~58 cycles whatever its N <= 96 and M
+// (tools/probe/mmarate.cu), so a third of the instructions is a third of the pipe time.  Only the
+// strides differ from a real volume: the next "row" is the next image, the next "plane" the next
+// image row.  Measured per layer at 512^2 / 256^2, B = 32 (fp16 raw outputs): 16->16 forward 0.233 ->
+// 0.207 ms, input gradient 0.218 -> 0.192 ms, 32->16 forward 0.427 -> 0.346 ms; slower only for
+// ACCUMULATING input gradients of >= 32 channels (0.172 -> 0.190 ms), which keep the 16x8 tiles.
 bool halo_plan_rows(const GConv& g, int in_dtype, int out_dtype, int cout_store, HaloParams* pp) {
-  if (!getenv("URN_HALO_ROWS")) return false;
+  if (const char* e = getenv("URN_HALO_ROWS")) { if (atoi(e) == 0) return false; }
+  if (g.n < 12 || (g.accumulate && g.cout >= 32)) return false;
   if (g.id != 1 || g.od != 1 || g.gd != 1 || g.is != 1 || g.os != 1 || g.ntaps != 9) return false;
   if (g.ood || g.ooh || g.oow || g.gh != g.oh || g.gw != g.ow || g.ih != g.oh || g.iw != g.ow) return false;
   if (cout_store > 0 && cout_store != g.cout) return false;
