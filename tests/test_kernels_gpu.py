@@ -345,6 +345,19 @@ def test_conv_halo_wgrad(lib, xdt, nd, n, sp, cin, cout, ldf):
     torch.cuda.synchronize()
 
 
+@pytest.mark.parametrize("rows", ["1", "0"])
+@pytest.mark.parametrize("n,sp,cin,cout,ldf", [(12, (20, 24), 16, 16, 1), (33, (12, 16), 32, 16, 2), (16, (24, 40), 16, 32, 1),
+                                               (20, (9, 11), 64, 32, 1), (17, (70, 40), 16, 16, 1), (13, (5, 8), 32, 32, 1)])
+def test_conv_halo_wgrad_images_as_rows(lib, monkeypatch, rows, n, sp, cin, cout, ldf):
+    """Filter gradient of 2D 3x3 stride-1 layers with >= 12 images: the images-as-rows plan (planes :=
+    image rows, the three kh taps concatenated along N; default) and the 16x8-tile plan
+    (URN_WHALO_ROWS=0) against the oracle: ragged sizes, pitched X, several depth chunks, batches that
+    are not multiples of the 16-image tile."""
+    monkeypatch.setenv("URN_WHALO_ROWS", rows)
+    for xdt in (BF16, F16):
+        test_conv_halo_wgrad(lib, xdt, 2, n, sp, cin, cout, ldf)
+
+
 @pytest.mark.parametrize("nd,n,sp,cin,cout,k,s", [
     (2, 3, (40, 72), 16, 16, 3, 1), (2, 2, (33, 19), 16, 32, 3, 1), (2, 1, (64, 64), 32, 64, 3, 1),
     (2, 2, (32, 48), 16, 32, 3, 2), (2, 2, (16, 40), 32, 16, 1, 1), (3, 1, (9, 20, 12), 16, 16, 3, 1),

@@ -67,6 +67,10 @@ struct WHParams {
   uint64_t adesc_hi, bdesc_hi;
   int tmem_cols;
   int ntaps;
+  // strides in bytes: next tile row / next plane / next image of X and of dY (images-as-rows plan: the
+  // "row" is the next IMAGE and the "plane" the next image row)
+  int xrow_b, yrow_b;
+  long long xplane_b, ximg_b, yplane_b2, yimg_b;
 };
 
 struct UnitIter {
@@ -136,8 +140,8 @@ wgrad_halo_kernel(const __grid_constant__ WHParams p, const void* __restrict__ x
     const int run = 8 * p.ks;
     const char* x_base = reinterpret_cast<const char*>(x);
     const char* y_base = reinterpret_cast<const char*>(dy);
-    const int xpix = (int)(p.ldx * 2), xrow = xpix * p.XW;
-    const int ypix = (int)(p.ldy * 2), yrow = ypix * p.W;
+    const int xpix = (int)(p.ldx * 2), xrow = p.xrow_b;
+    const int ypix = (int)(p.ldy * 2), yrow = p.yrow_b;
     const int H = p.H, W = p.W, XH = p.XH, XW = p.XW;
     int soff[kWNCH], hdv[kWNCH];          // hdv = halo row | X column << 8 (border test of edge tiles)
     uint32_t doff[kWNCH];
@@ -196,7 +200,7 @@ wgrad_halo_kernel(const __grid_constant__ WHParams p, const void* __restrict__ x
         if (yvalid) h_mbar_wait_warp(&yempty[yr.idx], yr.phase ^ 1);
         if (xvalid) {
           const uint32_t dst_base = h_smem_u32(smem_x + (size_t)st.idx * p.xplane_bytes);
-          const char* origin = x_base + ((long long)ui.nn * p.XD + z) * XH * (long long)xrow + xorg;
+          const char* origin = x_base + (long long)ui.nn * p.ximg_b + (long long)z * p.xplane_b + xorg;
           if (interior) {
 #pragma unroll
             for (int j = 0; j < kWNCH; ++j) cp_async16_zfill(dst_base + doff[j], origin + soff[j], 16u);
@@ -210,7 +214,7 @@ wgrad_halo_kernel(const __grid_constant__ WHParams p, const void* __restrict__ x
         }
         if (yvalid) {
           const uint32_t dst_base = h_smem_u32(smem_y + (size_t)yr.idx * p.yplane_bytes);
-          const char* origin = y_base + ((long long)ui.nn * p.D + yp) * H * (long long)yrow + yorg;
+          const char* origin = y_base + (long long)ui.nn * p.yimg_b + (long long)yp * p.yplane_b2 + yorg;
           // ring slots 0 and 1 are also written to their mirrors behind the ring, so that the
           // three-plane window of the MMA warp never wraps
           const int ncopy = (p.ymirror && yr.idx < p.ymirror) ? 2 : 1;
@@ -445,13 +449,15 @@ __global__ void wgrad_halo_reduce_kernel(const float* __restrict__ partial, int 
   dw[i] = accumulate ? dw[i] + s : s;
 }
 
-bool wh_plan(const urn_conv_desc& d, int x_dtype, int y_dtype, int64_t ldx, int64_t ldy, WHParams* pp) {
+bool wh_plan(const urn_conv_desc& d, int x_dtype, int y_dtype, int64_t ldx, int64_t ldy, WHParams* pp, bool rows = false) {
   WHParams& p = *pp;
   memset(&p, 0, sizeof(p));
   if (getenv("URN_NO_HALO_WGRAD")) return false;
   if ((x_dtype != URN_BF16 && x_dtype != URN_F16) || x_dtype != y_dtype) return false;
   if (d.s != 1 && d.s != 2) return false;
-  if (!((d.kh == 3 && d.kw == 3) || (d.kh == 1 && d.kw == 1)) || (d.kd != 1 && d.kd != d.kh)) return false;
+  if (rows) {       // images-as-rows relabelling of a 2D 3x3 layer: 1x3 in-plane taps, 3 "depth" taps (wh_plan_rows)
+    if (!(d.kd == 3 && d.kh == 1 && d.kw == 3 && d.s == 1)) return false;
+  } else if (!((d.kh == 3 && d.kw == 3) || (d.kh == 1 && d.kw == 1)) || (d.kd != 1 && d.kd != d.kh)) return false;
   if (getenv("URN_WHALO_ONLY3X3S1") && !(d.s == 1 && d.kh == 3)) return false;
   if (d.kh == 1 && d.s == 2) return false;      // only every other staged row would be used: the tap-box kernel is faster
   if (d.yd != (d.xd + d.s - 1) / d.s || d.yh != (d.xh + d.s - 1) / d.s || d.yw != (d.xw + d.s - 1) / d.s) return false;
@@ -469,6 +475,8 @@ bool wh_plan(const urn_conv_desc& d, int x_dtype, int y_dtype, int64_t ldx, int6
   p.ndc = (p.D + 47) / 48;
   p.DC = (p.D + p.ndc - 1) / p.ndc;
   p.ndc = (p.D + p.DC - 1) / p.DC;
+  p.xrow_b = (int)(ldx * 2 * p.XW); p.xplane_b = (long long)p.xrow_b * p.XH; p.ximg_b = p.xplane_b * p.XD;
+  p.yrow_b = (int)(ldy * 2 * p.W); p.yplane_b2 = (long long)p.yrow_b * p.H; p.yimg_b = p.yplane_b2 * p.D;
   p.tpm = 128 / p.cx;
   p.nM = (p.ntp + p.tpm - 1) / p.tpm;
   const int cols = p.nkd * p.nM * p.cy;
@@ -530,11 +538,56 @@ bool wh_plan(const urn_conv_desc& d, int x_dtype, int y_dtype, int64_t ldx, int6
   return true;
 }
 
+// Images-as-rows plan for the 2D 3x3 stride-1 layers of a batch of >= 12 images (default on,
+// URN_WHALO_ROWS=0 disables it; same idea as halo_plan_rows in gconv_halo.cu): planes := image rows,
+// tile rows := the IMAGES of the batch, columns := image columns.  The kh taps become the depth taps,
+// whose three dY "planes" (image rows y-1, y, y+1) are concatenated along N: per 16 positions ONE MMA
+// with M = (kw, cx), N = 3*cy instead of two with M = (8 taps | 1 tap, cx), N = cy -- every
+// tcgen05.mma occupies the tensor pipe >= ~58 cycles whatever its shape (tools/probe/mmarate.cu).
+// The chunking of the "depth" (image rows) is chosen so that the units spread evenly over the CTAs.
+bool wh_plan_rows(const urn_conv_desc& d, int x_dtype, int y_dtype, int64_t ldx, int64_t ldy, WHParams* pp) {
+  if (const char* e = getenv("URN_WHALO_ROWS")) { if (atoi(e) == 0) return false; }
+  if (d.n < 12 || d.xd != 1 || d.yd != 1 || d.kd != 1 || d.kh != 3 || d.kw != 3 || d.s != 1) return false;
+  if (d.xh != d.yh || d.xw != d.yw || d.xh < 4) return false;
+  const long long ximg = ldx * 2 * (long long)d.xw * d.xh, yimg = ldy * 2 * (long long)d.yw * d.yh;
+  if (ximg * 17 >= (1ll << 31) || yimg * 17 >= (1ll << 31)) return false;      // 32-bit offsets across the images of a tile
+  urn_conv_desc v = d;
+  v.n = 1;
+  v.xd = d.xh; v.xh = d.n; v.xw = d.xw;
+  v.yd = d.yh; v.yh = d.n; v.yw = d.yw;
+  v.kd = 3; v.kh = 1; v.kw = 3;
+  v.pad_d = d.pad_h; v.pad_h = 0; v.pad_w = d.pad_w;
+  if (!wh_plan(v, x_dtype, y_dtype, ldx, ldy, pp, true)) return false;
+  WHParams& p = *pp;
+  // depth chunks: few enough to keep the 2-plane halo per chunk small, balanced over the CTAs
+  {
+    const long long per_chunk = (long long)p.nth * p.ntw;
+    const int ctas = persistent_ctas();
+    int best = p.ndc; double best_cost = 1e30;
+    for (int ndc = std::max(1, (p.D + 95) / 96); ndc <= std::max(1, p.D / 8); ++ndc) {
+      const int dc = (p.D + ndc - 1) / ndc;
+      const long long units = per_chunk * ((p.D + dc - 1) / dc);
+      const double cost = (double)((units + ctas - 1) / ctas) * (dc + 2);      // planes staged by the busiest CTA
+      if (cost < best_cost - 1e-9) { best_cost = cost; best = ndc; }
+    }
+    p.DC = (p.D + best - 1) / best;
+    p.ndc = (p.D + p.DC - 1) / p.DC;
+    p.nunits = (long long)p.n * p.ndc * p.nth * p.ntw;
+  }
+  p.xplane_b = ldx * 2 * d.xw;              // next image row
+  p.xrow_b = (int)ximg;                     // next image
+  p.ximg_b = 0;
+  p.yplane_b2 = ldy * 2 * d.yw;
+  p.yrow_b = (int)yimg;
+  p.yimg_b = 0;
+  return true;
+}
+
 }  // namespace
 
 bool wgrad_halo_supported(const urn_conv_desc& d, int x_dtype, int y_dtype, int64_t ldx, int64_t ldy) {
   WHParams p;
-  return wh_plan(d, x_dtype, y_dtype, ldx, ldy, &p);
+  return wh_plan_rows(d, x_dtype, y_dtype, ldx, ldy, &p) || wh_plan(d, x_dtype, y_dtype, ldx, ldy, &p);
 }
 
 int64_t wgrad_halo_workspace(const urn_conv_desc& d) {
@@ -546,7 +599,8 @@ int64_t wgrad_halo_workspace(const urn_conv_desc& d) {
 int wgrad_halo_launch(const urn_conv_desc& d, int x_dtype, const void* x, int64_t ldx, int y_dtype,
                       const void* y, int64_t ldy, float* dw, int accumulate, void* ws, cudaStream_t st) {
   WHParams p;
-  URN_CHECK(wh_plan(d, x_dtype, y_dtype, ldx, ldy, &p), "wgrad_halo: unsupported shape/dtype");
+  if (!wh_plan_rows(d, x_dtype, y_dtype, ldx, ldy, &p))
+    URN_CHECK(wh_plan(d, x_dtype, y_dtype, ldx, ldy, &p), "wgrad_halo: unsupported shape/dtype");
   const int x_bytes = ((p.stages * p.xplane_bytes + 1023) / 1024) * 1024;
   const size_t smem = 1024 + (size_t)x_bytes + (size_t)(p.ystages + p.ymirror) * p.yplane_bytes + 1024;
   static bool attr_set = false;
