@@ -1,6 +1,7 @@
 """CPU tests of the host-side mirror of the reference interface: config reader, synthetic IO
 source, bucket planning, class-level validation (no GPU, no compute calls)."""
 import os
+import time
 
 import numpy as np
 import pytest
@@ -179,3 +180,29 @@ def test_synthetic_streams_do_not_overlap():
         io.start_manager(2)
         io.next()
     assert np.array_equal(a.fetch_data("data").data(), b.fetch_data("data").data())     # still deterministic
+
+
+def test_checkpoint_retention_nmax_and_nhour(tmp_path):
+    """tf.train.Saver(max_to_keep=CHECKPOINT_NMAX, keep_checkpoint_every_n_hours=CHECKPOINT_NHOUR)
+    (ssnet_trainval.py:133-135): the newest NMAX checkpoints stay; one that drops out of the window
+    is kept for good only if NHOUR hours passed since the last one kept for good."""
+    from collections import OrderedDict
+    from uresnet_b200.ssnet_trainval import ssnet_trainval
+
+    class FakeNet(object):
+        def get_variables(self):
+            return OrderedDict([("UResNet/conv0/weights", np.zeros((3, 3, 1, 4), np.float32)),
+                                ("UResNet/conv0/BatchNorm/beta", np.zeros(4, np.float32))])
+    for nhour, want in ((1e6, ["u-3.npz", "u-4.npz"]), (0.0, ["u-3.npz", "u-4.npz"]),
+                        (1e-12, ["u-0.npz", "u-1.npz", "u-2.npz", "u-3.npz", "u-4.npz"])):
+        d = tmp_path / ("h%g" % nhour)
+        d.mkdir()
+        t = ssnet_trainval()
+        t._cfg.SAVE_FILE, t._cfg.CHECKPOINT_NMAX, t._cfg.CHECKPOINT_NHOUR = str(d / "u"), 2, nhour
+        t._net = FakeNet()
+        for it in range(5):
+            t._iteration = it
+            t._save()
+            time.sleep(0.02)                                   # strictly increasing mtimes
+        assert sorted(p.name for p in d.glob("*.npz")) == want, (nhour, sorted(p.name for p in d.glob("*.npz")))
+        t._net = None

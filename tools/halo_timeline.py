@@ -12,13 +12,14 @@ d = _capi.conv_desc_same(nd, n, sp, cin, cout, 3, 1)
 x = torch.randn((n,) + sp + (cin,), device="cuda").half()
 w = torch.randn((3,) * nd + (cin, cout), device="cuda") * 0.05
 wpack = torch.empty(2 * w.numel() + 64, dtype=torch.uint8, device="cuda")
-y = torch.empty((n,) + sp + (cout,), dtype=torch.float32, device="cuda")
+ydt = int(os.environ.get("YDT", "2"))                       # raw output dtype: 2 = fp16 (mix16 product path), 0 = fp32
+y = torch.empty((n,) + sp + (cout,), dtype=torch.float16 if ydt == 2 else torch.float32, device="cuda")
 st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
 g = torch.randn((n,) + sp + (cout,), device="cuda").bfloat16()
 dx = torch.zeros((n,) + sp + (cin,), dtype=torch.bfloat16, device="cuda")
 for _ in range(3):
     if what == "fwd":
-        _capi.check(lib.urn_conv_fwd_tc(C.byref(d), 2, x.data_ptr(), cin, w.data_ptr(), wpack.data_ptr(), y.data_ptr(), cout, 0, 0, st))
+        _capi.check(lib.urn_conv_fwd_tc(C.byref(d), 2, x.data_ptr(), cin, w.data_ptr(), wpack.data_ptr(), y.data_ptr(), cout, ydt, 0, st))
     else:
         _capi.check(lib.urn_conv_dgrad_tc(C.byref(d), 1, g.data_ptr(), cout, w.data_ptr(), wpack.data_ptr(), dx.data_ptr(), cin, 1,
                                           int(what == "dgrad_acc"), st))

@@ -78,6 +78,7 @@ class ssnet_trainval(object):
         self._iteration = -1
         self._sess = None
         self._rank, self._world = 0, 1
+        self._saver_t0 = time.time()
 
     def __del__(self):
         try:
@@ -204,9 +205,20 @@ class ssnet_trainval(object):
                 v[name[:-4] + 'moving_mean'] = np.zeros_like(v[name])
                 v[name[:-4] + 'moving_variance'] = np.ones_like(v[name])
         np.savez(path, **v)
-        old = sorted(glob.glob(self._cfg.SAVE_FILE + '-*.npz'), key=os.path.getmtime)
+        # tf.train.Saver(max_to_keep=CHECKPOINT_NMAX, keep_checkpoint_every_n_hours=CHECKPOINT_NHOUR)
+        # (ssnet_trainval.py:133-135): the newest NMAX files are kept; a file that drops out of that
+        # window is deleted unless NHOUR hours of training passed since the last one kept for good
+        if not hasattr(self, '_kept_forever'):
+            self._kept_forever, self._last_kept = set(), self._saver_t0      # Saver starts its clock at construction
+        old = sorted((f for f in glob.glob(self._cfg.SAVE_FILE + '-*.npz') if f not in self._kept_forever),
+                     key=os.path.getmtime)
         for f in old[:-max(1, int(self._cfg.CHECKPOINT_NMAX))]:
-            os.remove(f)
+            nhour = float(self._cfg.CHECKPOINT_NHOUR)
+            if nhour > 0 and os.path.getmtime(f) >= self._last_kept + nhour * 3600.0:
+                self._kept_forever.add(f)
+                self._last_kept = os.path.getmtime(f)
+            else:
+                os.remove(f)
         return path
 
     def _train_batch(self):
