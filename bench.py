@@ -103,8 +103,12 @@ def conv_flops(layer_table):
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of committed `ncu --set full` captures
 # (profiles/): keyed by (workload, "cin->cout kK sS @side", phase)
 NCU_TRAFFIC = {
-    ("2d", "16->16 k3 s1 @512", "conv_fwd"): 289.1e6 + 485.8e6,     # profiles/raw_gconv_halo_kernel_r01e_2d.summary.txt
-    ("3d", "16->16 k3 s1 @192", "conv_fwd"): (1.51e9 + 1.76e9) / 2,  # profiles/README.md r01c (2 images per capture; B=4 -> x2)
+    # profiles/raw_*_r02a_{2d,3d}.summary.txt (ncu --set full, B = 32 / B = 4)
+    ("2d", "16->16 k3 s1 @512", "conv_fwd"): 331.5e6 + 228.8e6,    # gconv_halo_kernel<2,0,0,1> (images-as-rows, fp16 raw out)
+    ("2d", "16->16 k3 s1 @512", "dgrad"): 329.9e6 + 227.4e6,       # gconv_halo_kernel<1,0,0,0>
+    ("2d", "16->16 k3 s1 @512", "wgrad"): 603.5e6 + 4.2e6,         # wgrad_halo_kernel<0> (images-as-rows)
+    ("3d", "16->16 k3 s1 @192", "dgrad"): 1502.9e6 + 871.7e6,      # gconv_halo_kernel<1,0,1,0>
+    ("3d", "16->16 k3 s1 @192", "wgrad"): 2153.0e6 + 6.0e6,        # wgrad_halo_kernel<0>
 }
 
 

@@ -13,9 +13,9 @@ ncu --metrics gpu__time_duration.sum --clock-control none -s 2200 -c 640 --csv -
 echo "launch list rc=$?"
 python tools/summarize_launches.py $OUT/launches_${TAG}_$WL.csv > $OUT/launches_${TAG}_$WL.summary.txt
 # full captures: "<name>|<demangled-name regex>|<skip>": the full-resolution instances of each kernel family
-for SPEC in "gconv_halo_fwd|gconv_halo_kernel<2, 0, true, true>|14" "wgrad_halo|wgrad_halo_kernel<false>|1" \
-            "bn_bwd_apply|bn_bwd_apply_fast_kernel|0" "bn_bwd_reduce|bn_bwd_reduce_fast_kernel|0" "bn_apply|bn_apply_fast_kernel|0" \
-            "gconv_halo_dgrad|gconv_halo_kernel<1, 0, true, false>|0" "gconv_tc|gconv_tc_kernel|6"; do
+# (the halo conv / filter-gradient kernels: tools/profile_halo.sh)
+for SPEC in "bn_bwd_apply|bn_bwd_apply_fast_kernel|0" "bn_bwd_reduce|bn_bwd_reduce_fast_kernel|0" "bn_apply|bn_apply_fast_kernel|0" \
+            "gconv_tc|gconv_tc_kernel|6"; do
   NAME=${SPEC%%|*}; REST=${SPEC#*|}; RE=${REST%%|*}; SKIP=${REST##*|}
   ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k "regex:$RE" -s $SKIP -c 2 \
       -o $OUT/prof_${NAME}_${TAG}_$WL -f $CMD > $OUT/ncu_full_${NAME}_${TAG}_$WL.log 2>&1
