@@ -226,7 +226,10 @@ def run_reference(args):
     line = {"impl": "reference", "metric": "train images/sec", "value": cb["value"], "unit": "images/s",
             "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": sec * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOADS[args.workload]["name"], "note": "CPU restatement of the reference graph (TF-1.x reference cannot run here)"},
+            "config": {"workload": WORKLOADS[args.workload]["name"], "per_gpu_batch": WORKLOADS[args.workload]["batch"],
+                       "global_batch": args.gpus * WORKLOADS[args.workload]["batch"], "parallelism": "dp%d" % args.gpus,
+                       "note": "CPU restatement of the reference graph (the TF-1.x reference cannot run here), all host cores; "
+                               "every step is a bounded sample of the workload: " + cb["sample"]},
             "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))

@@ -73,6 +73,11 @@ struct HaloParams {
   long long in_plane_b, in_img_b;
   long long o_row, o_plane, o_img;   // output strides in pixels
   float* stats_part;         // fused BN statistics: per (CTA, epilogue warp, channel) (n, mean, M2) partials, or NULL
+  // TMA staging (stride-1 inputs): the halo plane is nkw tiled TMA boxes [hr rows][run pixels][cin] -- one per
+  // kw shift, hardware zero fill outside the tensor = TF 'same' padding -- issued by ONE thread and completed on
+  // the stage's mbarrier by byte count; staged rows are then ordered (kw, hy, w) instead of (hy, kw, w)
+  int tma;
+  int tma_slot[3];           // coordinate slot (2..4) of the tile row origin / plane / image in the tensor map (dims sorted by stride)
   int dbg;                   // URN_HALO_DBG bitmask (perf experiments): 1 no stores, 2 no loads, 4 no MMA
 };
 
@@ -113,7 +118,8 @@ __device__ __forceinline__ bool plane_used(const HaloParams& p, int z, int d0, i
 // each instantiation's code small.
 template <int OUTK, int MODE, bool FULL3, bool STATS>   // FULL3: 3x3 in-plane tap box (unrolled issue loop); STATS: fused BN statistics
 __global__ void __launch_bounds__(kHThreads, 1)
-gconv_halo_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ HaloParams p,
+gconv_halo_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_a,
+                  const __grid_constant__ HaloParams p,
                   const void* __restrict__ in, void* __restrict__ out, long long* __restrict__ tl) {
   constexpr bool OUT_F32 = OUTK == 0;
   using T16 = typename std::conditional<OUTK == 2, f16, bf16>::type;     // 16-bit output element
@@ -144,7 +150,7 @@ gconv_halo_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_consta
   const int my_tiles = (int)(t_end - t_begin);
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < p.stages; ++s) { h_mbar_init(&full[s], kNumProducerWarps); h_mbar_init(&empty[s], 1); }
+    for (int s = 0; s < p.stages; ++s) { h_mbar_init(&full[s], p.tma ? 1 : kNumProducerWarps); h_mbar_init(&empty[s], 1); }
     for (int a = 0; a < p.nacc; ++a) { h_mbar_init(&tfull[a], 1); h_mbar_init(&tempty[a], 4); }
     h_mbar_init(wfull, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -160,7 +166,42 @@ gconv_halo_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_consta
   h_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp < kNumProducerWarps) {
+  if (warp < kNumProducerWarps && p.tma) {
+    // ===================== TMA producer: nkw box loads per input plane, one elected thread =====================
+    if (warp == 0) {
+      TileIter ti; ti.init(p, t_begin);
+      Ring st; st.init(p.stages);
+      const int run = 8 * p.ks;
+      const uint32_t box_bytes = (uint32_t)(p.hr * run * pitch);
+      for (int k = 0; k < my_tiles; ++k, ti.next(p)) {
+        const int d0 = ti.dt * p.TD;
+        const int ybase = ti.ht * kTH + p.oh0, xbase = ti.wt * kTW * p.ks + p.ow0;
+        const int nd_out = min(d0 + p.TD, p.gd) - d0;
+        const int zlo = d0 + p.od0, zhi = d0 + nd_out - 1 + p.od0 + p.nkd - 1;
+        for (int z = zlo; z <= zhi; ++z) {
+          if (z < 0 || z >= p.D) continue;                 // a plane of zeros contributes nothing
+          h_mbar_wait_warp(&empty[st.idx], st.phase ^ 1);
+          if (lane == 0) TL(0, k, 0);
+          int crd[3];
+          crd[p.tma_slot[0] - 2] = ybase; crd[p.tma_slot[1] - 2] = z; crd[p.tma_slot[2] - 2] = ti.nn;
+          if (h_elect_one()) {
+            h_mbar_expect_tx(&full[st.idx], box_bytes * (uint32_t)p.nkw);
+            const uint32_t dst = h_smem_u32(smem_a + (size_t)st.idx * p.plane_bytes);
+            for (int kw = 0; kw < p.nkw; ++kw)
+              asm volatile(
+                  "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes"
+                  " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+                  ::"r"(dst + (uint32_t)kw * box_bytes), "l"(reinterpret_cast<uint64_t>(&map_a)), "r"(h_smem_u32(&full[st.idx])),
+                  "r"(0), "r"(xbase + kw), "r"(crd[0]), "r"(crd[1]), "r"(crd[2])
+                  : "memory");
+          }
+          __syncwarp();
+          if (lane == 0) TL(0, k, 2);
+          st.next();
+        }
+      }
+    }
+  } else if (warp < kNumProducerWarps) {
     // ===================== producers: stage one input plane per pipeline slot =====================
     // Per-thread chunk tables are tile-invariant and live in registers: byte offset of the chunk
     // from the tile's halo origin in global memory, byte offset of its swizzled slot in the
@@ -298,7 +339,11 @@ gconv_halo_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_consta
     const uint32_t w_tap16 = (uint32_t)p.w_tap_bytes >> 4;
     // tap view (kh,kw) of sub-tile j starts at staged row kh*RW + kw*8*KS + j*8
     const uint32_t row16 = (uint32_t)pitch >> 4;                  // 16-byte units per staged row
-    const uint32_t a_kw = (uint32_t)(8 * p.ks) * row16, a_kh = (uint32_t)p.rw * row16, a_sub = 8u * row16;   // a_kh: next tap ROW offset (one halo row)
+    // descriptor start offsets (16-byte units) of the next kw tap / next kh tap (one halo row) / next sub-tile.
+    // cp.async staging orders the rows (hy, kw, w); TMA staging (kw, hy, w): one box per kw shift
+    const uint32_t a_kw = p.tma ? (uint32_t)(p.hr * 8 * p.ks) * row16 : (uint32_t)(8 * p.ks) * row16;
+    const uint32_t a_kh = p.tma ? (uint32_t)(8 * p.ks) * row16 : (uint32_t)p.rw * row16;
+    const uint32_t a_sub = 8u * row16;
     const int ksteps = p.cin >> 4;                                 // K = 16 per MMA
     const bool no_mma = (p.dbg & 4) != 0;
     h_mbar_wait_warp(wfull, 0);
@@ -696,6 +741,12 @@ bool halo_plan(const GConv& g, int in_dtype, int out_dtype, int cout_store, Halo
   const uint64_t layout = pitch == 128 ? 2 : (pitch == 64 ? 4 : 6);
   // 8-row groups (consecutive output rows of the sub-tile) are is*RW staged rows apart
   p.adesc_hi = (layout << 61) | (1ull << 46) | ((((uint64_t)(g.is * p.rw) * pitch) >> 4) << 32) | (1ull << 16);
+  // TMA staging for stride-1 inputs (URN_HALO_TMA=0 keeps the cp.async producers): 8-row groups (consecutive
+  // output rows of a sub-tile) are then one halo row = 8*ks staged rows apart; every box starts on a multiple
+  // of the swizzle pattern (256 / 512 / 1024 B for SW32 / 64 / 128)
+  p.tma = (g.is == 1 && !(getenv("URN_HALO_TMA") && atoi(getenv("URN_HALO_TMA")) == 0)) ? 1 : 0;
+  if (p.tma && ((uint64_t)(p.hr * 8 * p.ks) * pitch) % (pitch == 128 ? 1024 : (pitch == 64 ? 512 : 256))) p.tma = 0;
+  if (p.tma) p.adesc_hi = (layout << 61) | (1ull << 46) | ((((uint64_t)(8 * p.ks) * pitch) >> 4) << 32) | (1ull << 16);
   p.bdesc_hi = (layout << 61) | (1ull << 46) | (((8 * pitch) >> 4) << 32) | (1ull << 16);
   // concat mode: 3x3x3 stride-1 convs; the zero block is one B tile of N = TD*cout rows
   p.coff[0][0] = g.ood; p.coff[0][1] = g.ooh; p.coff[0][2] = g.oow;
@@ -885,6 +936,30 @@ static int halo_launch_params(HaloParams& p, int cin, int cout, int in_dtype, in
                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     URN_CHECK(r == CUDA_SUCCESS, "gconv_halo: cuTensorMapEncodeTiled(W) failed: %d", (int)r);
   }
+  CUtensorMap map_a = map_w;             // (unused unless p.tma)
+  if (p.tma) {
+    // input as a 5-D tensor (c, w, row, plane, image) with the plan's byte strides (the images-as-rows plan
+    // relabels rows := images, planes := image rows); box = one kw-shifted run of 8*ks pixels x hr halo rows
+    const CUtensorMapDataType dt = in_dtype == URN_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+    const CUtensorMapSwizzle sw = cin == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (cin == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+    const cuuint64_t img_stride = p.in_img_b > 0 ? (cuuint64_t)p.in_img_b : (cuuint64_t)p.in_plane_b * (cuuint64_t)p.D;
+    // outer dims (tile rows, planes, images) in ascending stride order (the images-as-rows plan has row stride >
+    // plane stride); a dim of extent 1 goes last
+    struct OD { cuuint64_t size, stride; cuuint32_t box; int what; };
+    OD od[3] = {{(cuuint64_t)p.H, (cuuint64_t)p.in_row_b, (cuuint32_t)p.hr, 0}, {(cuuint64_t)p.D, (cuuint64_t)p.in_plane_b, 1u, 1},
+                {(cuuint64_t)p.n, img_stride, 1u, 2}};
+    std::stable_sort(od, od + 3, [](const OD& a, const OD& b) { return (a.size > 1 ? a.stride : ~0ull) < (b.size > 1 ? b.stride : ~0ull); });
+    for (int i = 0; i < 3; ++i) p.tma_slot[od[i].what] = 2 + i;
+    // strides of extent-1 dims only have to be legal: keep them ascending
+    for (int i = 1; i < 3; ++i) if (od[i].size <= 1 && od[i].stride < od[i - 1].stride * od[i - 1].size) od[i].stride = od[i - 1].stride * od[i - 1].size;
+    cuuint64_t dims[5] = {(cuuint64_t)cin, (cuuint64_t)p.W, od[0].size, od[1].size, od[2].size};
+    cuuint64_t strides[4] = {(cuuint64_t)p.ldin * 2, od[0].stride, od[1].stride, od[2].stride};
+    cuuint32_t box[5] = {(cuuint32_t)cin, (cuuint32_t)(8 * p.ks), od[0].box, od[1].box, od[2].box};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = enc(&map_a, dt, 5, const_cast<void*>(in), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    URN_CHECK(r == CUDA_SUCCESS, "gconv_halo: cuTensorMapEncodeTiled(A) failed: %d (dims %d %d %d %d %d)", (int)r, cin, p.W, p.H, p.D, p.n);
+  }
   const int w_bytes = ((p.ntaps_w * p.w_tap_bytes + 1023) / 1024) * 1024;
   const size_t smem = 1024 + (size_t)w_bytes + (size_t)p.zero_bytes + (size_t)p.stages * p.plane_bytes + 1024;
   const int grid = (int)std::min<long long>(p.ntiles, persistent_ctas());
@@ -901,7 +976,7 @@ static int halo_launch_params(HaloParams& p, int cin, int cout, int in_dtype, in
                                     227 * 1024));                                                             \
       attr_set = true;                                                                                        \
     }                                                                                                         \
-    gconv_halo_kernel<OK, MODE, F3, ST><<<grid, kHThreads, smem, st>>>(map_w, p, in, out, tl);                \
+    gconv_halo_kernel<OK, MODE, F3, ST><<<grid, kHThreads, smem, st>>>(map_w, map_a, p, in, out, tl);         \
   } while (0)
   URN_CHECK(mode != 2 || full3, "gconv_halo: padded filters only with 3x3 taps (cout %d store %d taps %dx%dx%d classes %d cin %d)", p.cout, p.cout_store, p.nkd, p.nkh, p.nkw, p.ncls, p.cin);
   URN_CHECK(!stats || (out_dtype != URN_BF16 && mode != 1), "gconv_halo: statistics need a freshly written raw output");
