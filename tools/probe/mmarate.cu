@@ -11,7 +11,7 @@ __device__ __forceinline__ void umma(uint32_t d, uint64_t a, uint64_t b, uint32_
   asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
                ::"r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
 }
-struct Cfg { int layout_a, layout_b, a_mn, b_mn, M, N, pitch_a, pitch_b, a_step, b_step, nacc; int rr; };   // rr: round-robin accumulators per MMA
+struct Cfg { int layout_a, layout_b, a_mn, b_mn, M, N, pitch_a, pitch_b, a_step, b_step, nacc; int rr; int sbo_a, lbo_a; };   // rr: round-robin accumulators per MMA; sbo_a/lbo_a: explicit A strides (un-swizzled)
 // layout: 0 none (core matrices), 6 SW32, 4 SW64, 2 SW128
 __global__ void probe(Cfg c, int groups, long long* out) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -45,7 +45,9 @@ __global__ void probe(Cfg c, int groups, long long* out) {
     const uint32_t a0 = su32(smem), b0 = su32(smem + 96 * 1024);
     const uint32_t idesc = (1u << 4) | ((uint32_t)c.a_mn << 15) | ((uint32_t)c.b_mn << 16) | ((uint32_t)(c.N >> 3) << 17) |
                            ((uint32_t)(c.M >> 4) << 24);
-    const uint64_t ad = mk(c.layout_a, c.a_mn, c.pitch_a, a0), bd = mk(c.layout_b, c.b_mn, c.pitch_b, b0);
+    uint64_t ad = mk(c.layout_a, c.a_mn, c.pitch_a, a0);
+    const uint64_t bd = mk(c.layout_b, c.b_mn, c.pitch_b, b0);
+    if (c.sbo_a) ad = (1ull << 46) | ((uint64_t)(c.sbo_a >> 4) << 32) | ((uint64_t)(c.lbo_a >> 4) << 16) | (uint64_t)((a0 >> 4) & 0x3fff);
     long long t0 = clock64();
     if (!c.rr) {
       for (int g = 0; g < groups; ++g) {
@@ -98,6 +100,17 @@ int main() {
       char nm[96]; snprintf(nm, sizeof nm, "K-major SW32 M=128 N=%-3d round-robin over %d accumulators", N, rr);
       run(nm, Cfg{6, 6, 0, 0, 128, N, 32, 32, 256, 0, 4, rr});
     }
+  // un-swizzled "planar" A (8 pixels x 16 B core matrices, halo rows 640 B apart, chunk planes 11584 B apart):
+  // tap = start address shifted by t pixels (16 B): aligned (t*128) vs unaligned (t*16) starts
+  for (int N : {16, 48}) {
+    char nm[96];
+    snprintf(nm, sizeof nm, "planar A (no swizzle) M=128 N=%-3d starts t*128 B (aligned)", N);
+    run(nm, Cfg{0, 6, 0, 0, 128, N, 16, 32, 128, 0, 4, 0, 640, 11584});
+    snprintf(nm, sizeof nm, "planar A (no swizzle) M=128 N=%-3d starts t*16 B (pixel shifts)", N);
+    run(nm, Cfg{0, 6, 0, 0, 128, N, 16, 32, 16, 0, 4, 0, 640, 11584});
+    snprintf(nm, sizeof nm, "planar A (no swizzle) M=128 N=%-3d starts t*16 B, planes 11648 B", N);
+    run(nm, Cfg{0, 6, 0, 0, 128, N, 16, 32, 16, 0, 4, 0, 640, 11648});
+  }
   // K-major A (conv forward): rows of pitch bytes, taps 32 B apart in the descriptor start (a_step)
   const int lay[4] = {6, 4, 2, 0}; const int pit[4] = {32, 64, 128, 16}; const char* ln[4] = {"SW32 (Cin=16)", "SW64 (Cin=32)", "SW128 (Cin=64)", "no swizzle"};
   for (int li = 0; li < 1; ++li)
