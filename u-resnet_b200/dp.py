@@ -20,6 +20,7 @@ On CPU tensors (gloo; tests/test_dp.py) the same bucket plan runs synchronously.
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import torch
 import torch.distributed as dist
@@ -63,8 +64,11 @@ class GradientExchange(object):
             (_, wo, wc), (_, bo, bc) = items[2 * l], items[2 * l + 1]
             hi = items[2 * l + 2][1] if l + 1 < num_layers else flat.numel()
             self.layer_ranges.append((wo, hi))          # includes the alignment padding
+        bucket_mb = float(os.environ.get("URESNET_B200_DP_BUCKET_MB", bucket_mb))
         self.buckets = plan_buckets(self.layer_ranges, int(bucket_mb * (1 << 20) / 4))
         self.cuda = flat.is_cuda
+        # URESNET_B200_DP_OVERLAP=0: no per-layer events; ONE all-reduce of the whole buffer before Adam
+        self.overlap = os.environ.get("URESNET_B200_DP_OVERLAP", "1") != "0"
         self.expected_minibatches = 1
         self._seen = 0
         self._works = []
@@ -86,7 +90,7 @@ class GradientExchange(object):
     def events_array(self):
         """Event array for urn_backward, or None when this backward is not the last
         minibatch of the step (gradients are still being accumulated locally)."""
-        if not self.active or not self.cuda:
+        if not self.active or not self.cuda or not self.overlap:
             return None
         return self._ev_array if self._seen + 1 >= self.expected_minibatches else None
 
@@ -94,7 +98,7 @@ class GradientExchange(object):
         """Called right after urn_backward returned (work is only enqueued): launch every
         bucket's all-reduce on the communication stream behind that bucket's events."""
         self._seen += 1
-        if not self.active or not self.cuda or self._seen < self.expected_minibatches:
+        if not self.active or not self.cuda or not self.overlap or self._seen < self.expected_minibatches:
             return
         for lo, hi, layers in self.buckets:
             for l in layers:
@@ -114,9 +118,12 @@ class GradientExchange(object):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()                   # compute stream: backward has been enqueued up to here
         if not self._launched:
-            for lo, hi, _ in self.buckets:
-                self._works.append(dist.all_reduce(self.flat[lo:hi], op=dist.ReduceOp.SUM,
-                                                   group=self.group, async_op=True))
+            if self.cuda and not self.overlap:
+                self._works.append(dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+            else:
+                for lo, hi, _ in self.buckets:
+                    self._works.append(dist.all_reduce(self.flat[lo:hi], op=dist.ReduceOp.SUM,
+                                                       group=self.group, async_op=True))
         for w in self._works:
             w.wait()
         self._works = []
@@ -146,8 +153,30 @@ class GradientExchange(object):
         return [float(v) for v in t.cpu()]
 
 
+_compute_stream = None
+
+
+def use_high_priority_compute_stream(device):
+    """Make a HIGH-priority stream the calling thread's current stream (once per process).  NCCL's
+    kernels run on lowest-priority streams; with the compute kernels at default (= lowest) priority
+    too, the CTAs of an in-flight bucket all-reduce displaced CTAs of the 148-CTA persistent conv /
+    batch-norm kernels (measured at 2 GPUs: 2D 28.01 ms single-GPU step -> 28.79 ms; with the compute
+    stream at high priority 28.50 ms, a single un-overlapped all-reduce 28.39 ms).
+    ``URESNET_B200_DP_HIPRI=0`` keeps the default stream."""
+    global _compute_stream
+    if os.environ.get("URESNET_B200_DP_HIPRI", "1") == "0" or not torch.cuda.is_available():
+        return None
+    if _compute_stream is None:
+        torch.cuda.synchronize(device)
+        _compute_stream = torch.cuda.Stream(device=device, priority=-1)
+    torch.cuda.set_stream(_compute_stream)
+    return _compute_stream
+
+
 def attach(net, group=None, bucket_mb=16.0, average=False, force=False):
     """Give a constructed, trainable ``uresnet`` a gradient exchange over ``group``."""
+    if net._accum.is_cuda and (force or (dist.is_initialized() and dist.get_world_size(group) > 1)):
+        use_high_priority_compute_stream(net._accum.device)
     ex = GradientExchange(net._param_table, net._num_layers, net._accum, group=group,
                           bucket_mb=bucket_mb, average=average, force=force)
     net._exchange = ex
