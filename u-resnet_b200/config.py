@@ -35,7 +35,7 @@ _REFERENCE_SCHEMA = OrderedDict([
 # Second block: keys the reference does not have -- numeric mode of this library and the
 # synthetic batch source that stands in for larcv.
 _EXTRA_SCHEMA = OrderedDict([
-    ("DTYPE", "mix16"),            # 'f32' | 'mix16' | 'bf16'
+    ("DTYPE", "f32"),              # 'f32' (default: the reference computes in float32) | 'mix16' | 'bf16'
     ("KERNEL_IMPL", "auto"),       # 'auto' | 'ffma' | 'tc'
     ("SYNTHETIC_DIMS", []),        # e.g. [512,512,1]; [] = infer 2D/3D from the larcv filler cfg name
     ("SYNTHETIC_SEED", 1234),

@@ -6,7 +6,9 @@ kernels behind ``include/uresnet_b200.h``).  PyTorch is used only for device buf
 pinned staging memory and streams.
 
 Differences that are deliberate and visible:
-  * ``construct`` takes extra keyword-only knobs (``dtype``, ``impl``, ``device``, ``seed``).
+  * ``construct`` takes extra keyword-only knobs (``dtype``, ``impl``, ``device``, ``seed``); the default
+    ``dtype`` is ``'f32'`` like the reference, ``'mix16'`` (fp16 activations, bf16 gradients, tcgen05 tensor
+    cores: ~13x faster, gradients within the graph's own sensitivity to 2^-11 operand rounding) is opt-in.
   * variables are exposed through ``get_variables`` / ``set_variables`` keyed by the TF
     variable names (``UResNet/<scope>/weights``, ``.../BatchNorm/beta``), TF layouts.
   * out-of-range labels raise ``ValueError`` (TF-CPU raises, TF-GPU yields NaN).
@@ -59,7 +61,9 @@ class ssnet_base(object):
         self._trainable = bool(trainable)
         self._use_weight = bool(use_weight)
         self._learning_rate = learning_rate
-        self._dtype = _capi.DTYPES[(dtype or os.environ.get("URESNET_B200_DTYPE", "mix16")).lower()]
+        # default numeric mode = the reference's: float32 storage and arithmetic (ssnet.py:30-32).  The 16-bit
+        # tensor-core mode is opt-in: dtype='mix16' / DTYPE 'mix16' in the .cfg / URESNET_B200_DTYPE=mix16
+        self._dtype = _capi.DTYPES[(dtype or os.environ.get("URESNET_B200_DTYPE", "f32")).lower()]
         self._impl = _capi.IMPLS[(impl or os.environ.get("URESNET_B200_IMPL", "auto")).lower()]
         self._lib = _capi.load()          # raises if the CUDA library is missing: no fallback
         if not torch.cuda.is_available():
