@@ -77,6 +77,7 @@ struct HaloParams {
   // kw shift, hardware zero fill outside the tensor = TF 'same' padding -- issued by ONE thread and completed on
   // the stage's mbarrier by byte count; staged rows are then ordered (kw, hy, w) instead of (hy, kw, w)
   int tma;
+  int dual;                  // TMA staging with 6 warps per CTA and TWO CTAs per SM (half-size rings each): two independent tile pipelines hide each other's hand-off latencies
   int tma_slot[3];           // coordinate slot (2..4) of the tile row origin / plane / image in the tensor map (dims sorted by stride)
   int dbg;                   // URN_HALO_DBG bitmask (perf experiments): 1 no stores, 2 no loads, 4 no MMA
 };
@@ -142,6 +143,10 @@ gconv_halo_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_consta
 
   const long long tl_t0 = tl ? clock64() : 0;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // roles: 13 warps (0-7 producers, 8 MMA, 9-12 epilogue), or -- dual mode, 6 warps -- 0 TMA, 1 MMA, 2-5 epilogue
+  const int w_mma = p.dual ? 1 : kMmaWarp;
+  const int n_prod = p.dual ? 1 : kNumProducerWarps;
+  const int w_epi0 = w_mma + 1;
   const int pitch = p.cin * 2;                  // bytes per staged row
   const int cpr = pitch / 16;                   // 16-byte chunks per row
   // contiguous tile range of this CTA
@@ -155,7 +160,7 @@ gconv_halo_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_consta
     h_mbar_init(wfull, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == kMmaWarp) {
+  if (warp == w_mma) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(h_smem_u32(tmem_slot)),
                  "r"((uint32_t)p.tmem_cols)
                  : "memory");
@@ -166,7 +171,7 @@ gconv_halo_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_consta
   h_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp < kNumProducerWarps && p.tma) {
+  if (warp < n_prod && p.tma) {
     // ===================== TMA producer: nkw box loads per input plane, one elected thread =====================
     if (warp == 0) {
       TileIter ti; ti.init(p, t_begin);
@@ -201,7 +206,7 @@ gconv_halo_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_consta
         }
       }
     }
-  } else if (warp < kNumProducerWarps) {
+  } else if (warp < n_prod) {
     // ===================== producers: stage one input plane per pipeline slot =====================
     // Per-thread chunk tables are tile-invariant and live in registers: byte offset of the chunk
     // from the tile's halo origin in global memory, byte offset of its swizzled slot in the
@@ -294,7 +299,7 @@ gconv_halo_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_consta
     __syncwarp();
     if (lane == 0)
       for (uint32_t j = (issued > (uint32_t)pf ? issued - pf : 0); j < issued; ++j) { h_mbar_arrive(&full[ar.idx]); ar.next(); }
-  } else if (warp == kMmaWarp) {
+  } else if (warp == w_mma) {
     // ===================== filter load + MMA issue =====================
     // The WHOLE warp runs this loop with warp-uniform values (so the address arithmetic lives in
     // the uniform datapath and no lane-0 branch serialises it); only the tcgen05 instructions
@@ -511,7 +516,7 @@ gconv_halo_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_consta
       const int y = ti.ht * kTH + lh, x0 = ti.wt * kTW * p.ks + lw;
       const int nsub = min(p.ks, (p.gw - ti.wt * kTW * p.ks + kTW - 1) / kTW);
       const int dmax = min(d0 + p.TD, p.gd);
-      if (warp == kEpiWarp0 && lane == 0) TL(2, k, 0);
+      if (warp == w_epi0 && lane == 0) TL(2, k, 0);
       // accumulate mode (bf16 gradients): the old values of a group of sub-tiles are fetched BEFORE
       // the accumulators are waited for, so the read-modify-write does not serialise behind the MMAs
       uint4 oldv[4][2];
@@ -534,7 +539,7 @@ gconv_halo_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_consta
       }
       h_mbar_wait_warp(&tfull[ac.idx], ac.phase);
       h_fence_after();
-      if (warp == kEpiWarp0 && lane == 0) TL(2, k, 1);
+      if (warp == w_epi0 && lane == 0) TL(2, k, 1);
       for (int cd = 0; cd < p.ncls * p.TD; ++cd) {
         const int cls = cd / p.TD, dd = cd - cls * p.TD;
         const int d = d0 + dd;
@@ -627,11 +632,11 @@ gconv_halo_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_consta
           }
         }
       }
-      if (warp == kEpiWarp0 && lane == 0) TL(2, k, 2);
+      if (warp == w_epi0 && lane == 0) TL(2, k, 2);
       h_fence_before();
       __syncwarp();
       if (lane == 0) h_mbar_arrive(&tempty[ac.idx]);
-      if (warp == kEpiWarp0 && lane == 0) TL(2, k, 3);
+      if (warp == w_epi0 && lane == 0) TL(2, k, 3);
       ac.next();
     }
     if (do_stats && !(lane & 1)) {
@@ -652,16 +657,39 @@ gconv_halo_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_consta
   }
   h_fence_before();
   __syncthreads();
-  if (warp == kMmaWarp) {
+  if (warp == w_mma) {
     h_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols)
                  : "memory");
   }
 }
 
+bool halo_plan_impl(const GConv& g, int in_dtype, int out_dtype, int cout_store, HaloParams* pp, int ncls, bool dual);
+// Dual mode: stride-1 (TMA-staged) launches with 6 warps per CTA, half the shared memory and TMEM columns, TWO
+// CTAs per SM -- two independent tile pipelines hide each other's hand-off latencies.  Measured per layer
+// (B200, mix16): a clear win for the parity-class launches of stride-2 input gradients / conv-transposes (2D
+// 16->32 @512: 0.519 -> 0.275 ms, deconv4 0.289 -> 0.169 ms; 3D 1.64 -> 1.22 ms, 1.32 -> 0.95 ms), the 3D
+// Cout = 16 full-resolution layers (0.82 -> 0.72 ms) and the zero-padded head (3D 1.16 -> 0.85 ms); a loss for
+// the 3D Cout = 32 layers (0.23 -> 0.32 ms: their accumulators no longer fit a half TMEM with the 512-position
+// tile) and for accumulating epilogues; neutral in 2D images-as-rows launches.  Hence the rule below
+// (URN_HALO_DUAL=0: never, =2: wherever the shape fits).  Falls back to the single-CTA plan when it does not fit.
 bool halo_plan(const GConv& g, int in_dtype, int out_dtype, int cout_store, HaloParams* pp, int ncls = 1) {
+  static const int mode = getenv("URN_HALO_DUAL") ? atoi(getenv("URN_HALO_DUAL")) : 1;
+  bool want = false;
+  if (mode == 2) want = true;
+  else if (mode == 1) {
+    const bool is3d = g.id > 1 && g.od > 1;
+    want = ncls > 1 || (is3d && g.cout == 16 && !g.accumulate && g.ntaps == 27) || (cout_store > 0 && cout_store < g.cout);
+  }
+  if (want && g.is == 1 && halo_plan_impl(g, in_dtype, out_dtype, cout_store, pp, ncls, true) && pp->tma) return true;
+  return halo_plan_impl(g, in_dtype, out_dtype, cout_store, pp, ncls, false);
+}
+bool halo_plan_impl(const GConv& g, int in_dtype, int out_dtype, int cout_store, HaloParams* pp, int ncls, bool dual) {
   HaloParams& p = *pp;
   memset(&p, 0, sizeof(p));
+  p.dual = dual ? 1 : 0;
+  const int tmem_limit = dual ? 256 : 512;              // TMEM columns and dynamic shared memory available to one CTA
+  const int smem_limit = dual ? 108 * 1024 : 224 * 1024;
   if (getenv("URN_NO_HALO")) return false;
   if (in_dtype != URN_BF16 && in_dtype != URN_F16) return false;
   if (out_dtype != URN_F32 && out_dtype != URN_BF16 && out_dtype != URN_F16) return false;
@@ -717,9 +745,11 @@ bool halo_plan(const GConv& g, int in_dtype, int out_dtype, int cout_store, Halo
   const bool has_d = g.gd > 1 || p.nkd > 1;
   p.TD = has_d ? 4 : 1;
   p.ncls = ncls;
-  while (p.TD > 1 && ncls * p.TD * p.ks * g.cout * 2 > 512) p.TD /= 2;
-  while (p.ks > 1 && ncls * p.TD * p.ks * g.cout * 2 > 512) p.ks /= 2;
-  if (ncls * p.TD * p.ks * g.cout * 2 > 512) return false;
+  if (dual)        // keep the depth tile (halo planes per output plane), narrow the super-tile first
+    while (p.ks > 1 && ncls * p.TD * p.ks * g.cout * 2 > tmem_limit) p.ks /= 2;
+  while (p.TD > 1 && ncls * p.TD * p.ks * g.cout * 2 > tmem_limit) p.TD /= 2;
+  while (p.ks > 1 && ncls * p.TD * p.ks * g.cout * 2 > tmem_limit) p.ks /= 2;
+  if (ncls * p.TD * p.ks * g.cout * 2 > tmem_limit) return false;
   p.rw = p.nkw * 8 * p.ks;
   if (p.hr * p.rw * cpr > kNCH * 256) return false;
   if (p.gd < p.TD) p.TD = std::max(1, p.gd);
@@ -729,7 +759,7 @@ bool halo_plan(const GConv& g, int in_dtype, int out_dtype, int cout_store, Halo
   p.w_tap_bytes = g.cout * g.cin * 2;
   p.ntaps_w = maxw + 1;
   const int w_bytes = ((p.ntaps_w * p.w_tap_bytes + 1023) / 1024) * 1024;
-  const int budget = 224 * 1024 - w_bytes;
+  const int budget = smem_limit - w_bytes;
   p.stages = std::min(kHMaxStages, budget / p.plane_bytes);
   if (p.stages < 2) return false;
   if (p.ntiles >= (1ll << 31)) return false;
@@ -747,6 +777,7 @@ bool halo_plan(const GConv& g, int in_dtype, int out_dtype, int cout_store, Halo
   p.tma = (g.is == 1 && !(getenv("URN_HALO_TMA") && atoi(getenv("URN_HALO_TMA")) == 0)) ? 1 : 0;
   if (p.tma && ((uint64_t)(p.hr * 8 * p.ks) * pitch) % (pitch == 128 ? 1024 : (pitch == 64 ? 512 : 256))) p.tma = 0;
   if (p.tma) p.adesc_hi = (layout << 61) | (1ull << 46) | ((((uint64_t)(8 * p.ks) * pitch) >> 4) << 32) | (1ull << 16);
+  if (dual && !p.tma) return false;
   p.bdesc_hi = (layout << 61) | (1ull << 46) | (((8 * pitch) >> 4) << 32) | (1ull << 16);
   // concat mode: 3x3x3 stride-1 convs; the zero block is one B tile of N = TD*cout rows
   p.coff[0][0] = g.ood; p.coff[0][1] = g.ooh; p.coff[0][2] = g.oow;
@@ -761,10 +792,10 @@ bool halo_plan(const GConv& g, int in_dtype, int out_dtype, int cout_store, Halo
     p.stages = std::min(kHMaxStages, (budget - p.zero_bytes) / p.plane_bytes);
     if (p.stages < 2) { p.concat = 0; p.zero_bytes = 0; p.stages = std::min(kHMaxStages, budget / p.plane_bytes); }
   }
-  p.nacc = std::max(2, std::min(kMaxAcc, 512 / (ncls * p.TD * p.ks * g.cout)));
+  p.nacc = std::max(2, std::min(kMaxAcc, tmem_limit / (ncls * p.TD * p.ks * g.cout)));
   if (const char* e = getenv("URN_HALO_NACC")) p.nacc = std::max(2, std::min(p.nacc, atoi(e)));
   p.tmem_cols = std::max(32, pow2c(p.nacc * ncls * p.TD * p.ks * g.cout));
-  if (p.tmem_cols > 512) return false;
+  if (p.tmem_cols > tmem_limit) return false;
   if (const char* e = getenv("URN_HALO_DBG")) p.dbg = atoi(e);
   // Cin = 64 with 1-4 taps: the tap-box kernel (128-byte TMA rows, few boxes) is as fast or faster
   if (g.cin == 64 && !(p.nkh == 3 && p.nkw == 3) && !getenv("URN_HALO_ALL")) return false;
@@ -849,7 +880,7 @@ bool halo_plan_classes(const GConv* gs, int ncls, int in_dtype, int out_dtype, H
   // smem budget again with the real number of resident taps
   {
     const int w_bytes = ((p.ntaps_w * p.w_tap_bytes + 1023) / 1024) * 1024;
-    p.stages = std::min(kHMaxStages, (224 * 1024 - w_bytes) / p.plane_bytes);
+    p.stages = std::min(kHMaxStages, ((p.dual ? 108 : 224) * 1024 - w_bytes) / p.plane_bytes);
     if (p.stages < 2) return false;
   }
   for (int c = 0; c < ncls; ++c) {
@@ -887,7 +918,7 @@ int gconv_halo_classes_launch(const GConv* gs, int ncls, int in_dtype, const voi
   if (stats_part && nparts && out_dtype != URN_BF16 && !gs[0].accumulate && !getenv("URN_NO_FUSED_STATS") &&
       (long long)gs[0].gd * 2 == gs[0].od + (gs[0].od == 1) && gs[0].gh * 2 == gs[0].oh && gs[0].gw * 2 == gs[0].ow) {
     p.stats_part = stats_part;
-    *nparts = (int)std::min<long long>(p.ntiles, persistent_ctas()) * 4;
+    *nparts = (int)std::min<long long>(p.ntiles, (long long)persistent_ctas() * (p.dual ? 2 : 1)) * 4;
   }
   return halo_launch_params(p, gs[0].cin, gs[0].cout, in_dtype, out_dtype, in, wpack, out, st);
 }
@@ -910,7 +941,7 @@ int gconv_halo_launch_stats(const GConv& g, int in_dtype, const void* in, const 
     URN_CHECK(halo_plan(g, in_dtype, out_dtype, cout_store, &p), "gconv_halo: unsupported shape/dtype");
   if (nparts) *nparts = 0;
   if (p.ntiles == 0) return 0;
-  const int grid_ = (int)std::min<long long>(p.ntiles, persistent_ctas());
+  const int grid_ = (int)std::min<long long>(p.ntiles, (long long)persistent_ctas() * (p.dual ? 2 : 1));
   // statistics only when this single launch produces the whole raw tensor, freshly written
   if (stats_part && nparts && out_dtype != URN_BF16 && !g.accumulate && g.os == 1 && g.gd == g.od && g.gh == g.oh &&
       g.gw == g.ow && !getenv("URN_NO_FUSED_STATS")) {
@@ -962,7 +993,8 @@ static int halo_launch_params(HaloParams& p, int cin, int cout, int in_dtype, in
   }
   const int w_bytes = ((p.ntaps_w * p.w_tap_bytes + 1023) / 1024) * 1024;
   const size_t smem = 1024 + (size_t)w_bytes + (size_t)p.zero_bytes + (size_t)p.stages * p.plane_bytes + 1024;
-  const int grid = (int)std::min<long long>(p.ntiles, persistent_ctas());
+  const int grid = (int)std::min<long long>(p.ntiles, (long long)persistent_ctas() * (p.dual ? 2 : 1));
+  const int nthreads = p.dual ? 192 : kHThreads;
   long long* tl = nullptr;
   if (const char* e = getenv("URN_HALO_TIMELINE")) tl = (long long*)strtoull(e, nullptr, 0);
   const int mode = (p.cout_store & 15) ? 2 : (p.accumulate ? 1 : 0);
@@ -976,7 +1008,7 @@ static int halo_launch_params(HaloParams& p, int cin, int cout, int in_dtype, in
                                     227 * 1024));                                                             \
       attr_set = true;                                                                                        \
     }                                                                                                         \
-    gconv_halo_kernel<OK, MODE, F3, ST><<<grid, kHThreads, smem, st>>>(map_w, map_a, p, in, out, tl);         \
+    gconv_halo_kernel<OK, MODE, F3, ST><<<grid, nthreads, smem, st>>>(map_w, map_a, p, in, out, tl);          \
   } while (0)
   URN_CHECK(mode != 2 || full3, "gconv_halo: padded filters only with 3x3 taps (cout %d store %d taps %dx%dx%d classes %d cin %d)", p.cout, p.cout_store, p.nkd, p.nkh, p.nkw, p.ncls, p.cin);
   URN_CHECK(!stats || (out_dtype != URN_BF16 && mode != 1), "gconv_halo: statistics need a freshly written raw output");
