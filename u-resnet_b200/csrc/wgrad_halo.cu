@@ -71,6 +71,9 @@ struct WHParams {
   // "row" is the next IMAGE and the "plane" the next image row)
   int xrow_b, yrow_b;
   long long xplane_b, ximg_b, yplane_b2, yimg_b;
+  // TMA staging (images-as-rows plan): ONE box of hr tile rows x xb pixels per X plane, the kw taps are
+  // views shifted by whole pixels (LBO = one pixel); one box of 16 x 8*ks positions per dY plane
+  int tma, xb;
 };
 
 struct UnitIter {
@@ -88,7 +91,8 @@ struct UnitIter {
 
 template <bool S2>    // S2: X sampled with stride 2 (compile-time, so that the stride-1 kernel keeps its tight loops)
 __global__ void __launch_bounds__(kWThreads, 1)
-wgrad_halo_kernel(const __grid_constant__ WHParams p, const void* __restrict__ x, const void* __restrict__ dy,
+wgrad_halo_kernel(const __grid_constant__ WHParams p, const __grid_constant__ CUtensorMap map_x,
+                  const __grid_constant__ CUtensorMap map_y, const void* __restrict__ x, const void* __restrict__ dy,
                   float* __restrict__ partial) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -110,7 +114,7 @@ wgrad_halo_kernel(const __grid_constant__ WHParams p, const void* __restrict__ x
   const int my_units = (int)(u_end - u_begin);
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < p.stages; ++s) { h_mbar_init(&full[s], kWProdWarps); h_mbar_init(&empty[s], 1); }
+    for (int s = 0; s < p.stages; ++s) { h_mbar_init(&full[s], p.tma ? 1 : kWProdWarps); h_mbar_init(&empty[s], 1); }
     for (int s = 0; s < p.ystages; ++s) h_mbar_init(&yempty[s], 1);
     h_mbar_init(tfull, 2);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -126,7 +130,50 @@ wgrad_halo_kernel(const __grid_constant__ WHParams p, const void* __restrict__ x
   h_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp < kWProdWarps) {
+  if (warp < kWProdWarps && p.tma) {
+    // ===================== TMA producer (stride 1, images-as-rows): one elected thread =====================
+    // Out-of-range coordinates are filled with zeros by the hardware: the 'same' padding of X and the
+    // positions of a ragged tile that must not contribute (dY = 0).
+    if (warp == 0) {
+      UnitIter ui; ui.init(p, u_begin);
+      Ring st, yr; st.init(p.stages); yr.init(p.ystages);
+      for (int k = 0; k < my_units; ++k, ui.next(p)) {
+        const int d0 = ui.dc * p.DC, d1 = min(d0 + p.DC, p.D);
+        const int y0 = ui.ht * kWTH, x0 = ui.wt * kWTW * p.ks;
+        for (int z = d0 + p.od0; z <= d1 - 1 + p.od0 + p.nkd - 1; ++z) {
+          const bool xvalid = z >= 0 && z < p.XD;
+          const int yp = z - p.od0;
+          const bool yvalid = yp >= d0 && yp < d1;
+          h_mbar_wait_warp(&empty[st.idx], st.phase ^ 1);
+          if (yvalid) h_mbar_wait_warp(&yempty[yr.idx], yr.phase ^ 1);
+          const int ncopy = (p.ymirror && yr.idx < p.ymirror) ? 2 : 1;
+          if (h_elect_one()) {
+            const uint32_t bar = h_smem_u32(&full[st.idx]);
+            h_mbar_expect_tx(&full[st.idx], (xvalid ? (uint32_t)p.xplane_bytes : 0u) +
+                                                (yvalid ? (uint32_t)(p.yplane_bytes * ncopy) : 0u));
+            if (xvalid)
+              asm volatile(
+                  "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes"
+                  " [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                  ::"r"(h_smem_u32(smem_x + (size_t)st.idx * p.xplane_bytes)), "l"(reinterpret_cast<uint64_t>(&map_x)), "r"(bar),
+                  "r"(0), "r"(x0 + p.ow0), "r"(z), "r"(y0 + p.oh0)
+                  : "memory");
+            if (yvalid)
+              for (int cpy = 0; cpy < ncopy; ++cpy)
+                asm volatile(
+                    "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes"
+                    " [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                    ::"r"(h_smem_u32(smem_y + (size_t)(yr.idx + cpy * p.ystages) * p.yplane_bytes)),
+                    "l"(reinterpret_cast<uint64_t>(&map_y)), "r"(bar), "r"(0), "r"(x0), "r"(yp), "r"(y0)
+                    : "memory");
+          }
+          __syncwarp();
+          if (yvalid) yr.next();
+          st.next();
+        }
+      }
+    }
+  } else if (warp < kWProdWarps) {
     // ===================== producers =====================
     // Register-resident chunk tables (see gconv_halo.cu): byte offset from the tile's halo origin,
     // swizzled slot in the stage, halo row / column for the border test; surplus slots replicate
@@ -258,9 +305,16 @@ wgrad_halo_kernel(const __grid_constant__ WHParams p, const void* __restrict__ x
     const uint32_t a_hi = (uint32_t)(p.adesc_hi >> 32), b_hi = (uint32_t)(p.bdesc_hi >> 32);
     const uint32_t a_lo_base = (uint32_t)p.adesc_hi, b_lo_base = (uint32_t)p.bdesc_hi;
     const uint32_t pitch = (uint32_t)p.cx * 2;
-    const uint32_t a_mstep = ((uint32_t)(p.tpm * 8 * p.ks) * pitch) >> 4;   // next M tile: tpm taps further (taps are 8*KS rows apart)
-    const uint32_t a_kstep = ((uint32_t)(2 * PS * p.rw) * pitch) >> 4;     // 16 positions = 2 output rows = 2*s halo rows
-    const uint32_t a_sub = (8u * pitch) >> 4;                               // next sub-tile: 8 pixels further in the run
+    // cp.async layout: taps are 8*KS rows apart; 16 positions = 2 output rows = 2*s halo rows; the next sub-tile
+    // is 8 pixels further in the run.  TMA layout (rows [h][xb pixels], positions ordered (h, w)): taps are one
+    // pixel apart; the K step kk of a 128-position block covers pixels 16*(kk & hm) .. +15 of row kk >> hs.
+    const uint32_t a_mstep = ((uint32_t)(p.tma ? p.tpm : p.tpm * 8 * p.ks) * pitch) >> 4;   // next M tile: tpm taps further
+    const uint32_t a_row = ((uint32_t)(p.tma ? p.xb : 2 * PS * p.rw) * pitch) >> 4;
+    const uint32_t a_h16 = (16u * pitch) >> 4;
+    const int hs = (p.tma && p.ks == 4) ? 1 : 0;
+    const uint32_t hm = (p.tma && p.ks == 4) ? 1u : 0u;
+    const uint32_t a_sub = p.tma ? (uint32_t)(128 / (8 * p.ks)) * a_row : (8u * pitch) >> 4;
+#define WH_AOFF(kk) ((uint32_t)((kk) >> hs) * a_row + ((uint32_t)(kk) & hm) * a_h16)
     const uint32_t b_kstep = (16u * (uint32_t)p.cy * 2u) >> 4;
     const uint32_t b_sub = (128u * (uint32_t)p.cy * 2u) >> 4;
     const uint32_t y_lo0 = h_smem_u32(smem_y) >> 4, y_stage = (uint32_t)p.yplane_bytes >> 4;
@@ -270,7 +324,8 @@ wgrad_halo_kernel(const __grid_constant__ WHParams p, const void* __restrict__ x
     const uint32_t ymask = (uint32_t)p.ystages - 1u;
     for (int k = 0; k < my_units; ++k, ui.next(p)) {
       const int d0 = ui.dc * p.DC, d1 = min(d0 + p.DC, p.D);
-      const int nsub = min(p.ks, (p.W - ui.wt * kWTW * p.ks + kWTW - 1) / kWTW);   // sub-tiles inside the image
+      // sub-tiles inside the image (TMA layout: 128-position blocks of whole rows, ragged columns hold dY = 0)
+      const int nsub = p.tma ? p.ks : min(p.ks, (p.W - ui.wt * kWTW * p.ks + kWTW - 1) / kWTW);
       for (int z = d0 * PS + p.od0; z <= (d1 - 1) * PS + p.od0 + p.nkd - 1; ++z) {
         const bool xvalid = z >= 0 && z < p.XD;
         h_mbar_wait(&full[st.idx], st.phase);
@@ -310,7 +365,7 @@ wgrad_halo_kernel(const __grid_constant__ WHParams p, const void* __restrict__ x
                   for (int sj = 0; sj < nsub; ++sj)
 #pragma unroll
                     for (int kk = 0; kk < 8; ++kk)
-                      h_umma2(d_tmem, a_lo + (uint32_t)sj * a_sub + (uint32_t)kk * a_kstep, a_hi,
+                      h_umma2(d_tmem, a_lo + (uint32_t)sj * a_sub + WH_AOFF(kk), a_hi,
                               b_lo0 + (uint32_t)sj * b_sub + (uint32_t)kk * b_kstep, b_hi, p.idesc_n[last][0],
                               (sj | kk) == 0 ? af : 1u);
                 }
@@ -348,7 +403,7 @@ wgrad_halo_kernel(const __grid_constant__ WHParams p, const void* __restrict__ x
                       for (int sj = 0; sj < nsub; ++sj)
 #pragma unroll
                         for (int kk = 0; kk < 8; ++kk)
-                          h_umma2(d_tmem + (uint32_t)(gi * p.cy), a_lo + (uint32_t)sj * a_sub + (uint32_t)kk * a_kstep, a_hi,
+                          h_umma2(d_tmem + (uint32_t)(gi * p.cy), a_lo + (uint32_t)sj * a_sub + WH_AOFF(kk), a_hi,
                                   b_lo0 + (uint32_t)gi * y_stage + (uint32_t)sj * b_sub + (uint32_t)kk * b_kstep, b_hi,
                                   p.idesc_n[last][0], (sj | kk) == 0 ? af : 1u);
                     }
@@ -360,7 +415,7 @@ wgrad_halo_kernel(const __grid_constant__ WHParams p, const void* __restrict__ x
                     for (int sj = 0; sj < nsub; ++sj)
 #pragma unroll
                       for (int kk = 0; kk < 8; ++kk)
-                        h_umma2(d_tmem, a_lo + (uint32_t)sj * a_sub + (uint32_t)kk * a_kstep, a_hi,
+                        h_umma2(d_tmem, a_lo + (uint32_t)sj * a_sub + WH_AOFF(kk), a_hi,
                                 b_lo0 + (uint32_t)sj * b_sub + (uint32_t)kk * b_kstep, b_hi, p.idesc_n[last][len - 1],
                                 (sj | kk) == 0 ? accf : 1u);
                   }
@@ -484,31 +539,53 @@ bool wh_plan(const urn_conv_desc& d, int x_dtype, int y_dtype, int64_t ldx, int6
   p.tmem_cols = std::max(32, pow2c(cols));
   // super-tile: KS sub-tiles share one staged X plane (<= 56 KB) and one barrier round trip
   const int cpr = p.cx * 2 / 16;
-  p.ks = 4;
-  if (const char* e = getenv("URN_WHALO_KS")) p.ks = std::max(1, std::min(p.ks, atoi(e)));
-  while (p.ks > 1 && (p.W + kWTW - 1) / kWTW <= p.ks / 2) p.ks /= 2;
-  while (p.ks > 1 && p.ks * 128 * (p.cy * 2 / 16) > kWYCH * kWProdThreads) p.ks /= 2;
-  while (p.ks > 1 && p.hr * p.nkw * 8 * p.ks * cpr > kWNCH * kWProdThreads) p.ks /= 2;
+  // TMA staging for the images-as-rows plan (URN_WHALO_TMA=0 keeps the cp.async producers): the X plane is
+  // staged ONCE (no kw-shifted copies: 20 KB instead of 48 KB for cx = 16), which leaves room for a deeper ring
+  bool want_tma = rows && !(getenv("URN_WHALO_TMA") && atoi(getenv("URN_WHALO_TMA")) == 0) && get_encode_h() != nullptr;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    p.ks = 4;
+    if (const char* e = getenv("URN_WHALO_KS")) p.ks = std::max(1, std::min(p.ks, atoi(e)));
+    while (p.ks > 1 && (p.W + kWTW - 1) / kWTW <= p.ks / 2) p.ks /= 2;
+    while (p.ks > 1 && p.ks * 128 * (p.cy * 2 / 16) > kWYCH * kWProdThreads) p.ks /= 2;
+    if (!want_tma)
+      while (p.ks > 1 && p.hr * p.nkw * 8 * p.ks * cpr > kWNCH * kWProdThreads) p.ks /= 2;
+    if (want_tma && p.ks < 2) { want_tma = false; continue; }
+    break;
+  }
+  p.tma = want_tma ? 1 : 0;
   p.rw = p.nkw * 8 * p.ks;
+  p.xb = 8 * p.ks + 8;                       // pixels per staged row (TMA): the run, its halo, padded to whole swizzle atoms
   p.ntw = (p.W + kWTW * p.ks - 1) / (kWTW * p.ks); p.nth = (p.H + kWTH - 1) / kWTH;
   p.nunits = (long long)p.n * p.ndc * p.nth * p.ntw;
   if (p.nunits >= (1ll << 31)) return false;
-  p.xplane_bytes = p.hr * p.rw * p.cx * 2;
+  p.xplane_bytes = p.tma ? p.hr * p.xb * p.cx * 2 : p.hr * p.rw * p.cx * 2;
   p.yplane_bytes = p.ks * 128 * p.cy * 2;
-  if (p.hr * p.rw * cpr > kWNCH * kWProdThreads) return false;
-  // the garbage taps of the last M tile read up to (nM*tpm - ntp) tap strides past the plane: keep
-  // that inside the dY region that follows the X stages
-  if ((p.nM * p.tpm - p.ntp) * 8 * p.ks * p.cx * 2 > 2 * p.yplane_bytes + 8192) return false;
+  if (!p.tma) {
+    if (p.hr * p.rw * cpr > kWNCH * kWProdThreads) return false;
+    // the garbage taps of the last M tile read up to (nM*tpm - ntp) tap strides past the plane: keep
+    // that inside the dY region that follows the X stages
+    if ((p.nM * p.tpm - p.ntp) * 8 * p.ks * p.cx * 2 > 2 * p.yplane_bytes + 8192) return false;
+  }
   // Producers run `pf` cp.async groups ahead of the full-barrier arrival; the dY slot of plane z+1
   // frees two steps after its previous tenant's last use, so the dY ring needs >= pf + 3 slots
   // (and the X ring >= pf + 1) or producers and MMA warp would wait on each other.
   const int budget = 222 * 1024;
   p.pf = 0;
   p.ymirror = (p.nkd == 3 && p.s == 1) ? 2 : 0;
-  for (int pf : {4, 2, 1}) {
-    const int ys = pow2c(pf + (p.nkd == 3 ? 3 : 1));
-    const int st = std::min(kWMaxStages, (budget - (ys + p.ymirror) * p.yplane_bytes) / p.xplane_bytes);
-    if (st >= std::max(2, pf + 1)) { p.pf = pf; p.ystages = ys; p.stages = st; break; }
+  if (p.tma) {
+    // no cp.async groups: the look-ahead is the ring depth.  dY ring of 8 (3 planes live + 5 ahead) when at
+    // least 3 X stages still fit, else 4.
+    for (int ys : {8, 4}) {
+      if (const char* e = getenv("URN_WHALO_YS")) { if (atoi(e) != ys) continue; }
+      const int st = std::min(kWMaxStages, (budget - (ys + p.ymirror) * p.yplane_bytes) / p.xplane_bytes);
+      if (st >= (ys == 8 ? 3 : 2)) { p.pf = 1; p.ystages = ys; p.stages = st; break; }
+    }
+  } else {
+    for (int pf : {4, 2, 1}) {
+      const int ys = pow2c(pf + (p.nkd == 3 ? 3 : 1));
+      const int st = std::min(kWMaxStages, (budget - (ys + p.ymirror) * p.yplane_bytes) / p.xplane_bytes);
+      if (st >= std::max(2, pf + 1)) { p.pf = pf; p.ystages = ys; p.stages = st; break; }
+    }
   }
   if (!p.pf) return false;
   const int fmt = x_dtype == URN_BF16 ? 1 : 0;
@@ -532,6 +609,8 @@ bool wh_plan(const urn_conv_desc& d, int x_dtype, int y_dtype, int64_t ldx, int6
   const uint64_t xp = (uint64_t)p.cx * 2, yp = (uint64_t)p.cy * 2;
   // MN-major: SBO = next 8 positions (K), LBO = next channel group (MN)
   p.adesc_hi = (layout_of(xp) << 61) | (1ull << 46) | ((((uint64_t)(p.s * p.rw) * xp) >> 4) << 32) | ((((uint64_t)(8 * p.ks) * xp) >> 4) << 16);
+  // TMA layout: the next 8 positions are the next 8 pixels of the row, the next tap (M group) is ONE pixel further
+  if (p.tma) p.adesc_hi = (layout_of(xp) << 61) | (1ull << 46) | (((8 * xp) >> 4) << 32) | ((xp >> 4) << 16);
   // B: N groups of cy channels = consecutive dY ring slots (LBO = slot stride)
   p.bdesc_hi = (layout_of(yp) << 61) | (1ull << 46) | (((8 * yp) >> 4) << 32) | ((((uint64_t)p.yplane_bytes) >> 4) << 16);
   if (((uint64_t)p.yplane_bytes >> 4) >= (1u << 14)) return false;
@@ -611,8 +690,34 @@ int wgrad_halo_launch(const urn_conv_desc& d, int x_dtype, const void* x, int64_
   }
   const int grid = (int)std::min<long long>(p.nunits, persistent_ctas());
   float* partial = (float*)ws;
-  if (p.s == 2) wgrad_halo_kernel<true><<<grid, kWThreads, smem, st>>>(p, x, y, partial);
-  else wgrad_halo_kernel<false><<<grid, kWThreads, smem, st>>>(p, x, y, partial);
+  CUtensorMap map_x, map_y;
+  memset(&map_x, 0, sizeof(map_x)); memset(&map_y, 0, sizeof(map_y));
+  if (p.tma) {
+    // X and dY as 4-D tensors (c, w, plane, tile row) with the plan's byte strides (images-as-rows: plane =
+    // image row, tile row = image)
+    EncodeTiledFnH enc = get_encode_h();
+    const CUtensorMapDataType dt = x_dtype == URN_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+    auto swz = [](int c) { return c == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (c == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B); };
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    {
+      cuuint64_t dims[4] = {(cuuint64_t)p.cx, (cuuint64_t)p.XW, (cuuint64_t)p.XD, (cuuint64_t)p.XH};
+      cuuint64_t strides[3] = {(cuuint64_t)ldx * 2, (cuuint64_t)p.xplane_b, (cuuint64_t)p.xrow_b};
+      cuuint32_t box[4] = {(cuuint32_t)p.cx, (cuuint32_t)p.xb, 1u, (cuuint32_t)p.hr};
+      CUresult r = enc(&map_x, dt, 4, const_cast<void*>(x), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz(p.cx),
+                       CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      URN_CHECK(r == CUDA_SUCCESS, "wgrad_halo: cuTensorMapEncodeTiled(X) failed: %d", (int)r);
+    }
+    {
+      cuuint64_t dims[4] = {(cuuint64_t)p.cy, (cuuint64_t)p.W, (cuuint64_t)p.D, (cuuint64_t)p.H};
+      cuuint64_t strides[3] = {(cuuint64_t)ldy * 2, (cuuint64_t)p.yplane_b2, (cuuint64_t)p.yrow_b};
+      cuuint32_t box[4] = {(cuuint32_t)p.cy, (cuuint32_t)(8 * p.ks), 1u, (cuuint32_t)kWTH};
+      CUresult r = enc(&map_y, dt, 4, const_cast<void*>(y), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz(p.cy),
+                       CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      URN_CHECK(r == CUDA_SUCCESS, "wgrad_halo: cuTensorMapEncodeTiled(dY) failed: %d", (int)r);
+    }
+  }
+  if (p.s == 2) wgrad_halo_kernel<true><<<grid, kWThreads, smem, st>>>(p, map_x, map_y, x, y, partial);
+  else wgrad_halo_kernel<false><<<grid, kWThreads, smem, st>>>(p, map_x, map_y, x, y, partial);
   URN_LAUNCH_CHECK();
   const int nw = p.ntaps * d.cx * d.cy;
   wgrad_halo_reduce_kernel<<<(nw + 127) / 128, 128, 0, st>>>(partial, nw, grid, dw, accumulate);
