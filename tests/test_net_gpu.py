@@ -339,7 +339,7 @@ def test_trainval_driver_train_checkpoint_and_ana(tmp_path, capsys):
     b.reset()
 
 
-@pytest.mark.parametrize("dims,B", [([32, 64, 1], 2), ([8, 16, 16, 1], 1)])
+@pytest.mark.parametrize("dims,B", [([32, 64, 1], 2), ([8, 16, 16, 1], 1), ([24, 40, 1], 13)])   # batch >= 12: images-as-rows plan
 def test_padded_head_matches_cuda_core_head(dims, B, monkeypatch):
     """The head conv2 (Cout = 3) runs on the tensor cores with its filter zero-padded to 16 output
     channels (forward stores 3; d(raw) is kept at pitch 16 with zero pad channels so that dgrad /

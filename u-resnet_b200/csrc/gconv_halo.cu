@@ -818,7 +818,7 @@ bool halo_plan_rows(const GConv& g, int in_dtype, int out_dtype, int cout_store,
   if (g.n < 12 || (g.accumulate && g.cout >= 32)) return false;
   if (g.id != 1 || g.od != 1 || g.gd != 1 || g.is != 1 || g.os != 1 || g.ntaps != 9) return false;
   if (g.ood || g.ooh || g.oow || g.gh != g.oh || g.gw != g.ow || g.ih != g.oh || g.iw != g.ow) return false;
-  if (cout_store > 0 && cout_store != g.cout) return false;
+  if (cout_store > 0 && cout_store != g.cout && getenv("URN_HALO_ROWS_NO_HEAD")) return false;
   if (g.ih < 4 || (long long)g.n * g.ih * g.iw * g.ldin * 2 >= (1ll << 31)) return false;   // 32-bit offsets across the images of a plane
   GConv v = g;
   v.n = 1;
@@ -1010,7 +1010,6 @@ static int halo_launch_params(HaloParams& p, int cin, int cout, int in_dtype, in
     }                                                                                                         \
     gconv_halo_kernel<OK, MODE, F3, ST><<<grid, nthreads, smem, st>>>(map_w, map_a, p, in, out, tl);          \
   } while (0)
-  URN_CHECK(mode != 2 || full3, "gconv_halo: padded filters only with 3x3 taps (cout %d store %d taps %dx%dx%d classes %d cin %d)", p.cout, p.cout_store, p.nkd, p.nkh, p.nkw, p.ncls, p.cin);
   URN_CHECK(!stats || (out_dtype != URN_BF16 && mode != 1), "gconv_halo: statistics need a freshly written raw output");
   if (out_dtype == URN_F32) {
     if (mode == 0) {
@@ -1019,7 +1018,8 @@ static int halo_launch_params(HaloParams& p, int cin, int cout, int in_dtype, in
     } else if (mode == 1) {
       if (full3) HALO_GO(0, 1, true, false); else HALO_GO(0, 1, false, false);
     } else {
-      if (stats) HALO_GO(0, 2, true, true); else HALO_GO(0, 2, true, false);
+      if (stats) { if (full3) HALO_GO(0, 2, true, true); else HALO_GO(0, 2, false, true); }
+      else { if (full3) HALO_GO(0, 2, true, false); else HALO_GO(0, 2, false, false); }
     }
   } else if (out_dtype == URN_F16) {
     URN_CHECK(mode == 0, "gconv_halo: fp16 outputs are plain stores");
@@ -1028,7 +1028,7 @@ static int halo_launch_params(HaloParams& p, int cin, int cout, int in_dtype, in
   } else {
     if (mode == 0) { if (full3) HALO_GO(1, 0, true, false); else HALO_GO(1, 0, false, false); }
     else if (mode == 1) { if (full3) HALO_GO(1, 1, true, false); else HALO_GO(1, 1, false, false); }
-    else HALO_GO(1, 2, true, false);
+    else { if (full3) HALO_GO(1, 2, true, false); else HALO_GO(1, 2, false, false); }
   }
 #undef HALO_GO
   URN_LAUNCH_CHECK();

@@ -285,7 +285,8 @@ wgrad_halo_kernel(const __grid_constant__ WHParams p, const __grid_constant__ CU
           if (pf >= 4) asm volatile("cp.async.wait_group 4;" ::: "memory");
           else if (pf == 3) asm volatile("cp.async.wait_group 3;" ::: "memory");
           else if (pf == 2) asm volatile("cp.async.wait_group 2;" ::: "memory");
-          else asm volatile("cp.async.wait_group 1;" ::: "memory");
+          else if (pf == 1) asm volatile("cp.async.wait_group 1;" ::: "memory");
+          else asm volatile("cp.async.wait_group 0;" ::: "memory");
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // cp.async (generic proxy) -> UMMA (async proxy)
           __syncwarp();
           if (lane == 0) h_mbar_arrive(&full[ar.idx]);
@@ -568,9 +569,9 @@ bool wh_plan(const urn_conv_desc& d, int x_dtype, int y_dtype, int64_t ldx, int6
   }
   // Producers run `pf` cp.async groups ahead of the full-barrier arrival; the dY slot of plane z+1
   // frees two steps after its previous tenant's last use, so the dY ring needs >= pf + 3 slots
-  // (and the X ring >= pf + 1) or producers and MMA warp would wait on each other.
+  // (and the X ring >= pf + 2, see below) or producers and MMA warp would wait on each other.
   const int budget = 222 * 1024;
-  p.pf = 0;
+  p.pf = -1;
   p.ymirror = (p.nkd == 3 && p.s == 1) ? 2 : 0;
   if (p.tma) {
     // no cp.async groups: the look-ahead is the ring depth.  dY ring of 8 (3 planes live + 5 ahead) when at
@@ -581,13 +582,21 @@ bool wh_plan(const urn_conv_desc& d, int x_dtype, int y_dtype, int64_t ldx, int6
       if (st >= (ys == 8 ? 3 : 2)) { p.pf = 1; p.ystages = ys; p.stages = st; break; }
     }
   } else {
-    for (int pf : {4, 2, 1}) {
+    // The arrival of plane i is posted after the loads of plane i+pf have been issued, which needs the slot
+    // of plane i+pf-stages: with stages == pf+1 that is plane i-1, i.e. every MMA batch would wait for its
+    // predecessor to finish PLUS the issue time of a plane (measured: 3D 16->16 5130 cycles per plane against
+    // 3712 of MMA issue).  Require stages >= pf+2; a 2-stage ring runs with pf = 0 (wait for the plane's own
+    // loads, arrive, then wait for the next free slot).
+    p.pf = -1;
+    int pf_max = 4;
+    if (const char* e = getenv("URN_WHALO_PF")) pf_max = std::max(0, std::min(4, atoi(e)));
+    for (int pf = pf_max; pf >= 0; --pf) {
       const int ys = pow2c(pf + (p.nkd == 3 ? 3 : 1));
       const int st = std::min(kWMaxStages, (budget - (ys + p.ymirror) * p.yplane_bytes) / p.xplane_bytes);
-      if (st >= std::max(2, pf + 1)) { p.pf = pf; p.ystages = ys; p.stages = st; break; }
+      if (st >= pf + 2) { p.pf = pf; p.ystages = ys; p.stages = st; break; }
     }
   }
-  if (!p.pf) return false;
+  if (p.pf < 0) return false;
   const int fmt = x_dtype == URN_BF16 ? 1 : 0;
   const uint32_t idesc0 = (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | (1u << 15) | (1u << 16) |
                           ((uint32_t)(p.cy >> 3) << 17);
