@@ -76,7 +76,8 @@ struct HaloParams {
   // TMA staging (stride-1 inputs): the halo plane is nkw tiled TMA boxes [hr rows][run pixels][cin] -- one per
   // kw shift, hardware zero fill outside the tensor = TF 'same' padding -- issued by ONE thread and completed on
   // the stage's mbarrier by byte count; staged rows are then ordered (kw, hy, w) instead of (hy, kw, w)
-  int tma;
+  int tma;                   // 0 cp.async producers, 1 one TMA box per kw shift, 2 ONE box per plane (kw taps = views shifted by whole pixels)
+  int xb;                    // tma == 2: staged pixels per halo row
   int dual;                  // TMA staging with 6 warps per CTA and TWO CTAs per SM (half-size rings each): two independent tile pipelines hide each other's hand-off latencies
   int tma_slot[3];           // coordinate slot (2..4) of the tile row origin / plane / image in the tensor map (dims sorted by stride)
   int dbg;                   // URN_HALO_DBG bitmask (perf experiments): 1 no stores, 2 no loads, 4 no MMA
@@ -177,7 +178,7 @@ gconv_halo_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_consta
       TileIter ti; ti.init(p, t_begin);
       Ring st; st.init(p.stages);
       const int run = 8 * p.ks;
-      const uint32_t box_bytes = (uint32_t)(p.hr * run * pitch);
+      const uint32_t box_bytes = p.tma == 2 ? (uint32_t)p.plane_bytes : (uint32_t)(p.hr * run * pitch);
       for (int k = 0; k < my_tiles; ++k, ti.next(p)) {
         const int d0 = ti.dt * p.TD;
         const int ybase = ti.ht * kTH + p.oh0, xbase = ti.wt * kTW * p.ks + p.ow0;
@@ -190,9 +191,10 @@ gconv_halo_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_consta
           int crd[3];
           crd[p.tma_slot[0] - 2] = ybase; crd[p.tma_slot[1] - 2] = z; crd[p.tma_slot[2] - 2] = ti.nn;
           if (h_elect_one()) {
-            h_mbar_expect_tx(&full[st.idx], box_bytes * (uint32_t)p.nkw);
+            const int nbox = p.tma == 2 ? 1 : p.nkw;
+            h_mbar_expect_tx(&full[st.idx], box_bytes * (uint32_t)nbox);
             const uint32_t dst = h_smem_u32(smem_a + (size_t)st.idx * p.plane_bytes);
-            for (int kw = 0; kw < p.nkw; ++kw)
+            for (int kw = 0; kw < nbox; ++kw)
               asm volatile(
                   "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes"
                   " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
@@ -346,8 +348,9 @@ gconv_halo_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_consta
     const uint32_t row16 = (uint32_t)pitch >> 4;                  // 16-byte units per staged row
     // descriptor start offsets (16-byte units) of the next kw tap / next kh tap (one halo row) / next sub-tile.
     // cp.async staging orders the rows (hy, kw, w); TMA staging (kw, hy, w): one box per kw shift
-    const uint32_t a_kw = p.tma ? (uint32_t)(p.hr * 8 * p.ks) * row16 : (uint32_t)(8 * p.ks) * row16;
-    const uint32_t a_kh = p.tma ? (uint32_t)(8 * p.ks) * row16 : (uint32_t)p.rw * row16;
+    // (tma == 2: rows (hy, w) staged once, the kw tap is a view shifted by one pixel)
+    const uint32_t a_kw = p.tma == 2 ? row16 : (p.tma ? (uint32_t)(p.hr * 8 * p.ks) * row16 : (uint32_t)(8 * p.ks) * row16);
+    const uint32_t a_kh = p.tma == 2 ? (uint32_t)p.xb * row16 : (p.tma ? (uint32_t)(8 * p.ks) * row16 : (uint32_t)p.rw * row16);
     const uint32_t a_sub = 8u * row16;
     const int ksteps = p.cin >> 4;                                 // K = 16 per MMA
     const bool no_mma = (p.dbg & 4) != 0;
@@ -741,7 +744,17 @@ bool halo_plan_impl(const GConv& g, int in_dtype, int out_dtype, int cout_store,
   p.ks = 4;
   if (const char* e = getenv("URN_HALO_KS")) p.ks = std::max(1, std::min(p.ks, atoi(e)));
   while (p.ks > 1 && (p.gw + kTW - 1) / kTW <= p.ks / 2) p.ks /= 2;
-  while (p.ks > 1 && p.hr * p.nkw * 8 * p.ks * cpr > kNCH * 256) p.ks /= 2;
+  // (the single-box TMA staging has no per-thread chunk tables: its limit is the shared memory, checked below)
+  const int tmode = getenv("URN_HALO_TMA") ? std::max(0, std::min(2, atoi(getenv("URN_HALO_TMA")))) : 2;
+  const bool one_box = g.is == 1 && tmode == 2 && get_encode_h() != nullptr && !getenv("URN_HALO_KS_CPASYNC");
+  if (one_box) {
+    // as wide as three stages allow (beside the filter taps), but never narrower than the cp.async rule's choice
+    int ks_cp = p.ks;
+    while (ks_cp > 1 && p.hr * p.nkw * 8 * ks_cp * cpr > kNCH * 256) ks_cp /= 2;
+    const int room = smem_limit - (((maxw + 1) * g.cout * g.cin * 2 + 1023) / 1024) * 1024 - 4096;
+    while (p.ks > ks_cp && 3 * p.hr * (8 * p.ks + 8) * g.cin * 2 > room) p.ks /= 2;
+  } else
+    while (p.ks > 1 && p.hr * p.nkw * 8 * p.ks * cpr > kNCH * 256) p.ks /= 2;
   const bool has_d = g.gd > 1 || p.nkd > 1;
   p.TD = has_d ? 4 : 1;
   p.ncls = ncls;
@@ -751,11 +764,21 @@ bool halo_plan_impl(const GConv& g, int in_dtype, int out_dtype, int cout_store,
   while (p.ks > 1 && ncls * p.TD * p.ks * g.cout * 2 > tmem_limit) p.ks /= 2;
   if (ncls * p.TD * p.ks * g.cout * 2 > tmem_limit) return false;
   p.rw = p.nkw * 8 * p.ks;
-  if (p.hr * p.rw * cpr > kNCH * 256) return false;
+  if (!one_box && p.hr * p.rw * cpr > kNCH * 256) return false;
   if (p.gd < p.TD) p.TD = std::max(1, p.gd);
   p.ntw = (p.gw + kTW * p.ks - 1) / (kTW * p.ks); p.nth = (p.gh + kTH - 1) / kTH; p.ntd = (p.gd + p.TD - 1) / p.TD;
   p.ntiles = (long long)p.n * p.ntd * p.nth * p.ntw;
-  p.plane_bytes = p.hr * p.rw * g.cin * 2;
+  // TMA staging for stride-1 inputs (URN_HALO_TMA=0 keeps the cp.async producers, =1 one box per kw shift with
+  // the rows ordered (kw, hy, w)); default 2: ONE box of hr x xb pixels per plane, the kw taps are descriptor
+  // views shifted by whole pixels (the swizzle is a function of the shared-memory address, so a view may start
+  // anywhere on a 16-byte boundary) -- a third of the L2 -> shared-memory traffic and 2.4x smaller stages
+  const uint64_t pitch = (uint64_t)g.cin * 2;
+  p.tma = g.is == 1 ? tmode : 0;
+  if (p.tma == 1 && ((uint64_t)(p.hr * 8 * p.ks) * pitch) % (pitch == 128 ? 1024 : (pitch == 64 ? 512 : 256))) p.tma = 0;
+  if (p.tma && !get_encode_h()) p.tma = 0;
+  if (one_box && p.tma != 2) return false;
+  p.xb = 8 * p.ks + (p.nkw > 1 ? 8 : 0);
+  p.plane_bytes = p.tma == 2 ? p.hr * p.xb * g.cin * 2 : p.hr * p.rw * g.cin * 2;
   p.w_tap_bytes = g.cout * g.cin * 2;
   p.ntaps_w = maxw + 1;
   const int w_bytes = ((p.ntaps_w * p.w_tap_bytes + 1023) / 1024) * 1024;
@@ -767,16 +790,12 @@ bool halo_plan_impl(const GConv& g, int in_dtype, int out_dtype, int cout_store,
   const int fmt = in_dtype == URN_BF16 ? 1 : 0;
   p.idesc = (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)(g.cout >> 3) << 17) |
             ((uint32_t)(128 >> 4) << 24);
-  const uint64_t pitch = (uint64_t)g.cin * 2;
   const uint64_t layout = pitch == 128 ? 2 : (pitch == 64 ? 4 : 6);
   // 8-row groups (consecutive output rows of the sub-tile) are is*RW staged rows apart
   p.adesc_hi = (layout << 61) | (1ull << 46) | ((((uint64_t)(g.is * p.rw) * pitch) >> 4) << 32) | (1ull << 16);
-  // TMA staging for stride-1 inputs (URN_HALO_TMA=0 keeps the cp.async producers): 8-row groups (consecutive
-  // output rows of a sub-tile) are then one halo row = 8*ks staged rows apart; every box starts on a multiple
-  // of the swizzle pattern (256 / 512 / 1024 B for SW32 / 64 / 128)
-  p.tma = (g.is == 1 && !(getenv("URN_HALO_TMA") && atoi(getenv("URN_HALO_TMA")) == 0)) ? 1 : 0;
-  if (p.tma && ((uint64_t)(p.hr * 8 * p.ks) * pitch) % (pitch == 128 ? 1024 : (pitch == 64 ? 512 : 256))) p.tma = 0;
-  if (p.tma) p.adesc_hi = (layout << 61) | (1ull << 46) | ((((uint64_t)(8 * p.ks) * pitch) >> 4) << 32) | (1ull << 16);
+  // TMA staging: 8-row groups (consecutive output rows of a sub-tile) are one staged halo row apart (8*ks or xb
+  // pixels); every box starts on a multiple of the swizzle pattern (256 / 512 / 1024 B for SW32 / 64 / 128)
+  if (p.tma) p.adesc_hi = (layout << 61) | (1ull << 46) | ((((uint64_t)(p.tma == 2 ? p.xb : 8 * p.ks) * pitch) >> 4) << 32) | (1ull << 16);
   if (dual && !p.tma) return false;
   p.bdesc_hi = (layout << 61) | (1ull << 46) | (((8 * pitch) >> 4) << 32) | (1ull << 16);
   // concat mode: 3x3x3 stride-1 convs; the zero block is one B tile of N = TD*cout rows
@@ -985,7 +1004,7 @@ static int halo_launch_params(HaloParams& p, int cin, int cout, int in_dtype, in
     for (int i = 1; i < 3; ++i) if (od[i].size <= 1 && od[i].stride < od[i - 1].stride * od[i - 1].size) od[i].stride = od[i - 1].stride * od[i - 1].size;
     cuuint64_t dims[5] = {(cuuint64_t)cin, (cuuint64_t)p.W, od[0].size, od[1].size, od[2].size};
     cuuint64_t strides[4] = {(cuuint64_t)p.ldin * 2, od[0].stride, od[1].stride, od[2].stride};
-    cuuint32_t box[5] = {(cuuint32_t)cin, (cuuint32_t)(8 * p.ks), od[0].box, od[1].box, od[2].box};
+    cuuint32_t box[5] = {(cuuint32_t)cin, (cuuint32_t)(p.tma == 2 ? p.xb : 8 * p.ks), od[0].box, od[1].box, od[2].box};
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
     CUresult r = enc(&map_a, dt, 5, const_cast<void*>(in), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
