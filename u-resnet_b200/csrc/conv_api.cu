@@ -135,6 +135,7 @@ extern "C" int urn_conv_dgrad(const urn_conv_desc* d, int dtype, int impl, const
       for (int pw = 0; pw < d->s; ++pw) {
         GConv g;
         if (!gconv_scatter_class(*d, ldy, ldx, pd, ph, pw, accumulate, &g)) continue;
+        if (g.ntaps == 0 && accumulate) continue;          // a class no tap reaches (1x1 stride 2): nothing to add
         if (gconv_ffma_launch(g, dtype, dy, w, dx, x_dtype, (cudaStream_t)stream)) return 1;
       }
   return 0;
@@ -246,6 +247,7 @@ extern "C" int urn_conv_dgrad_tc(const urn_conv_desc* d, int dtype, const void* 
         GConv g;
         if (!gconv_scatter_class(*d, ldy, ldx, pd, ph, pw, accumulate, &g)) continue;
         if (g.ntaps == 0) {   // parity class without taps (1x1 stride-2): zeros, CUDA-core kernel
+          if (accumulate) continue;                         // ... or nothing at all when adding
           if (gconv_ffma_launch(g, dtype, dy, w, dx, x_dtype, st)) return 1;
           continue;
         }

@@ -748,11 +748,13 @@ bool halo_plan_impl(const GConv& g, int in_dtype, int out_dtype, int cout_store,
   const int tmode = getenv("URN_HALO_TMA") ? std::max(0, std::min(2, atoi(getenv("URN_HALO_TMA")))) : 2;
   const bool one_box = g.is == 1 && tmode == 2 && get_encode_h() != nullptr && !getenv("URN_HALO_KS_CPASYNC");
   if (one_box) {
-    // as wide as three stages allow (beside the filter taps), but never narrower than the cp.async rule's choice
+    // as wide as two stages allow beside the filter taps and the zero block of the concat mode (losing the
+    // N-concatenation costs far more than a narrow tile), but never narrower than the cp.async rule's choice
     int ks_cp = p.ks;
     while (ks_cp > 1 && p.hr * p.nkw * 8 * ks_cp * cpr > kNCH * 256) ks_cp /= 2;
-    const int room = smem_limit - (((maxw + 1) * g.cout * g.cin * 2 + 1023) / 1024) * 1024 - 4096;
-    while (p.ks > ks_cp && 3 * p.hr * (8 * p.ks + 8) * g.cin * 2 > room) p.ks /= 2;
+    const int zero_est = (g.gd > 1 || p.nkd > 1) ? ((4 * g.cout * g.cin * 2 + 1023) / 1024) * 1024 : 0;
+    const int room = smem_limit - (((maxw + 1) * g.cout * g.cin * 2 + 1023) / 1024) * 1024 - zero_est - 2048;
+    while (p.ks > ks_cp && 2 * p.hr * (8 * p.ks + 8) * g.cin * 2 > room) p.ks /= 2;
   } else
     while (p.ks > 1 && p.hr * p.nkw * 8 * p.ks * cpr > kNCH * 256) p.ks /= 2;
   const bool has_d = g.gd > 1 || p.nkd > 1;

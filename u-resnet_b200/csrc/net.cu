@@ -951,6 +951,9 @@ static int backward_steps(urn_net* h, const float* params, float* grads, int acc
             for (int pw = 0; pw < L.d.s; ++pw) {
               GConv g;
               if (!gconv_scatter_class(L.d, L.cout, in.ld, pd, ph, pw, s.accumulate, &g)) continue;
+              // a parity class no tap reaches (1x1 stride-2 shortcut: 3 of 4 / 7 of 8 classes) adds nothing to an
+              // initialised gradient; only a first writer has to store its zeros
+              if (g.ntaps == 0 && s.accumulate) continue;
               if (run_gconv(h, g, T, draw(L), w, P(ws, h->wps_off + L.w_off * 2), gptr(in), T, st)) return 1;
             }
       } else {
