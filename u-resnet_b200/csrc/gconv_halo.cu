@@ -80,6 +80,11 @@ struct HaloParams {
   int xb;                    // tma == 2: staged pixels per halo row
   int dual;                  // TMA staging with 6 warps per CTA and TWO CTAs per SM (half-size rings each): two independent tile pipelines hide each other's hand-off latencies
   int tma_slot[3];           // coordinate slot (2..4) of the tile row origin / plane / image in the tensor map (dims sorted by stride)
+  // Accumulating bf16 outputs through the TMA reduce unit (stride-1 outputs, one class): every epilogue warp packs
+  // its 32 positions x cout channels into shared memory and ONE thread issues cp.reduce.async.bulk.tensor .add --
+  // the addition happens in L2, the SM never reads the old gradient.
+  int red, red_bytes;        // on/off; shared memory of the 4 warps x 2 staging buffers
+  int red_slot[3];           // coordinate slot (2..4) of tile row / plane / image in the output tensor map
   int dbg;                   // URN_HALO_DBG bitmask (perf experiments): 1 no stores, 2 no loads, 4 no MMA
 };
 
@@ -121,7 +126,7 @@ __device__ __forceinline__ bool plane_used(const HaloParams& p, int z, int d0, i
 template <int OUTK, int MODE, bool FULL3, bool STATS>   // FULL3: 3x3 in-plane tap box (unrolled issue loop); STATS: fused BN statistics
 __global__ void __launch_bounds__(kHThreads, 1)
 gconv_halo_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_a,
-                  const __grid_constant__ HaloParams p,
+                  const __grid_constant__ CUtensorMap map_o, const __grid_constant__ HaloParams p,
                   const void* __restrict__ in, void* __restrict__ out, long long* __restrict__ tl) {
   constexpr bool OUT_F32 = OUTK == 0;
   using T16 = typename std::conditional<OUTK == 2, f16, bf16>::type;     // 16-bit output element
@@ -141,6 +146,7 @@ gconv_halo_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_consta
   uint64_t* tempty = tfull + kMaxAcc;
   uint64_t* wfull = tempty + kMaxAcc;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wfull + 1);
+  uint8_t* smem_red = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(bars) + 512 + 1023) & ~uintptr_t(1023));
 
   const long long tl_t0 = tl ? clock64() : 0;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -514,6 +520,7 @@ gconv_halo_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_consta
     RunStat rs[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) { rs[i].n = 0.f; rs[i].mean = 0.f; rs[i].m2 = 0.f; }
+    uint32_t red_buf = 0;
     for (int k = 0; k < my_tiles; ++k, ti.next(p)) {
       const int d0 = ti.dt * p.TD;
       const int y = ti.ht * kTH + lh, x0 = ti.wt * kTW * p.ks + lw;
@@ -534,7 +541,7 @@ gconv_halo_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_consta
           }
         }
       };
-      if (!OUT_F32 && MODE == 1) {
+      if (!OUT_F32 && MODE == 1 && !p.red) {
         const long long opix_first = (long long)ti.nn * p.o_img + (long long)(d0 * p.os + p.coff[0][0]) * p.o_plane +
                                      (long long)(y * p.os + p.coff[0][1]) * p.o_row + (x0 * p.os + p.coff[0][2]);
         fetch_old(opix_first, 0);
@@ -543,6 +550,52 @@ gconv_halo_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_consta
       h_mbar_wait_warp(&tfull[ac.idx], ac.phase);
       h_fence_after();
       if (warp == w_epi0 && lane == 0) TL(2, k, 1);
+      if (!OUT_F32 && MODE == 1 && p.red) {
+        // accumulate through the TMA reduce unit: per (plane, sub-tile) the warp's 32 x cout block goes to one of
+        // its two staging buffers (swizzled like the tensor map, conflict-free 16-byte stores), then one box
+        // [cout][8 w][4 rows] is added to the gradient in L2
+        const int rpitch = p.cout * 2;
+        const int rsw = rpitch == 128 ? (lane & 7) : (rpitch == 64 ? ((lane >> 1) & 3) : ((lane >> 2) & 1));
+        uint8_t* rbase = smem_red + (size_t)q * 2 * 32 * rpitch;
+        for (int dd = 0; dd < p.TD; ++dd) {
+          const int d = d0 + dd;
+          if (d >= dmax) continue;
+          const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)ac.idx * acc_cols +
+                                  (uint32_t)((p.concat ? dd : dd * p.ks) * p.cout);
+          const uint32_t sj_cols = (uint32_t)((p.concat ? p.TD : 1) * p.cout);
+          for (int sj = 0; sj < nsub; ++sj) {
+            uint8_t* rb = rbase + (size_t)(red_buf & 1) * 32 * rpitch;
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the buffer's previous box has been read
+            __syncwarp();
+            for (int c0 = 0; c0 < p.cout; c0 += 16) {
+              float v[16];
+              h_tmem_ld16(taddr0 + (uint32_t)sj * sj_cols + (uint32_t)c0, v);
+              uint32_t w[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                __nv_bfloat162 b2 = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+                w[j] = *reinterpret_cast<uint32_t*>(&b2);
+              }
+              const int ch = c0 >> 3;                                  // 16-byte chunk of this position's row
+              *reinterpret_cast<uint4*>(rb + lane * rpitch + ((ch ^ rsw) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+              *reinterpret_cast<uint4*>(rb + lane * rpitch + (((ch + 1) ^ rsw) << 4)) = make_uint4(w[4], w[5], w[6], w[7]);
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0 && !(p.dbg & 1)) {
+              int crd[3];
+              crd[p.red_slot[0] - 2] = ti.ht * kTH + 4 * q; crd[p.red_slot[1] - 2] = d; crd[p.red_slot[2] - 2] = ti.nn;
+              asm volatile(
+                  "cp.reduce.async.bulk.tensor.5d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
+                  ::"l"(reinterpret_cast<uint64_t>(&map_o)), "r"(h_smem_u32(rb)), "r"(0), "r"((ti.wt * p.ks + sj) * kTW),
+                  "r"(crd[0]), "r"(crd[1]), "r"(crd[2])
+                  : "memory");
+              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+            ++red_buf;
+          }
+        }
+      } else
       for (int cd = 0; cd < p.ncls * p.TD; ++cd) {
         const int cls = cd / p.TD, dd = cd - cls * p.TD;
         const int d = d0 + dd;
@@ -642,6 +695,7 @@ gconv_halo_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_consta
       if (warp == w_epi0 && lane == 0) TL(2, k, 3);
       ac.next();
     }
+    if (!OUT_F32 && MODE == 1 && p.red && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     if (do_stats && !(lane & 1)) {
       // partial[(cta*4 + q)][channel][3]
       float* dst = p.stats_part + ((long long)(blockIdx.x * 4 + q) * p.cout) * 3;
@@ -784,7 +838,11 @@ bool halo_plan_impl(const GConv& g, int in_dtype, int out_dtype, int cout_store,
   p.w_tap_bytes = g.cout * g.cin * 2;
   p.ntaps_w = maxw + 1;
   const int w_bytes = ((p.ntaps_w * p.w_tap_bytes + 1023) / 1024) * 1024;
-  const int budget = smem_limit - w_bytes;
+  p.red = (out_dtype == URN_BF16 && g.accumulate && g.os == 1 && ncls == 1 && !dual && (cout_store == 0 || cout_store == g.cout) &&
+           (g.cout == 16 || g.cout == 32 || g.cout == 64) && g.ldout % 8 == 0 && get_encode_h() != nullptr &&
+           !(getenv("URN_HALO_RED") && atoi(getenv("URN_HALO_RED")) == 0)) ? 1 : 0;
+  p.red_bytes = p.red ? 4 * 2 * 32 * g.cout * 2 + 1024 : 0;
+  const int budget = smem_limit - w_bytes - p.red_bytes;
   p.stages = std::min(kHMaxStages, budget / p.plane_bytes);
   if (p.stages < 2) return false;
   if (p.ntiles >= (1ll << 31)) return false;
@@ -1013,7 +1071,27 @@ static int halo_launch_params(HaloParams& p, int cin, int cout, int in_dtype, in
     URN_CHECK(r == CUDA_SUCCESS, "gconv_halo: cuTensorMapEncodeTiled(A) failed: %d (dims %d %d %d %d %d)", (int)r, cin, p.W, p.H, p.D, p.n);
   }
   const int w_bytes = ((p.ntaps_w * p.w_tap_bytes + 1023) / 1024) * 1024;
-  const size_t smem = 1024 + (size_t)w_bytes + (size_t)p.zero_bytes + (size_t)p.stages * p.plane_bytes + 1024;
+  CUtensorMap map_o = map_w;             // (unused unless p.red)
+  if (p.red) {
+    // output gradient as a 5-D bf16 tensor (c, w, row, plane, image) in the plan's strides; box = 8 pixels x 4 tile rows
+    const cuuint64_t pix = (cuuint64_t)p.ldout * 2;
+    const cuuint64_t img_stride = p.o_img > 0 ? (cuuint64_t)p.o_img * pix : (cuuint64_t)p.o_plane * pix * (cuuint64_t)p.OD;
+    struct OD { cuuint64_t size, stride; cuuint32_t box; int what; };
+    OD od[3] = {{(cuuint64_t)p.OH, (cuuint64_t)p.o_row * pix, 4u, 0}, {(cuuint64_t)p.OD, (cuuint64_t)p.o_plane * pix, 1u, 1},
+                {(cuuint64_t)p.n, img_stride, 1u, 2}};
+    std::stable_sort(od, od + 3, [](const OD& a, const OD& b) { return (a.size > 1 ? a.stride : ~0ull) < (b.size > 1 ? b.stride : ~0ull); });
+    for (int i = 0; i < 3; ++i) p.red_slot[od[i].what] = 2 + i;
+    for (int i = 1; i < 3; ++i) if (od[i].size <= 1 && od[i].stride < od[i - 1].stride * od[i - 1].size) od[i].stride = od[i - 1].stride * od[i - 1].size;
+    const CUtensorMapSwizzle sw = p.cout == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (p.cout == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+    cuuint64_t dims[5] = {(cuuint64_t)p.cout, (cuuint64_t)p.OW, od[0].size, od[1].size, od[2].size};
+    cuuint64_t strides[4] = {pix, od[0].stride, od[1].stride, od[2].stride};
+    cuuint32_t box[5] = {(cuuint32_t)p.cout, (cuuint32_t)kTW, od[0].box, od[1].box, od[2].box};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = enc(&map_o, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, out, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                     CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    URN_CHECK(r == CUDA_SUCCESS, "gconv_halo: cuTensorMapEncodeTiled(out) failed: %d", (int)r);
+  }
+  const size_t smem = 1024 + (size_t)w_bytes + (size_t)p.zero_bytes + (size_t)p.stages * p.plane_bytes + 1024 + (size_t)p.red_bytes;
   const int grid = (int)std::min<long long>(p.ntiles, (long long)persistent_ctas() * (p.dual ? 2 : 1));
   const int nthreads = p.dual ? 192 : kHThreads;
   long long* tl = nullptr;
@@ -1029,7 +1107,7 @@ static int halo_launch_params(HaloParams& p, int cin, int cout, int in_dtype, in
                                     227 * 1024));                                                             \
       attr_set = true;                                                                                        \
     }                                                                                                         \
-    gconv_halo_kernel<OK, MODE, F3, ST><<<grid, nthreads, smem, st>>>(map_w, map_a, p, in, out, tl);          \
+    gconv_halo_kernel<OK, MODE, F3, ST><<<grid, nthreads, smem, st>>>(map_w, map_a, map_o, p, in, out, tl);          \
   } while (0)
   URN_CHECK(!stats || (out_dtype != URN_BF16 && mode != 1), "gconv_halo: statistics need a freshly written raw output");
   if (out_dtype == URN_F32) {
