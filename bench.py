@@ -103,12 +103,12 @@ def conv_flops(layer_table):
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of committed `ncu --set full` captures
 # (profiles/): keyed by (workload, "cin->cout kK sS @side", phase)
 NCU_TRAFFIC = {
-    # profiles/raw_*_r02a_{2d,3d}.summary.txt (ncu --set full, B = 32 / B = 4)
-    ("2d", "16->16 k3 s1 @512", "conv_fwd"): 331.5e6 + 228.8e6,    # gconv_halo_kernel<2,0,0,1> (images-as-rows, fp16 raw out)
-    ("2d", "16->16 k3 s1 @512", "dgrad"): 329.9e6 + 227.4e6,       # gconv_halo_kernel<1,0,0,0>
-    ("2d", "16->16 k3 s1 @512", "wgrad"): 603.5e6 + 4.2e6,         # wgrad_halo_kernel<0> (images-as-rows)
-    ("3d", "16->16 k3 s1 @192", "dgrad"): 1502.9e6 + 871.7e6,      # gconv_halo_kernel<1,0,1,0>
-    ("3d", "16->16 k3 s1 @192", "wgrad"): 2153.0e6 + 6.0e6,        # wgrad_halo_kernel<0>
+    # profiles/raw_*_r02c_{2d,3d}.summary.txt (ncu --set full, B = 32 / B = 4; dram bytes read + written per launch)
+    ("2d", "16->16 k3 s1 @512", "conv_fwd"): 331.9e6 + 224.8e6,    # gconv_halo_kernel<2,0,0,1> (images-as-rows, fp16 raw out)
+    ("2d", "16->16 k3 s1 @512", "dgrad"): 332.7e6 + 225.9e6,       # gconv_halo_kernel<1,0,0,0>
+    ("2d", "16->16 k3 s1 @512", "wgrad"): 634.5e6 + 3.7e6,         # wgrad_halo_kernel<0> (images-as-rows, TMA)
+    ("3d", "16->16 k3 s1 @192", "dgrad"): 1515.7e6 + 871.0e6,      # gconv_halo_kernel<1,0,1,0>
+    ("3d", "16->16 k3 s1 @192", "wgrad"): 2153.0e6 + 4.8e6,        # wgrad_halo_kernel<0>
 }
 
 
