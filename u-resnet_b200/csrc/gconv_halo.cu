@@ -33,7 +33,8 @@
 namespace {
 
 constexpr int kHThreads = 416;       // 13 warps: 8 producers, 1 MMA, 4 epilogue
-constexpr int kHMaxStages = 8;
+constexpr int kHMaxStages = 16;         // barrier slots; the ring depth in use is max_stages() (URN_HALO_MAXST)
+inline int max_stages() { static const int v = getenv("URN_HALO_MAXST") ? std::max(2, std::min(kHMaxStages, atoi(getenv("URN_HALO_MAXST")))) : 8; return v; }
 constexpr int kMaxAcc = 8;           // TMEM accumulator ring (hides the MMA<->epilogue hand-off latency)
 constexpr int kMaxPF = 4;            // cp.async groups kept in flight per producer thread (<= stages-1)
 constexpr int kTH = 16, kTW = 8;     // 128 positions per sub-tile
@@ -843,7 +844,7 @@ bool halo_plan_impl(const GConv& g, int in_dtype, int out_dtype, int cout_store,
            !(getenv("URN_HALO_RED") && atoi(getenv("URN_HALO_RED")) == 0)) ? 1 : 0;
   p.red_bytes = p.red ? 4 * 2 * 32 * g.cout * 2 + 1024 : 0;
   const int budget = smem_limit - w_bytes - p.red_bytes;
-  p.stages = std::min(kHMaxStages, budget / p.plane_bytes);
+  p.stages = std::min(max_stages(), budget / p.plane_bytes);
   if (p.stages < 2) return false;
   if (p.ntiles >= (1ll << 31)) return false;
   p.accumulate = g.accumulate; p.out_dtype = out_dtype; p.in_dtype = in_dtype;
@@ -868,8 +869,8 @@ bool halo_plan_impl(const GConv& g, int in_dtype, int out_dtype, int cout_store,
     const uint32_t id0 = (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)(128 >> 4) << 24);
     for (int i = 0; i < 3; ++i) p.idesc_n[i] = id0 | ((uint32_t)(((i + 1) * g.cout) >> 3) << 17);
     p.idesc_zero = id0 | ((uint32_t)((p.TD * g.cout) >> 3) << 17);
-    p.stages = std::min(kHMaxStages, (budget - p.zero_bytes) / p.plane_bytes);
-    if (p.stages < 2) { p.concat = 0; p.zero_bytes = 0; p.stages = std::min(kHMaxStages, budget / p.plane_bytes); }
+    p.stages = std::min(max_stages(), (budget - p.zero_bytes) / p.plane_bytes);
+    if (p.stages < 2) { p.concat = 0; p.zero_bytes = 0; p.stages = std::min(max_stages(), budget / p.plane_bytes); }
   }
   p.nacc = std::max(2, std::min(kMaxAcc, tmem_limit / (ncls * p.TD * p.ks * g.cout)));
   if (const char* e = getenv("URN_HALO_NACC")) p.nacc = std::max(2, std::min(p.nacc, atoi(e)));
@@ -959,7 +960,7 @@ bool halo_plan_classes(const GConv* gs, int ncls, int in_dtype, int out_dtype, H
   // smem budget again with the real number of resident taps
   {
     const int w_bytes = ((p.ntaps_w * p.w_tap_bytes + 1023) / 1024) * 1024;
-    p.stages = std::min(kHMaxStages, ((p.dual ? 108 : 224) * 1024 - w_bytes) / p.plane_bytes);
+    p.stages = std::min(max_stages(), ((p.dual ? 108 : 224) * 1024 - w_bytes) / p.plane_bytes);
     if (p.stages < 2) return false;
   }
   for (int c = 0; c < ncls; ++c) {
