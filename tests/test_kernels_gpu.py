@@ -304,6 +304,52 @@ def test_conv_images_as_rows_plan(lib, monkeypatch, rows, nd, n, sp, cin, cout, 
     test_conv_kernels_stay_inside_their_buffers(lib, nd, n, sp, cin, cout, k, s)
 
 
+ACC_CASES = [
+    # nd, n, spatial, cin (gradient written), cout (gradient read), k   -- stride 1
+    (2, 2, (33, 19), 16, 16, 3),          # ragged tiles
+    (2, 2, (40, 72), 32, 16, 1),          # 1x1 shortcut into a 32-channel gradient (64-byte rows)
+    (2, 13, (24, 40), 16, 16, 3),         # batch >= 12: images-as-rows plan, images not a multiple of the 16-row tile
+    (2, 1, (16, 24), 64, 32, 1),          # 128-byte rows
+    (3, 1, (9, 20, 12), 16, 16, 3),       # 27 taps, depth tile with a ragged last tile
+    (3, 1, (6, 16, 16), 32, 16, 1),
+]
+
+
+@pytest.mark.parametrize("red,tma", [("1", "2"), ("0", "2"), ("1", "1"), ("1", "0")])
+@pytest.mark.parametrize("nd,n,sp,cin,cout,k", ACC_CASES)
+def test_conv_dgrad_bf16_accumulate_variants(lib, monkeypatch, red, tma, nd, n, sp, cin, cout, k):
+    """Accumulating bf16 input gradient (dX += dgrad) into a CHANNEL SLICE of a wider gradient buffer (the
+    concat / skip layout): through the TMA reduce unit (URN_HALO_RED=1, default) or the read-modify-write
+    epilogue (=0), with the input halo staged as one TMA box per plane (URN_HALO_TMA=2, default), one box
+    per kw shift (=1) or by cp.async (=0).  Expected: old + oracle gradient to bf16 storage precision; the
+    other half of the buffer must not be touched."""
+    monkeypatch.setenv("URN_HALO_RED", red)
+    monkeypatch.setenv("URN_HALO_TMA", tma)
+    rng = np.random.default_rng(hash((nd, n, sp, cin, cout, k, 77)) % 2**32)
+    w = (rng.standard_normal((k,) * nd + (cin, cout)) / np.sqrt(k**nd * cin)).astype(np.float32)
+    wqb = host(dev(w, BF16))
+    d = _capi.conv_desc_same(nd, n, sp, cin, cout, k, 1)
+    g_cl = host(dev(rng.standard_normal((n,) + sp + (cout,)).astype(np.float32), BF16))
+    xt = torch.zeros((n, cin) + sp, dtype=torch.float64, requires_grad=True)
+    yb = O.conv_same(xt, torch.tensor(wqb, dtype=torch.float64), 1)
+    (dxo,) = torch.autograd.grad(yb, xt, torch.tensor(np.moveaxis(g_cl, -1, 1), dtype=torch.float64))
+    dxo = np.moveaxis(dxo.numpy(), 1, -1)
+    old = host(dev(rng.standard_normal((n,) + sp + (2 * cin,)).astype(np.float32), BF16))
+    buf = dev(old, BF16)
+    gd, wd = dev(g_cl, BF16), dev(w)
+    wpack = torch.empty(2 * w.size + 64, dtype=torch.uint8, device=DEV)
+    for off in (cin, 0):                                      # second, then first half of the channels
+        _capi.check(lib.urn_conv_dgrad_tc(C.byref(d), BF16, gd.data_ptr(), cout, wd.data_ptr(), wpack.data_ptr(),
+                                          buf.data_ptr() + 2 * off, 2 * cin, BF16, 1, st()))
+        got = host(buf)
+        want = old.copy()
+        want[..., off:off + cin] += dxo
+        assert relerr(got[..., off:off + cin], want[..., off:off + cin]) < 1e-2
+        other = slice(0, cin) if off else slice(cin, 2 * cin)
+        assert np.array_equal(got[..., other], old[..., other])
+        old = got
+
+
 HALO_WGRAD_CASES = [
     # nd, n, spatial, cin, cout, ldx factor  (stride-1 3x3(x3): the halo-tile filter-gradient kernel)
     (2, 3, (40, 24), 16, 16, 1),         # several tiles per image, ragged in h

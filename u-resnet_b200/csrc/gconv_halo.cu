@@ -20,6 +20,17 @@
 //   warps 9-12: epilogue (tcgen05.ld -> fp32 raw output / bf16 gradient, accumulate flag)
 // Every CTA owns a contiguous range of tiles; ring indices and tile coordinates advance
 // incrementally (no divisions in the role loops).
+//
+// Round 2 -- stride-1 inputs (everything but the stride-2 forward convs) are staged by TMA instead:
+// ONE tiled box [halo rows][8*KS + 8 pixels][Cin] per plane (hardware zero fill outside the tensor =
+// 'same' padding), rows ordered (hy, w).  The kw tap is the SAME rows viewed one pixel further: the
+// swizzle of a UMMA operand is a function of the shared-memory address, so a descriptor may start
+// on any 16-byte boundary of a swizzled tile.  Stages shrink from 49-55 KB to 20-23 KB, the ring
+// deepens to 8, the L2 -> shared-memory traffic drops to a third, and with one issuing thread a CTA
+// needs 6 warps: launch classes that gain from it run TWO CTAs per SM (halo_plan).  The
+// images-as-rows plan (halo_plan_rows) relabels a 2D batch as a volume so that the kh taps are
+// concatenated along N like the depth taps of a real volume.  Accumulating bf16 outputs leave
+// through the TMA reduce unit (cp.reduce.async.bulk.tensor .add from swizzled staging buffers).
 #include <cuda.h>
 #include <stdlib.h>
 #include <string.h>
