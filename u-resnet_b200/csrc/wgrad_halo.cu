@@ -557,6 +557,23 @@ bool wh_plan(const urn_conv_desc& d, int x_dtype, int y_dtype, int64_t ldx, int6
   p.rw = p.nkw * 8 * p.ks;
   p.xb = 8 * p.ks + 8;                       // pixels per staged row (TMA): the run, its halo, padded to whole swizzle atoms
   p.ntw = (p.W + kWTW * p.ks - 1) / (kWTW * p.ks); p.nth = (p.H + kWTH - 1) / kWTH;
+  if (!rows && p.D >= 16 && !getenv("URN_WHALO_NO_BALANCE")) {
+    // small grids: fewer units than two waves of CTAs -- cut the depth into more chunks when that shortens
+    // the busiest CTA's walk (each chunk re-stages nkd - 1 halo planes)
+    const long long per_chunk = (long long)p.n * p.nth * p.ntw;
+    const int ctas = persistent_ctas();
+    if (per_chunk * p.ndc < 2ll * ctas) {
+      int best = p.ndc; long long best_cost = -1;
+      for (int ndc = p.ndc; ndc <= std::max(p.ndc, p.D / 8); ++ndc) {
+        const int dc = (p.D + ndc - 1) / ndc;
+        const long long units = per_chunk * ((p.D + dc - 1) / dc);
+        const long long cost = ((units + ctas - 1) / ctas) * (dc + p.nkd - 1);
+        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = ndc; }
+      }
+      p.DC = (p.D + best - 1) / best;
+      p.ndc = (p.D + p.DC - 1) / p.DC;
+    }
+  }
   p.nunits = (long long)p.n * p.ndc * p.nth * p.ntw;
   if (p.nunits >= (1ll << 31)) return false;
   p.xplane_bytes = p.tma ? p.hr * p.xb * p.cx * 2 : p.hr * p.rw * p.cx * 2;
@@ -671,24 +688,58 @@ bool wh_plan_rows(const urn_conv_desc& d, int x_dtype, int y_dtype, int64_t ldx,
   return true;
 }
 
+// 3D stride-1 3x3x3 layers whose 27 x cx x cy fp32 accumulators exceed the TMEM (cx = cy = 64): ONE PASS PER DEPTH
+// TAP -- each pass is the nkd = 1 plan with the X planes shifted by the tap (pad_d - kd), so X and dY are streamed
+// three times out of L2 instead of 27 times through the tap-shifted TMA boxes of wgrad_tc_kernel
+// (URN_WHALO_SPLIT=0 disables it).
+static bool wh_split_desc(const urn_conv_desc& d, int kd_sel, urn_conv_desc* o) {
+  if (d.kd != 3 || d.kh != 3 || d.kw != 3 || d.s != 1 || d.xd < 2) return false;
+  if (const char* e = getenv("URN_WHALO_SPLIT")) { if (atoi(e) == 0) return false; }
+  *o = d;
+  o->kd = 1;
+  o->pad_d = d.pad_d - kd_sel;
+  return true;
+}
+
 }  // namespace
 
 bool wgrad_halo_supported(const urn_conv_desc& d, int x_dtype, int y_dtype, int64_t ldx, int64_t ldy) {
   WHParams p;
-  return wh_plan_rows(d, x_dtype, y_dtype, ldx, ldy, &p) || wh_plan(d, x_dtype, y_dtype, ldx, ldy, &p);
+  if (wh_plan_rows(d, x_dtype, y_dtype, ldx, ldy, &p) || wh_plan(d, x_dtype, y_dtype, ldx, ldy, &p)) return true;
+  urn_conv_desc sd;
+  return wh_split_desc(d, 0, &sd) && wh_plan(sd, x_dtype, y_dtype, ldx, ldy, &p);
 }
 
 int64_t wgrad_halo_workspace(const urn_conv_desc& d) {
   WHParams p;
-  if (!wh_plan(d, URN_BF16, URN_BF16, 64, 64, &p)) return 0;
-  return (int64_t)num_sms() * p.ntaps * d.cx * d.cy * 4;
+  if (wh_plan(d, URN_BF16, URN_BF16, 64, 64, &p)) return (int64_t)num_sms() * p.ntaps * d.cx * d.cy * 4;
+  urn_conv_desc sd;
+  if (wh_split_desc(d, 0, &sd) && wh_plan(sd, URN_BF16, URN_BF16, 64, 64, &p)) return (int64_t)num_sms() * p.ntaps * d.cx * d.cy * 4;
+  return 0;
+}
+
+namespace {
+int wh_launch_planned(const urn_conv_desc& d, WHParams& p, int x_dtype, const void* x, int64_t ldx, int y_dtype,
+                      const void* y, int64_t ldy, float* dw, int accumulate, void* ws, cudaStream_t st);
 }
 
 int wgrad_halo_launch(const urn_conv_desc& d, int x_dtype, const void* x, int64_t ldx, int y_dtype,
                       const void* y, int64_t ldy, float* dw, int accumulate, void* ws, cudaStream_t st) {
   WHParams p;
-  if (!wh_plan_rows(d, x_dtype, y_dtype, ldx, ldy, &p))
-    URN_CHECK(wh_plan(d, x_dtype, y_dtype, ldx, ldy, &p), "wgrad_halo: unsupported shape/dtype");
+  if (wh_plan_rows(d, x_dtype, y_dtype, ldx, ldy, &p) || wh_plan(d, x_dtype, y_dtype, ldx, ldy, &p))
+    return wh_launch_planned(d, p, x_dtype, x, ldx, y_dtype, y, ldy, dw, accumulate, ws, st);
+  for (int kd = 0; kd < 3; ++kd) {
+    urn_conv_desc sd;
+    URN_CHECK(wh_split_desc(d, kd, &sd) && wh_plan(sd, x_dtype, y_dtype, ldx, ldy, &p), "wgrad_halo: unsupported shape/dtype");
+    if (wh_launch_planned(sd, p, x_dtype, x, ldx, y_dtype, y, ldy, dw + (long long)kd * d.kh * d.kw * d.cx * d.cy, accumulate, ws, st))
+      return 1;
+  }
+  return 0;
+}
+
+namespace {
+int wh_launch_planned(const urn_conv_desc& d, WHParams& p, int x_dtype, const void* x, int64_t ldx, int y_dtype,
+                      const void* y, int64_t ldy, float* dw, int accumulate, void* ws, cudaStream_t st) {
   const int x_bytes = ((p.stages * p.xplane_bytes + 1023) / 1024) * 1024;
   const size_t smem = 1024 + (size_t)x_bytes + (size_t)(p.ystages + p.ymirror) * p.yplane_bytes + 1024;
   static bool attr_set = false;
@@ -733,3 +784,4 @@ int wgrad_halo_launch(const urn_conv_desc& d, int x_dtype, const void* x, int64_
   URN_LAUNCH_CHECK();
   return 0;
 }
+}  // namespace
