@@ -22,6 +22,14 @@
 // <= 148 partials (deterministic).
 //   warps 0-7 : cp.async producers (X plane + dY tile per step, register-resident offset tables)
 //   warp 8    : TMEM alloc, MMA issue        warps 9-12: final epilogue (tcgen05.ld -> fp32 partial)
+//
+// Round 2.  (i) Images-as-rows plan (wh_plan_rows): a 2D batch of >= 12 images is relabelled as a volume (planes
+// := image rows, tile rows := images), so the kh taps become depth taps concatenated along N.  Its operands are
+// staged by TMA, ONE box per X plane and per dY plane: rows (image, pixel), positions ordered (image, w), and
+// the kw taps are M groups ONE pixel apart (LBO = pixel pitch) -- a UMMA view may start on any 16-byte boundary
+// of a swizzled tile.  (ii) Rings: `pf` cp.async groups in flight need pf + 2 stages (see wh_plan).  (iii) 3D
+// layers whose 27 x cx x cy accumulators exceed TMEM run one pass per depth tap (wh_split_desc); the depth
+// chunks of small grids are balanced over the CTAs.
 #include <cuda.h>
 #include <stdlib.h>
 #include <string.h>
