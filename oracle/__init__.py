@@ -12,4 +12,15 @@ oracle restates ``lib/uresnet.py:22-123``, ``lib/resnet_module.py:10-87`` and
 SURVEY.md section 3.4, is cross-checked against an independent naive NumPy
 implementation (``oracle/naive.py``) and fp64 finite differences, and its
 outputs are frozen under ``tests/golden/``.
+
+What IS pinned by the reference: the one artefact it produced itself, the
+TensorBoard GraphDef dump under ``libs/uresnet_graph/`` (an older revision of
+the model).  ``tests/golden/reference_graph.json`` is its committed extract and
+``tests/test_reference_graph.py`` holds the oracle to it: the 58 filter names,
+shapes and TensorFlow's own Xavier limits, the wiring / strides / padding of
+every conv-type op, the skip map and concat operand order, the residual adds,
+slim's lowering of conv2d_transpose to Conv2DBackpropInput, and the dumped
+batch_norm and accuracy expressions EXECUTED against ``batch_norm`` /
+``loss_and_metrics``.  Structure and op semantics are pinned that way; tensor
+VALUES of the reference exist nowhere, so numerics remain unpinned.
 """

@@ -75,6 +75,16 @@ def param_names(nd, base=16, num_strides=5, num_class=3, in_ch=1):
     return out
 
 
+def xavier_limit(wshape):
+    """Limit of slim's default ``weights_initializer`` (``xavier_initializer()``, uniform):
+    sqrt(6 / (fan_in + fan_out)) with fan = receptive field x channels, ``wshape`` in the TF layout
+    (``[k..,Cin,Cout]``; the conv-transpose layout ``[k..,Cout,Cin]`` gives the same sum).  Pinned
+    by the float32 constants TensorFlow itself wrote into the reference's graph dump
+    (tests/test_reference_graph.py)."""
+    rf = int(np.prod(wshape[:-2]))
+    return math.sqrt(6.0 / (rf * wshape[-2] + rf * wshape[-1]))
+
+
 def init_params(nd, base=16, num_strides=5, num_class=3, in_ch=1, seed=4321,
                 beta_std=0.1):
     """Xavier-uniform filters (slim default), betas ~ N(0, beta_std).
@@ -85,9 +95,7 @@ def init_params(nd, base=16, num_strides=5, num_class=3, in_ch=1, seed=4321,
     rng = np.random.Generator(np.random.PCG64(seed))
     P = OrderedDict()
     for l in layer_table(nd, base, num_strides, num_class, in_ch):
-        rf = l["k"] ** nd
-        fan_in, fan_out = rf * l["cin"], rf * l["cout"]
-        lim = math.sqrt(6.0 / (fan_in + fan_out))
+        lim = xavier_limit(l["wshape"])
         P["UResNet/%s/weights" % l["scope"]] = rng.uniform(
             -lim, lim, size=l["wshape"]).astype(np.float32)
         P["UResNet/%s/BatchNorm/beta" % l["scope"]] = (
