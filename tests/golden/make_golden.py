@@ -8,6 +8,10 @@ itself cross-checked against oracle/naive.py and finite differences in
 tests/test_oracle.py.  Inputs come from the seeded synthetic generator and the seeded
 Xavier initialiser; both inputs and outputs are stored so that the fixtures do not
 depend on those generators staying bit-stable.
+
+Since the end of round 2 the same cases also exist as gref*.npz, made by executing the
+reference's own lib/*.py over oracle/tf1_shim.py (make_reference_run_golden.py);
+tests/test_reference_run.py asserts that the files written here hold the same numbers.
 """
 import os
 import sys
