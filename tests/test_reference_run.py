@@ -284,3 +284,60 @@ def test_live_error_behaviour_of_the_reference():
     with pytest.raises(ValueError):
         net.accum_gradients(sess, d, bad, d)
     shim.uninstall()
+
+
+@needs_ref
+@pytest.mark.parametrize("dims,B,F,St", [([32, 32, 32, 1], 1, 2, 5), ([64, 32, 1], 2, 3, 5)])
+def test_live_five_stride_topologies_numerics(dims, B, F, St):
+    """S=5 (the default depth: decoder scopes resnet_module5..9, five skips) in 3D and on a non-square 2D image,
+    odd base width: the reference code's run against the oracle, every gradient."""
+    import uresnet_b200.synthetic_io as S
+    mk = _mk()
+    nd = len(dims) - 1
+    d, l, w = S.make_batch(B, dims, seed=77)
+    w = w / w.sum(axis=1, keepdims=True)
+    P = O.init_params(nd, base=F, num_strides=St, seed=5)
+    r = mk.run_reference(dims, F, St, 3, True, P, [(d, l, w)])
+    shp = [B] + dims[:-1]
+    o = O.run(P, d.reshape(shp + [1]), l.reshape(shp), w.reshape(shp), base=F, num_strides=St)
+    assert rel(r["logits"], o["logits"]) < 1e-10 and abs(r["metrics"][0][0] - o["loss"]) < 1e-12 * abs(o["loss"])
+    assert r["metrics"][0][1] == pytest.approx(o["acc_all"], abs=1e-7)
+    assert r["metrics"][0][2] == pytest.approx(o["acc_nonzero"], abs=1e-7)
+    assert len(r["grads"]) == 116
+    for k in P:
+        assert rel(r["grads"][k], o["grads"][k]) < 1e-9, k
+
+
+@needs_ref
+def test_live_inference_network():
+    """The analysis configuration (ssnet_trainval.py:101-103,237: trainable=False, no weights): softmax and the
+    two accuracies of ``inference`` against the oracle; no optimizer, no accumulators' ops."""
+    import uresnet_b200.synthetic_io as S
+    from oracle import tf1_shim as shim
+    dims, B, F, St = [32, 32, 1], 2, 4, 3
+    d, l, _ = S.make_batch(B, dims, seed=3)
+    P = O.init_params(2, base=F, num_strides=St, seed=8)
+    shim.reset_default_graph(torch.float64)
+    uresnet = shim.load_reference()
+    import tensorflow as tf
+    net = uresnet(dims=dims, num_class=3, num_strides=St, base_num_outputs=F)
+    net.construct(trainable=False, use_weight=False)
+    assert net._loss is None and not hasattr(net, "_opt")
+    # trainable=False reaches the filters; slim does not forward it to normalizer_fn, so the betas stay "trainable"
+    assert [v.op.name for v in tf.trainable_variables()] == [k for k in P if k.endswith("/beta")]
+    sess = tf.Session()
+    sess.run(tf.global_variables_initializer())
+    byname = {v.op.name: v for v in tf.global_variables()}
+    for k, v in P.items():
+        byname[k].load(v, sess)
+    sm, acc_all, acc_nz = net.inference(sess, d, l)
+    only = net.inference(sess, d)
+    shp = [B] + dims[:-1]
+    o = O.run(P, d.reshape(shp + [1]), l.reshape(shp), None, base=F, num_strides=St, want_grads=False)
+    assert sm.shape == tuple(shp + [3]) and len(only) == 1 and np.array_equal(only[0], sm)
+    assert rel(sm, o["softmax"]) < 1e-12
+    assert float(acc_all) == pytest.approx(o["acc_all"], abs=1e-7) and float(acc_nz) == pytest.approx(o["acc_nonzero"], abs=1e-7)
+    # the shower / track map the analysis step derives from it (ssnet_trainval.py:269-287)
+    dec = O.ssnet_decision(sm, d.reshape(shp))
+    assert set(np.unique(dec)) <= {0.0, 1.0, 2.0} and np.all(dec[d.reshape(shp) <= 1.0] == 0)
+    shim.uninstall()
