@@ -246,7 +246,25 @@ class Variable(Tensor):
 
 
 def get_variable(name, shape, init, trainable=True):
-    return Variable(name=name, shape=shape, trainable=trainable, _init=init)
+    v = Variable(name=name, shape=shape, trainable=trainable, _init=init)
+    v._model = True                  # slim puts layer variables into GraphKeys.MODEL_VARIABLES
+    return v
+
+
+class GraphKeys(object):
+    MODEL_VARIABLES = "model_variables"
+    TRAINABLE_VARIABLES = "trainable_variables"
+    GLOBAL_VARIABLES = "variables"
+
+
+def get_collection(key):
+    if key == GraphKeys.MODEL_VARIABLES:
+        return [v for v in _G.variables if getattr(v, "_model", False)]
+    if key == GraphKeys.TRAINABLE_VARIABLES:
+        return trainable_variables()
+    if key == GraphKeys.GLOBAL_VARIABLES:
+        return global_variables()
+    return []
 
 
 def trainable_variables():
@@ -509,7 +527,7 @@ def _merge_all():
     items = [(n, t) for n, t in _G.summaries if t is not None]
 
     def fn(ctx):
-        return {n: float(t._eval(ctx)) for n, t in items}
+        return {n: float(t._eval(ctx).detach()) for n, t in items}
     return Tensor(fn, (), ())
 
 
@@ -517,7 +535,66 @@ def _grayscale_to_rgb(t, name=None):
     return Tensor(lambda c, v: v.expand(*v.shape[:-1], 3), (t,), t.shape.as_list()[:-1] + [3])
 
 
+class FileWriter(object):
+    """tf.summary.FileWriter: keeps what it is given (``records`` of this writer and, by directory, in
+    ``FileWriter.by_dir``) instead of writing event files."""
+    by_dir = {}
+
+    def __init__(self, logdir, graph=None, **k):
+        self.logdir, self.records, self.graphs = logdir, [], 0
+        FileWriter.by_dir[logdir] = self
+
+    def add_graph(self, graph):
+        self.graphs += 1
+
+    def add_summary(self, summary, global_step=None):
+        self.records.append((None if global_step is None else int(global_step), summary))
+
+    def flush(self):
+        pass
+
+    close = flush
+
+
+class Saver(object):
+    """tf.train.Saver: ``save`` writes ``<path>-<global_step>.npz`` (variable values keyed by ``var.op.name``)
+    and returns ``<path>-<global_step>`` like TF; retention follows TF's rule (the newest ``max_to_keep``
+    files; one that drops out of that window survives only if ``keep_checkpoint_every_n_hours`` have passed
+    since the last one kept for good)."""
+
+    def __init__(self, var_list=None, max_to_keep=5, keep_checkpoint_every_n_hours=10000.0, **k):
+        import time
+        self._vars, self._max, self._nhour = var_list, max_to_keep, keep_checkpoint_every_n_hours
+        self._last, self._next_keep = [], time.time() + keep_checkpoint_every_n_hours * 3600.0
+
+    def save(self, sess, save_path, global_step=None):
+        import os
+        import time
+        prefix = save_path if global_step is None else "%s-%d" % (save_path, int(global_step))
+        vs = self._vars if self._vars is not None else global_variables()
+        np.savez(prefix + ".npz", **{v.op.name: v.value.detach().numpy() for v in vs})
+        self._last.append((prefix, time.time()))
+        while self._max and len(self._last) > self._max:
+            old, t = self._last.pop(0)
+            if t > self._next_keep:
+                self._next_keep += self._nhour * 3600.0
+            elif os.path.exists(old + ".npz"):
+                os.remove(old + ".npz")
+        return prefix
+
+    def restore(self, sess, save_path):
+        z = np.load(save_path if save_path.endswith(".npz") else save_path + ".npz")
+        for v in (self._vars if self._vars is not None else global_variables()):
+            v.load(z[v.op.name], sess)
+
+
+def _max_bytes_in_use():
+    return Tensor(lambda c: 0.0, (), ())
+
+
 class Session(object):
+    graph = "default-graph"
+
     def __init__(self, *a, **k):
         pass
 
@@ -564,8 +641,10 @@ def install(reference_lib=REFERENCE_LIB):
               "Variable", "trainable_variables", "global_variables", "global_variables_initializer", "Session",
               "InteractiveSession", "reset_default_graph", "set_random_seed", "nn"):
         setattr(tf, k, getattr(me, k))
-    tf.train = types.SimpleNamespace(AdamOptimizer=AdamOptimizer)
-    tf.summary = types.SimpleNamespace(scalar=_summary_scalar, image=_summary_image, merge_all=_merge_all)
+    tf.train = types.SimpleNamespace(AdamOptimizer=AdamOptimizer, Saver=Saver)
+    tf.summary = types.SimpleNamespace(scalar=_summary_scalar, image=_summary_image, merge_all=_merge_all,
+                                       FileWriter=FileWriter)
+    tf.GraphKeys, tf.get_collection = GraphKeys, get_collection
     tf.image = types.SimpleNamespace(grayscale_to_rgb=_grayscale_to_rgb)
     tf.__version__ = "1.x-shim"
     slim = types.ModuleType("tensorflow.contrib.slim")
@@ -576,6 +655,7 @@ def install(reference_lib=REFERENCE_LIB):
     layers.batch_norm = batch_norm
     contrib = types.ModuleType("tensorflow.contrib")
     contrib.slim, contrib.layers = slim, layers
+    contrib.memory_stats = types.SimpleNamespace(MaxBytesInUse=_max_bytes_in_use)
     python = types.ModuleType("tensorflow.python")
     platform = types.ModuleType("tensorflow.python.platform")
     python.platform = platform
@@ -594,14 +674,43 @@ def uninstall(reference_lib=REFERENCE_LIB):
     if getattr(sys.modules.get("tensorflow"), "__version__", None) == "1.x-shim":
         for k in [k for k in sys.modules if k == "tensorflow" or k.startswith("tensorflow.")]:
             del sys.modules[k]
-    for k in ("uresnet", "ssnet", "resnet_module"):
+    for k in ("uresnet", "ssnet", "resnet_module", "ssnet_trainval", "config"):
         m = sys.modules.get(k)
         if m is not None and (getattr(m, "__file__", None) or "").startswith(reference_lib):
             del sys.modules[k]
+    if getattr(sys.modules.get("larcv"), "__version__", None) == "shim":
+        del sys.modules["larcv"], sys.modules["larcv.dataloader2"]
     if reference_lib in sys.path:
         sys.path.remove(reference_lib)
     if getattr(builtins, "xrange", None) is range:
         del builtins.xrange
+
+
+def install_larcv(make_threadio):
+    """Registers a stand-in ``larcv`` package whose ``larcv.dataloader2.larcv_threadio`` is ``make_threadio``
+    (a class with the larcv_threadio call surface, ssnet_trainval.py:64-91), so that the reference's DRIVER
+    (lib/ssnet_trainval.py) imports.  The stand-in ``larcv.larcv`` has no IOManager: ANA_OUTPUT_CONFIG must
+    stay empty."""
+    pkg = types.ModuleType("larcv")
+    pkg.__version__ = "shim"
+    pkg.larcv = types.SimpleNamespace()
+    dl = types.ModuleType("larcv.dataloader2")
+    dl.larcv_threadio = make_threadio
+    pkg.dataloader2 = dl
+    sys.modules.update({"larcv": pkg, "larcv.dataloader2": dl})
+
+
+def load_reference_driver(make_threadio, reference_lib=REFERENCE_LIB):
+    """Imports the UNMODIFIED reference driver (lib/ssnet_trainval.py, with lib/config.py and the model code)
+    over the shim and the stand-in larcv; returns its ``ssnet_trainval`` class."""
+    install(reference_lib)
+    install_larcv(make_threadio)
+    import importlib
+    for k in ("uresnet", "ssnet", "resnet_module", "ssnet_trainval", "config"):
+        sys.modules.pop(k, None)
+    mod = importlib.import_module("ssnet_trainval")
+    assert mod.__file__.startswith(reference_lib), mod.__file__
+    return mod.ssnet_trainval
 
 
 def load_reference(reference_lib=REFERENCE_LIB):
