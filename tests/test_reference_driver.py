@@ -248,3 +248,24 @@ def test_analysis_drivers_agree(tmp_path, capsys, monkeypatch):
             assert np.array_equal(np.asarray(r[k]), np.asarray(o[k])), k
     assert not np.array_equal(ref["ana"][0]["input"], ref["ana"][1]["input"])          # the stream advanced
     assert list(ref["ana"][1]["entries"]) == [2, 3]
+
+
+def test_config_schema_defaults_are_the_reference_s():
+    """lib/config.py:6-36 imported as is: every key of the reference schema exists in the product's schema with
+    the same default value and type (``override`` / ``dump`` themselves rely on Python-2 ``exec`` semantics --
+    assignments to function locals -- and cannot run under Python 3; tests/test_host_cpu.py covers the
+    product's reader on the reference's own .cfg files)."""
+    from oracle import tf1_shim as shim
+    from uresnet_b200.config import ssnet_config as ours
+    shim.load_reference_driver(_threadio)
+    import config as ref_config
+    assert ref_config.__file__.startswith("/root/reference/lib")
+    ref = {k: v for k, v in ref_config.ssnet_config.__dict__.items() if k == k.upper() and not k.startswith("_")}
+    assert len(ref) == 29
+    mine = ours()
+    for k, v in ref.items():
+        assert hasattr(mine, k), k
+        assert getattr(mine, k) == v and type(getattr(mine, k)) is type(v), (k, getattr(mine, k), v)
+    extra = set(ours._keys()) - set(ref)
+    assert extra == {"DTYPE", "KERNEL_IMPL", "SYNTHETIC_DIMS", "SYNTHETIC_SEED"}, extra
+    shim.uninstall()
