@@ -206,3 +206,30 @@ def test_checkpoint_retention_nmax_and_nhour(tmp_path):
             time.sleep(0.02)                                   # strictly increasing mtimes
         assert sorted(p.name for p in d.glob("*.npz")) == want, (nhour, sorted(p.name for p in d.glob("*.npz")))
         t._net = None
+
+
+def test_initialiser_draws_the_filters_the_reference_driver_transcript_started_from():
+    """tests/golden/refdriver_train.json records the initial filters of the reference driver's run over the TF
+    shim (PCG64(TF_RANDOM_SEED), Xavier-uniform filter by filter in creation order).  ``ssnet_base._init_variables``
+    -- called here on a host-side stand-in for the network object, no GPU -- must draw the same ones, so that the
+    product's driver started with that TF_RANDOM_SEED begins where the transcript began."""
+    import json
+    import types
+    import torch
+    from oracle import uresnet_oracle as O
+    from uresnet_b200.ssnet import ssnet_base
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", "refdriver_train.json")))
+    names = O.param_names(2, base=g["cfg"]["BASE_NUM_FILTERS"], num_strides=5, num_class=g["cfg"]["NUM_CLASS"])
+    assert [n for n, _ in names] == g["names"]
+    table, off = {}, 0
+    for n, s in names:
+        cnt = int(np.prod(s))
+        table[n] = (tuple(s), off, cnt)
+        off += (cnt + 63) // 64 * 64
+    fake = types.SimpleNamespace(_param_total=off, _param_table=table, _params=torch.zeros(off))
+    ssnet_base._init_variables(fake, g["cfg"]["TF_RANDOM_SEED"])
+    host = fake._params.numpy().astype(np.float64)
+    for i, (n, (s, o, c)) in enumerate(table.items()):
+        v = host[o:o + c]
+        assert np.sqrt((v ** 2).sum()) == pytest.approx(g["init_l2"][i], rel=1e-6, abs=1e-12), n
+        assert v.sum() == pytest.approx(g["init_sum"][i], rel=1e-5, abs=1e-5), n

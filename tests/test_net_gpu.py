@@ -339,6 +339,53 @@ def test_trainval_driver_train_checkpoint_and_ana(tmp_path, capsys):
     b.reset()
 
 
+@pytest.mark.parametrize("dtype", ["f32", "mix16"])
+def test_driver_reproduces_reference_driver_transcript(dtype, capsys):
+    """tests/golden/refdriver_train.json is the transcript of the REFERENCE'S OWN DRIVER (lib/ssnet_trainval.py run
+    unmodified over oracle/tf1_shim.py, float64) training the default-depth net on the synthetic source: 6
+    iterations x 2 minibatches, a test stream evaluated at every report.  The product's driver with the same
+    configuration -- same TF_RANDOM_SEED, hence the same initial filters (tests/test_host_cpu.py) -- must print
+    the same report: every loss within 5e-3 (f32) / 2e-2 (mix16), accuracies within a few pixels' worth."""
+    import importlib.util
+    import json
+    from uresnet_b200.ssnet_trainval import ssnet_trainval
+    spec = importlib.util.spec_from_file_location("mkdrv", os.path.join(GOLD, "make_reference_driver_golden.py"))
+    mk = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mk)
+    g = json.load(open(os.path.join(GOLD, "refdriver_train.json")))
+    t = ssnet_trainval()
+    for k, v in g["cfg"].items():
+        setattr(t._cfg, k, v)
+    t._cfg.SYNTHETIC_DIMS, t._cfg.SYNTHETIC_SEED, t._cfg.DTYPE = list(g["dims"]), int(g["synthetic_seed"]), dtype
+    t.initialize()
+    v0 = t._net.get_variables()
+    assert list(v0.keys()) == g["names"]
+    for i, k in enumerate(g["names"]):
+        assert np.sqrt((v0[k].astype(np.float64) ** 2).sum()) == pytest.approx(g["init_l2"][i], rel=1e-6, abs=1e-12), k
+    capsys.readouterr()
+    t.batch_process()
+    reps = mk.parse_transcript(capsys.readouterr().out)
+    v1 = t._net.get_variables()
+    t.reset()
+    # measured on B200: f32 2.1e-3 / 1.2e-3 / 8.3e-3, mix16 5.5e-3 / 3.3e-3 / 1.2e-2 (the 2 x 2 x 2-value batch norms at
+    # the bottom of a five-stride net on 64 x 64 images amplify rounding; Adam's first steps are sign-like)
+    tol_loss, tol_all, tol_nz = {"f32": (5e-3, 5e-3, 2e-2), "mix16": (2e-2, 2e-2, 6e-2)}[dtype]
+    assert [r["iteration"] for r in reps] == [r["iteration"] for r in g["reports"]] == list(range(6))
+    worst = [0.0, 0.0, 0.0]
+    for r, w in zip(reps, g["reports"]):
+        assert r["lr"] == w["lr"]
+        for key in ("train", "test"):
+            d = [abs(r[key][0] - w[key][0]) / w[key][0], abs(r[key][1] - w[key][1]), abs(r[key][2] - w[key][2])]
+            worst = [max(a, b) for a, b in zip(worst, d)]
+    upd = np.array([np.sqrt(((v1[k].astype(np.float64) - v0[k]) ** 2).sum()) for k in g["names"]])
+    print("\ndriver vs reference-driver transcript [%s]: worst loss deviation %.2e, acc. all %.2e, acc. nonzero %.2e; "
+          "update norms vs reference: median ratio %.4f" % (dtype, worst[0], worst[1], worst[2],
+                                                            float(np.median(upd / np.array(g["update_l2"])))))
+    assert worst[0] < tol_loss and worst[1] < tol_all and worst[2] < tol_nz, worst
+    # six Adam applies moved every tensor about as far as they moved the reference's
+    np.testing.assert_allclose(upd, g["update_l2"], rtol=0.25)
+
+
 @pytest.mark.parametrize("dims,B", [([32, 64, 1], 2), ([8, 16, 16, 1], 1), ([24, 40, 1], 13)])   # batch >= 12: images-as-rows plan
 def test_padded_head_matches_cuda_core_head(dims, B, monkeypatch):
     """The head conv2 (Cout = 3) runs on the tensor cores with its filter zero-padded to 16 output

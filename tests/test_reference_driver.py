@@ -269,3 +269,28 @@ def test_config_schema_defaults_are_the_reference_s():
     extra = set(ours._keys()) - set(ref)
     assert extra == {"DTYPE", "KERNEL_IMPL", "SYNTHETIC_DIMS", "SYNTHETIC_SEED"}, extra
     shim.uninstall()
+
+
+# ------------------------------------------------------------------------------------------------
+# the committed transcript of the reference driver (tests/golden/refdriver_train.json): consumed by
+# tests/test_net_gpu.py::test_driver_reproduces_reference_driver_transcript on the B200
+# ------------------------------------------------------------------------------------------------
+def _mkdrv():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location(
+        "mkdrv", os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "make_reference_driver_golden.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m
+
+
+def test_reference_driver_transcript_regenerates():
+    mk = _mkdrv()
+    want = json.load(open(mk.OUT))
+    got = json.loads(json.dumps(mk.run()))
+    assert got["reports"] == want["reports"] and got["names"] == want["names"] and got["cfg"] == want["cfg"]
+    assert len(got["reports"]) == 6 and all(set(r) == {"iteration", "lr", "train", "test"} for r in got["reports"])
+    for k in ("init_l2", "init_sum", "final_l2", "update_l2"):
+        np.testing.assert_allclose(got[k], want[k], rtol=1e-9, atol=1e-12)
+    losses = [r["train"][0] for r in want["reports"]]
+    assert losses[-1] < 0.7 * losses[0]                       # it trains
