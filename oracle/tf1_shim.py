@@ -246,6 +246,9 @@ class Variable(Tensor):
 
 
 def get_variable(name, shape, init, trainable=True):
+    if _scoped(name) in _G.names:       # tf.get_variable (what slim calls), unlike tf.Variable, never renames
+        raise ValueError("Variable %s already exists, disallowed. Did you mean to set reuse=True in VarScope?"
+                         % _scoped(name))
     v = Variable(name=name, shape=shape, trainable=trainable, _init=init)
     v._model = True                  # slim puts layer variables into GraphKeys.MODEL_VARIABLES
     return v

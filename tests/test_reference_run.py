@@ -270,6 +270,11 @@ def test_live_error_behaviour_of_the_reference():
     import tensorflow as tf
     with pytest.raises(NotImplementedError):                                    # ssnet.py:12-14
         uresnet(dims=[32, 32], num_class=3)
+    # uresnet.py:100 hard-codes the decoder scopes as step+5: a sixth stride re-creates resnet_module5 (TF refuses;
+    # so does the product: tests/test_capi_cpu.py::test_create_rejects_more_than_five_strides)
+    with pytest.raises(ValueError, match="resnet_module5/module1/shortcut/weights already exists"):
+        uresnet(dims=[64, 64, 1], num_class=3, num_strides=6, base_num_outputs=2).construct(True, True, 1e-3)
+    shim.reset_default_graph(torch.float64)
     net = uresnet(dims=[8, 8, 1], num_class=3, num_strides=1, base_num_outputs=2)
     net.construct(trainable=True, use_weight=True, learning_rate=1e-3)
     sess = tf.Session()
