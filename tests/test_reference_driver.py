@@ -294,3 +294,77 @@ def test_reference_driver_transcript_regenerates():
         np.testing.assert_allclose(got[k], want[k], rtol=1e-9, atol=1e-12)
     losses = [r["train"][0] for r in want["reports"]]
     assert losses[-1] < 0.7 * losses[0]                       # it trains
+
+
+class _io_manager(object):
+    """stand-in for ``larcv.IOManager`` (ssnet_trainval.py:81-83,254-302): hands out the producers the analysis
+    step asks for and keeps what it stores"""
+    stored = []
+
+    def __init__(self, cfg):
+        self.cfg, self.entry = cfg, None
+
+    def initialize(self):
+        pass
+
+    def finalize(self):
+        pass
+
+    def read_entry(self, e):
+        self.entry = int(e)
+
+    def save_entry(self):
+        pass
+
+    def get_data(self, kind, name):
+        mgr = self
+
+        class product(object):
+            def as_vector(self):
+                return self
+
+            def front(self):
+                return self
+
+            def meta(self):
+                return ("meta", mgr.entry)
+
+            def append(self, img):
+                _io_manager.stored.append((mgr.entry, kind, name, img))
+
+            def set(self, vs, meta):
+                _io_manager.stored.append((mgr.entry, kind, name, vs))
+        return product()
+
+
+@pytest.mark.parametrize("dims", [[32, 32, 1], [32, 32, 32, 1]])
+def test_analysis_output_map_is_the_oracle_s_decision(dims, tmp_path, capsys, monkeypatch):
+    """The shower / track map the reference's analysis step writes to its larcv output (ssnet_trainval.py:254-302,
+    executed here with a stand-in IOManager) equals ``oracle.ssnet_decision`` of the same softmax -- the function
+    the device kernel ``urn_decision`` is held to bit for bit in tests/test_net_gpu.py / test_kernels_gpu.py."""
+    import sys
+    from oracle import tf1_shim as shim
+    from oracle import uresnet_oracle as O
+    monkeypatch.setattr(sys.modules[__name__], "DIMS", dims)
+    shim.reset_default_graph(torch.float64)
+    cls = shim.load_reference_driver(_threadio)
+    larcv = sys.modules["larcv"].larcv
+    larcv.IOManager = _io_manager
+    larcv.as_image2d_meta = lambda arr, meta: np.array(arr)
+    larcv.as_tensor3d = lambda arr: np.array(arr)
+    _io_manager.stored = []
+    drv = cls()
+    _configure(drv._cfg, tmp_path, "ref", TRAIN=False, USE_WEIGHTS=False, TEST_INPUT_CONFIG="", LOGDIR="", SAVE_FILE="",
+               ANA_OUTPUT_CONFIG="out.cfg", BASE_NUM_FILTERS=2, MINIBATCH_SIZE=2)
+    drv.initialize()
+    res = drv.ana_step()
+    out = capsys.readouterr().out
+    drv.reset()
+    shim.uninstall()
+    assert len(_io_manager.stored) == 2 and out.count("Entry") == 2
+    nd = len(dims) - 1
+    for b, (entry, kind, name, img) in enumerate(_io_manager.stored):
+        assert (entry, kind, name) == (b, "image2d" if nd == 2 else "sparse3d", "ssnet")
+        want = O.ssnet_decision(res["softmax"][b], res["input"][b, ..., 0])
+        assert img.dtype == np.float32 and img.shape == tuple(dims[:-1]) and np.array_equal(img, want)
+        assert set(np.unique(img)) <= {0.0, 1.0, 2.0} and (img > 0).sum() == (res["input"][b, ..., 0] > 1.0).sum()
