@@ -346,3 +346,53 @@ def test_live_inference_network():
     dec = O.ssnet_decision(sm, d.reshape(shp))
     assert set(np.unique(dec)) <= {0.0, 1.0, 2.0} and np.all(dec[d.reshape(shp) <= 1.0] == 0)
     shim.uninstall()
+
+
+@needs_ref
+def test_live_baseline_config0_inference_512():
+    """BASELINE configs[0] as the reference states it: the default net (F=16, S=5, 3 classes) on one 512 x 512
+    image, inference -- the reference code's softmax and accuracies against the oracle's."""
+    import time
+    import uresnet_b200.synthetic_io as S
+    from oracle import tf1_shim as shim
+    dims, B = [512, 512, 1], 1
+    d, l, _ = S.make_batch(B, dims, seed=1234)
+    P = O.init_params(2, seed=4321)
+    shim.reset_default_graph(torch.float64)
+    uresnet = shim.load_reference()
+    import tensorflow as tf
+    net = uresnet(dims=dims, num_class=3)
+    net.construct(trainable=False, use_weight=False)
+    sess = tf.Session()
+    sess.run(tf.global_variables_initializer())
+    byname = {v.op.name: v for v in tf.global_variables()}
+    for k, v in P.items():
+        byname[k].load(v, sess)
+    t0 = time.time()
+    sm, acc_all, acc_nz = net.inference(sess, d, l)
+    t1 = time.time()
+    o = O.run(P, d.reshape(1, 512, 512, 1), l.reshape(1, 512, 512), None, want_grads=False)
+    assert sm.shape == (1, 512, 512, 3) and rel(sm, o["softmax"]) < 1e-12
+    assert float(acc_all) == pytest.approx(o["acc_all"], abs=1e-7) and float(acc_nz) == pytest.approx(o["acc_nonzero"], abs=1e-7)
+    assert (sm.argmax(-1) == o["softmax"].argmax(-1)).all()
+    print("reference inference over the shim, 512x512 B=1, fp64: %.1f s" % (t1 - t0))
+    shim.uninstall()
+
+
+@needs_ref
+def test_live_baseline_geometry_train_step_512():
+    """BASELINE configs[1] geometry (512 x 512, F=16, S=5, weighted CE; one image): the reference code's training
+    step -- logits, loss, all 116 accumulated gradients -- against the oracle, the very numbers
+    tests/test_parity_gpu.py::test_baseline_size_2d_512 holds the CUDA path to."""
+    import uresnet_b200.synthetic_io as S
+    mk = _mk()
+    dims, B = [512, 512, 1], 1
+    d, l, w = S.make_batch(B, dims, seed=1234)
+    w = w / w.sum(axis=1, keepdims=True)
+    P = O.init_params(2, seed=4321)
+    r = mk.run_reference(dims, 16, 5, 3, True, P, [(d, l, w)])
+    o = O.run(P, d.reshape(1, 512, 512, 1), l.reshape(1, 512, 512), w.reshape(1, 512, 512))
+    assert rel(r["logits"], o["logits"]) < 1e-12 and abs(r["metrics"][0][0] - o["loss"]) < 1e-12 * abs(o["loss"])
+    assert len(r["grads"]) == 116
+    worst = max(rel(r["grads"][k], o["grads"][k]) for k in P)
+    assert worst < 1e-10, worst
