@@ -186,12 +186,21 @@ class ssnet_trainval(object):
             path = cfg.LOAD_FILE if cfg.LOAD_FILE.endswith('.npz') else cfg.LOAD_FILE + '.npz'
             stored = np.load(path)
             values = {}
+            # the reference walks tf.GraphKeys.MODEL_VARIABLES (ssnet_trainval.py:139-151): weights, beta and the
+            # two moving statistics of every layer.  The statistics are part of the checkpoint (_save) but of no
+            # computation -- nothing updates or reads them -- so "loading" them only reports
+            names = []
             for name, _ in self._net.trainable_variables():
+                names.append(name)
+                if name.endswith('/BatchNorm/beta'):
+                    names += [name[:-4] + 'moving_mean', name[:-4] + 'moving_variance']
+            for name in names:
                 if (name + ':0') in cfg.AVOID_LOAD_PARAMS or name in cfg.AVOID_LOAD_PARAMS:
                     print('\033[91mSkipping\033[00m loading variable', name + ':0', 'from input weight...')
                     continue
                 print('\033[95mLoading\033[00m variable', name + ':0', 'from', cfg.LOAD_FILE)
-                values[name] = stored[name]
+                if not name.split('/')[-1].startswith('moving_'):
+                    values[name] = stored[name]
             self._net.set_variables(values)
         self._batch_metrics = None
         self._descr_metrics = None
