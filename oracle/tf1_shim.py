@@ -60,6 +60,7 @@ class _Graph(object):
         self.variables = []          # creation order (tf.global_variables())
         self.names = set()
         self.summaries = []
+        self.layers = {}             # scope -> dict(raw=<conv output>, out=<after normalizer / activation>): fetchable
         self.float = float_dtype
         self.rng = np.random.Generator(np.random.PCG64(seed))
 
@@ -466,12 +467,20 @@ def _conv_layer(nd, transpose):
             else:
                 out = Tensor(lambda c, x, wv: _to_cl(_conv_same_cf(_to_cf(x), wv, stride)), (inputs, w),
                              [s[0]] + [None if n is None else -(-n // stride) for n in s[1:-1]] + [cout])
+            raw = out
             if normalizer_fn is not None:
                 out = normalizer_fn(out, **(normalizer_params or {}))
             elif b is not None:
                 out = out + b
-            return activation_fn(out) if activation_fn is not None else out
+            out = activation_fn(out) if activation_fn is not None else out
+            _G.layers[_scoped("")] = dict(raw=raw, out=out)      # TF: any tensor can be fetched by name
+            return out
     return layer
+
+
+def layer_tensors():
+    """{variable scope of a slim layer: {'raw': conv output, 'out': layer output}} of the current graph"""
+    return dict(_G.layers)
 
 
 # ------------------------------------------------------------------------------------------ optimizer

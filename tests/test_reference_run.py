@@ -396,3 +396,44 @@ def test_live_baseline_geometry_train_step_512():
     assert len(r["grads"]) == 116
     worst = max(rel(r["grads"][k], o["grads"][k]) for k in P)
     assert worst < 1e-10, worst
+
+
+@needs_ref
+@pytest.mark.parametrize("dims,B,F,St", [([32, 32, 1], 2, 4, 3), ([16, 16, 16, 1], 1, 4, 2)])
+def test_live_every_intermediate_tensor_of_the_step_oracle(dims, B, F, St):
+    """oracle/steps.py keeps every intermediate by TF scope name and hands them to the CUDA schedule steps in the
+    teacher-forced GPU tests.  Here the same tensors are FETCHED FROM THE REFERENCE'S GRAPH (raw conv output and
+    layer output of every slim layer, by variable scope) and compared, layer by layer."""
+    import uresnet_b200.synthetic_io as S
+    from oracle import tf1_shim as shim
+    from oracle.steps import StepOracle
+    nd = len(dims) - 1
+    d, l, w = S.make_batch(B, dims, seed=12)
+    w = w / w.sum(axis=1, keepdims=True)
+    P = O.init_params(nd, base=F, num_strides=St, seed=6)
+    shp = [B] + dims[:-1]
+    so = StepOracle(P, d.reshape(shp + [1]), l.reshape(shp), w.reshape(shp), base=F, num_strides=St)
+    shim.reset_default_graph(torch.float64)
+    uresnet = shim.load_reference()
+    import tensorflow as tf
+    net = uresnet(dims=dims, num_class=3, num_strides=St, base_num_outputs=F)
+    net.construct(trainable=True, use_weight=True, learning_rate=1e-3)
+    sess = tf.Session()
+    sess.run(tf.global_variables_initializer())
+    for v in tf.trainable_variables():
+        v.load(P[v.op.name], sess)
+    lt = shim.layer_tensors()
+    assert set(lt) == {"UResNet/" + s for s in so.layers}
+    scopes = list(so.layers)
+    vals = sess.run([[lt["UResNet/" + s]["raw"], lt["UResNet/" + s]["out"]] for s in scopes],
+                    feed_dict=net.feed_dict(d, l, w))
+    cl = lambda t: t.detach().permute(0, *range(2, nd + 2), 1).numpy()        # noqa: E731
+    for s, (raw, out) in zip(scopes, vals):
+        L = so.layers[s]
+        assert rel(raw, cl(L["raw"])) < 1e-11, s
+        if L["out"] is not None:                       # simple layers and resnet_conv1: BN(+ReLU) output is a node
+            assert rel(out, cl(so.nodes[L["out"]])) < 1e-11, s
+        else:                                          # shortcut / resnet_conv2: BN output feeds the residual add
+            want = O.batch_norm(L["raw"], so.P["UResNet/%s/BatchNorm/beta" % s])
+            assert rel(out, cl(want)) < 1e-11, s
+    shim.uninstall()
