@@ -478,6 +478,24 @@ def _conv_layer(nd, transpose):
     return layer
 
 
+def gradients(ys, xs):
+    """tf.gradients(ys, xs) for a scalar ``ys``: d ys / d x for every tensor x of the graph (variables or
+    intermediates; the values autograd differentiates are the very ones the forward evaluation memoised)."""
+    xs = list(xs)
+
+    def grad_of(i):
+        def fn(ctx):
+            key = ("gradients", ys, tuple(xs))
+            if key not in ctx.grads:
+                xv = [x._eval(ctx) for x in xs]
+                yv = ys._eval(ctx)
+                gs = torch.autograd.grad(yv, xv, allow_unused=True, retain_graph=True)
+                ctx.grads[key] = [torch.zeros_like(x) if g is None else g.detach() for g, x in zip(gs, xv)]
+            return ctx.grads[key][i]
+        return Tensor(fn, (), xs[i].shape.as_list())
+    return [grad_of(i) for i in range(len(xs))]
+
+
 def layer_tensors():
     """{variable scope of a slim layer: {'raw': conv output, 'out': layer output}} of the current graph"""
     return dict(_G.layers)
@@ -651,7 +669,7 @@ def install(reference_lib=REFERENCE_LIB):
     for k in ("float32", "int64", "int32", "variable_scope", "name_scope", "placeholder", "reshape", "cast", "argmax",
               "equal", "reduce_mean", "reduce_sum", "where", "to_float", "gather_nd", "multiply", "zeros_like", "concat",
               "Variable", "trainable_variables", "global_variables", "global_variables_initializer", "Session",
-              "InteractiveSession", "reset_default_graph", "set_random_seed", "nn"):
+              "InteractiveSession", "reset_default_graph", "set_random_seed", "nn", "gradients"):
         setattr(tf, k, getattr(me, k))
     tf.train = types.SimpleNamespace(AdamOptimizer=AdamOptimizer, Saver=Saver)
     tf.summary = types.SimpleNamespace(scalar=_summary_scalar, image=_summary_image, merge_all=_merge_all,

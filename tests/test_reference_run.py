@@ -428,6 +428,17 @@ def test_live_every_intermediate_tensor_of_the_step_oracle(dims, B, F, St):
     vals = sess.run([[lt["UResNet/" + s]["raw"], lt["UResNet/" + s]["out"]] for s in scopes],
                     feed_dict=net.feed_dict(d, l, w))
     cl = lambda t: t.detach().permute(0, *range(2, nd + 2), 1).numpy()        # noqa: E731
+    # ... and the backward intermediates: tf.gradients of the reference's loss with respect to the raw conv output
+    # of every layer (what the BN-backward steps produce and the filter- / input-gradient steps consume) and to
+    # every layer output that is a node of the schedule
+    so.backward()
+    node_scopes = [s for s in scopes if so.layers[s]["out"] is not None]
+    gr = sess.run(tf.gradients(net._loss, [lt["UResNet/" + s]["raw"] for s in scopes]
+                               + [lt["UResNet/" + s]["out"] for s in node_scopes]), feed_dict=net.feed_dict(d, l, w))
+    for s, g in zip(scopes, gr[:len(scopes)]):
+        assert rel(g, cl(so.bn[s]["draw"])) < 1e-9, ("d(raw)", s)
+    for s, g in zip(node_scopes, gr[len(scopes):]):
+        assert rel(g, cl(so.node_grad[so.layers[s]["out"]])) < 1e-9, ("node gradient", s)
     for s, (raw, out) in zip(scopes, vals):
         L = so.layers[s]
         assert rel(raw, cl(L["raw"])) < 1e-11, s
