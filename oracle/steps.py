@@ -1,5 +1,6 @@
-"""Step-by-step form of the CPU oracle (TEST INFRASTRUCTURE ONLY; parity unpinned, see
-``oracle/__init__.py``).
+"""Step-by-step form of the CPU oracle (TEST INFRASTRUCTURE ONLY; what is and is not pinned by the
+reference: ``oracle/__init__.py``.  Every forward and backward intermediate kept here is compared with
+the tensors of the reference's own graph in tests/test_reference_run.py).
 
 ``uresnet_oracle.forward`` states the graph of /root/reference/lib/uresnet.py:22-123 and
 lib/resnet_module.py:10-87 as one autograd expression.  ``StepOracle`` states the SAME graph one

@@ -1,6 +1,8 @@
 """CPU restatement of the reference U-ResNet graph (TEST INFRASTRUCTURE ONLY).
 
-Parity unpinned (see ``oracle/__init__.py``).  Follows, line by line:
+Checked against the reference's own code executed over ``oracle/tf1_shim.py`` and against its GraphDef
+dump; the numerics of TensorFlow's kernels themselves stay unpinned (see ``oracle/__init__.py``).
+Follows, line by line:
 
 * topology ............ /root/reference/lib/uresnet.py:22-123
 * residual block ...... /root/reference/lib/resnet_module.py:10-87
