@@ -2,10 +2,9 @@
 
     python tests/golden/make_golden.py
 
-PARITY UNPINNED: the reference ships no golden vectors and cannot run here (TF 1.x
-absent), so these vectors freeze the *oracle* (oracle/uresnet_oracle.py, fp64), which is
-itself cross-checked against oracle/naive.py and finite differences in
-tests/test_oracle.py.  Inputs come from the seeded synthetic generator and the seeded
+The reference ships no golden vectors and its TensorFlow cannot run here, so these
+vectors (round 1) freeze the *oracle* (oracle/uresnet_oracle.py, fp64), which is
+cross-checked against oracle/naive.py and finite differences in tests/test_oracle.py.  Inputs come from the seeded synthetic generator and the seeded
 Xavier initialiser; both inputs and outputs are stored so that the fixtures do not
 depend on those generators staying bit-stable.
 
