@@ -448,3 +448,26 @@ def test_live_every_intermediate_tensor_of_the_step_oracle(dims, B, F, St):
             want = O.batch_norm(L["raw"], so.P["UResNet/%s/BatchNorm/beta" % s])
             assert rel(out, cl(want)) < 1e-11, s
     shim.uninstall()
+
+
+def test_reference_run_vectors_detect_semantic_mutations(monkeypatch):
+    """The comparison has teeth: change one TF semantic in the oracle -- batch-norm epsilon, which side the
+    asymmetric SAME padding goes, the concat operand order -- and the reference-run vectors reject it."""
+    z = np.load(os.path.join(GOLD, "gref2d_f4s3.npz"))
+
+    def deviation():
+        _, _, r = _oracle_on(z)
+        return rel(r["logits"], z["logits"])
+    assert deviation() < 2e-7
+    with monkeypatch.context() as m:
+        m.setattr(O, "BN_EPS", 1e-5)                      # the dumped older revision's epsilon
+        assert deviation() > 1e-3
+    with monkeypatch.context() as m:
+        sp = O.same_pads
+        m.setattr(O, "same_pads", lambda n, k, s: sp(n, k, s)[::-1])
+        assert deviation() > 1e-1
+    with monkeypatch.context() as m:
+        cat = torch.cat
+        m.setattr(torch, "cat", lambda ts, dim=0: cat(list(ts)[::-1], dim=dim))
+        assert deviation() > 1e-1
+    assert deviation() < 2e-7
