@@ -50,6 +50,7 @@ def fx():
 @pytest.mark.skipif(not os.path.exists(DUMP), reason="reference tree not on this box")
 def test_fixture_is_what_the_dump_says(fx):
     import importlib.util
+    pytest.importorskip("tensorboard.compat.proto.graph_pb2")          # GraphDef protos only; no TensorFlow needed
     spec = importlib.util.spec_from_file_location("mk", os.path.join(HERE, "golden", "make_reference_graph_fixture.py"))
     mk = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mk)
